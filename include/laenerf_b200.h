@@ -1,0 +1,227 @@
+/*
+ * laenerf_b200.h -- C ABI of liblaenerf_b200.so (hand-written sm_100a CUDA, no torch types).
+ *
+ * One entry point per function the reference's pybind11 `_backend` modules export for the ray-marched NeRF
+ * step (citations are paths under /root/reference):
+ *     raymarching/src/bindings.cpp:5-21   (12 functions)
+ *     gridencoder/src/bindings.cpp        (3 functions)
+ *     ffmlp/src/bindings.cpp              (5 functions)
+ *     shencoder/src/bindings.cpp          (2 functions; adjacent row f-1 of SURVEY.md section 8)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are caller-allocated and the
+ *     library never allocates device memory.  Scratch, where needed, is passed in; its size is queried with the
+ *     matching *_scratch_bytes function.  Scratch given to lnrf_march_rays_train must be zero-filled before its
+ *     FIRST use only (the kernels leave it zeroed again) and must not be shared by launches that can overlap.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream, which is what the reference uses).
+ *   - return value: 0 on success, a negative lnrf_status otherwise; lnrf_last_error() returns a thread-local
+ *     message (the reference raises RuntimeError through TORCH_CHECK; the Python shim re-raises the same way).
+ *   - float tensors are fp32 row-major contiguous exactly as the reference's at::Tensor arguments; `*_f16`
+ *     pointers are IEEE binary16.
+ *   - zero-initialisation contracts of the reference wrappers are stated per function ("ZERO-IN" = the caller
+ *     must pass zero-filled memory as the reference wrapper does; "SELF-ZERO" = the kernel writes every element,
+ *     so the caller may pass uninitialised memory and sees what the reference's torch.zeros + kernel produce).
+ */
+#ifndef LAENERF_B200_H_
+#define LAENERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LNRF_API __attribute__((visibility("default")))
+#else
+#define LNRF_API
+#endif
+
+typedef void* lnrf_stream_t;
+
+typedef enum {
+    LNRF_OK = 0,
+    LNRF_ERR_INVALID_ARGUMENT = -1,
+    LNRF_ERR_CUDA = -2,
+    LNRF_ERR_UNSUPPORTED = -3,
+    LNRF_ERR_SCRATCH_TOO_SMALL = -4
+} lnrf_status;
+
+typedef enum { LNRF_F32 = 0, LNRF_F16 = 1 } lnrf_dtype;
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+LNRF_API const char* lnrf_last_error(void);
+/* Library/ABI version and the SM architecture the kernels were compiled for (100 => sm_100a). */
+LNRF_API int lnrf_version(void);
+LNRF_API int lnrf_compiled_arch(void);
+/* Number of kernels this library has launched from this process (all threads); used by bench.py gpu_launches. */
+LNRF_API uint64_t lnrf_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * raymarching utilities -- replaces raymarching/src/raymarching.cu:148-156, 201-209, 229-232, 257-260, 292-300
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* near_far_from_aabb (raymarching.h:7).  rays_o/rays_d [N,3]; aabb [6]; nears/fars [N] (written for all N). */
+LNRF_API int lnrf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                     float min_near, float* nears, float* fars, lnrf_stream_t stream);
+/* sph_from_ray (raymarching.h:8).  coords [N,2]. */
+LNRF_API int lnrf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                               lnrf_stream_t stream);
+/* morton3D / morton3D_invert (raymarching.h:9-10).  coords [N,3] int32 in [0,1024); indices [N] int32. */
+LNRF_API int lnrf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, lnrf_stream_t stream);
+LNRF_API int lnrf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, lnrf_stream_t stream);
+/* packbits (raymarching.h:11).  grid [N*8] fp32; bitfield [N] bytes; bit i of byte n = grid[8n+i] > thresh. */
+LNRF_API int lnrf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                           lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * training march + compositing -- replaces raymarching.cu:482-490, 580-588, 685-693
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* march_rays_train (raymarching.h:13).
+ *   rays_o, rays_d [N,3]; grid = density bitfield [C*H^3/8]; nears, fars, noises [N];
+ *   xyzs, dirs [M,3], deltas [M,2]  SELF-ZERO (rows not covered by a ray are written as zeros);
+ *   rays [N,3] int32 = (ray id, point offset, point count) -- all N rows written;
+ *   counter [2] int32: counter[0] += total points, counter[1] += N (the caller zeroes it, renderer.py:287-288).
+ * Slot assignment is DETERMINISTIC: row n of `rays` is ray n and offsets are the exclusive prefix sum of the
+ * per-ray counts in ray-id order, starting at the incoming counter[0] (the reference hands out slots with
+ * atomicAdd in warp arrival order -- a run-dependent permutation of this layout).  Rays with
+ * offset + count > M write nothing (raymarching.cu:416).
+ *   scratch: lnrf_march_rays_train_scratch_bytes(N) bytes, zero before first use. */
+LNRF_API size_t lnrf_march_rays_train_scratch_bytes(uint32_t N);
+LNRF_API int lnrf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                   float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                   const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                   int32_t* rays, int32_t* counter, const float* noises, void* scratch,
+                                   size_t scratch_bytes, lnrf_stream_t stream);
+
+/* composite_rays_train_forward (raymarching.h:14).  sigmas [M], rgbs [M,3], deltas [M,2], rays [N,3];
+ * weights_sum, depth [N], image [N,3] written at index rays[n,0] for every row n. */
+LNRF_API int lnrf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                               const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                               float* weights_sum, float* depth, float* image, lnrf_stream_t stream);
+/* composite_rays_train_backward (raymarching.h:15).  grad_sigmas [M], grad_rgbs [M,3]: ZERO-IN when
+ * zero_fill == 0 (reference contract, raymarching.py:283-284).  With zero_fill != 0 the kernel itself clears
+ * every element no ray covers; this requires the canonical `rays` layout lnrf_march_rays_train produces
+ * (ray ranges ascending and contiguous) and is what the Python shim uses. */
+LNRF_API int lnrf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                                const float* sigmas, const float* rgbs, const float* deltas,
+                                                const int32_t* rays, const float* weights_sum, const float* image,
+                                                uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                                float* grad_rgbs, int zero_fill, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * inference / distillation march + compositing -- replaces raymarching.cu:929-945, 1145-1159
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* march_rays (raymarching.h:17) and march_rays_distill (raymarching.h:18; edit_grid/edit_occ non-NULL).
+ *   rays_alive [n_alive] int32 ray ids; rays_t, nears, fars [N]; noises [n_alive] (indexed by slot);
+ *   xyzs, dirs [M_rows,3], deltas [M_rows,2], edit_occ [M_rows] bytes (bool): SELF-ZERO over all M_rows rows
+ *   (M_rows >= n_alive*n_step is the padded row count the wrapper allocated, raymarching.py:329-336). */
+LNRF_API int lnrf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                             const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                             uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                             float* xyzs, float* dirs, float* deltas, const float* noises, uint32_t M_rows,
+                             lnrf_stream_t stream);
+LNRF_API int lnrf_march_rays_distill(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                                     const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                                     uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                                     const uint8_t* edit_grid, const float* nears, const float* fars, float* xyzs,
+                                     float* dirs, float* deltas, uint8_t* edit_occ, const float* noises,
+                                     uint32_t M_rows, lnrf_stream_t stream);
+/* composite_rays (raymarching.h:19) / composite_rays_distill (raymarching.h:20): in-place on rays_alive, rays_t,
+ * weights_sum, depth, image (+ weights_edit_sum, depth_edit). */
+LNRF_API int lnrf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                 const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                                 float* depth, float* image, lnrf_stream_t stream);
+LNRF_API int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                                         float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
+                                         float* weights_sum, float* weights_edit_sum, float* depth, float* depth_edit,
+                                         const uint8_t* edit_occ, float* image, lnrf_stream_t stream);
+/* Device-side replacement for `rays_alive = rays_alive[rays_alive >= 0]` (renderer.py:375): stable compaction of
+ * the non-negative entries of rays_alive[0..n_alive) into out, count written to n_out (device int32[1], must be
+ * zero on entry).  Row f-3 of SURVEY.md section 8. */
+LNRF_API int lnrf_compact_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* out, int32_t* n_out,
+                                lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * hash-grid encoder -- replaces gridencoder/src/gridencoder.cu:448-503, 639-645 (gridencoder.h:12-15)
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* layout of the per-level feature axis in outputs / grad */
+typedef enum {
+    LNRF_GRID_LBC = 0, /* [L, B, C]: what the reference kernel writes (gridencoder.cu:388) */
+    LNRF_GRID_BLC = 1  /* [B, L*C]: what grid.py:57 returns after its permute copy -- written directly */
+} lnrf_grid_layout;
+
+/* grid_encode_forward.  inputs [B,D] fp32 in [0,1]; embeddings [offsets[L], C] (dtype emb_dtype);
+ * offsets_host [L+1] int32 on the HOST (the reference passes a device tensor; the shim keeps a host copy);
+ * outputs in emb_dtype, layout out_layout; dy_dx optional ([B, L*D*C], emb_dtype) or NULL.
+ * S = log2(per_level_scale), H = base_resolution, gridtype 0 hash / 1 tiled, interp 0 linear / 1 smoothstep.
+ * Supported: D in {2,3}, C in {1,2,4,8}, L <= 32. */
+LNRF_API int lnrf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets_host,
+                                      void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                      uint32_t H, void* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
+                                      lnrf_dtype emb_dtype, lnrf_grid_layout out_layout, lnrf_stream_t stream);
+/* grid_encode_backward.  grad in emb_dtype with layout grad_layout; grad_embeddings [offsets[L], C] emb_dtype
+ * ZERO-IN (grid.py:77); dy_dx/grad_inputs optional (grad_inputs [B,D] emb_dtype). */
+LNRF_API int lnrf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                       const int32_t* offsets_host, void* grad_embeddings, uint32_t B, uint32_t D,
+                                       uint32_t C, uint32_t L, float S, uint32_t H, const void* dy_dx,
+                                       void* grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                                       lnrf_dtype emb_dtype, lnrf_grid_layout grad_layout, lnrf_stream_t stream);
+/* grad_total_variation: accumulates into grad in place. inputs [B,D] in emb_dtype as in the reference. */
+LNRF_API int lnrf_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                                       const int32_t* offsets_host, float weight, uint32_t B, uint32_t D, uint32_t C,
+                                       uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                       lnrf_dtype emb_dtype, lnrf_stream_t stream);
+/* Test hook: the per-level `scale` (exp2f(level*S)*H - 1) exactly as the device evaluates it; scales [L] fp32. */
+LNRF_API int lnrf_grid_level_scales(uint32_t L, float S, uint32_t H, float* scales, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fully fused MLP (tcgen05 / TMEM) -- replaces ffmlp/src/ffmlp.cu:635-709, 721-740, 749-895 (ffmlp.h)
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Weights are the reference's flat fp16 vector: [hidden,in] + (num_layers-1) x [hidden,hidden] + [out,hidden],
+ * each row-major (ffmlp.cu:632).  B must be a multiple of 128 (the shim pads, ffmlp.py:157-159); hidden_dim 64
+ * (the width every LAENeRF net uses) ; input_dim a multiple of 16 up to 64; output_dim == 16 (padded).
+ * activation ids as ffmlp.py:89-96 (0 relu, 3 sigmoid ... 6 none).
+ * ffmlp_forward: inputs [B,in], forward_buffer [num_layers,B,hidden] (saved activations), outputs [B,out]. */
+LNRF_API int lnrf_ffmlp_forward(const void* inputs_f16, const void* weights_f16, uint32_t B, uint32_t input_dim,
+                                uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                uint32_t output_activation, void* forward_buffer_f16, void* outputs_f16,
+                                lnrf_stream_t stream);
+/* ffmlp_inference: no activations saved (inference_buffer is accepted for signature parity and unused). */
+LNRF_API int lnrf_ffmlp_inference(const void* inputs_f16, const void* weights_f16, uint32_t B, uint32_t input_dim,
+                                  uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                  uint32_t output_activation, void* inference_buffer_f16, void* outputs_f16,
+                                  lnrf_stream_t stream);
+/* ffmlp_backward: grad [B,out]; backward_buffer [num_layers,B,hidden] scratch (accepted for parity; the fused
+ * kernel keeps dL/dhidden on chip and only uses it when non-NULL for debugging); grad_inputs [B,in] or NULL
+ * (calc_grad_inputs); grad_weights flat fp16 like weights (written, not accumulated);
+ * wgrad_scratch: lnrf_ffmlp_wgrad_scratch_bytes(...) bytes of fp32 partial sums (any contents). */
+LNRF_API size_t lnrf_ffmlp_wgrad_scratch_bytes(uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
+                                               uint32_t num_layers);
+LNRF_API int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void* weights_f16,
+                                 const void* forward_buffer_f16, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                 uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                 uint32_t output_activation, int calc_grad_inputs, void* backward_buffer_f16,
+                                 void* grad_inputs_f16, void* grad_weights_f16, void* wgrad_scratch,
+                                 size_t wgrad_scratch_bytes, lnrf_stream_t stream);
+/* allocate_splitk / free_splitk (ffmlp.cu:721-740): the reference creates side streams for its split-K wgrad
+ * GEMMs.  The fused backward needs none; both are kept as no-ops so that the binding surface is identical. */
+LNRF_API int lnrf_allocate_splitk(size_t size);
+LNRF_API int lnrf_free_splitk(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * spherical-harmonics direction encoder (adjacent row f-1) -- shencoder/src/shencoder.cu:385-439
+ * --------------------------------------------------------------------------------------------------------- */
+/* inputs [B,3] fp32; outputs [B, degree^2] in out_dtype; degree in 1..8; dy_dx optional [B, 3*degree^2]. */
+LNRF_API int lnrf_sh_encode_forward(const float* inputs, void* outputs, uint32_t B, uint32_t degree, void* dy_dx,
+                                    lnrf_dtype out_dtype, lnrf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAENERF_B200_H_ */

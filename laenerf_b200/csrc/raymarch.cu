@@ -1,0 +1,859 @@
+// raymarch.cu -- occupancy-grid ray marching and front-to-back compositing for sm_100a.
+//
+// Replaces raymarching/src/raymarching.cu of the reference (kernels :91-1142).  Design:
+//   * marching: a GROUP of lanes per ray (32 for training, 8 for inference rounds) evaluates a window of
+//     consecutive members of the ray's t-sequence in parallel -- occupancy-byte loads of a whole window are in
+//     flight together instead of one dependent load per visited voxel -- and ballots resolve which members the
+//     reference visits (march_core.cuh).  Training is ONE pass: sample parameters are parked in shared memory,
+//     slots are handed out by a warp-level scan inside the block plus a decoupled look-back across blocks
+//     (deterministic ray-id order; the reference uses two marches and global atomics), and the sample buffers are
+//     written as flat, fully coalesced 16-byte vectors.
+//   * compositing: warp per ray; transmittance is a multiplicative warp scan, colour/depth are warp reductions.
+#include "common.cuh"
+#include "march_core.cuh"
+
+namespace lnrf {
+
+// =========================================================================================================
+// utilities (bit-exact integer / IEEE work)
+// =========================================================================================================
+
+// raymarching.cu:91-145
+__global__ void __launch_bounds__(256) k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                  const float* __restrict__ aabb, uint32_t N, float min_near,
+                                                  float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = f_div(1.0f, rays_d[n * 3]), rdy = f_div(1.0f, rays_d[n * 3 + 1]), rdz = f_div(1.0f, rays_d[n * 3 + 2]);
+    const float a0 = __ldg(aabb), a1 = __ldg(aabb + 1), a2 = __ldg(aabb + 2), a3 = __ldg(aabb + 3), a4 = __ldg(aabb + 4), a5 = __ldg(aabb + 5);
+    float near = f_mul(f_add(a0, -ox), rdx), far = f_mul(f_add(a3, -ox), rdx);
+    if (near > far) { const float c = near; near = far; far = c; }
+    float near_y = f_mul(f_add(a1, -oy), rdy), far_y = f_mul(f_add(a4, -oy), rdy);
+    if (near_y > far_y) { const float c = near_y; near_y = far_y; far_y = c; }
+    bool miss = (near > far_y || near_y > far);
+    if (!miss) {
+        if (near_y > near) near = near_y;
+        if (far_y < far) far = far_y;
+        float near_z = f_mul(f_add(a2, -oz), rdz), far_z = f_mul(f_add(a5, -oz), rdz);
+        if (near_z > far_z) { const float c = near_z; near_z = far_z; far_z = c; }
+        miss = (near > far_z || near_z > far);
+        if (!miss) {
+            if (near_z > near) near = near_z;
+            if (far_z < far) far = far_z;
+            if (near < min_near) near = min_near;
+        }
+    }
+    if (miss) near = far = 3.402823466e+38f;  // std::numeric_limits<float>::max(), raymarching.cu:122
+    nears[n] = near;
+    fars[n] = far;
+}
+
+// raymarching.cu:162-198
+__global__ void __launch_bounds__(256) k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                      float radius, uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float RPI = 0.3183098861837907f;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float C = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * C)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    coords[n * 2] = 2 * theta * RPI - 1;
+    coords[n * 2 + 1] = phi * RPI;
+}
+
+// raymarching.cu:214-254
+__global__ void __launch_bounds__(256) k_morton3d(const int* __restrict__ coords, uint32_t N, int* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int)morton3d((uint32_t)coords[n * 3], (uint32_t)coords[n * 3 + 1], (uint32_t)coords[n * 3 + 2]);
+}
+__global__ void __launch_bounds__(256) k_morton3d_invert(const int* __restrict__ indices, uint32_t N, int* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int ind = indices[n];
+    coords[n * 3] = (int)morton3d_invert((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int)morton3d_invert((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int)morton3d_invert((uint32_t)(ind >> 2));
+}
+
+// raymarching.cu:267-289.  One thread packs 4 output bytes from 32 floats (8 x 16-byte loads), so a warp reads
+// 4 KiB contiguous and writes 128 B contiguous.  N = number of output bytes.
+__global__ void __launch_bounds__(256) k_packbits(const float* __restrict__ grid, uint32_t N, float thresh,
+                                                  uint8_t* __restrict__ bitfield) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // output word index
+    const uint32_t n0 = w * 4;
+    if (n0 >= N) return;
+    if (n0 + 4 <= N && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0) && ((reinterpret_cast<uintptr_t>(bitfield) & 3) == 0)) {
+        const float4* g4 = reinterpret_cast<const float4*>(grid) + (size_t)w * 8;
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 v = __ldcs(g4 + i);
+            const uint32_t nib = (v.x > thresh ? 1u : 0u) | (v.y > thresh ? 2u : 0u) | (v.z > thresh ? 4u : 0u) | (v.w > thresh ? 8u : 0u);
+            word |= nib << (4 * i);
+        }
+        reinterpret_cast<uint32_t*>(bitfield)[w] = word;
+    } else {
+        for (uint32_t n = n0; n < N && n < n0 + 4; n++) {
+            uint32_t bits = 0;
+            for (int i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? (1u << i) : 0u;
+            bitfield[n] = (uint8_t)bits;
+        }
+    }
+}
+
+// =========================================================================================================
+// group marcher
+// =========================================================================================================
+
+template <int G>
+struct Group {
+    int gl, gshift;
+    __device__ Group() {
+        const int lane = threadIdx.x & 31;
+        gl = lane & (G - 1);
+        gshift = lane & ~(G - 1);
+    }
+    static constexpr unsigned kMask = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    __device__ __forceinline__ unsigned ballot(bool pred) const { return (__ballot_sync(kFull, pred) >> gshift) & kMask; }
+    __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(kFull, v, gshift + src); }
+};
+
+__device__ __forceinline__ unsigned low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// Marches one ray per group until `max_emit` samples were visited or t >= far.  `emit(rank, s, dt, probe,
+// prev_after)` is called by the lane that holds visited sample number `rank` (0-based); prev_after is the t after
+// the previous emitted sample (or t_start), only maintained when TRACK_LAST.  With EDIT the probe carries the bit
+// index so the caller can test a second bitfield.  Control flow is warp-uniform (groups that finished idle).
+template <int G, bool TRACK_LAST, class Emit>
+__device__ __forceinline__ uint32_t march_group(const Group<G>& grp, const MarchParams& p, const Ray& r,
+                                                const uint8_t* __restrict__ grid, float t, float far, uint32_t max_emit,
+                                                bool alive, Emit&& emit) {
+    uint32_t cnt = 0;
+    float pend = -INFINITY;  // target of a skip that ran past the previous window
+    float last_after = t;
+    while (__any_sync(kFull, alive)) {
+        float nxt;
+        const float s = march_window<G>(p, t, grp.gl, &nxt);
+        const float dt = p.dt_const ? p.dt0 : march_dt(p, s);
+        const bool valid = alive && (s < far);
+        Probe q;
+        q.x = q.y = q.z = 0.f; q.tt = 0.f; q.index = 0u;
+        bool occ = false;
+        if (valid) {
+            q = march_probe(p, r, s, dt);
+            occ = (__ldg(grid + (q.index >> 3)) >> (q.index & 7u)) & 1u;
+        }
+        const unsigned occm = grp.ballot(occ), valm = grp.ballot(valid);
+        const unsigned reach = grp.ballot(s >= pend);
+        unsigned vis = 0;
+        int v = reach ? (__ffs(reach) - 1) : G;
+        if (v < G) pend = -INFINITY;
+        bool res = alive && (v < G);
+        while (__any_sync(kFull, res)) {
+            const int vv = v < G ? v : (G - 1);
+            const float tt = grp.shfl(q.tt, vv);
+            const unsigned ge = grp.ballot(s >= tt);
+            if (res) {
+                if (!((valm >> v) & 1u)) {  // t >= far at a visited member: the ray is finished
+                    alive = false;
+                    res = false;
+                } else if ((occm >> v) & 1u) {  // occupied: every following occupied lane is visited too (t += dt)
+                    const unsigned rest = (~occm & Group<G>::kMask) >> v;
+                    int run = rest ? (__ffs(rest) - 1) : (G - v);
+                    const int room = (int)(max_emit - cnt) - __popc(vis);
+                    if (run >= room) {  // reached the sample budget (num_steps < max_steps, raymarching.cu:359)
+                        run = room;
+                        alive = false;
+                        res = false;
+                    }
+                    vis |= low_bits(run) << v;
+                    v += run;
+                    if (v >= G) res = false;
+                } else {  // empty: do { t += dt } while (t < tt)  ==> first later member with s >= tt
+                    const unsigned m = ge & ~low_bits(v + 1) & Group<G>::kMask;
+                    if (m) {
+                        v = __ffs(m) - 1;
+                    } else {
+                        pend = tt;
+                        v = G;
+                        res = false;
+                    }
+                }
+            }
+        }
+        // emit the visited samples of this window
+        const float after = f_add(s, dt);
+        float prev_after = last_after;
+        if (TRACK_LAST) {
+            const unsigned below = vis & low_bits(grp.gl);
+            const int pl = below ? (31 - __clz(below)) : 0;
+            const float pa = grp.shfl(after, pl);
+            if (below) prev_after = pa;
+            const int hl = vis ? (31 - __clz(vis)) : 0;
+            const float la = grp.shfl(after, hl);
+            if (vis) last_after = la;
+        }
+        if ((vis >> grp.gl) & 1u) emit(cnt + (uint32_t)__popc(vis & low_bits(grp.gl)), s, dt, q, prev_after);
+        cnt += (uint32_t)__popc(vis);
+        t = nxt;
+    }
+    return cnt;
+}
+
+// =========================================================================================================
+// training march: one pass, deterministic slots
+// =========================================================================================================
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Flat, coalesced write of `nflt` floats starting at float index `first` of `base` where element e is produced by
+// f(e); uses 16-byte stores for the aligned body.  `base` must be 16-byte aligned (torch allocations are).
+template <class F>
+__device__ __forceinline__ void warp_write_flat(float* __restrict__ base, size_t first, uint32_t nflt, int lane, F&& f) {
+    const uint32_t head0 = (uint32_t)((4 - (first & 3)) & 3);
+    const uint32_t head = head0 < nflt ? head0 : nflt;
+    if ((uint32_t)lane < head) st_cs(base + first + lane, f((uint32_t)lane));
+    const uint32_t nvec = (nflt - head) >> 2;
+    float4* vb = reinterpret_cast<float4*>(base + first + head);
+    for (uint32_t v = lane; v < nvec; v += 32) {
+        const uint32_t e = head + 4 * v;
+        float4 o;
+        o.x = f(e); o.y = f(e + 1); o.z = f(e + 2); o.w = f(e + 3);
+        st_cs(vb + v, o);
+    }
+    const uint32_t done = head + 4 * nvec;
+    if (done + lane < nflt) st_cs(base + first + done + lane, f(done + (uint32_t)lane));
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+              const MarchParams p, const uint32_t N, const uint32_t M, const float* __restrict__ nears,
+              const float* __restrict__ fars, const float* __restrict__ noises, float* __restrict__ xyzs,
+              float* __restrict__ dirs, float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
+              unsigned long long* __restrict__ scratch) {
+    extern __shared__ float s_tl[];  // WARPS x max_steps visited t values
+    __shared__ uint32_t s_cnt[WARPS];
+    __shared__ uint32_t s_excl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n = blockIdx.x * WARPS + warp;
+    float* tl = s_tl + (size_t)warp * p.max_steps;
+    const Group<32> grp;
+
+    Ray r;
+    float t0 = 0.f, far = 0.f;
+    const bool active = n < N;
+    if (active) {
+        r = make_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
+        const float near = nears[n];
+        far = fars[n];
+        t0 = f_fma(f_clamp(f_mul(near, p.dt_gamma), p.dt_min, p.dt_max), noises[n], near);  // raymarching.cu:348-351
+    } else {
+        r = Ray{};
+    }
+    const uint32_t count = march_group<32, false>(grp, p, r, grid, t0, far, p.max_steps, active,
+                                                  [&](uint32_t rank, float s, float, const Probe&, float) { tl[rank] = s; });
+    if (lane == 0) s_cnt[warp] = count;
+    __syncthreads();
+
+    // ---- slot assignment: in-block prefix + decoupled look-back over blocks (status = flag<<32 | value) ----
+    // scratch[0] = 1 + first sample row no ray wrote, scratch[1] = incoming counter[0], scratch[2..] = look-back words
+    unsigned long long* status = scratch + 2;
+    if (warp == 0) {
+        uint32_t agg = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) agg += s_cnt[w];
+        uint32_t excl = 0;
+        const uint32_t b = blockIdx.x;
+        if (b == 0) {
+            excl = (uint32_t)counter[0];  // slots continue from the incoming counter, like the reference's atomicAdd
+            if (lane == 0) {
+                scratch[1] = (unsigned long long)excl;
+                if (excl > M) scratch[0] = 1ull;  // nothing can be written at all: everything is zero-fill
+            }
+        } else {
+            if (lane == 0) st_relaxed_u64(status + b, (1ull << 32) | agg);
+            int idx = (int)b - 1;
+            while (true) {
+                const int j = idx - lane;
+                unsigned long long st;
+                do {
+                    st = (j >= 0) ? ld_relaxed_u64(status + j) : (2ull << 32);
+                } while (__any_sync(kFull, (st >> 32) == 0ull));
+                const unsigned incl = __ballot_sync(kFull, (st >> 32) == 2ull);
+                uint32_t v = (uint32_t)st;
+                if (incl) {
+                    const int first = __ffs(incl) - 1;
+                    if (lane > first) v = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+                excl += v;
+                if (incl) break;
+                idx -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_relaxed_u64(status + b, (2ull << 32) | (unsigned long long)(excl + agg));
+            s_excl = excl;
+            if (b == gridDim.x - 1) {
+                const uint32_t total_end = excl + agg;
+                counter[0] = (int)total_end;
+                counter[1] += (int)N;
+                if (total_end <= M) scratch[0] = (unsigned long long)total_end + 1ull;  // first row nobody wrote
+            }
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    uint32_t offset = s_excl;
+    for (int w = 0; w < warp; w++) offset += s_cnt[w];
+
+    if (lane == 0) {
+        rays[(size_t)n * 3] = (int)n;
+        rays[(size_t)n * 3 + 1] = (int)offset;
+        rays[(size_t)n * 3 + 2] = (int)count;
+    }
+    if (count == 0) return;
+    if (offset + count > M) {  // dropped (raymarching.cu:416); the first dropped ray marks where zero-fill starts
+        if (offset <= M && lane == 0) scratch[0] = (unsigned long long)offset + 1ull;
+        return;
+    }
+    __syncwarp();
+
+    // ---- coalesced writes straight from the parked t values ----
+    const float o3[3] = {r.ox, r.oy, r.oz};
+    const float d3[3] = {r.dx, r.dy, r.dz};
+    warp_write_flat(xyzs, (size_t)offset * 3, count * 3, lane, [&](uint32_t e) {
+        const uint32_t k = e / 3u, c = e - 3u * k;
+        const float oc = c == 0 ? o3[0] : (c == 1 ? o3[1] : o3[2]);
+        const float dc = c == 0 ? d3[0] : (c == 1 ? d3[1] : d3[2]);
+        return f_clamp(f_fma(tl[k], dc, oc), p.neg_bound, p.bound);
+    });
+    warp_write_flat(dirs, (size_t)offset * 3, count * 3, lane, [&](uint32_t e) {
+        const uint32_t c = e % 3u;
+        return c == 0 ? d3[0] : (c == 1 ? d3[1] : d3[2]);
+    });
+    float2* dl = reinterpret_cast<float2*>(deltas) + offset;
+    for (uint32_t k = lane; k < count; k += 32) {
+        const float s = tl[k];
+        const float dt = p.dt_const ? p.dt0 : march_dt(p, s);
+        const float after = f_add(s, dt);
+        float last = t0;
+        if (k > 0) {
+            const float sp = tl[k - 1];
+            last = f_add(sp, p.dt_const ? p.dt0 : march_dt(p, sp));
+        }
+        st_cs(dl + k, make_float2(dt, f_add(after, -last)));  // (dt, t - last_t), raymarching.cu:459-462
+    }
+}
+
+// Zero rows [E, M) of the three sample buffers (what torch.zeros leaves behind in the reference wrapper,
+// raymarching.py:205-207) and re-arm the look-back words for the next launch.
+__global__ void __launch_bounds__(256)
+k_march_train_tail(unsigned long long* __restrict__ scratch, uint32_t nblocks, float* __restrict__ xyzs,
+                   float* __restrict__ dirs, float* __restrict__ deltas, uint32_t M) {
+    const unsigned long long e1 = scratch[0];
+    size_t head = (size_t)scratch[1];  // rows below the incoming counter value are nobody's: zero them too
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < nblocks; i += nth) scratch[2 + i] = 0ull;
+    if (head > M) head = M;
+    for (size_t i = tid; i < head * 3; i += nth) {
+        xyzs[i] = 0.f;
+        dirs[i] = 0.f;
+    }
+    for (size_t i = tid; i < head * 2; i += nth) deltas[i] = 0.f;
+    if (e1 == 0ull) return;
+    const size_t E = (size_t)(e1 - 1ull);
+    if (E >= M) return;
+    for (size_t i = E * 3 + tid; i < (size_t)M * 3; i += nth) {
+        xyzs[i] = 0.f;
+        dirs[i] = 0.f;
+    }
+    for (size_t i = E * 2 + tid; i < (size_t)M * 2; i += nth) deltas[i] = 0.f;
+}
+
+// =========================================================================================================
+// training compositing (warp per ray)
+// =========================================================================================================
+
+// raymarching.cu:500-577
+__global__ void __launch_bounds__(256)
+k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                   num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    if (num_steps != 0 && offset + num_steps <= M) {
+        const float* ps = sigmas + offset;
+        const float* pc = rgbs + (size_t)offset * 3;
+        const float2* pl = reinterpret_cast<const float2*>(deltas) + offset;
+        float T_carry = 1.0f, t_carry = 0.0f;
+        for (uint32_t base = 0; base < num_steps; base += 32) {
+            const uint32_t k = base + lane;
+            const bool act = k < num_steps;
+            float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dd = 0.f;
+            if (act) {
+                const float2 dl = __ldcs(pl + k);
+                alpha = 1.0f - __expf(-__ldcs(ps + k) * dl.x);
+                dd = dl.y;
+                cr = __ldcs(pc + (size_t)k * 3); cg = __ldcs(pc + (size_t)k * 3 + 1); cb = __ldcs(pc + (size_t)k * 3 + 2);
+            }
+            float P = 1.0f - alpha;  // inclusive product scan of (1 - alpha)
+            float S = dd;            // inclusive sum scan of the depth deltas
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float Pn = __shfl_up_sync(kFull, P, o), Sn = __shfl_up_sync(kFull, S, o);
+                if (lane >= o) { P *= Pn; S += Sn; }
+            }
+            float Pex = __shfl_up_sync(kFull, P, 1);
+            if (lane == 0) Pex = 1.0f;
+            const float T_before = T_carry * Pex, T_after = T_carry * P;
+            // the reference accumulates the sample that drives T below the threshold, then stops (:554-557)
+            const unsigned stop = __ballot_sync(kFull, act && (T_after < T_thresh));
+            const bool use = act && (stop == 0u || lane <= (__ffs(stop) - 1));
+            if (use) {
+                const float w = alpha * T_before;
+                r += w * cr; g += w * cg; b += w * cb;
+                d += w * (t_carry + S);
+                ws += w;
+            }
+            if (stop) break;
+            T_carry = __shfl_sync(kFull, T_after, 31);
+            t_carry += __shfl_sync(kFull, S, 31);
+        }
+        r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+    }
+    if (lane == 0) {
+        weights_sum[index] = ws;
+        depth[index] = d;
+        image[(size_t)index * 3] = r;
+        image[(size_t)index * 3 + 1] = g;
+        image[(size_t)index * 3 + 2] = b;
+    }
+}
+
+__device__ __forceinline__ void warp_zero_range(float* __restrict__ p, size_t lo, size_t hi, int lane) {
+    for (size_t i = lo + lane; i < hi; i += 32) p[i] = 0.f;
+}
+
+// raymarching.cu:601-682
+template <bool ZERO_FILL>
+__global__ void __launch_bounds__(256)
+k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
+                      const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
+                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                   num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+    const bool fits = offset + num_steps <= M;
+    if (ZERO_FILL) {
+        // canonical layout: rows no fitting ray covers are [first dropped ray's offset, M), or [end of last ray, M)
+        size_t z0 = M;
+        if (num_steps != 0 && !fits && offset <= M) z0 = offset;
+        else if (n == N - 1 && fits) z0 = (size_t)offset + num_steps;
+        if (z0 < M) {
+            warp_zero_range(grad_sigmas, z0, M, lane);
+            warp_zero_range(grad_rgbs, z0 * 3, (size_t)M * 3, lane);
+        }
+        if (n == 0 && offset > 0) {
+            const size_t z1 = offset < M ? offset : M;
+            warp_zero_range(grad_sigmas, 0, z1, lane);
+            warp_zero_range(grad_rgbs, 0, z1 * 3, lane);
+        }
+    }
+    if (num_steps == 0 || !fits) return;
+
+    const float gws = grad_weights_sum[index];
+    const float gr = grad_image[(size_t)index * 3], gg = grad_image[(size_t)index * 3 + 1], gb = grad_image[(size_t)index * 3 + 2];
+    const float ws_final = weights_sum[index];
+    const float r_final = image[(size_t)index * 3], g_final = image[(size_t)index * 3 + 1], b_final = image[(size_t)index * 3 + 2];
+    const float* ps = sigmas + offset;
+    const float* pc = rgbs + (size_t)offset * 3;
+    const float2* pl = reinterpret_cast<const float2*>(deltas) + offset;
+    float* gs = grad_sigmas + offset;
+    float* gc = grad_rgbs + (size_t)offset * 3;
+    const float ws_term = gws * (1.0f - ws_final);
+
+    float T_carry = 1.0f, r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
+    uint32_t base = 0;
+    for (; base < num_steps; base += 32) {
+        const uint32_t k = base + lane;
+        const bool act = k < num_steps;
+        float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dt = 0.f;
+        if (act) {
+            dt = __ldcs(pl + k).x;
+            alpha = 1.0f - __expf(-__ldcs(ps + k) * dt);
+            cr = __ldcs(pc + (size_t)k * 3); cg = __ldcs(pc + (size_t)k * 3 + 1); cb = __ldcs(pc + (size_t)k * 3 + 2);
+        }
+        float P = 1.0f - alpha;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float Pn = __shfl_up_sync(kFull, P, o);
+            if (lane >= o) P *= Pn;
+        }
+        float Pex = __shfl_up_sync(kFull, P, 1);
+        if (lane == 0) Pex = 1.0f;
+        const float T_before = T_carry * Pex, T_after = T_carry * P;
+        const float w = alpha * T_before;
+        float ar = w * cr, ag = w * cg, ab = w * cb;  // inclusive sums of the accumulated colour
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float xr = __shfl_up_sync(kFull, ar, o), xg = __shfl_up_sync(kFull, ag, o), xb = __shfl_up_sync(kFull, ab, o);
+            if (lane >= o) { ar += xr; ag += xg; ab += xb; }
+        }
+        ar += r_carry; ag += g_carry; ab += b_carry;
+        const unsigned stop = __ballot_sync(kFull, act && (T_after < T_thresh));
+        const bool use = act && (stop == 0u || lane <= (__ffs(stop) - 1));
+        if (use) {
+            __stcs(gc + (size_t)k * 3, gr * w);
+            __stcs(gc + (size_t)k * 3 + 1, gg * w);
+            __stcs(gc + (size_t)k * 3 + 2, gb * w);
+            __stcs(gs + k, dt * (gr * (T_after * cr - (r_final - ar)) + gg * (T_after * cg - (g_final - ag)) +
+                                 gb * (T_after * cb - (b_final - ab)) + ws_term));
+        } else if (ZERO_FILL && act) {
+            __stcs(gc + (size_t)k * 3, 0.f); __stcs(gc + (size_t)k * 3 + 1, 0.f); __stcs(gc + (size_t)k * 3 + 2, 0.f);
+            __stcs(gs + k, 0.f);
+        }
+        if (stop) { base += 32; break; }
+        T_carry = __shfl_sync(kFull, T_after, 31);
+        r_carry = __shfl_sync(kFull, ar, 31);
+        g_carry = __shfl_sync(kFull, ag, 31);
+        b_carry = __shfl_sync(kFull, ab, 31);
+    }
+    if (ZERO_FILL && base < num_steps) {  // samples behind the early-out keep zero gradients
+        warp_zero_range(gs, base, num_steps, lane);
+        warp_zero_range(gc, (size_t)base * 3, (size_t)num_steps * 3, lane);
+    }
+}
+
+// =========================================================================================================
+// inference / distillation march (group of 8 lanes per alive ray, fixed n_step slots per ray)
+// =========================================================================================================
+
+constexpr int kInferGroup = 8;
+
+template <bool DISTILL>
+__global__ void __launch_bounds__(256)
+k_march_infer(const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive,
+              const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+              const MarchParams p, const uint8_t* __restrict__ grid, const uint8_t* __restrict__ edit_grid,
+              const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+              float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, const float* __restrict__ noises,
+              const uint32_t M_rows, const uint32_t n_groups) {
+    constexpr int G = kInferGroup;
+    const Group<G> grp;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = g < n_alive;
+    Ray r = Ray{};
+    float t = 0.f, far = 0.f;
+    if (active) {
+        const int index = __ldg(rays_alive + g);
+        r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+        far = fars[index];
+        const float t_in = rays_t[index];
+        t = f_fma(f_clamp(f_mul(t_in, p.dt_gamma), p.dt_min, p.dt_max), noises[g], t_in);  // raymarching.cu:746
+    }
+    const size_t row0 = (size_t)g * n_step;
+    const uint32_t cnt = march_group<G, true>(
+        grp, p, r, grid, t, far, n_step, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
+            const size_t row = row0 + rank;
+            xyzs[row * 3] = q.x; xyzs[row * 3 + 1] = q.y; xyzs[row * 3 + 2] = q.z;
+            dirs[row * 3] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz;
+            reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, f_add(f_add(s, dt), -prev_after));
+            if (DISTILL) edit_occ[row] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
+        });
+    if (g >= n_groups) return;
+    // zero-fill the slots this ray did not use, and whole padding groups (torch.zeros in raymarching.py:334-336)
+    const size_t zlo = row0 + (active ? cnt : 0u);
+    size_t zhi = row0 + n_step;
+    if (zhi > M_rows) zhi = M_rows;
+    for (size_t i = zlo * 3 + grp.gl; i < zhi * 3; i += G) { xyzs[i] = 0.f; dirs[i] = 0.f; }
+    for (size_t i = zlo * 2 + grp.gl; i < zhi * 2; i += G) deltas[i] = 0.f;
+    if (DISTILL)
+        for (size_t i = zlo + grp.gl; i < zhi; i += G) edit_occ[i] = 0;
+}
+
+// raymarching.cu:948-1035 and :1037-1142.  Thread per alive ray: at most n_step <= 8 samples, and the reference's
+// sequential float order (T = 1 - weight_sum; t += delta) is kept so that rays_t and the kill pattern are exact.
+template <bool DISTILL>
+__global__ void __launch_bounds__(256)
+k_composite_infer(const uint32_t n_alive, const uint32_t n_step, const float T_thresh, int* __restrict__ rays_alive,
+                  float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                  const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ weights_edit_sum,
+                  float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
+                  float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float* ps = sigmas + (size_t)n * n_step;
+    const float* pc = rgbs + (size_t)n * n_step * 3;
+    const float2* pl = reinterpret_cast<const float2*>(deltas) + (size_t)n * n_step;
+    const uint8_t* pe = DISTILL ? edit_occ + (size_t)n * n_step : nullptr;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth[index];
+    float weight_edit_sum = 0.f, d_edit = 0.f;
+    if (DISTILL) { weight_edit_sum = weights_edit_sum[index]; d_edit = depth_edit[index]; }
+    float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float2 dl = __ldg(pl + step);
+        if (dl.x == 0.f) break;
+        const float alpha = 1.0f - __expf(-__ldg(ps + step) * dl.x);
+        const float T = f_add(1.0f, -weight_sum);
+        const float weight = f_mul(alpha, T);
+        weight_sum = f_add(weight_sum, weight);
+        if (DISTILL && pe[step]) {
+            weight_edit_sum = f_add(weight_edit_sum, weight);
+            d_edit = f_fma(weight, t, d_edit);  // t BEFORE the increment (:1098-1101); nvcc contracts w*t + d
+        }
+        t = f_add(t, dl.y);
+        d = f_fma(weight, t, d);
+        r = f_fma(weight, __ldg(pc + step * 3), r);
+        g = f_fma(weight, __ldg(pc + step * 3 + 1), g);
+        b = f_fma(weight, __ldg(pc + step * 3 + 2), b);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+    if (DISTILL) { weights_edit_sum[index] = weight_edit_sum; depth_edit[index] = d_edit; }
+    weights_sum[index] = weight_sum;
+    depth[index] = d;
+    image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+}
+
+}  // namespace lnrf
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+using namespace lnrf;
+
+static inline cudaStream_t S(lnrf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int lnrf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                            float* nears, float* fars, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(rays_o && rays_d && aabb && nears && fars, "near_far_from_aabb: null pointer");
+    k_near_far<<<div_up(N, 256u), 256, 0, S(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    LNRF_LAUNCH_CHECK("near_far_from_aabb");
+    return LNRF_OK;
+}
+
+int lnrf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(rays_o && rays_d && coords, "sph_from_ray: null pointer");
+    k_sph_from_ray<<<div_up(N, 256u), 256, 0, S(stream)>>>(rays_o, rays_d, radius, N, coords);
+    LNRF_LAUNCH_CHECK("sph_from_ray");
+    return LNRF_OK;
+}
+
+int lnrf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(coords && indices, "morton3D: null pointer");
+    k_morton3d<<<div_up(N, 256u), 256, 0, S(stream)>>>(coords, N, indices);
+    LNRF_LAUNCH_CHECK("morton3D");
+    return LNRF_OK;
+}
+
+int lnrf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(coords && indices, "morton3D_invert: null pointer");
+    k_morton3d_invert<<<div_up(N, 256u), 256, 0, S(stream)>>>(indices, N, coords);
+    LNRF_LAUNCH_CHECK("morton3D_invert");
+    return LNRF_OK;
+}
+
+int lnrf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(grid && bitfield, "packbits: null pointer");
+    const uint32_t words = div_up(N, 4u);
+    k_packbits<<<div_up(words, 256u), 256, 0, S(stream)>>>(grid, N, density_thresh, bitfield);
+    LNRF_LAUNCH_CHECK("packbits");
+    return LNRF_OK;
+}
+
+size_t lnrf_march_rays_train_scratch_bytes(uint32_t N) { return sizeof(unsigned long long) * ((size_t)N + 2); }
+
+static int check_march_common(uint32_t C, uint32_t H, uint32_t max_steps, const char* who) {
+    LNRF_REQUIRE(C >= 1 && C <= 8, "%s: cascade count C=%u out of range [1,8]", who, C);
+    LNRF_REQUIRE(H >= 2 && H <= 1024, "%s: grid size H=%u out of range", who, H);
+    // the reference evaluates the bit index in float (H3 is a float, raymarching.cu:339,378): exact only below 2^24
+    LNRF_REQUIRE((uint64_t)C * H * H * H <= (1ull << 24), "%s: C*H^3 = %llu exceeds 2^24 (index is computed in float)", who,
+                 (unsigned long long)C * H * H * H);
+    LNRF_REQUIRE(max_steps >= 1, "%s: max_steps must be >= 1", who);
+    return LNRF_OK;
+}
+
+int lnrf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                          const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                          const float* noises, void* scratch, size_t scratch_bytes, lnrf_stream_t stream) {
+    if (int e = check_march_common(C, H, max_steps, "march_rays_train")) return e;
+    LNRF_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises, "march_rays_train: null pointer");
+    LNRF_REQUIRE(M == 0 || (xyzs && dirs && deltas), "march_rays_train: null sample buffer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(xyzs) & 15) == 0 && (reinterpret_cast<uintptr_t>(dirs) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(deltas) & 15) == 0,
+                 "march_rays_train: sample buffers must be 16-byte aligned");
+    if (N == 0) return LNRF_OK;
+    if (scratch_bytes < lnrf_march_rays_train_scratch_bytes(N) || !scratch) {
+        set_error("march_rays_train: scratch too small (%zu < %zu)", scratch_bytes, lnrf_march_rays_train_scratch_bytes(N));
+        return LNRF_ERR_SCRATCH_TOO_SMALL;
+    }
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    unsigned long long* sc = reinterpret_cast<unsigned long long*>(scratch);
+    uint32_t nblocks;
+    if ((size_t)max_steps * 4 * sizeof(float) <= 96 * 1024) {
+        constexpr int W = 4;
+        const size_t smem = (size_t)W * max_steps * sizeof(float);
+        nblocks = div_up(N, (uint32_t)W);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_march_train<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "march_rays_train: smem attribute");
+        }
+        k_march_train<W><<<nblocks, W * 32, smem, S(stream)>>>(rays_o, rays_d, grid, p, N, M, nears, fars, noises, xyzs, dirs,
+                                                               deltas, rays, counter, sc);
+    } else {
+        constexpr int W = 1;
+        const size_t smem = (size_t)W * max_steps * sizeof(float);
+        LNRF_REQUIRE(smem <= 227 * 1024, "march_rays_train: max_steps=%u needs %zu B of shared memory (> 227 KiB)", max_steps, smem);
+        nblocks = N;
+        cudaError_t e = cudaFuncSetAttribute(k_march_train<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "march_rays_train: smem attribute");
+        k_march_train<W><<<nblocks, W * 32, smem, S(stream)>>>(rays_o, rays_d, grid, p, N, M, nears, fars, noises, xyzs, dirs,
+                                                               deltas, rays, counter, sc);
+    }
+    LNRF_LAUNCH_CHECK("march_rays_train");
+    k_march_train_tail<<<kNumSMs, 256, 0, S(stream)>>>(sc, nblocks, xyzs, dirs, deltas, M);
+    LNRF_LAUNCH_CHECK("march_rays_train(tail)");
+    return LNRF_OK;
+}
+
+int lnrf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                      uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth, float* image,
+                                      lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(rays && weights_sum && depth && image, "composite_rays_train_forward: null pointer");
+    LNRF_REQUIRE(M == 0 || (sigmas && rgbs && deltas), "composite_rays_train_forward: null sample buffer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays_train_forward: deltas must be 8-byte aligned");
+    k_composite_train_fwd<<<div_up(N, 8u), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    LNRF_LAUNCH_CHECK("composite_rays_train_forward");
+    return LNRF_OK;
+}
+
+int lnrf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                       const float* rgbs, const float* deltas, const int32_t* rays, const float* weights_sum,
+                                       const float* image, uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                       float* grad_rgbs, int zero_fill, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(grad_weights_sum && grad_image && rays && weights_sum && image, "composite_rays_train_backward: null pointer");
+    LNRF_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs), "composite_rays_train_backward: null sample buffer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays_train_backward: deltas must be 8-byte aligned");
+    if (zero_fill)
+        k_composite_train_bwd<true><<<div_up(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
+                                                                          weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    else
+        k_composite_train_bwd<false><<<div_up(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
+                                                                           weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    LNRF_LAUNCH_CHECK("composite_rays_train_backward");
+    return LNRF_OK;
+}
+
+static int march_infer_launch(bool distill, uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                              const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                              uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars,
+                              float* xyzs, float* dirs, float* deltas, uint8_t* edit_occ, const float* noises,
+                              uint32_t M_rows, cudaStream_t st) {
+    const char* who = distill ? "march_rays_distill" : "march_rays";
+    if (int e = check_march_common(C, H, max_steps, who)) return e;
+    LNRF_REQUIRE(n_step >= 1, "%s: n_step must be >= 1", who);
+    LNRF_REQUIRE((uint64_t)n_alive * n_step <= M_rows, "%s: M_rows=%u smaller than n_alive*n_step", who, M_rows);
+    if (M_rows == 0) return LNRF_OK;
+    LNRF_REQUIRE(xyzs && dirs && deltas && (!distill || (edit_occ && edit_grid)), "%s: null output", who);
+    LNRF_REQUIRE(n_alive == 0 || (rays_alive && rays_t && rays_o && rays_d && grid && fars && noises), "%s: null input", who);
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "%s: deltas must be 8-byte aligned", who);
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    const uint32_t n_groups = div_up(M_rows, n_step);
+    const uint32_t blocks = div_up(n_groups, 256u / kInferGroup);
+    if (distill)
+        k_march_infer<true><<<blocks, 256, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, p, grid, edit_grid, fars,
+                                                    xyzs, dirs, deltas, edit_occ, noises, M_rows, n_groups);
+    else
+        k_march_infer<false><<<blocks, 256, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, p, grid, nullptr, fars,
+                                                     xyzs, dirs, deltas, nullptr, noises, M_rows, n_groups);
+    LNRF_LAUNCH_CHECK(who);
+    return LNRF_OK;
+}
+
+int lnrf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                    const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                    const uint8_t* grid, const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                    const float* noises, uint32_t M_rows, lnrf_stream_t stream) {
+    (void)nears;  // loaded but unused by the reference kernel too (raymarching.cu:737)
+    return march_infer_launch(false, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                              nullptr, fars, xyzs, dirs, deltas, nullptr, noises, M_rows, S(stream));
+}
+
+int lnrf_march_rays_distill(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                            const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                            uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* nears,
+                            const float* fars, float* xyzs, float* dirs, float* deltas, uint8_t* edit_occ,
+                            const float* noises, uint32_t M_rows, lnrf_stream_t stream) {
+    (void)nears;
+    return march_infer_launch(true, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                              edit_grid, fars, xyzs, dirs, deltas, edit_occ, noises, M_rows, S(stream));
+}
+
+int lnrf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                        const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                        float* image, lnrf_stream_t stream) {
+    if (n_alive == 0) return LNRF_OK;
+    LNRF_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, "composite_rays: null pointer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays: deltas must be 8-byte aligned");
+    k_composite_infer<false><<<div_up(n_alive, 256u), 256, 0, S(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
+                                                                           deltas, weights_sum, nullptr, depth, nullptr, nullptr, image);
+    LNRF_LAUNCH_CHECK("composite_rays");
+    return LNRF_OK;
+}
+
+int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                                float* weights_edit_sum, float* depth, float* depth_edit, const uint8_t* edit_occ, float* image,
+                                lnrf_stream_t stream) {
+    if (n_alive == 0) return LNRF_OK;
+    LNRF_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && weights_edit_sum && depth && depth_edit &&
+                     edit_occ && image,
+                 "composite_rays_distill: null pointer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays_distill: deltas must be 8-byte aligned");
+    k_composite_infer<true><<<div_up(n_alive, 256u), 256, 0, S(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
+                                                                          deltas, weights_sum, weights_edit_sum, depth, depth_edit,
+                                                                          edit_occ, image);
+    LNRF_LAUNCH_CHECK("composite_rays_distill");
+    return LNRF_OK;
+}
+
+}  // extern "C"
