@@ -140,10 +140,12 @@ LNRF_API int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, floa
                                          float* weights_sum, float* weights_edit_sum, float* depth, float* depth_edit,
                                          const uint8_t* edit_occ, float* image, lnrf_stream_t stream);
 /* Device-side replacement for `rays_alive = rays_alive[rays_alive >= 0]` (renderer.py:375): stable compaction of
- * the non-negative entries of rays_alive[0..n_alive) into out, count written to n_out (device int32[1], must be
- * zero on entry).  Row f-3 of SURVEY.md section 8. */
-LNRF_API int lnrf_compact_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* out, int32_t* n_out,
-                                lnrf_stream_t stream);
+ * the non-negative entries of rays_alive[0..n_alive) into out (which must not alias rays_alive); the count is
+ * written to n_out (device int32[1]).  scratch: lnrf_compact_alive_scratch_bytes(n_alive) bytes, zero before first
+ * use (the kernel leaves it zeroed).  Row f-3 of SURVEY.md section 8. */
+LNRF_API size_t lnrf_compact_alive_scratch_bytes(uint32_t n_alive);
+LNRF_API int lnrf_compact_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* out, int32_t* n_out, void* scratch,
+                                size_t scratch_bytes, lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * hash-grid encoder -- replaces gridencoder/src/gridencoder.cu:448-503, 639-645 (gridencoder.h:12-15)
@@ -220,6 +222,10 @@ LNRF_API int lnrf_free_splitk(void);
 /* inputs [B,3] fp32; outputs [B, degree^2] in out_dtype; degree in 1..8; dy_dx optional [B, 3*degree^2]. */
 LNRF_API int lnrf_sh_encode_forward(const float* inputs, void* outputs, uint32_t B, uint32_t degree, void* dy_dx,
                                     lnrf_dtype out_dtype, lnrf_stream_t stream);
+/* sh_encode_backward (shencoder.cu:394-397): grad [B, degree^2], dy_dx [B, 3*degree^2], grad_inputs [B,3] fp32,
+ * accumulated in place (ZERO-IN, sphere_harmonics.py:49). */
+LNRF_API int lnrf_sh_encode_backward(const float* grad, uint32_t B, uint32_t degree, const float* dy_dx,
+                                     float* grad_inputs, lnrf_stream_t stream);
 
 #ifdef __cplusplus
 }

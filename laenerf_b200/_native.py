@@ -1,0 +1,96 @@
+"""ctypes loader for liblaenerf_b200.so -- the C-ABI boundary of the package (include/laenerf_b200.h).
+
+PyTorch only supplies device memory and streams: every call passes raw `data_ptr()` addresses, sizes and the
+current CUDA stream.  There is NO fallback: if the shared library is missing, or a call fails, a RuntimeError is
+raised (the reference raises RuntimeError through TORCH_CHECK / std::runtime_error).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liblaenerf_b200.so")
+_lib = None
+
+vp, u32, i32, f32, sz, u64 = C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_size_t, C.c_uint64
+
+# name -> (restype, argtypes); must list every symbol include/laenerf_b200.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "lnrf_last_error": (C.c_char_p, []),
+    "lnrf_version": (i32, []),
+    "lnrf_compiled_arch": (i32, []),
+    "lnrf_launch_count": (u64, []),
+    "lnrf_near_far_from_aabb": (i32, [vp, vp, vp, u32, f32, vp, vp, vp]),
+    "lnrf_sph_from_ray": (i32, [vp, vp, f32, u32, vp, vp]),
+    "lnrf_morton3D": (i32, [vp, u32, vp, vp]),
+    "lnrf_morton3D_invert": (i32, [vp, u32, vp, vp]),
+    "lnrf_packbits": (i32, [vp, u32, f32, vp, vp]),
+    "lnrf_march_rays_train_scratch_bytes": (sz, [u32]),
+    "lnrf_march_rays_train": (i32, [vp, vp, vp, f32, f32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "lnrf_composite_rays_train_forward": (i32, [vp, vp, vp, vp, u32, u32, f32, vp, vp, vp, vp]),
+    "lnrf_composite_rays_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, f32, vp, vp, i32, vp]),
+    "lnrf_march_rays": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+    "lnrf_march_rays_distill": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
+    "lnrf_composite_rays": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "lnrf_composite_rays_distill": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "lnrf_compact_alive_scratch_bytes": (sz, [u32]),
+    "lnrf_compact_alive": (i32, [vp, u32, vp, vp, vp, sz, vp]),
+    "lnrf_grid_encode_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp, u32, i32, u32, i32, i32, vp]),
+    "lnrf_grid_encode_backward": (i32, [vp, vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, vp, vp, u32, i32, u32, i32, i32, vp]),
+    "lnrf_grad_total_variation": (i32, [vp, vp, vp, vp, f32, u32, u32, u32, u32, f32, u32, u32, i32, i32, vp]),
+    "lnrf_grid_level_scales": (i32, [u32, f32, u32, vp, vp]),
+    "lnrf_ffmlp_forward": (i32, [vp, vp, u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]),
+    "lnrf_ffmlp_inference": (i32, [vp, vp, u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]),
+    "lnrf_ffmlp_wgrad_scratch_bytes": (sz, [u32, u32, u32, u32]),
+    "lnrf_ffmlp_backward": (i32, [vp, vp, vp, vp, u32, u32, u32, u32, u32, u32, u32, i32, vp, vp, vp, vp, sz, vp]),
+    "lnrf_allocate_splitk": (i32, [sz]),
+    "lnrf_free_splitk": (i32, []),
+    "lnrf_sh_encode_forward": (i32, [vp, vp, u32, u32, vp, i32, vp]),
+    "lnrf_sh_encode_backward": (i32, [vp, u32, u32, vp, vp, vp]),
+}
+
+F32, F16 = 0, 1  # lnrf_dtype
+GRID_LBC, GRID_BLC = 0, 1  # lnrf_grid_layout
+
+
+def build(verbose: bool = False) -> str:
+    """Compile liblaenerf_b200.so in-tree with nvcc for sm_100a (seconds; no torch headers involved)."""
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc"), "-j8"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    return SO_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"laenerf_b200: {SO_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C laenerf_b200/csrc).  There is no CPU or PyTorch fallback for this package.")
+        l = C.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise RuntimeError(lib().lnrf_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().lnrf_launch_count())

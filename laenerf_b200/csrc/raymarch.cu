@@ -644,6 +644,78 @@ k_composite_infer(const uint32_t n_alive, const uint32_t n_step, const float T_t
     image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
 }
 
+// =========================================================================================================
+// device-side alive-ray compaction (row f-3): stable, one launch, decoupled look-back over 1024-ray blocks
+// =========================================================================================================
+// scratch[0] = finished-block counter, scratch[1 + b] = look-back word of block b (flag << 32 | count).  The block
+// that finishes last re-zeroes everything, so the scratch is ready for the next launch on the same stream.
+__global__ void __launch_bounds__(1024)
+k_compact_alive(const int* __restrict__ rays_alive, const uint32_t n_alive, int* __restrict__ out, int* __restrict__ n_out,
+                unsigned long long* __restrict__ scratch) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_excl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    const int v = i < n_alive ? rays_alive[i] : -1;
+    const bool keep = v >= 0;
+    const unsigned bal = __ballot_sync(kFull, keep);
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
+    __syncthreads();
+    unsigned long long* status = scratch + 1;
+    if (warp == 0) {
+        uint32_t c = s_warp[lane], incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += n;
+        }
+        s_warp[lane] = incl - c;  // exclusive prefix of the warps inside the block
+        const uint32_t agg = __shfl_sync(kFull, incl, 31);
+        uint32_t excl = 0;
+        const uint32_t b = blockIdx.x;
+        if (b > 0) {
+            if (lane == 0) st_relaxed_u64(status + b, (1ull << 32) | agg);
+            int idx = (int)b - 1;
+            while (true) {
+                const int j = idx - lane;
+                unsigned long long st;
+                do {
+                    st = (j >= 0) ? ld_relaxed_u64(status + j) : (2ull << 32);
+                } while (__any_sync(kFull, (st >> 32) == 0ull));
+                const unsigned inc = __ballot_sync(kFull, (st >> 32) == 2ull);
+                uint32_t x = (uint32_t)st;
+                if (inc) {
+                    const int first = __ffs(inc) - 1;
+                    if (lane > first) x = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+                excl += x;
+                if (inc) break;
+                idx -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_relaxed_u64(status + b, (2ull << 32) | (unsigned long long)(excl + agg));
+            s_excl = excl;
+            if (b == gridDim.x - 1) *n_out = (int)(excl + agg);
+        }
+    }
+    __syncthreads();
+    if (keep) out[s_excl + s_warp[warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = v;
+    // last block out cleans up
+    __syncthreads();
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(scratch, 1ull) == (unsigned long long)gridDim.x - 1ull;
+    }
+    __syncthreads();
+    if (s_last) {
+        for (uint32_t k = threadIdx.x; k < gridDim.x + 1u; k += 1024u) scratch[k] = 0ull;
+    }
+}
+
 }  // namespace lnrf
 
 // =========================================================================================================
@@ -853,6 +925,27 @@ int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, float T_thres
                                                                           deltas, weights_sum, weights_edit_sum, depth, depth_edit,
                                                                           edit_occ, image);
     LNRF_LAUNCH_CHECK("composite_rays_distill");
+    return LNRF_OK;
+}
+
+size_t lnrf_compact_alive_scratch_bytes(uint32_t n_alive) { return sizeof(unsigned long long) * ((size_t)div_up(n_alive, 1024u) + 1); }
+
+int lnrf_compact_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* out, int32_t* n_out, void* scratch,
+                       size_t scratch_bytes, lnrf_stream_t stream) {
+    LNRF_REQUIRE(n_out, "compact_alive: null counter");
+    if (n_alive == 0) {
+        cudaError_t e = cudaMemsetAsync(n_out, 0, sizeof(int32_t), S(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "compact_alive");
+        return LNRF_OK;
+    }
+    LNRF_REQUIRE(rays_alive && out, "compact_alive: null pointer");
+    if (!scratch || scratch_bytes < lnrf_compact_alive_scratch_bytes(n_alive)) {
+        set_error("compact_alive: scratch too small (%zu < %zu)", scratch_bytes, lnrf_compact_alive_scratch_bytes(n_alive));
+        return LNRF_ERR_SCRATCH_TOO_SMALL;
+    }
+    k_compact_alive<<<div_up(n_alive, 1024u), 1024, 0, S(stream)>>>(rays_alive, n_alive, out, n_out,
+                                                                   reinterpret_cast<unsigned long long*>(scratch));
+    LNRF_LAUNCH_CHECK("compact_alive");
     return LNRF_OK;
 }
 

@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference CALLERS of the hot path, so that tests and bench.py drive the kernels exactly
+the way LAENeRF does: `NeRFNetwork.forward/density` (nerf/network_ff.py:11-100) and the `cuda_ray` branches of
+`NeRFRenderer.run_cuda` / `run_cuda_distill` (nerf/renderer.py:259-392, 394-480), plus the `Trainer.train_step`
+loss/optimizer recipe (nerf/utils.py:535-642, main_nerf.py:223).  This is plumbing around the drop-in modules, not
+a re-implementation of the reference's trainer, GUI, datasets or checkpointing (out of scope).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.amp import custom_bwd, custom_fwd
+
+from . import raymarching
+from .ffmlp import FFMLP
+from .gridencoder import GridEncoder
+from .shencoder import SHEncoder
+
+
+class _trunc_exp(Function):  # activation.py:5-17
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x = ctx.saved_tensors[0]
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+trunc_exp = _trunc_exp.apply
+
+
+class NeRFNetwork(nn.Module):
+    """network_ff.NeRFNetwork + the state NeRFRenderer keeps for cuda_ray (renderer.py:72-126)."""
+
+    def __init__(self, bound=1, num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                 density_scale=1, min_near=0.2, density_thresh=0.01, grid_size=128):
+        super().__init__()
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = grid_size
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.bg_radius = -1
+        aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        self.register_buffer("aabb_train", aabb)
+        self.register_buffer("aabb_infer", aabb.clone())
+        self.register_buffer("density_grid", torch.zeros([self.cascade, grid_size ** 3]))
+        self.register_buffer("density_bitfield", torch.zeros(self.cascade * grid_size ** 3 // 8, dtype=torch.uint8))
+        self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
+        self.mean_density = 0
+        self.iter_density = 0
+        self.mean_count = 0
+        self.local_step = 0
+
+        self.geo_feat_dim = geo_feat_dim
+        self.encoder = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                                   desired_resolution=2048 * bound, gridtype="hash", align_corners=False)  # encoding.py:68-70
+        self.in_dim = self.encoder.output_dim
+        self.sigma_net = FFMLP(input_dim=self.in_dim, output_dim=1 + geo_feat_dim, hidden_dim=hidden_dim, num_layers=num_layers)
+        self.encoder_dir = SHEncoder(input_dim=3, degree=4)
+        self.in_dim_color = self.encoder_dir.output_dim + geo_feat_dim + 1  # padded to 32 (network_ff.py:43)
+        self.color_net = FFMLP(input_dim=self.in_dim_color, output_dim=3, hidden_dim=hidden_dim_color, num_layers=num_layers_color)
+
+    # ---- network_ff.py:51-79 -------------------------------------------------------------------------------
+    def forward(self, x, d):
+        x = self.encoder(x, bound=self.bound)
+        h = self.sigma_net(x)
+        sigma = trunc_exp(h[..., 0])
+        geo_feat = h[..., 1:]
+        d = self.encoder_dir(d)
+        p = torch.zeros_like(geo_feat[..., :1])
+        h = torch.cat([d, geo_feat, p], dim=-1)
+        h = self.color_net(h)
+        rgb = torch.sigmoid(h)
+        return sigma, rgb
+
+    def density(self, x):  # network_ff.py:81-95
+        x = self.encoder(x, bound=self.bound)
+        h = self.sigma_net(x)
+        return {"sigma": trunc_exp(h[..., 0]), "geo_feat": h[..., 1:]}
+
+    # ---- occupancy state ---------------------------------------------------------------------------------------
+    def set_density_grid(self, density_grid: torch.Tensor, thresh: float | None = None):
+        """Install a [C, H^3] Morton-ordered density grid and derive the bitfield (renderer.py:640-641)."""
+        self.density_grid.copy_(density_grid)
+        self.mean_density = float(self.density_grid.clamp(min=0).mean().item())
+        t = min(self.mean_density, self.density_thresh) if thresh is None else thresh
+        raymarching.packbits(self.density_grid, t, self.density_bitfield)
+
+    def update_mean_count(self):
+        """The step-counter part of update_extra_state (renderer.py:643-647)."""
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
+    # ---- renderer.py:259-392 ---------------------------------------------------------------------------------
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
+                 T_thresh=1e-4, scale_depth=True, edit_grid=None, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        dens_grid = edit_grid if edit_grid is not None else self.density_bitfield
+        n_rays = rays_o.shape[0]
+        device = rays_o.device
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer,
+                                                     self.min_near)
+        if bg_color is None:
+            bg_color = 1
+        results = {}
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
+                                                                    self.grid_size, nears, fars, counter, self.mean_count, perturb,
+                                                                    128, force_all_rays, dt_gamma, max_steps)
+            sigmas, rgbs = self(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+            if not kwargs.get("distill", False):
+                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+            image = image.view(*prefix, 3)
+            depth = depth.view(*prefix)
+            results["weights_sum"] = weights_sum
+            results["nears"] = nears
+            results["num_points"] = xyzs.shape[0]
+        else:
+            weights_sum = torch.zeros(n_rays, dtype=torch.float32, device=device)
+            depth = torch.zeros(n_rays, dtype=torch.float32, device=device)
+            image = torch.zeros(n_rays, 3, dtype=torch.float32, device=device)
+            n_alive = n_rays
+            rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+            spare = torch.empty_like(rays_alive)
+            count = torch.empty(1, dtype=torch.int32, device=device)
+            rays_t = nears.clone()
+            step = 0
+            total_samples = 0
+            while step < max_steps:
+                if n_alive <= 0:
+                    break
+                n_step = max(min(n_rays // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
+                                                            dens_grid, self.cascade, self.grid_size, nears, fars, 128,
+                                                            perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs = self(xyzs, dirs)
+                sigmas = self.density_scale * sigmas
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image,
+                                           T_thresh)
+                total_samples += xyzs.shape[0]
+                # rays_alive = rays_alive[rays_alive >= 0] (renderer.py:375), compacted on the device
+                raymarching.compact_alive(rays_alive, n_alive, spare, count)
+                rays_alive, spare = spare, rays_alive
+                n_alive = int(count.item())
+                step += n_step
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+            if scale_depth:
+                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+            else:
+                results["t"] = weights_sum
+            image = image.view(*prefix, 3)
+            depth = depth.view(*prefix)
+            results["num_points"] = total_samples
+        results["depth"] = depth
+        results["image"] = image
+        return results
+
+    # ---- renderer.py:394-480 (edit-grid distillation render used to build LAENeRF's EditDataset) --------------
+    @torch.no_grad()
+    def run_cuda_distill(self, rays_o, rays_d, edit_bitfield, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024,
+                         T_thresh=1e-4, **kwargs):
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        n_rays = rays_o.shape[0]
+        device = rays_o.device
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer, self.min_near)
+        if bg_color is None:
+            bg_color = 1
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        weights_sum, weights_edit_sum, depth, depth_edit, image = z(n_rays), z(n_rays), z(n_rays), z(n_rays), z(n_rays, 3)
+        n_alive = n_rays
+        rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+        spare = torch.empty_like(rays_alive)
+        count = torch.empty(1, dtype=torch.int32, device=device)
+        rays_t = nears.clone()
+        step = 0
+        while step < max_steps and n_alive > 0:
+            n_step = max(min(n_rays // n_alive, 8), 1)
+            xyzs, dirs, deltas, edit_occ = raymarching.march_rays_distill(
+                n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, edit_bitfield, self.cascade,
+                self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
+            sigmas, rgbs = self(xyzs, dirs)
+            sigmas = self.density_scale * sigmas
+            raymarching.composite_rays_distill(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
+                                               weights_edit_sum, depth, depth_edit, image, edit_occ, T_thresh)
+            raymarching.compact_alive(rays_alive, n_alive, spare, count)
+            rays_alive, spare = spare, rays_alive
+            n_alive = int(count.item())
+            step += n_step
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum,
+                "weights_edit_sum": weights_edit_sum, "depth_edit": depth_edit, "x_term": rays_o + depth_edit.unsqueeze(-1) * rays_d}
+
+    def render(self, rays_o, rays_d, **kwargs):
+        return self.run_cuda(rays_o, rays_d, **kwargs)
+
+    def get_params(self, lr):  # network_ff.py:139-153
+        return [{"params": self.encoder.parameters(), "lr": lr}, {"params": self.sigma_net.parameters(), "lr": lr},
+                {"params": self.encoder_dir.parameters(), "lr": lr}, {"params": self.color_net.parameters(), "lr": lr}]
+
+
+class TrainStep:
+    """One NeRF training step as `Trainer.train_one_epoch` runs it under `-O` (nerf/utils.py:1474-1484):
+    fp16 autocast forward, MSE on RGB, GradScaler backward, Adam(lr 1e-2, betas (0.9, 0.99), eps 1e-15)."""
+
+    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True):
+        self.model = model
+        self.fp16 = fp16
+        self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
+        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
+
+    def __call__(self, rays_o, rays_d, gt_rgb, bg_color=1, perturb=True):
+        self.model.train()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
+            out = self.model.render(rays_o, rays_d, bg_color=bg_color, perturb=perturb, force_all_rays=False, dt_gamma=0,
+                                    max_steps=1024)
+            loss = torch.nn.functional.mse_loss(out["image"], gt_rgb, reduction="none").mean(-1).mean()
+        self.scaler.scale(loss).backward()
+        self.scaler.step(self.optimizer)
+        self.scaler.update()
+        return loss, out
