@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ray-marched NeRF step (BASELINE.json: train rays/s & render Msamples/s on a
+lego-shape 800x800 synthetic scene, % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); training shards RAYS (4096 per GPU, weak scaling) with one
+all-reduce of the hash-grid + MLP gradients per step.  A "step" is one full training step of configs[1]:
+near/far -> march_rays_train -> hash-grid encode -> sigma MLP -> SH -> colour MLP -> composite -> MSE -> backward of
+all of it -> Adam, under fp16 autocast exactly as `-O` runs it.  One JSON line is printed by rank 0.
+
+`--impl reference` times the CPU arm: the PyTorch-CPU restatement of the reference's non-cuda_ray renderer
+(oracle/cpu_renderer.py, BASELINE.json configs[0]) on the host cores, same metric and unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_RAYS = 4096
+WORKLOAD = "lego-shape 800x800 hash-grid NeRF training step (16 levels, 2^19 table, 4096 rays/GPU, cuda_ray, fp16 autocast, Adam)"
+
+# algorithmic bytes / FLOPs per unit (restated in DESIGN.md section 7)
+ALGO = {
+    "lnrf_march_rays_train": dict(bound="hbm", per_ray=48, per_sample=32),
+    "lnrf_grid_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
+    "lnrf_grid_encode_backward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
+    "lnrf_composite_rays_train_forward": dict(bound="hbm", per_ray=32, per_sample=24),
+    "lnrf_composite_rays_train_backward": dict(bound="hbm", per_ray=44, per_sample=40),
+    "lnrf_ffmlp_forward": dict(bound="tensor", flops_per_sample_padded=36864 / 2),   # mean of sigma (14336) and colour (22528) nets
+    "lnrf_ffmlp_backward": dict(bound="tensor", flops_per_sample_padded=73728 / 2),
+    "lnrf_sh_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=12 + 64),
+    "lnrf_near_far_from_aabb": dict(bound="hbm", per_ray=32, per_sample=0),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]), tensor=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class TimedLib:
+    """Proxy around the ctypes library that brackets selected entry points with CUDA events on the launching stream
+    (per-kernel durations measured live inside the timed region, as the roofline contract asks)."""
+
+    def __init__(self, lib, names, torch):
+        self._lib, self._names, self._torch = lib, set(names), torch
+        self.events = {n: [] for n in names}
+        self.enabled = False
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name not in self._names:
+            return fn
+
+        def wrapped(*a):
+            if not self.enabled:
+                return fn(*a)
+            torch = self._torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a)
+            e1.record()
+            self.events[name].append((e0, e1))
+            return r
+        return wrapped
+
+    def summary(self):
+        out = {}
+        for n, ev in self.events.items():
+            if ev:
+                ms = [a.elapsed_time(b) for a, b in ev]
+                out[n] = dict(calls=len(ms), mean_ms=sum(ms) / len(ms), total_ms=sum(ms))
+        return out
+
+
+def run_reference(args, rank, world):
+    """CPU arm: oracle/cpu_renderer.py (PyTorch-CPU port of NeRFRenderer.run + nn.Linear NeRFNetwork, freq encodings)."""
+    if rank != 0:
+        return
+    import torch
+    from cases import scene_rays
+    from oracle import cpu_renderer
+    n = min(N_RAYS, int(os.environ.get("LNRF_CPU_RAYS", "2048")))
+    sc, ro, rd, rng = scene_rays("lego", n, 0)
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(0))
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    sec, threads, used = cpu_renderer.time_train_steps(torch.from_numpy(ro), torch.from_numpy(rd), gt, steps=steps, warmup=warm,
+                                                       num_steps=512, bound=sc.bound, min_near=sc.min_near)
+    value = used / sec
+    sample = f"{used} rays x 512 uniform samples/ray per step (hits of a {n}-ray draw), {steps} timed + {warm} warm-up steps, fp32"
+    line = {"impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "arm": "reference non-cuda_ray renderer (nerf/renderer.py run + nerf/network.py, "
+                                            "frequency encodings) restated for CPU in oracle/cpu_renderer.py; bounded sample"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-render", action="store_true", help="skip the full-image render measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from laenerf_b200 import _native
+    from laenerf_b200.nerf import NeRFNetwork, TrainStep
+    from laenerf_b200.parallel import gather_image, init_distributed, shard_range
+    from laenerf_b200.scene import get_rays_np, make_scene
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    rank, world, local = init_distributed()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    timed = TimedLib(_native.lib(), list(ALGO), torch)
+    _native._lib = timed
+
+    # ---- synthetic lego-shape scene, random-init weights (seed = rank for the ray draws) -------------------------
+    sc = make_scene("lego", seed=0, n_poses=8)
+    torch.manual_seed(0)
+    model = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_thresh=sc.density_thresh).to(dev)
+    model.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+    step = TrainStep(model, world_size=world)
+    rng = np.random.default_rng(1000 + rank)
+    n_batches = 8
+    host_batches = []
+    for b in range(n_batches):
+        ro, rd, _ = get_rays_np(sc.poses[b % len(sc.poses)], sc.intrinsics, sc.H, sc.W, N=N_RAYS, rng=rng)
+        gt = rng.random((N_RAYS, 3), dtype=np.float32)
+        host_batches.append(tuple(torch.from_numpy(x).pin_memory() for x in (ro, rd, gt)))
+    dev_batches = [tuple(x.to(dev) for x in hb) for hb in host_batches]
+
+    # ---- warm-up: the first step sizes the sample buffer from the counters like the reference (renderer.py:643-647) ----
+    for i in range(args.warmup):
+        step(*dev_batches[i % n_batches])
+        if i == 0:
+            model.update_mean_count()
+    model.update_mean_count()
+    barrier()
+
+    # ---- timed region: device-resident inputs ---------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = _native.launch_count()
+    timed.enabled = True
+    points = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss, out = step(*dev_batches[i % n_batches])
+        points.append(out["num_points"])
+    e1.record()
+    barrier()
+    timed.enabled = False
+    ms = e0.elapsed_time(e1)
+    launches = _native.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    actual = int(model.step_counter[: min(16, args.steps), 0].float().mean().item())
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * N_RAYS * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----------------------------------------
+    h2d = sum(x.numel() * x.element_size() for x in host_batches[0])
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        ro, rd, gt = (x.to(dev, non_blocking=True) for x in host_batches[i % n_batches])
+        loss, out = step(ro, rd, gt)
+        float(loss.item())
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_RAYS * args.steps / (float(t.item()) * 1e-3)
+
+    # ---- per-kernel roofline (events recorded live inside the timed region above) -----------------------------------
+    peaks = measured_peaks()
+    m_pad = int(statistics.mean(points))
+    kern = timed.summary()
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+    table = {}
+    for name, k in kern.items():
+        a = ALGO[name]
+        calls_per_step = k["calls"] / args.steps
+        if a["bound"] == "hbm":
+            byts = a.get("per_ray", 0) * N_RAYS + a.get("per_sample", 0) * actual + a.get("per_sample_padded", 0) * m_pad
+            ach = byts / (k["mean_ms"] * 1e-3) / 1e9
+            table[name] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], mean_ms=k["mean_ms"],
+                               calls_per_step=calls_per_step, algorithmic_bytes=byts, traffic=traffic.get(name))
+        else:
+            fl = a["flops_per_sample_padded"] * m_pad
+            ach = fl / (k["mean_ms"] * 1e-3) / 1e12
+            table[name] = dict(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s", frac=ach / peaks["tensor"],
+                               mean_ms=k["mean_ms"], calls_per_step=calls_per_step, algorithmic_flops=fl, traffic=traffic.get(name))
+    dominant = max(table, key=lambda n: kern[n]["total_ms"]) if table else None
+    roofline = None
+    if dominant:
+        d = table[dominant]
+        roofline = dict(bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=d["traffic"],
+                        kernel=dominant, mean_ms=d["mean_ms"], peak_source=peaks["source"] + (" (sustained)" if d["bound"] == "tensor" else ""),
+                        share_of_step=kern[dominant]["total_ms"] / ms)
+
+    # ---- render: one full 800x800 view, tile-sharded over ranks (no collective but the final gather) -------------------
+    render = None
+    if not args.no_render:
+        ro, rd, _ = get_rays_np(sc.poses[0], sc.intrinsics, sc.H, sc.W)
+        lo, hi = shard_range(ro.shape[0], rank, world)
+        ro_d, rd_d = torch.from_numpy(ro[lo:hi]).to(dev), torch.from_numpy(rd[lo:hi]).to(dev)
+        model.eval()
+        frames, samples = 0, 0
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            model.render(ro_d, rd_d, perturb=False, bg_color=1)  # warm-up frame
+            barrier()
+            e0.record()
+            for _ in range(2):
+                out = model.render(ro_d, rd_d, perturb=False, bg_color=1)
+                img = gather_image(out["image"], ro.shape[0], rank, world)
+                samples += out["num_points"]
+                frames += 1
+            e1.record()
+            barrier()
+        tt = torch.tensor([e0.elapsed_time(e1), float(samples)], device=dev)
+        if world > 1:
+            tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            tt = torch.stack([tmax[0], tsum[1]])
+        rms, rs = float(tt[0].item()), float(tt[1].item())
+        render = dict(value=rs / (rms * 1e-3) / 1e6, unit="Msamples/s", ms_per_frame=rms / frames, rays_per_frame=int(ro.shape[0]),
+                      sample_slots_per_frame=rs / frames, rays_per_s=ro.shape[0] * frames / (rms * 1e-3), image_shape=list(img.shape))
+        model.train()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import cpu_renderer
+        n = int(os.environ.get("LNRF_CPU_RAYS", "1024"))
+        hb = host_batches[0]
+        sec, threads, used = cpu_renderer.time_train_steps(hb[0][:n].clone(), hb[1][:n].clone(), hb[2][:n].clone(), steps=2, warmup=1,
+                                                           num_steps=512, bound=sc.bound, min_near=sc.min_near)
+        cpu = dict(value=used / sec, unit="rays/s", cores=threads, kind="port",
+                   sample=f"{used} rays x 512 uniform samples/ray per step (non-cuda_ray renderer restated in oracle/cpu_renderer.py), 2 timed + 1 warm-up steps")
+
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "samples_per_step_padded": m_pad, "samples_per_step": actual,
+                   "samples_per_ray": actual / N_RAYS, "scene_occupancy": sc.occupancy_fraction(),
+                   "l2": "no explicit flush: one step touches ~245 MB (fp32 table + grads + Adam moments + fp16 copies) > 126 MB L2",
+                   "occupancy_update": "excluded (row f-2 of SURVEY.md section 8: fixed procedural occupancy grid)",
+                   "parallelism": f"ray-sharded dp{world}" if world > 1 else "single GPU"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": table,
+        "render": render,
+        "cpu_baseline": cpu,
+        "train_msamples_per_s": world * actual * args.steps / (ms * 1e-3) / 1e6,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

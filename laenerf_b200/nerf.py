@@ -223,9 +223,10 @@ class TrainStep:
     """One NeRF training step as `Trainer.train_one_epoch` runs it under `-O` (nerf/utils.py:1474-1484):
     fp16 autocast forward, MSE on RGB, GradScaler backward, Adam(lr 1e-2, betas (0.9, 0.99), eps 1e-15)."""
 
-    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True):
+    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True, world_size: int = 1):
         self.model = model
         self.fp16 = fp16
+        self.world_size = world_size
         self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
 
@@ -237,6 +238,9 @@ class TrainStep:
                                     max_steps=1024)
             loss = torch.nn.functional.mse_loss(out["image"], gt_rgb, reduction="none").mean(-1).mean()
         self.scaler.scale(loss).backward()
+        if self.world_size > 1:  # the one exchange step of ray-sharded training
+            from .parallel import allreduce_gradients
+            allreduce_gradients([p for g in self.optimizer.param_groups for p in g["params"]], self.world_size)
         self.scaler.step(self.optimizer)
         self.scaler.update()
         return loss, out

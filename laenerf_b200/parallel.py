@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), `torch.distributed` over NCCL/NVLink.
+
+The reference is single-GPU (its DistributedDataParallel hooks are dead code, nerf/utils.py:380-382); SURVEY.md
+section 8(e) defines what the hot path needs:
+  * training = data parallel over RAYS: every rank marches/encodes/composites its own ray batch against replicated
+    parameters and a replicated occupancy bitfield; the one exchange step is the sum of the hash-grid gradient and
+    of the two flat MLP weight gradients, followed by the identical Adam step on every rank;
+  * rendering = contiguous ray ranges (image tiles) per rank, no collective except the final gather.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend: str | None = None):
+    """Returns (rank, world_size, local_rank); initialises the default process group when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous [lo, hi) share of n units (rays of an image, views of a dataset) for `rank`; sizes differ by <= 1."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_gradients(params, world: int, group=None, average: bool = True):
+    """Sum (or mean) the gradients of `params` over ranks, in place, largest tensor first so that the 49 MB hash-grid
+    gradient is in flight while the small MLP gradients are coalesced into one extra call."""
+    if world <= 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    grads.sort(key=lambda g: -g.numel())
+    big = [g for g in grads if g.numel() >= (1 << 20)]
+    small = [g for g in grads if g.numel() < (1 << 20)]
+    works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in big]
+    if small:
+        flat = torch.cat([g.reshape(-1).float() for g in small])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for g in small:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    for w in works:
+        w.wait()
+    if average:
+        for g in grads:
+            g.div_(world)
+
+
+def broadcast_occupancy(model, src: int = 0, group=None):
+    """Keep the occupancy state identical on every rank (the reference's update uses RNG, renderer.py:590-620)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(model.density_bitfield, src=src, group=group)
+        dist.broadcast(model.density_grid, src=src, group=group)
+
+
+def gather_image(local: torch.Tensor, n_total: int, rank: int, world: int, group=None):
+    """Final gather of a tile-sharded render: `local` is this rank's [hi-lo, ...] slice; returns the full
+    [n_total, ...] tensor on every rank (what nerf/utils.py:1560-1566 does with all_gather)."""
+    if world <= 1:
+        return local
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    maxlen = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((maxlen,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)

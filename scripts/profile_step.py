@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Workload for ncu: warm up the lego-shape training step, then run a few steps (and optionally render rounds)
+between cudaProfilerStart/Stop so that `ncu --profile-from-start off` captures steady-state launches only."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+
+from laenerf_b200.nerf import NeRFNetwork, TrainStep
+from laenerf_b200.scene import get_rays_np, make_scene
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--warmup", type=int, default=6)
+ap.add_argument("--render-rays", type=int, default=0, help="also profile one render of this many rays")
+args = ap.parse_args()
+
+dev = torch.device("cuda", 0)
+sc = make_scene("lego", seed=0, n_poses=4)
+torch.manual_seed(0)
+model = NeRFNetwork(bound=sc.bound, min_near=sc.min_near).to(dev)
+model.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+step = TrainStep(model)
+rng = np.random.default_rng(0)
+ro, rd, _ = get_rays_np(sc.poses[0], sc.intrinsics, sc.H, sc.W, N=4096, rng=rng)
+ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+gt = torch.rand(4096, 3, device=dev)
+for i in range(args.warmup):
+    step(ro, rd, gt)
+    if i == 0:
+        model.update_mean_count()
+model.update_mean_count()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for i in range(args.steps):
+    step(ro, rd, gt)
+if args.render_rays > 0:
+    fo, fd, _ = get_rays_np(sc.poses[1], sc.intrinsics, sc.H, sc.W)
+    fo, fd = torch.from_numpy(fo[: args.render_rays]).to(dev), torch.from_numpy(fd[: args.render_rays]).to(dev)
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        model.render(fo, fd, perturb=False)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("profiled", args.steps, "steps; mean_count", model.mean_count)

@@ -1,0 +1,312 @@
+"""Seeded parity cases for the hot path, written once against the back-end interface of tests/backends.py.
+
+`run_case(name, backend)` returns a flat dict of numpy arrays.  oracle/gen_golden.py evaluates every case with the
+reference's own extensions on a B200 and freezes the result as tests/golden/ref_<name>.npz; the tests evaluate the
+same case with the CPU oracle (no GPU needed) and with liblaenerf_b200.so (GPU) and compare key by key with the
+tolerances in TOL.  Sizes are kept small enough for the oracle to finish in seconds and the fixtures to stay small.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from backends import canonical_rays, canonicalize
+
+EXACT = "exact"
+
+# key-prefix -> tolerance; (rtol, atol) means |a-b| <= atol + rtol*|b|.  First matching prefix wins.
+TOL = {
+    # integer / index / IEEE work: bit-exact
+    "nears": EXACT, "fars": EXACT, "morton": EXACT, "packbits": EXACT, "counts": EXACT, "counter": EXACT,
+    "xyzs": EXACT, "dirs": EXACT, "deltas": EXACT, "edit_occ": EXACT, "alive": EXACT,
+    # inference compositing keeps the reference's sequential fp32 order: exact kill pattern, values to 1 ulp-ish
+    "rays_t": (1e-6, 1e-7), "inf_": (2e-6, 1e-7),
+    # training compositing: warp scan re-associates the fp32 sums/products (rtol 1e-4)
+    "ws": (1e-4, 1e-6), "depth": (1e-4, 1e-6), "image": (1e-4, 1e-6), "gsig": (2e-3, 2e-5), "grgb": (1e-4, 1e-7),
+    # encoder: fp32 interpolation; fp16 tables |d| <= 2^-9 max(1,|v|) (the reference rounds 8x per level)
+    "enc32": (2e-5, 2e-6), "enc16": (2.0 ** -9, 2.0 ** -9), "dydx32": (1e-4, 1e-3), "genc32": (1e-4, 1e-5), "genc16": (2e-2, 2e-2),
+    # MLP: fp16 storage, fp32 accumulate here vs fp16 accumulate in the reference
+    "mlp_out": (2e-2, 4e-3), "mlp_fb": (2e-2, 4e-3), "mlp_gw": (3e-2, 2e-2), "mlp_gi": (3e-2, 2e-3),
+    "sh": (1e-6, 1e-6),
+}
+
+
+def tol_for(key: str):
+    for p, t in TOL.items():
+        if key.startswith(p):
+            return t
+    raise KeyError(f"no tolerance registered for {key}")
+
+
+def compare(got: dict, want: dict, keys=None, scale: float = 1.0):
+    """Assert got[k] ~ want[k] for every shared output key (inputs are prefixed with 'in_' and skipped)."""
+    checked = 0
+    for k in (keys or want.keys()):
+        if k.startswith("in_") or k not in got or k not in want:
+            continue
+        a, b = np.asarray(got[k]), np.asarray(want[k])
+        assert a.shape == b.shape, f"{k}: shape {a.shape} vs {b.shape}"
+        t = tol_for(k)
+        if t == EXACT:
+            if a.dtype.kind == "f":
+                same = (a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0))
+            else:
+                same = a == b
+            assert same.all(), f"{k}: {int((~same).sum())} of {same.size} elements differ (bit-exact required); first at {np.argwhere(~same)[0]}"
+        else:
+            rtol, atol = t
+            err = np.abs(a.astype(np.float64) - b.astype(np.float64))
+            bound = scale * (atol + rtol * np.abs(b.astype(np.float64)))
+            bad = ~(err <= bound)
+            assert not bad.any(), (f"{k}: {int(bad.sum())} of {bad.size} elements outside rtol={rtol} atol={atol} "
+                                   f"(max err {err.max():.3e}, max |ref| {np.abs(b).max():.3e})")
+        checked += 1
+    assert checked > 0, "nothing compared"
+    return checked
+
+
+@functools.lru_cache(maxsize=None)
+def scene(name: str):
+    from laenerf_b200.scene import make_scene
+    return make_scene(name, seed=0, n_poses=4)
+
+
+def scene_rays(name: str, n_rays: int, seed: int):
+    from laenerf_b200.scene import get_rays_np
+    sc = scene(name)
+    rng = np.random.default_rng(seed)
+    ro, rd, _ = get_rays_np(sc.poses[seed % len(sc.poses)], sc.intrinsics, sc.H, sc.W, N=n_rays, rng=rng)
+    return sc, ro, rd, rng
+
+
+# ---------------------------------------------------------------------------------------------------------
+def case_utils(be):
+    sc, ro, rd, rng = scene_rays("lego", 1536, 1)
+    # a third of the rays look away from the box (miss -> FLT_MAX), some start inside it
+    rd[::3] = -rd[::3]
+    ro[1::7] = rng.uniform(-0.5, 0.5, size=ro[1::7].shape).astype(np.float32)
+    nears, fars = be.near_far(ro, rd, sc.aabb, sc.min_near)
+    coords = rng.integers(0, 1024, size=(4096, 3)).astype(np.int32)
+    coords[:256] = rng.integers(0, 128, size=(256, 3))
+    m = be.morton3D(coords)
+    inv = be.morton3D_invert(m)
+    grid = rng.random(4096 * 8, dtype=np.float32)
+    grid[::5] = 0.5
+    bits = be.packbits(grid, 0.5)
+    return {"nears": nears, "fars": fars, "morton": m, "morton_inv": inv, "packbits": bits}
+
+
+def _march_train(be, name, n_rays, seed, dt_gamma):
+    sc, ro, rd, rng = scene_rays(name, n_rays, seed)
+    nears, fars = be.near_far(ro, rd, sc.aabb, sc.min_near)
+    noises = rng.random(n_rays, dtype=np.float32)
+    M = n_rays * sc.max_steps
+    xyzs, dirs, deltas, rays, counter = be.march_train(ro, rd, sc.density_bitfield, sc.bound, dt_gamma, sc.max_steps, sc.cascade,
+                                                       128, M, nears, fars, noises)
+    total = int(counter[0])
+    assert total <= M
+    assert np.all(xyzs[total:] == 0) and np.all(dirs[total:] == 0) and np.all(deltas[total:] == 0), "rows past the total must be zero"
+    counts, cx, cd, cl = canonicalize(xyzs, dirs, deltas, rays)
+    return sc, ro, rd, rng, {"nears": nears, "fars": fars, "counts": counts, "counter": counter.astype(np.int32), "xyzs": cx,
+                             "dirs": cd, "deltas": cl}
+
+
+def case_march_lego(be):
+    return _march_train(be, "lego", 512, 2, 0.0)[4]
+
+
+def case_march_flower(be):
+    return _march_train(be, "flower", 256, 3, 0.0)[4]
+
+
+def case_march_bonsai(be):
+    return _march_train(be, "bonsai", 256, 4, 1.0 / 256.0)[4]
+
+
+def _sample_fields(rng, counts, total):
+    """Per-sample sigma/rgb with per-ray opacity classes so that early termination and long tails both occur."""
+    per_ray = rng.choice(np.array([0.05, 5.0, 60.0, 600.0], np.float32), size=len(counts))
+    sig = (rng.random(total, dtype=np.float32) * np.repeat(per_ray, counts)).astype(np.float32)
+    rgb = rng.random((total, 3), dtype=np.float32)
+    return sig, rgb
+
+
+def case_composite_lego(be):
+    sc, ro, rd, rng, m = _march_train(be, "lego", 512, 2, 0.0)
+    counts, deltas = m["counts"], m["deltas"]
+    total = int(counts.sum())
+    pad = 128 - total % 128
+    M = total + pad
+    rays = canonical_rays(counts)
+    sig, rgb = _sample_fields(rng, counts, total)
+    sig = np.concatenate([sig, np.zeros(pad, np.float32)])
+    rgb = np.concatenate([rgb, np.zeros((pad, 3), np.float32)])
+    dl = np.concatenate([deltas, np.zeros((pad, 2), np.float32)])
+    T = 1e-4
+    ws, depth, image = be.composite_train_fwd(sig, rgb, dl, rays, T)
+    gws = rng.standard_normal(len(counts)).astype(np.float32)
+    gimg = rng.standard_normal((len(counts), 3)).astype(np.float32)
+    gs, gc = be.composite_train_bwd(gws, gimg, sig, rgb, dl, rays, ws, image, T)
+    assert M == sig.shape[0]
+    return {"ws": ws, "depth": depth, "image": image, "gsig": gs, "grgb": gc}
+
+
+def _infer(be, name, n_rays, seed, distill, rounds=4):
+    sc, ro, rd, rng = scene_rays(name, n_rays, seed)
+    nears, fars = be.near_far(ro, rd, sc.aabb, sc.min_near)
+    edit = None
+    if distill:
+        edit = sc.density_bitfield.copy()
+        edit[rng.random(edit.shape[0]) < 0.5] = 0
+    rays_alive = np.arange(n_rays, dtype=np.int32)
+    rays_t = nears.copy()
+    ws, depth, image = np.zeros(n_rays, np.float32), np.zeros(n_rays, np.float32), np.zeros((n_rays, 3), np.float32)
+    wes, depth_edit = np.zeros(n_rays, np.float32), np.zeros(n_rays, np.float32)
+    out = {}
+    T = 1e-2
+    for r in range(rounds):
+        n_alive = rays_alive.shape[0]
+        if n_alive == 0:
+            break
+        n_step = max(min(n_rays // n_alive, 8), 1)
+        M_rows = n_alive * n_step
+        M_rows += 128 - M_rows % 128
+        noises = rng.random(n_alive, dtype=np.float32) if r == 0 else np.zeros(n_alive, np.float32)
+        res = be.march(n_alive, n_step, rays_alive, rays_t, ro, rd, sc.bound, sc.density_bitfield, sc.cascade, 128, nears, fars, noises,
+                       M_rows, 0.0, sc.max_steps, edit)
+        xyzs, dirs, deltas = res[:3]
+        out[f"xyzs_r{r}"], out[f"dirs_r{r}"], out[f"deltas_r{r}"] = xyzs, dirs, deltas
+        sig = (rng.random(M_rows, dtype=np.float32) * 40.0).astype(np.float32)
+        rgb = rng.random((M_rows, 3), dtype=np.float32)
+        if distill:
+            out[f"edit_occ_r{r}"] = res[3].astype(np.uint8)
+            rays_alive, rays_t, ws, depth, image, wes, depth_edit = be.composite(n_alive, n_step, rays_alive, rays_t, sig, rgb, deltas,
+                                                                                  ws, depth, image, T, wes, depth_edit, res[3])
+            out[f"inf_wes_r{r}"], out[f"inf_depth_edit_r{r}"] = wes.copy(), depth_edit.copy()
+        else:
+            rays_alive, rays_t, ws, depth, image = be.composite(n_alive, n_step, rays_alive, rays_t, sig, rgb, deltas, ws, depth, image, T)
+        out[f"alive_r{r}"] = rays_alive.copy()
+        out[f"rays_t_r{r}"] = rays_t.copy()
+        out[f"inf_ws_r{r}"], out[f"inf_depth_r{r}"], out[f"inf_image_r{r}"] = ws.copy(), depth.copy(), image.copy()
+        rays_alive = rays_alive[rays_alive >= 0]
+    return out
+
+
+def case_infer_lego(be):
+    return _infer(be, "lego", 768, 5, False)
+
+
+def case_distill_flower(be):
+    return _infer(be, "flower", 512, 6, True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def grid_config(L=8, C=2, D=3, base=16, log2_T=12, desired=512, align=False):
+    from oracle import pyoracle
+    offsets, pls = pyoracle.grid_offsets(D, L, C, 2.0, base, log2_T, desired, align)
+    return offsets, float(pls)
+
+
+def _grid_inputs(rng, B, D):
+    x = rng.random((B, D), dtype=np.float32)
+    x[0] = 0.0
+    x[1] = 1.0
+    x[2] = 0.5
+    x[3, 0] = -0.01   # out of range -> zero output (gridencoder.cu:110-135)
+    x[4, D - 1] = 1.001
+    x[5] = np.float32(1.0) - np.float32(2.0 ** -24)
+    return x
+
+
+def case_grid_small(be):
+    rng = np.random.default_rng(7)
+    L, C, D, H = 8, 2, 3, 16
+    offsets, pls = grid_config(L, C, D, H, 12, 512)
+    B = 2048 + 37  # ragged: not a multiple of the 128-sample tile
+    x = _grid_inputs(rng, B, D)
+    emb = rng.uniform(-1, 1, size=(int(offsets[-1]), C)).astype(np.float32)
+    emb16 = emb.astype(np.float16).astype(np.float32)
+    scales = getattr(be, "grid_level_scales", lambda *a: None)(L, pls, H)
+    out = {}
+    out["enc32"] = be.grid_fwd(x, emb, offsets, pls, H, half=False, scales=scales)
+    out["enc16"] = be.grid_fwd(x, emb16, offsets, pls, H, half=True, scales=scales)
+    e2, dd = be.grid_fwd(x, emb, offsets, pls, H, half=False, dy_dx=True, scales=scales)
+    out["enc32_b"], out["dydx32"] = e2, dd
+    out["enc32_smooth"] = be.grid_fwd(x, emb, offsets, pls, H, half=False, interp=1, scales=scales)
+    out["enc32_tiled"] = be.grid_fwd(x, emb, offsets, pls, H, half=False, gridtype=1, scales=scales)
+    g = rng.standard_normal((B, L * C)).astype(np.float32)
+    out["genc32"] = np.asarray(be.grid_bwd(g, x, offsets, C, pls, H, half=False, scales=scales), np.float32)
+    g16 = (g * 1e-2).astype(np.float16).astype(np.float32)
+    out["genc16"] = np.asarray(be.grid_bwd(g16, x, offsets, C, pls, H, half=True, scales=scales), np.float32) * 1e2
+    return out
+
+
+def case_grid_d2c4(be):
+    rng = np.random.default_rng(8)
+    L, C, D, H = 4, 4, 2, 16
+    offsets, pls = grid_config(L, C, D, H, 10, 128)
+    B = 777
+    x = _grid_inputs(rng, B, D)
+    emb = rng.uniform(-1, 1, size=(int(offsets[-1]), C)).astype(np.float32)
+    scales = getattr(be, "grid_level_scales", lambda *a: None)(L, pls, H)
+    out = {"enc32": be.grid_fwd(x, emb, offsets, pls, H, half=False, scales=scales)}
+    g = rng.standard_normal((B, L * C)).astype(np.float32)
+    out["genc32"] = np.asarray(be.grid_bwd(g, x, offsets, C, pls, H, half=False, scales=scales), np.float32)
+    return out
+
+
+def _h(a):
+    return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def _ffmlp(be, in_dim, n_layers, B, seed, calc_gi):
+    rng = np.random.default_rng(seed)
+    hidden, out_dim = 64, 16
+    nparams = hidden * (in_dim + hidden * (n_layers - 1) + out_dim)
+    std = np.sqrt(3.0 / hidden)
+    w = _h(rng.uniform(-std, std, size=nparams))
+    x = _h(rng.standard_normal((B, in_dim)) * 0.5)
+    out, fb = be.ffmlp_fwd(x, w, in_dim, out_dim, hidden, n_layers)
+    g = _h(rng.standard_normal((B, out_dim)) * 1e-2)
+    # the backward consumes the (fp16) activations of THIS back-end's forward, like the autograd Function does
+    gw, gi = be.ffmlp_bwd(g, x, w, fb, in_dim, out_dim, hidden, n_layers, 0, calc_gi)
+    res = {"mlp_out": out, "mlp_fb": fb, "mlp_gw": np.asarray(gw, np.float32)}
+    if calc_gi:
+        res["mlp_gi"] = np.asarray(gi, np.float32)
+    return res
+
+
+def case_ffmlp_sigma(be):
+    return _ffmlp(be, 32, 2, 384, 9, False)
+
+
+def case_ffmlp_color(be):
+    return _ffmlp(be, 32, 3, 256, 10, True)
+
+
+def case_sh(be):
+    rng = np.random.default_rng(11)
+    d = rng.standard_normal((1000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    return {"sh4": be.sh(d, 4), "sh3": be.sh(d, 3), "sh1": be.sh(d, 1)}
+
+
+CASES = {
+    "utils": case_utils,
+    "march_lego": case_march_lego,
+    "march_flower": case_march_flower,
+    "march_bonsai": case_march_bonsai,
+    "composite_lego": case_composite_lego,
+    "infer_lego": case_infer_lego,
+    "distill_flower": case_distill_flower,
+    "grid_small": case_grid_small,
+    "grid_d2c4": case_grid_d2c4,
+    "ffmlp_sigma": case_ffmlp_sigma,
+    "ffmlp_color": case_ffmlp_color,
+    "sh": case_sh,
+}
+
+
+def run_case(name: str, be) -> dict:
+    return CASES[name](be)

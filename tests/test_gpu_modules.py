@@ -1,0 +1,181 @@
+"""GPU tier: the drop-in Python modules (autograd, AMP contract) and the full training / rendering step."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from cases import scene, scene_rays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def test_native_library_is_loaded(dev):
+    from laenerf_b200 import _native as N
+    N.lib()
+    maps = open("/proc/self/maps").read()
+    assert "liblaenerf_b200.so" in maps
+
+
+def test_grid_encoder_module_autograd_fp32_vs_torch_reference(dev):
+    """Numerics of the CUDA kernel against a plain PyTorch fp32 restatement of the same op (dense level only)."""
+    from laenerf_b200.gridencoder import GridEncoder
+    enc = GridEncoder(input_dim=3, num_levels=2, level_dim=2, base_resolution=4, log2_hashmap_size=19, desired_resolution=8).to(dev)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    x = (torch.rand(513, 3, device=dev) * 2 - 1)
+    y = enc(x, bound=1)
+    y.square().sum().backward()
+    # torch reference: trilinear interpolation on the dense (res+1)^3 lattice of each level
+    emb = enc.embeddings.detach().clone().requires_grad_(True)
+    outs = []
+    x01 = (x + 1) / 2
+    for lvl in range(2):
+        scale = 2.0 ** (lvl * math.log2(enc.per_level_scale)) * 4 - 1
+        res = math.ceil(scale) + 1
+        pos = x01 * scale + 0.5
+        p0 = pos.floor()
+        f = pos - p0
+        p0 = p0.long()
+        acc = 0
+        for c in range(8):
+            o = torch.tensor([(c >> 0) & 1, (c >> 1) & 1, (c >> 2) & 1], device=dev)
+            w = torch.where(o.bool(), f, 1 - f).prod(-1, keepdim=True)
+            idx = (p0 + o) @ torch.tensor([1, res + 1, (res + 1) ** 2], device=dev)
+            acc = acc + w * emb[enc.offsets[lvl].item() + idx]
+        outs.append(acc)
+    ref = torch.cat(outs, -1)
+    assert torch.allclose(y, ref, rtol=1e-5, atol=1e-6)
+    ref.square().sum().backward()
+    assert torch.allclose(enc.embeddings.grad, emb.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_ffmlp_module_autograd_vs_torch_reference(dev):
+    from laenerf_b200.ffmlp import FFMLP
+    net = FFMLP(32, 3, 64, 3).to(dev)
+    x = (torch.randn(1000, 32, device=dev) * 0.5).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = net(x)
+    assert y.shape == (1000, 3) and y.dtype == torch.float16
+    g = torch.randn_like(y, dtype=torch.float32) * 1e-2
+    (y.float() * g).sum().backward()
+    # fp32 torch reference on the fp16-rounded weights
+    w = net.weights.detach().half().float().requires_grad_(True)
+    xr = x.detach().half().float().requires_grad_(True)
+    W0, W1, W2, W3 = w[:2048].view(64, 32), w[2048:6144].view(64, 64), w[6144:10240].view(64, 64), w[10240:].view(16, 64)
+    h = torch.relu(xr @ W0.T)
+    h = torch.relu(h @ W1.T)
+    h = torch.relu(h @ W2.T)
+    yr = (h @ W3.T)[:, :3]
+    (yr * g).sum().backward()
+    assert torch.allclose(y.float(), yr, rtol=2e-2, atol=2e-3)
+    scale = float(w.grad.abs().max())
+    assert float((net.weights.grad - w.grad).abs().max()) <= 2e-2 * scale + 1e-4
+    assert float((x.grad - xr.grad).abs().max()) <= 2e-2 * float(xr.grad.abs().max()) + 1e-5
+    net.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        assert torch.allclose(net(x).float(), y.float(), rtol=0, atol=0)
+
+
+def test_composite_rays_train_autograd_vs_torch_reference(dev):
+    from laenerf_b200 import raymarching
+    sc, ro, rd, rng = scene_rays("lego", 256, 41)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    bitfield = torch.from_numpy(sc.density_bitfield).to(dev)
+    nears, fars = raymarching.near_far_from_aabb(ro, rd, torch.from_numpy(sc.aabb).to(dev), sc.min_near)
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(ro, rd, sc.bound, bitfield, 1, 128, nears, fars, None, -1, True, 128, False, 0, 1024)
+    M = xyzs.shape[0]
+    assert M % 128 == 0 and rays.shape == (256, 3)
+    sig = (torch.rand(M, device=dev) * 30).requires_grad_(True)
+    rgb = torch.rand(M, 3, device=dev).requires_grad_(True)
+    ws, depth, image = raymarching.composite_rays_train(sig, rgb, deltas, rays, 1e-4)
+    loss = (image * torch.linspace(0.5, 1.5, 3, device=dev)).sum() + (ws * 0.3).sum()
+    loss.backward()
+    # torch reference per ray (no early termination inside this sigma range would change the sums beyond 1e-4)
+    sig2, rgb2 = sig.detach().clone().requires_grad_(True), rgb.detach().clone().requires_grad_(True)
+    tot = 0
+    r = rays.cpu().numpy()
+    for n in range(0, 256, 8):
+        o, c = int(r[n, 1]), int(r[n, 2])
+        if c == 0:
+            continue
+        a = 1 - torch.exp(-sig2[o:o + c] * deltas[o:o + c, 0])
+        T = torch.cumprod(torch.cat([torch.ones(1, device=dev), 1 - a[:-1]]), 0)
+        keep = (T * (1 - a) >= 1e-4).float().cumprod(0)
+        keep = torch.cat([torch.ones(1, device=dev), keep[:-1]])
+        w = a * T * keep
+        img = (w[:, None] * rgb2[o:o + c]).sum(0)
+        assert torch.allclose(image[n], img, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(ws[n], w.sum(), rtol=1e-4, atol=1e-5)
+        tot = tot + (img * torch.linspace(0.5, 1.5, 3, device=dev)).sum() + 0.3 * w.sum()
+    tot.backward()
+    for n in range(0, 256, 8):
+        o, c = int(r[n, 1]), int(r[n, 2])
+        assert torch.allclose(sig.grad[o:o + c], sig2.grad[o:o + c], rtol=2e-3, atol=2e-5)
+        assert torch.allclose(rgb.grad[o:o + c], rgb2.grad[o:o + c], rtol=1e-4, atol=1e-6)
+
+
+def _model(dev, name="lego"):
+    from laenerf_b200.nerf import NeRFNetwork
+    sc = scene(name)
+    torch.manual_seed(0)
+    model = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_thresh=sc.density_thresh).to(dev)
+    model.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+    assert np.array_equal(model.density_bitfield.cpu().numpy(), sc.density_bitfield)
+    return sc, model
+
+
+def test_training_step_runs_and_learns(dev):
+    from laenerf_b200.nerf import TrainStep
+    sc, model = _model(dev)
+    step = TrainStep(model)
+    _, ro, rd, rng = scene_rays("lego", 4096, 42)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    gt = torch.full((4096, 3), 0.25, device=dev)
+    losses = []
+    for i in range(40):
+        loss, out = step(ro, rd, gt, perturb=True)
+        losses.append(float(loss))
+        if i == 0 or (i + 1) % 16 == 0:
+            model.update_mean_count()
+    assert all(math.isfinite(l) for l in losses)
+    assert model.mean_count > 0 and out["num_points"] % 128 == 0
+    assert losses[-1] < 0.5 * losses[0], losses[::8]
+    assert float(model.encoder.embeddings.abs().max()) > 1e-4  # the table moved
+
+
+def test_render_full_loop_matches_training_composite(dev):
+    """Inference loop (march_rays/composite_rays rounds + device-side compaction) against the one-shot training
+    marcher + composite on the same rays without perturbation: same image within T_thresh-level differences."""
+    sc, model = _model(dev)
+    _, ro, rd, rng = scene_rays("lego", 2048, 43)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        model.eval()
+        a = model.render(ro, rd, perturb=False, bg_color=1, T_thresh=1e-4)
+        model.train()
+        model.mean_count = 0
+        b = model.render(ro, rd, perturb=False, bg_color=1, force_all_rays=True, T_thresh=1e-4)
+    assert torch.allclose(a["image"], b["image"], rtol=0, atol=2e-3)
+    mse = float((a["image"] - b["image"]).square().mean())
+    assert mse < 1e-7  # PSNR between the two paths > 70 dB
+
+
+def test_distill_render_runs(dev):
+    sc, model = _model(dev, "flower")
+    _, ro, rd, rng = scene_rays("flower", 1024, 44)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    edit = model.density_bitfield.clone()
+    edit[::2] = 0
+    model.eval()
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = model.run_cuda_distill(ro, rd, edit)
+    assert out["image"].shape == (1024, 3) and torch.isfinite(out["image"]).all()
+    assert (out["weights_edit_sum"] <= out["weights_sum"] + 1e-5).all()

@@ -1,0 +1,91 @@
+"""CPU tier: host-side logic of the drop-in modules (no kernels run): table sizing, parameter layouts, padding rules,
+alias packages, and the hot path's product code never importing the oracle."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_grid_encoder_table_sizing_matches_reference_formula():
+    from laenerf_b200.gridencoder import GridEncoder
+    from oracle import pyoracle
+    for bound, expect_head in ((1, [4920, 13824, 32768, 85184, 216000]), (2, [4920, 15632, 42880, 125000, 373248])):
+        enc = GridEncoder(desired_resolution=2048 * bound)
+        off = enc.offsets.numpy()
+        sizes = np.diff(off)
+        assert list(sizes[:5]) == expect_head
+        assert all(s == 524288 for s in sizes[5:])
+        ref_off, pls = pyoracle.grid_offsets(desired_resolution=2048 * bound)
+        assert np.array_equal(off, ref_off) and abs(pls - enc.per_level_scale) < 1e-12
+        assert enc.embeddings.shape == (off[-1], 2) and enc.embeddings.dtype == torch.float32
+        assert enc.output_dim == 32 and float(enc.embeddings.abs().max()) <= 1e-4
+    assert GridEncoder(desired_resolution=2048).offsets[-1].item() == 6119864
+
+
+def test_ffmlp_parameter_layout_and_seed_side_effect():
+    from laenerf_b200.ffmlp import FFMLP
+    torch.manual_seed(7)
+    a = FFMLP(32, 16, 64, 2)
+    assert a.num_parameters == 64 * (32 + 64 + 16) == a.weights.numel()
+    b = FFMLP(32, 3, 64, 3)
+    assert b.padded_output_dim == 16 and b.num_parameters == 64 * (32 + 2 * 64 + 16)
+    # construction reseeds the global RNG with 42 (ffmlp.py:142): the next draw is the same after either constructor
+    FFMLP(32, 16, 64, 2)
+    x = torch.rand(3)
+    FFMLP(32, 16, 64, 2)
+    assert torch.equal(x, torch.rand(3))
+    assert float(a.weights.abs().max()) <= (3 / 64) ** 0.5
+    with pytest.raises(AssertionError):
+        FFMLP(30, 16, 64, 2)
+    with pytest.raises(AssertionError):
+        FFMLP(32, 17, 64, 2)
+    with pytest.raises(AssertionError):
+        FFMLP(32, 16, 64, 1)
+
+
+def test_dropin_alias_packages_resolve():
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    try:
+        import raymarching
+        from ffmlp import FFMLP
+        from gridencoder import GridEncoder
+        from raymarching import raymarching as rm_mod
+        from shencoder import SHEncoder
+        for fn in ("near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits", "march_rays_train",
+                   "composite_rays_train", "march_rays", "march_rays_distill", "composite_rays", "composite_rays_distill"):
+            assert callable(getattr(raymarching, fn)) and callable(getattr(rm_mod, fn))
+        assert GridEncoder.__name__ == "GridEncoder" and FFMLP.__name__ == "FFMLP" and SHEncoder.__name__ == "SHEncoder"
+    finally:
+        sys.path.remove(os.path.join(ROOT, "dropin"))
+
+
+def test_product_code_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "laenerf_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"(from|import)\s+oracle|pyoracle|liblaenerf_oracle|oracle/_ref|oracle\.c", text):
+                    bad.append(os.path.join(d, f))
+    for d in ("dropin",):
+        for dd, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith(".py") and "oracle" in open(os.path.join(dd, f)).read():
+                    bad.append(os.path.join(dd, f))
+    assert not bad, bad
+
+
+def test_scene_generator_shapes():
+    from cases import scene
+    sc = scene("lego")
+    assert sc.cascade == 1 and sc.density_bitfield.shape == (128 ** 3 // 8,) and sc.density_grid.shape == (1, 128 ** 3)
+    assert 0.005 < sc.occupancy_fraction() < 0.2
+    from laenerf_b200.scene import packbits_np
+    from oracle import pyoracle
+    assert np.array_equal(packbits_np(sc.density_grid, 10.0), pyoracle.packbits(sc.density_grid, 10.0))
