@@ -11,8 +11,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are caller-allocated and the
  *     library never allocates device memory.  Scratch, where needed, is passed in; its size is queried with the
- *     matching *_scratch_bytes function.  Scratch given to lnrf_march_rays_train must be zero-filled before its
- *     FIRST use only (the kernels leave it zeroed again) and must not be shared by launches that can overlap.
+ *     matching *_scratch_bytes function.  Scratch given to lnrf_march_rays_train / lnrf_compact_alive must be
+ *     zero-filled before its FIRST use only (the kernels leave their look-back words zeroed again), must not be
+ *     shared between the two functions, nor by launches that can overlap.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream, which is what the reference uses).
  *   - return value: 0 on success, a negative lnrf_status otherwise; lnrf_last_error() returns a thread-local
  *     message (the reference raises RuntimeError through TORCH_CHECK; the Python shim re-raises the same way).

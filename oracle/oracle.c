@@ -410,13 +410,15 @@ ORC_API void orc_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thres
             const float T = 1 - weight_sum;
             const float weight = alpha * T;
             weight_sum += weight;
+            /* nvcc contracts every `acc += weight * v` below into one FFMA (checked against the reference build:
+             * tests/golden/ref_infer_lego.npz, ref_distill_flower.npz are reproduced bit for bit only with fmaf) */
             if (pe && *pe) { /* :1098-1101: uses t BEFORE the increment */
                 weight_edit_sum += weight;
-                d_edit += weight * t;
+                d_edit = fmaf(weight, t, d_edit);
             }
             t += pl[1];
-            d += weight * t;
-            r += weight * pc[0]; g += weight * pc[1]; b += weight * pc[2];
+            d = fmaf(weight, t, d);
+            r = fmaf(weight, pc[0], r); g = fmaf(weight, pc[1], g); b = fmaf(weight, pc[2], b);
             if (T < T_thresh) break;
             ps++; pc += 3; pl += 2;
             if (pe) pe++;

@@ -21,9 +21,10 @@ TOL = {
     "nears": EXACT, "fars": EXACT, "morton": EXACT, "packbits": EXACT, "counts": EXACT, "counter": EXACT,
     "xyzs": EXACT, "dirs": EXACT, "deltas": EXACT, "edit_occ": EXACT, "alive": EXACT,
     # inference compositing keeps the reference's sequential fp32 order: exact kill pattern, values to 1 ulp-ish
-    "rays_t": (1e-6, 1e-7), "inf_": (2e-6, 1e-7),
-    # training compositing: warp scan re-associates the fp32 sums/products (rtol 1e-4)
-    "ws": (1e-4, 1e-6), "depth": (1e-4, 1e-6), "image": (1e-4, 1e-6), "gsig": (2e-3, 2e-5), "grgb": (1e-4, 1e-7),
+    "rays_t": (1e-6, 1e-7), "inf_": (2e-6, 1e-6),
+    # training compositing: warp scan re-associates the fp32 sums/products (rtol 1e-4); atol covers the
+    # cancellation in alpha = 1 - __expf(-sigma*dt) for tiny sigma*dt (1 ulp of 1.0 per sample, ~60 samples per ray)
+    "ws": (1e-4, 1e-5), "depth": (1e-4, 1e-5), "image": (1e-4, 1e-5), "gsig": (2e-3, 2e-5), "grgb": (1e-4, 1e-6),
     # encoder: fp32 interpolation; fp16 tables |d| <= 2^-9 max(1,|v|) (the reference rounds 8x per level)
     "enc32": (2e-5, 2e-6), "enc16": (2.0 ** -9, 2.0 ** -9), "dydx32": (1e-4, 1e-3), "genc32": (1e-4, 1e-5), "genc16": (2e-2, 2e-2),
     # MLP: fp16 storage, fp32 accumulate here vs fp16 accumulate in the reference

@@ -48,7 +48,8 @@ def test_grid_encoder_module_autograd_fp32_vs_torch_reference(dev):
         for c in range(8):
             o = torch.tensor([(c >> 0) & 1, (c >> 1) & 1, (c >> 2) & 1], device=dev)
             w = torch.where(o.bool(), f, 1 - f).prod(-1, keepdim=True)
-            idx = (p0 + o) @ torch.tensor([1, res + 1, (res + 1) ** 2], device=dev)
+            q = p0 + o
+            idx = q[:, 0] + q[:, 1] * (res + 1) + q[:, 2] * (res + 1) ** 2
             acc = acc + w * emb[enc.offsets[lvl].item() + idx]
         outs.append(acc)
     ref = torch.cat(outs, -1)
@@ -70,15 +71,18 @@ def test_ffmlp_module_autograd_vs_torch_reference(dev):
     w = net.weights.detach().half().float().requires_grad_(True)
     xr = x.detach().half().float().requires_grad_(True)
     W0, W1, W2, W3 = w[:2048].view(64, 32), w[2048:6144].view(64, 64), w[6144:10240].view(64, 64), w[10240:].view(16, 64)
-    h = torch.relu(xr @ W0.T)
-    h = torch.relu(h @ W1.T)
-    h = torch.relu(h @ W2.T)
+    # activations are STORED in fp16 (forward_buffer) and the stored value feeds the next layer and the ReLU mask,
+    # in the reference as here; round with a straight-through gradient so the torch reference does the same
+    r16 = lambda t: t + (t.half().float() - t).detach()
+    h = r16(torch.relu(xr @ W0.T))
+    h = r16(torch.relu(h @ W1.T))
+    h = r16(torch.relu(h @ W2.T))
     yr = (h @ W3.T)[:, :3]
     (yr * g).sum().backward()
     assert torch.allclose(y.float(), yr, rtol=2e-2, atol=2e-3)
     scale = float(w.grad.abs().max())
-    assert float((net.weights.grad - w.grad).abs().max()) <= 2e-2 * scale + 1e-4
-    assert float((x.grad - xr.grad).abs().max()) <= 2e-2 * float(xr.grad.abs().max()) + 1e-5
+    assert float((net.weights.grad - w.grad).abs().max()) <= 3e-3 * scale
+    assert float((x.grad - xr.grad).abs().max()) <= 3e-3 * float(xr.grad.abs().max())
     net.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         assert torch.allclose(net(x).float(), y.float(), rtol=0, atol=0)
@@ -139,15 +143,17 @@ def test_training_step_runs_and_learns(dev):
     _, ro, rd, rng = scene_rays("lego", 4096, 42)
     ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
     gt = torch.full((4096, 3), 0.25, device=dev)
-    losses = []
-    for i in range(40):
+    losses, hit_err = [], []
+    for i in range(48):
         loss, out = step(ro, rd, gt, perturb=True)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
+        hit = out["weights_sum"].detach() > 0.5   # rays that miss the object keep the white background (loss floor)
+        hit_err.append(float(((out["image"].detach() - gt)[hit] ** 2).mean()))
         if i == 0 or (i + 1) % 16 == 0:
             model.update_mean_count()
     assert all(math.isfinite(l) for l in losses)
     assert model.mean_count > 0 and out["num_points"] % 128 == 0
-    assert losses[-1] < 0.5 * losses[0], losses[::8]
+    assert losses[-1] < losses[0] and hit_err[-1] < 0.5 * hit_err[0], (losses[::8], hit_err[::8])
     assert float(model.encoder.embeddings.abs().max()) > 1e-4  # the table moved
 
 

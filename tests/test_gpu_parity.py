@@ -50,15 +50,19 @@ def test_march_overflow_drops_rays_like_the_reference(ours_backend, oracle_backe
             assert np.array_equal(a, b), nm
 
 
-def test_march_empty_and_tiny_inputs(ours_backend):
+def test_march_empty_and_tiny_inputs(ours_backend, oracle_backend):
     sc, ro, rd, rng = scene_rays("lego", 3, 32)
     nears, fars = ours_backend.near_far(ro, rd, sc.aabb, sc.min_near)
     empty = np.zeros_like(sc.density_bitfield)
     x, d, dl, rays, cnt = ours_backend.march_train(ro, rd, empty, sc.bound, 0.0, 1024, 1, 128, 256, nears, fars, np.zeros(3, np.float32))
     assert cnt[0] == 0 and cnt[1] == 3 and not x.any() and not dl.any() and np.array_equal(rays[:, 2], [0, 0, 0])
-    full = np.full_like(sc.density_bitfield, 255)  # every cell occupied: every ray emits until far or max_steps
-    x, d, dl, rays, cnt = ours_backend.march_train(ro, rd, full, sc.bound, 0.0, 64, 1, 128, 3 * 64, nears, fars, np.zeros(3, np.float32))
-    assert np.array_equal(rays[:, 2], [64, 64, 64]) and cnt[0] == 192
+    full = np.full_like(sc.density_bitfield, 255)  # every cell occupied: rays emit until far or the max_steps budget
+    for max_steps in (16, 64, 1024):
+        got = ours_backend.march_train(ro, rd, full, sc.bound, 0.0, max_steps, 1, 128, 3 * max_steps, nears, fars, np.zeros(3, np.float32))
+        want = oracle_backend.march_train(ro, rd, full, sc.bound, 0.0, max_steps, 1, 128, 3 * max_steps, nears, fars, np.zeros(3, np.float32))
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    assert (got[3][:, 2] > 100).all()
 
 
 def test_composite_backward_zero_fill_equals_reference_contract(ours_backend):
