@@ -173,7 +173,7 @@ def main():
     import torch
     import torch.distributed as dist
     from laenerf_b200 import _native
-    from laenerf_b200.nerf import NeRFNetwork, TrainStep
+    from laenerf_b200.nerf import GraphedTrainStep, NeRFNetwork, TrainStep
     from laenerf_b200.parallel import gather_image, init_distributed, shard_range
     from laenerf_b200.scene import get_rays_np, make_scene
 
@@ -214,47 +214,67 @@ def main():
     model.update_mean_count()
     barrier()
 
-    # ---- timed region: device-resident inputs ---------------------------------------------------------------------
+    def timed_loop(fn, n):
+        """n calls of fn(i) bracketed by barrier + synchronize, CUDA events, max over ranks -> total ms."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- pass 1 (eager, Python-issued launches): per-kernel CUDA events live on the launching stream ------------------
+    points = []
+    timed.enabled = True
+    eager_l0 = _native.launch_count()
+    eager_ms = timed_loop(lambda i: points.append(step(*dev_batches[i % n_batches])[1]["num_points"]), args.steps)
+    timed.enabled = False
+    eager_launches = _native.launch_count() - eager_l0
+    actual = int(model.step_counter[: min(16, args.steps), 0].float().mean().item())
+    model.update_mean_count()
+
+    # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
+    gstep, graph_note = None, "cuda graph (one capture per sample-buffer size)"
+    if os.environ.get("LNRF_NO_GRAPH", "0") != "1":
+        try:
+            gstep = GraphedTrainStep(step, N_RAYS)
+            gstep.capture(*dev_batches[0])
+            for i in range(3):
+                gstep(*dev_batches[i % n_batches])
+        except Exception as e:  # never silently: the JSON line says which path was timed
+            gstep, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"[:300]
+            torch.cuda.synchronize()
+    run = gstep if gstep is not None else (lambda *b: step(*b))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     launches0 = _native.launch_count()
-    timed.enabled = True
-    points = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        loss, out = step(*dev_batches[i % n_batches])
-        points.append(out["num_points"])
-    e1.record()
-    barrier()
-    timed.enabled = False
-    ms = e0.elapsed_time(e1)
+    ms = timed_loop(lambda i: run(*dev_batches[i % n_batches]), args.steps)
     launches = _native.launch_count() - launches0
+    if gstep is not None:  # replays do not pass through the C ABI: count the launches the captured step contains
+        launches = eager_launches  # same step, same number of steps, counted when it was issued through the C ABI
     clk = clocks.stop() if rank == 0 else None
-    actual = int(model.step_counter[: min(16, args.steps), 0].float().mean().item())
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * N_RAYS * args.steps / (ms * 1e-3)
 
     # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----------------------------------------
     h2d = sum(x.numel() * x.element_size() for x in host_batches[0])
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        ro, rd, gt = (x.to(dev, non_blocking=True) for x in host_batches[i % n_batches])
-        loss, out = step(ro, rd, gt)
+
+    def e2e_iter(i):
+        hb = host_batches[i % n_batches]
+        if gstep is not None:
+            loss, _ = gstep(*hb)  # static device buffers are filled straight from pinned memory (non_blocking copies)
+        else:
+            loss, _ = step(*(x.to(dev, non_blocking=True) for x in hb))
         float(loss.item())
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_RAYS * args.steps / (float(t.item()) * 1e-3)
+
+    e2e_ms = timed_loop(e2e_iter, args.steps)
+    e2e_value = world * N_RAYS * args.steps / (e2e_ms * 1e-3)
 
     # ---- per-kernel roofline (events recorded live inside the timed region above) -----------------------------------
     peaks = measured_peaks()
@@ -282,7 +302,8 @@ def main():
         d = table[dominant]
         roofline = dict(bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=d["traffic"],
                         kernel=dominant, mean_ms=d["mean_ms"], peak_source=peaks["source"] + (" (sustained)" if d["bound"] == "tensor" else ""),
-                        share_of_step=kern[dominant]["total_ms"] / ms)
+                        share_of_step=kern[dominant]["total_ms"] / sum(k["total_ms"] for k in kern.values()),
+                        timing="CUDA events around each C-ABI launch during the eager pass of the same step (graph replays cannot be bracketed)")
 
     # ---- render: one full 800x800 view, tile-sharded over ranks (no collective but the final gather) -------------------
     render = None
@@ -292,6 +313,7 @@ def main():
         ro_d, rd_d = torch.from_numpy(ro[lo:hi]).to(dev), torch.from_numpy(rd[lo:hi]).to(dev)
         model.eval()
         frames, samples = 0, 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
             model.render(ro_d, rd_d, perturb=False, bg_color=1)  # warm-up frame
             barrier()
@@ -338,6 +360,9 @@ def main():
                    "occupancy_update": "excluded (row f-2 of SURVEY.md section 8: fixed procedural occupancy grid)",
                    "parallelism": f"ray-sharded dp{world}" if world > 1 else "single GPU"},
         "clocks": clk,
+        "step_mode": graph_note,
+        "eager": {"ms_per_step": eager_ms / args.steps, "value": world * N_RAYS * args.steps / (eager_ms * 1e-3), "unit": "rays/s",
+                  "note": "same step issued launch by launch from Python (the drop-in modules without graph capture)"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "roofline": roofline,

@@ -124,17 +124,31 @@ __device__ __forceinline__ float act_bwd(uint32_t a, float g, float fwd) {  // u
     }
 }
 
-// rows x K fp16 row-major (global) -> SWIZZLE_128B tile; TRANSPOSE stores element (r, k) at tile row k, column r
-__device__ __forceinline__ void load_rows(uint8_t* tile, const __half* __restrict__ src, uint32_t rows, uint32_t K, int tid) {
-    const uint32_t cpr = K >> 3;
-    for (uint32_t c = tid; c < rows * cpr; c += 128) {
+// ---- asynchronous global -> shared copies (LDGSTS): all 16-byte pieces of a tile are in flight together ----
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// rows x K fp16 row-major (global) -> SWIZZLE_128B tile at shared address `tile`
+__device__ __forceinline__ void load_rows_async(uint32_t tile, const __half* __restrict__ src, uint32_t rows, uint32_t K, int tid) {
+    const uint32_t cpr = K >> 3, n = rows * cpr;
+    const uint4* g = reinterpret_cast<const uint4*>(src);
+    for (uint32_t c = tid; c < n; c += 128) {
         const uint32_t r = c / cpr, cc = c - r * cpr;
-        *reinterpret_cast<uint4*>(tile + sw128(r, cc)) = __ldg(reinterpret_cast<const uint4*>(src) + c);
+        cp_async16(tile + sw128(r, cc), g + c);
     }
 }
-__device__ __forceinline__ void load_rows_transposed(uint8_t* tile, const __half* __restrict__ src, uint32_t rows, uint32_t K, int tid) {
+// raw copy of n16 16-byte pieces (staging area, no swizzle)
+__device__ __forceinline__ void copy_raw_async(uint32_t dst, const void* __restrict__ src, uint32_t n16, int tid) {
+    const uint4* g = reinterpret_cast<const uint4*>(src);
+    for (uint32_t c = tid; c < n16; c += 128) cp_async16(dst + c * 16u, g + c);
+}
+// shared (row-major [rows][K] fp16 at `src`) -> SWIZZLE_128B tile holding the TRANSPOSE: element (r, k) -> tile row k, column r
+__device__ __forceinline__ void transpose_to_tile(uint8_t* tile, const __half* src, uint32_t rows, uint32_t K, int tid) {
     for (uint32_t e = tid; e < rows * K; e += 128) {
-        const uint32_t r = e / K, k = e - r * K;  // src[r][k] -> tile row k, column r
+        const uint32_t r = e / K, k = e - r * K;
         *reinterpret_cast<__half*>(tile + sw128(k, r >> 3) + (r & 7u) * 2u) = src[e];
     }
 }
@@ -155,9 +169,24 @@ __device__ __forceinline__ void unpack8(uint4 u, float* v) {
     }
 }
 
+// 32 consecutive fp32 columns of this thread's TMEM lane, WITHOUT waiting (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // =========================================================================================================
 // forward / inference
 // =========================================================================================================
+// shared memory: W_0..W_{NL-1} (8 KB each), W_NL (out_dim rows), X double buffer (next tile prefetched with
+// cp.async while this one is computed), two activation tiles (ping-pong), mbarrier + TMEM slot
 template <bool TRAIN>
 __global__ void __launch_bounds__(128)
 k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weights, __half* __restrict__ fwd_buf,
@@ -165,34 +194,42 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     const uint32_t NL = sh.n_layers, in_dim = sh.in_dim, out_dim = sh.out_dim;
-    uint8_t* sW = sm;                                        // W_0 .. W_{NL-1}: 8 KB each, W_NL: out_dim rows
-    uint8_t* sA = sW + NL * kWBytes + ((out_dim * 128u + 1023u) & ~1023u);  // two activation tiles (ping-pong)
+    uint8_t* sW = sm;
+    uint8_t* sX = sW + NL * kWBytes + ((out_dim * 128u + 1023u) & ~1023u);
+    uint8_t* sA = sX + 2 * kTileBytes;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sA + 2 * kTileBytes);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t row = tid;  // this thread's row of the tile == its TMEM lane
 
+    // everything the first tile needs is requested at once; TMEM allocation overlaps the copies
+    load_rows_async(smem_u32(sW), weights, 64, in_dim, tid);
+    for (uint32_t m = 1; m < NL; m++) load_rows_async(smem_u32(sW + m * kWBytes), weights + 64 * in_dim + (m - 1) * 4096, 64, 64, tid);
+    load_rows_async(smem_u32(sW + NL * kWBytes), weights + 64 * in_dim + (NL - 1) * 4096, out_dim, 64, tid);
+    load_rows_async(smem_u32(sX), inputs + (size_t)blockIdx.x * kRows * in_dim, kRows, in_dim, tid);
+    cp_async_commit();
     if (warp == 0) tmem_alloc(tslot, 64);
     if (tid == 32) { mbar_init(mbar, 1); fence_mbar_init(); }
-    load_rows(sW, weights, 64, in_dim, tid);
-    for (uint32_t m = 1; m < NL; m++) load_rows(sW + m * kWBytes, weights + 64 * in_dim + (m - 1) * 4096, 64, 64, tid);
-    load_rows(sW + NL * kWBytes, weights + 64 * in_dim + (NL - 1) * 4096, out_dim, 64, tid);
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tslot;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t phase = 0;
+    uint32_t phase = 0, it = 0;
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
         const size_t r0 = (size_t)tile * kRows;
-        load_rows(sA, inputs + r0 * in_dim, kRows, in_dim, tid);
+        uint8_t* X = sX + (it & 1u) * kTileBytes;
+        cp_async_wait_all();
         fence_proxy_async();
-        __syncthreads();
+        __syncthreads();  // X (and on the first pass the weights) landed; the previous tile is completely done
+        if (tile + gridDim.x < ntiles) {
+            load_rows_async(smem_u32(sX + ((it + 1u) & 1u) * kTileBytes), inputs + (size_t)(tile + gridDim.x) * kRows * in_dim, kRows, in_dim, tid);
+            cp_async_commit();
+        }
         for (uint32_t m = 0; m <= NL; m++) {
-            uint8_t* cur = sA + (m & 1u) * kTileBytes;
-            uint8_t* nxt = sA + ((m + 1u) & 1u) * kTileBytes;
+            uint8_t* cur = m == 0 ? X : sA + ((m - 1u) & 1u) * kTileBytes;
+            uint8_t* nxt = sA + (m & 1u) * kTileBytes;
             if (tid == 0) {
                 tc_fence_after();
                 const uint32_t K = m == 0 ? in_dim : 64u, N = m == NL ? out_dim : 64u;
@@ -201,7 +238,7 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
                 for (uint32_t k = 0; k < K / 16; k++) umma_f16(tmem, a + 2 * k, b + 2 * k, idesc, k > 0);
                 umma_commit(mbar);
             }
-            if (TRAIN && m > 0) {  // save H_{m-1} (== cur) while the tensor core works: coalesced 16-byte rows
+            if (TRAIN && m > 0) {  // save H_{m-1} (== cur) while the tensor core works: coalesced 16-byte pieces
                 uint4* dst = reinterpret_cast<uint4*>(fwd_buf + ((size_t)(m - 1) * B + r0) * 64);
 #pragma unroll
                 for (uint32_t i = 0; i < 8; i++) {
@@ -213,14 +250,16 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
             phase ^= 1u;
             tc_fence_after();
             if (m < NL) {
+                uint32_t r[64];
+                tmem_ld32_nowait(taddr, r);
+                tmem_ld32_nowait(taddr + 32, r + 32);
+                tmem_wait_ld();
 #pragma unroll
-                for (uint32_t q = 0; q < 4; q++) {
-                    float v[16];
-                    tmem_ld16(taddr + q * 16, v);
+                for (uint32_t q = 0; q < 8; q++) {
+                    float v[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = act_fwd(sh.act, v[i]);
-                    *reinterpret_cast<uint4*>(nxt + sw128(row, 2 * q)) = pack8(v);
-                    *reinterpret_cast<uint4*>(nxt + sw128(row, 2 * q + 1)) = pack8(v + 8);
+                    for (int i = 0; i < 8; i++) v[i] = act_fwd(sh.act, __uint_as_float(r[q * 8 + i]));
+                    *reinterpret_cast<uint4*>(nxt + sw128(row, q)) = pack8(v);
                 }
                 tc_fence_before();
                 fence_proxy_async();
@@ -236,10 +275,10 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
                     __stcs(reinterpret_cast<uint4*>(o + q * 16) + 1, pack8(v + 8));
                 }
                 tc_fence_before();
-                __syncthreads();
             }
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);
 }
@@ -254,32 +293,53 @@ __device__ __host__ inline uint32_t bwd_tmem_cols(uint32_t in_dim, uint32_t out_
     return c;
 }
 
+// shared memory: W_m^T tiles (m = 1..NL, then W_0^T), the G ping-pong pair, and NBUF input sets
+// {X, H_0..H_{NL-1}, dY}: with NBUF = 2 the next tile's 60-76 KB are prefetched (cp.async) during this tile's chain.
+// Every tile that serves as an M=128 MN-major A operand (H_l, G_0) is followed by another tile: the "second atom"
+// the MMA reads for D rows 64..127, which are never used.
 __global__ void __launch_bounds__(128)
 k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, const __half* __restrict__ weights,
             const __half* __restrict__ fwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ wgrad, const uint32_t B,
-            const MlpShape sh, const uint32_t ntiles, const int calc_grad_inputs) {
+            const MlpShape sh, const uint32_t ntiles, const int calc_grad_inputs, const uint32_t nbuf) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     const uint32_t NL = sh.n_layers, in_dim = sh.in_dim, out_dim = sh.out_dim;
-    // W_m^T tiles: index m-1 for m = 1..NL ([64 rows = input feature][K = n_m]); then W_0^T ([in rows][K = 64])
-    uint8_t* sWT = sm;
-    uint8_t* sWT0 = sWT + NL * kWBytes;
-    uint8_t* sX = sWT0 + kWBytes;              // order matters: every tile used as an M=128 MN-major A operand
-    uint8_t* sH = sX + kTileBytes;             // is followed by another tile (the ignored second atom, rows 64..127 of D)
-    uint8_t* sG = sH + NL * kTileBytes;        // G_m lives in sG[m & 1]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sG + 2 * kTileBytes);
+    uint8_t* sWT = sm;                         // index m-1 for m = 1..NL: [64 rows = input feature][K = n_m]
+    uint8_t* sWT0 = sWT + NL * kWBytes;        // W_0^T: [in rows][K = 64]
+    uint8_t* sG = sWT0 + kWBytes;              // G_m (m < NL) lives in sG[m & 1]
+    uint8_t* sIN = sG + 2 * kTileBytes;
+    const uint32_t in_bytes = (NL + 2) * kTileBytes;  // X, H_0..H_{NL-1}, dY
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sIN + nbuf * in_bytes);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t row = tid;
     const uint32_t ncols = bwd_tmem_cols(in_dim, out_dim, NL);
 
+    auto load_inputs = [&](uint32_t tile, uint32_t buf) {
+        const size_t r0 = (size_t)tile * kRows;
+        const uint32_t base = smem_u32(sIN + buf * in_bytes);
+        load_rows_async(base, inputs + r0 * in_dim, kRows, in_dim, tid);
+        for (uint32_t l = 0; l < NL; l++) load_rows_async(base + (1 + l) * kTileBytes, fwd_buf + ((size_t)l * B + r0) * 64, kRows, 64, tid);
+        load_rows_async(base + (1 + NL) * kTileBytes, grad + r0 * out_dim, kRows, out_dim, tid);
+    };
+
+    // stage the raw weights in the (still unused) first input set, request the first tile, then transpose in shared memory
+    const uint32_t nparams = 64 * (in_dim + 64 * (NL - 1) + out_dim);
+    uint8_t* stage = sG;  // 32 KB >= 2 * nparams for every supported shape (<= 22.5 KB)
+    copy_raw_async(smem_u32(stage), weights, nparams * 2 / 16, tid);
+    cp_async_commit();
+    load_inputs(blockIdx.x, 0);
+    cp_async_commit();
     if (warp == 0) tmem_alloc(tslot, ncols);
     if (tid == 32) { mbar_init(mbar, 1); fence_mbar_init(); }
-    const __half* W_last = weights + 64 * in_dim + (NL - 1) * 4096;
-    load_rows_transposed(sWT + (NL - 1) * kWBytes, W_last, out_dim, 64, tid);  // W_NL [out,64] -> [64][out]
-    for (uint32_t m = 1; m < NL; m++) load_rows_transposed(sWT + (m - 1) * kWBytes, weights + 64 * in_dim + (m - 1) * 4096, 64, 64, tid);
-    if (calc_grad_inputs) load_rows_transposed(sWT0, weights, 64, in_dim, tid);  // W_0 [64,in] -> [in][64]
-    fence_proxy_async();
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // the weights (first group) have landed
+    __syncthreads();
+    {
+        const __half* w = reinterpret_cast<const __half*>(stage);
+        transpose_to_tile(sWT + (NL - 1) * kWBytes, w + 64 * in_dim + (NL - 1) * 4096, out_dim, 64, tid);  // W_NL [out,64] -> [64][out]
+        for (uint32_t m = 1; m < NL; m++) transpose_to_tile(sWT + (m - 1) * kWBytes, w + 64 * in_dim + (m - 1) * 4096, 64, 64, tid);
+        if (calc_grad_inputs) transpose_to_tile(sWT0, w, 64, in_dim, tid);  // W_0 [64,in] -> [in][64]
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -295,13 +355,19 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, iter++) {
         const size_t r0 = (size_t)tile * kRows;
-        load_rows(sG + (NL & 1u) * kTileBytes, grad + r0 * out_dim, kRows, out_dim, tid);
-        load_rows(sX, inputs + r0 * in_dim, kRows, in_dim, tid);
-        for (uint32_t l = 0; l < NL; l++) load_rows(sH + l * kTileBytes, fwd_buf + ((size_t)l * B + r0) * 64, kRows, 64, tid);
+        const uint32_t buf = nbuf == 2 ? (iter & 1u) : 0u;
+        uint8_t* sX = sIN + buf * in_bytes;
+        uint8_t* sH = sX + kTileBytes;
+        uint8_t* sDY = sH + NL * kTileBytes;
+        cp_async_wait_all();
         fence_proxy_async();
         __syncthreads();
+        if (nbuf == 2 && tile + gridDim.x < ntiles) {
+            load_inputs(tile + gridDim.x, buf ^ 1u);
+            cp_async_commit();
+        }
         for (uint32_t m = NL; m >= 1; m--) {
-            uint8_t* Gm = sG + (m & 1u) * kTileBytes;
+            uint8_t* Gm = m == NL ? sDY : sG + (m & 1u) * kTileBytes;
             uint8_t* Gp = sG + ((m - 1u) & 1u) * kTileBytes;
             uint8_t* Hp = sH + (m - 1) * kTileBytes;  // H_{m-1}: activation mask AND the input of matmul m
             const uint32_t n_m = m == NL ? out_dim : 64u;
@@ -317,19 +383,24 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
                 const uint32_t widesc = make_idesc(128, n_m, true, true);
                 for (uint32_t k = 0; k < 8; k++) umma_f16(tmem + acc_col(m), wa + 128 * k, wb + 128 * k, widesc, (iter | k) > 0);
             }
+            // the saved activations of this row, fetched while the tensor core works
+            uint4 hrow[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) hrow[q] = *reinterpret_cast<const uint4*>(Hp + sw128(row, q));
             mbar_wait(mbar, phase);
             phase ^= 1u;
             tc_fence_after();
+            uint32_t r[64];
+            tmem_ld32_nowait(taddr, r);
+            tmem_ld32_nowait(taddr + 32, r + 32);
+            tmem_wait_ld();
 #pragma unroll
-            for (uint32_t q = 0; q < 4; q++) {
-                float v[16], h[16];
-                tmem_ld16(taddr + q * 16, v);
-                unpack8(*reinterpret_cast<const uint4*>(Hp + sw128(row, 2 * q)), h);
-                unpack8(*reinterpret_cast<const uint4*>(Hp + sw128(row, 2 * q + 1)), h + 8);
+            for (uint32_t q = 0; q < 8; q++) {
+                float v[8], h[8];
+                unpack8(hrow[q], h);
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = act_bwd(sh.act, v[i], h[i]);
-                *reinterpret_cast<uint4*>(Gp + sw128(row, 2 * q)) = pack8(v);
-                *reinterpret_cast<uint4*>(Gp + sw128(row, 2 * q + 1)) = pack8(v + 8);
+                for (int i = 0; i < 8; i++) v[i] = act_bwd(sh.act, __uint_as_float(r[q * 8 + i]), h[i]);
+                *reinterpret_cast<uint4*>(Gp + sw128(row, q)) = pack8(v);
             }
             tc_fence_before();
             fence_proxy_async();
@@ -348,7 +419,7 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
             for (uint32_t k = 0; k < 8; k++) umma_f16(tmem + acc_col(0), wa + 128 * k, wb + 128 * k, widesc, (iter | k) > 0);
             umma_commit(mbar);
         }
-        mbar_wait(mbar, phase);  // every MMA of this tile has finished: shared-memory tiles may be overwritten
+        mbar_wait(mbar, phase);  // every MMA of this tile has finished: its shared-memory tiles may be overwritten
         phase ^= 1u;
         tc_fence_after();
         if (calc_grad_inputs) {
@@ -361,10 +432,16 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
             }
         }
         tc_fence_before();
-        __syncthreads();
+        if (nbuf == 1 && tile + gridDim.x < ntiles) {
+            __syncthreads();
+            load_inputs(tile + gridDim.x, 0);
+            cp_async_commit();
+        }
     }
 
     // ---- flush the weight-gradient accumulators (rows 0..63 are real; lanes 64..127 hold the ignored atom) ----
+    cp_async_wait_all();
+    __syncthreads();
     tc_fence_after();
     if (iter > 0 && warp < 2) {
         const uint32_t w_first = 64 * in_dim;
@@ -424,10 +501,10 @@ static int check_mlp(const char* who, uint32_t B, uint32_t input_dim, uint32_t o
 }
 
 static size_t fwd_smem_bytes(const MlpShape& sh) {
-    return 1024 + sh.n_layers * kWBytes + ((sh.out_dim * 128u + 1023u) & ~1023u) + 2 * kTileBytes + 64;
+    return 1024 + sh.n_layers * kWBytes + ((sh.out_dim * 128u + 1023u) & ~1023u) + 4 * kTileBytes + 64;
 }
-static size_t bwd_smem_bytes(const MlpShape& sh) {
-    return 1024 + (sh.n_layers + 1) * kWBytes + kTileBytes * (1 + sh.n_layers + 2) + 64;
+static size_t bwd_smem_bytes(const MlpShape& sh, uint32_t nbuf) {
+    return 1024 + (sh.n_layers + 1) * kWBytes + kTileBytes * (2 + nbuf * (sh.n_layers + 2)) + 64;
 }
 
 template <bool TRAIN>
@@ -438,8 +515,12 @@ static int ffmlp_fwd_launch(const char* who, const void* inputs, const void* wei
     LNRF_REQUIRE(((reinterpret_cast<uintptr_t>(inputs) | reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(outputs) |
                    reinterpret_cast<uintptr_t>(fwd_buf)) & 15) == 0, "%s: tensors must be 16-byte aligned", who);
     const size_t smem = fwd_smem_bytes(sh);
-    cudaError_t e = cudaFuncSetAttribute(k_ffmlp_fwd<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, who);
+    static std::atomic<size_t> s_max_smem{0};  // per instantiation: raise the opt-in limit only when it grows
+    if (smem > s_max_smem.load(std::memory_order_relaxed)) {
+        cudaError_t e = cudaFuncSetAttribute(k_ffmlp_fwd<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, who);
+        s_max_smem.store(smem, std::memory_order_relaxed);
+    }
     const uint32_t ntiles = B / kRows;
     const uint32_t per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
     const uint32_t cap = (uint32_t)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
@@ -495,10 +576,15 @@ int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void
     cudaError_t e = cudaMemsetAsync(wgrad_scratch, 0, need, st);
     if (e != cudaSuccess) return cuda_fail(e, "ffmlp_backward: memset");
     if (B > 0) {
-        const size_t smem = bwd_smem_bytes(sh);
+        const uint32_t nbuf = bwd_smem_bytes(sh, 2) <= 227 * 1024 ? 2u : 1u;  // prefetch the next tile when it fits
+        const size_t smem = bwd_smem_bytes(sh, nbuf);
         LNRF_REQUIRE(smem <= 227 * 1024, "ffmlp_backward: network needs %zu B of shared memory (> 227 KiB)", smem);
-        e = cudaFuncSetAttribute(k_ffmlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "ffmlp_backward: smem attribute");
+        static std::atomic<size_t> s_max_smem{0};
+        if (smem > s_max_smem.load(std::memory_order_relaxed)) {
+            e = cudaFuncSetAttribute(k_ffmlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "ffmlp_backward: smem attribute");
+            s_max_smem.store(smem, std::memory_order_relaxed);
+        }
         const uint32_t ntiles = B / kRows;
         const uint32_t per_sm_smem = (uint32_t)((227 * 1024) / (smem + 1024));
         const uint32_t per_sm_tmem = 512u / bwd_tmem_cols(input_dim, output_dim, num_layers);
@@ -508,7 +594,7 @@ int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void
         const uint32_t grid = ntiles < cap ? ntiles : cap;
         k_ffmlp_bwd<<<grid, 128, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
                                              (const __half*)forward_buffer_f16, (__half*)grad_inputs_f16, (float*)wgrad_scratch, B, sh,
-                                             ntiles, calc_grad_inputs);
+                                             ntiles, calc_grad_inputs, nbuf);
         LNRF_LAUNCH_CHECK("ffmlp_backward");
     }
     k_ffmlp_wgrad_finalize<<<div_up(nparams, 256u), 256, 0, st>>>((const float*)wgrad_scratch, (__half*)grad_weights_f16, nparams);

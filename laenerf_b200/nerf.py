@@ -227,7 +227,9 @@ class TrainStep:
         self.model = model
         self.fp16 = fp16
         self.world_size = world_size
-        self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
+        # fused=True: one multi-tensor kernel that also consumes GradScaler's scale / found_inf on the device, so the
+        # step has no host synchronisation and can be captured into a CUDA graph (GraphedTrainStep below)
+        self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
 
     def __call__(self, rays_o, rays_d, gt_rgb, bg_color=1, perturb=True):
@@ -244,3 +246,64 @@ class TrainStep:
         self.scaler.step(self.optimizer)
         self.scaler.update()
         return loss, out
+
+
+class GraphedTrainStep:
+    """The same training step replayed from ONE CUDA graph (march -> encode -> MLPs -> composite -> loss -> backward
+    -> Adam, ~100 launches): the 4096-ray step is launch-bound when issued from Python ("hard
+    parts"), so the steady state is captured once per sample-buffer size and replayed.  Inputs are copied into static
+    device buffers; `loss` / `out` are views of graph-owned memory that the next replay overwrites."""
+
+    def __init__(self, step: TrainStep, n_rays: int, bg_color=1, perturb=True):
+        self.step, self.model = step, step.model
+        dev = next(self.model.parameters()).device
+        self.ro = torch.zeros(n_rays, 3, device=dev)
+        self.rd = torch.zeros(n_rays, 3, device=dev)
+        self.gt = torch.zeros(n_rays, 3, device=dev)
+        self.bg_color, self.perturb = bg_color, perturb
+        self.graph = None
+        self.captured_mean_count = 0
+        self.loss = self.out = None
+
+    def _load(self, rays_o, rays_d, gt_rgb):
+        self.ro.copy_(rays_o, non_blocking=True)
+        self.rd.copy_(rays_d, non_blocking=True)
+        self.gt.copy_(gt_rgb, non_blocking=True)
+
+    def capture(self, rays_o, rays_d, gt_rgb, warmup: int = 3):
+        m = self.model
+        self._load(rays_o, rays_d, gt_rgb)
+        if m.mean_count <= 0:  # the first (eager) steps size the sample buffer, as in the reference
+            self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
+            m.update_mean_count()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
+        torch.cuda.current_stream().wait_stream(side)
+        m.local_step = 0  # the captured march always counts into step_counter[0]; rotated after each replay
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.out = self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
+        self.captured_mean_count = m.mean_count
+        m.local_step = 0
+        self._replays = 0
+
+    def needs_recapture(self) -> bool:
+        """After update_mean_count(): re-capture when the running mean outgrew the captured buffer or shrank by > 1/8."""
+        mc, cap = self.model.mean_count, self.captured_mean_count
+        return self.graph is None or mc > cap or mc < cap - cap // 8
+
+    def __call__(self, rays_o, rays_d, gt_rgb):
+        if self.graph is None:
+            self.capture(rays_o, rays_d, gt_rgb)
+        self._load(rays_o, rays_d, gt_rgb)
+        self.graph.replay()
+        m = self.model
+        row = self._replays % 16
+        if row:  # keep the 16-entry counter history the occupancy update averages (renderer.py:643-647)
+            m.step_counter[row].copy_(m.step_counter[0], non_blocking=True)
+        self._replays += 1
+        m.local_step = min(16, self._replays)
+        return self.loss, self.out

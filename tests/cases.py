@@ -27,20 +27,28 @@ TOL = {
     "ws": (1e-4, 1e-5), "depth": (1e-4, 1e-5), "image": (1e-4, 1e-5), "gsig": (2e-3, 2e-5), "grgb": (1e-4, 1e-6),
     # encoder: fp32 interpolation; fp16 tables |d| <= 2^-9 max(1,|v|) (the reference rounds 8x per level)
     "enc32": (2e-5, 2e-6), "enc16": (2.0 ** -9, 2.0 ** -9), "dydx32": (1e-4, 1e-3), "genc32": (1e-4, 1e-5), "genc16": (2e-2, 2e-2),
-    # MLP: fp16 storage, fp32 accumulate here vs fp16 accumulate in the reference
-    "mlp_out": (2e-2, 4e-3), "mlp_fb": (2e-2, 4e-3), "mlp_gw": (3e-2, 2e-2), "mlp_gi": (3e-2, 2e-3),
+    # MLP: fp16 storage, fp32 accumulate here vs fp16 accumulate in the reference.  Gradients are
+    # compared relative to the largest element ("relmax"): the reference's own fp16-accumulated wgrad / dgrad
+    # deviate from the fp32 oracle by 2.5-4.2 % / 11.7 % of max on these cases (measured);
+    # liblaenerf_b200 agrees with the fp32 oracle to ~3e-4 of max (TOL_VS_ORACLE below).
+    "mlp_out": (2e-2, 4e-3), "mlp_fb": (2e-2, 4e-3), "mlp_gw": ("relmax", 6e-2), "mlp_gi": ("relmax", 0.15),
     "sh": (1e-6, 1e-6),
 }
 
 
-def tol_for(key: str):
-    for p, t in TOL.items():
-        if key.startswith(p):
-            return t
+# tighter bounds that apply when BOTH sides accumulate in fp32 (our kernels vs the CPU oracle)
+TOL_VS_ORACLE = {"mlp_out": (2e-3, 1e-3), "mlp_fb": (2e-3, 1e-3), "mlp_gw": ("relmax", 2e-3), "mlp_gi": ("relmax", 3e-3)}
+
+
+def tol_for(key: str, table=None):
+    for tab in ((table or {}), TOL):
+        for p, t in tab.items():
+            if key.startswith(p):
+                return t
     raise KeyError(f"no tolerance registered for {key}")
 
 
-def compare(got: dict, want: dict, keys=None, scale: float = 1.0):
+def compare(got: dict, want: dict, keys=None, scale: float = 1.0, table=None):
     """Assert got[k] ~ want[k] for every shared output key (inputs are prefixed with 'in_' and skipped)."""
     checked = 0
     for k in (keys or want.keys()):
@@ -48,7 +56,13 @@ def compare(got: dict, want: dict, keys=None, scale: float = 1.0):
             continue
         a, b = np.asarray(got[k]), np.asarray(want[k])
         assert a.shape == b.shape, f"{k}: shape {a.shape} vs {b.shape}"
-        t = tol_for(k)
+        t = tol_for(k, table)
+        if t != EXACT and t[0] == "relmax":
+            err = np.abs(a.astype(np.float64) - b.astype(np.float64)).max()
+            ref = np.abs(b.astype(np.float64)).max()
+            assert err <= scale * t[1] * ref, f"{k}: max err {err:.3e} > {t[1]} x max |ref| {ref:.3e}"
+            checked += 1
+            continue
         if t == EXACT:
             if a.dtype.kind == "f":
                 same = (a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0))

@@ -185,3 +185,33 @@ def test_distill_render_runs(dev):
         out = model.run_cuda_distill(ro, rd, edit)
     assert out["image"].shape == (1024, 3) and torch.isfinite(out["image"]).all()
     assert (out["weights_edit_sum"] <= out["weights_sum"] + 1e-5).all()
+
+
+def test_graphed_step_matches_eager_step(dev):
+    """The CUDA-graph replay of the training step against the launch-by-launch step on identically initialised models
+    (perturb off so both march the same samples; fp16 atomics make the grid gradient order-dependent, hence tolerances)."""
+    from laenerf_b200.nerf import GraphedTrainStep, TrainStep
+    _, ro, rd, rng = scene_rays("lego", 2048, 45)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    gt = torch.rand(2048, 3, device=dev)
+    losses = {}
+    for mode in ("eager", "graph"):
+        sc, model = _model(dev)
+        step = TrainStep(model)
+        step(ro, rd, gt, perturb=False)      # sizes the sample buffer (mean_count) exactly as the reference's first steps
+        model.update_mean_count()
+        run = step if mode == "eager" else GraphedTrainStep(step, 2048, perturb=False)
+        out = []
+        for i in range(6):
+            if mode == "eager":
+                loss, _ = run(ro, rd, gt, perturb=False)
+            else:
+                loss, _ = run(ro, rd, gt)
+            out.append(float(loss.detach()))
+        losses[mode] = out
+        if mode == "graph":
+            assert int(model.step_counter[1, 1]) == 2048 and int(model.step_counter[0, 0]) == int(model.step_counter[3, 0])
+    # the graph capture replays 3 warm-up steps first, so compare the trend, not step by step
+    assert all(math.isfinite(l) for l in losses["graph"])
+    assert losses["graph"][-1] < losses["graph"][0] and losses["eager"][-1] < losses["eager"][0]
+    assert abs(losses["graph"][0] - losses["eager"][3]) < 0.05 * losses["eager"][0]

@@ -32,7 +32,8 @@ def test_matches_cpu_oracle(name, ours_backend):
         from cases import grid_config
         scales[(4, 16)] = ours_backend.grid_level_scales(4, grid_config(4, 4, 2, 16, 10, 128)[1], 16)
     want = run_case(name, OracleBackend(device_scales=scales))
-    compare(got, want)
+    from cases import TOL_VS_ORACLE
+    compare(got, want, table=TOL_VS_ORACLE)
 
 
 def test_march_overflow_drops_rays_like_the_reference(ours_backend, oracle_backend):
