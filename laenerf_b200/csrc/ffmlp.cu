@@ -102,6 +102,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// ACT template parameter of the kernels: 0 = ReLU (every LAENeRF net), kActRuntime = decided per launch from MlpShape.
+// Keeping the 7-way switch out of the 64-element epilogue loops matters: with a runtime switch the epilogue, not
+// the tensor core, bounds the kernel (ncu source page, profiles/r1_ffmlp_fwd_stalls.txt).
+constexpr int kActRuntime = -1;
+
 __device__ __forceinline__ float act_fwd(uint32_t a, float x) {  // ffmlp/src/utils.h:424-475
     switch (a) {
         case 0: return fmaxf(x, 0.0f);
@@ -187,7 +192,7 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // =========================================================================================================
 // shared memory: W_0..W_{NL-1} (8 KB each), W_NL (out_dim rows), X double buffer (next tile prefetched with
 // cp.async while this one is computed), two activation tiles (ping-pong), mbarrier + TMEM slot
-template <bool TRAIN>
+template <bool TRAIN, int ACT>
 __global__ void __launch_bounds__(128)
 k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weights, __half* __restrict__ fwd_buf,
             __half* __restrict__ outputs, const uint32_t B, const MlpShape sh, const uint32_t ntiles) {
@@ -258,7 +263,10 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
                 for (uint32_t q = 0; q < 8; q++) {
                     float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) v[i] = act_fwd(sh.act, __uint_as_float(r[q * 8 + i]));
+                    for (int i = 0; i < 8; i++) {
+                        const float a = __uint_as_float(r[q * 8 + i]);
+                        v[i] = ACT == 0 ? fmaxf(a, 0.0f) : act_fwd(sh.act, a);
+                    }
                     *reinterpret_cast<uint4*>(nxt + sw128(row, q)) = pack8(v);
                 }
                 tc_fence_before();
@@ -270,7 +278,10 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
                     float v[16];
                     tmem_ld16(taddr + q * 16, v);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = act_fwd(sh.out_act, v[i]);
+                    if (sh.out_act != 6u) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = act_fwd(sh.out_act, v[i]);
+                    }
                     __stcs(reinterpret_cast<uint4*>(o + q * 16), pack8(v));
                     __stcs(reinterpret_cast<uint4*>(o + q * 16) + 1, pack8(v + 8));
                 }
@@ -297,6 +308,7 @@ __device__ __host__ inline uint32_t bwd_tmem_cols(uint32_t in_dim, uint32_t out_
 // {X, H_0..H_{NL-1}, dY}: with NBUF = 2 the next tile's 60-76 KB are prefetched (cp.async) during this tile's chain.
 // Every tile that serves as an M=128 MN-major A operand (H_l, G_0) is followed by another tile: the "second atom"
 // the MMA reads for D rows 64..127, which are never used.
+template <int ACT>
 __global__ void __launch_bounds__(128)
 k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, const __half* __restrict__ weights,
             const __half* __restrict__ fwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ wgrad, const uint32_t B,
@@ -399,7 +411,10 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
                 float v[8], h[8];
                 unpack8(hrow[q], h);
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = act_bwd(sh.act, __uint_as_float(r[q * 8 + i]), h[i]);
+                for (int i = 0; i < 8; i++) {
+                    const float gacc = __uint_as_float(r[q * 8 + i]);
+                    v[i] = ACT == 0 ? (h[i] > 0.0f ? gacc : 0.0f) : act_bwd(sh.act, gacc, h[i]);
+                }
                 *reinterpret_cast<uint4*>(Gp + sw128(row, q)) = pack8(v);
             }
             tc_fence_before();
@@ -515,17 +530,19 @@ static int ffmlp_fwd_launch(const char* who, const void* inputs, const void* wei
     LNRF_REQUIRE(((reinterpret_cast<uintptr_t>(inputs) | reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(outputs) |
                    reinterpret_cast<uintptr_t>(fwd_buf)) & 15) == 0, "%s: tensors must be 16-byte aligned", who);
     const size_t smem = fwd_smem_bytes(sh);
-    static std::atomic<size_t> s_max_smem{0};  // per instantiation: raise the opt-in limit only when it grows
-    if (smem > s_max_smem.load(std::memory_order_relaxed)) {
-        cudaError_t e = cudaFuncSetAttribute(k_ffmlp_fwd<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = sh.act == 0 ? k_ffmlp_fwd<TRAIN, 0> : k_ffmlp_fwd<TRAIN, kActRuntime>;
+    static std::atomic<size_t> s_max_smem[2] = {{0}, {0}};  // per instantiation: raise the opt-in limit only when it grows
+    std::atomic<size_t>& mx = s_max_smem[sh.act == 0 ? 0 : 1];
+    if (smem > mx.load(std::memory_order_relaxed)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, who);
-        s_max_smem.store(smem, std::memory_order_relaxed);
+        mx.store(smem, std::memory_order_relaxed);
     }
     const uint32_t ntiles = B / kRows;
     const uint32_t per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
     const uint32_t cap = (uint32_t)kNumSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
     const uint32_t grid = ntiles < cap ? ntiles : cap;
-    k_ffmlp_fwd<TRAIN><<<grid, 128, smem, st>>>((const __half*)inputs, (const __half*)weights, (__half*)fwd_buf, (__half*)outputs, B, sh, ntiles);
+    kern<<<grid, 128, smem, st>>>((const __half*)inputs, (const __half*)weights, (__half*)fwd_buf, (__half*)outputs, B, sh, ntiles);
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }
@@ -579,11 +596,13 @@ int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void
         const uint32_t nbuf = bwd_smem_bytes(sh, 2) <= 227 * 1024 ? 2u : 1u;  // prefetch the next tile when it fits
         const size_t smem = bwd_smem_bytes(sh, nbuf);
         LNRF_REQUIRE(smem <= 227 * 1024, "ffmlp_backward: network needs %zu B of shared memory (> 227 KiB)", smem);
-        static std::atomic<size_t> s_max_smem{0};
-        if (smem > s_max_smem.load(std::memory_order_relaxed)) {
-            e = cudaFuncSetAttribute(k_ffmlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        auto kern = sh.act == 0 ? k_ffmlp_bwd<0> : k_ffmlp_bwd<kActRuntime>;
+        static std::atomic<size_t> s_max_smem[2] = {{0}, {0}};
+        std::atomic<size_t>& mx = s_max_smem[sh.act == 0 ? 0 : 1];
+        if (smem > mx.load(std::memory_order_relaxed)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "ffmlp_backward: smem attribute");
-            s_max_smem.store(smem, std::memory_order_relaxed);
+            mx.store(smem, std::memory_order_relaxed);
         }
         const uint32_t ntiles = B / kRows;
         const uint32_t per_sm_smem = (uint32_t)((227 * 1024) / (smem + 1024));
@@ -592,7 +611,7 @@ int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void
         if (per_sm < 1) per_sm = 1;
         const uint32_t cap = (uint32_t)kNumSMs * per_sm;
         const uint32_t grid = ntiles < cap ? ntiles : cap;
-        k_ffmlp_bwd<<<grid, 128, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
+        kern<<<grid, 128, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
                                              (const __half*)forward_buffer_f16, (__half*)grad_inputs_f16, (float*)wgrad_scratch, B, sh,
                                              ntiles, calc_grad_inputs, nbuf);
         LNRF_LAUNCH_CHECK("ffmlp_backward");

@@ -30,6 +30,7 @@ struct Level {
     uint32_t res, hs, base;
     uint32_t str1, str2;  // strides of dims 1 and 2 when they take part in the dense index, else 0
     uint32_t hashed;
+    uint32_t mask;        // hs - 1 when hs is a power of two (every hashed level of a 2^k table), else 0
 };
 
 // gridencoder.cu:66-84 + :138-139, for one level
@@ -55,6 +56,7 @@ __device__ __forceinline__ Level make_level(uint32_t level, float S, uint32_t H,
         }
     }
     lv.hashed = (gridtype == 0u && stride > lv.hs) ? 1u : 0u;
+    lv.mask = (lv.hs & (lv.hs - 1u)) == 0u ? lv.hs - 1u : 0u;
     return lv;
 }
 
@@ -70,7 +72,11 @@ __device__ __forceinline__ uint32_t grid_index(const Level& lv, const uint32_t* 
         if (D > 1) index += pg[1] * lv.str1;
         if (D > 2) index += pg[2] * lv.str2;
     }
-    return index % lv.hs;
+    // index % hashmap_size (gridencoder.cu:83) without the integer division on the hot shapes: a mask for
+    // power-of-two tables, nothing at all when a dense index is already in range (the reference sizes dense levels
+    // as (res+1)^D rounded up, so this is the common case), the real remainder otherwise
+    if (lv.mask) return index & lv.mask;
+    return index < lv.hs ? index : index % lv.hs;
 }
 
 template <typename T> struct Vec2;

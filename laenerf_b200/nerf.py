@@ -229,7 +229,7 @@ class TrainStep:
         self.world_size = world_size
         # fused=True: one multi-tensor kernel that also consumes GradScaler's scale / found_inf on the device, so the
         # step has no host synchronisation and can be captured into a CUDA graph (GraphedTrainStep below)
-        self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True)
+        self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
         self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
 
     def __call__(self, rays_o, rays_d, gt_rgb, bg_color=1, perturb=True):
