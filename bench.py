@@ -41,6 +41,11 @@ ALGO = {
     "lnrf_ffmlp_backward": dict(bound="tensor", flops_per_sample_padded=73728 / 2),
     "lnrf_sh_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=12 + 64),
     "lnrf_near_far_from_aabb": dict(bound="hbm", per_ray=32, per_sample=0),
+    # fused rows f-1 / f-4 (one C-ABI call each; nerf_backward = colour-net + sigma-net launches and two finalize launches)
+    "lnrf_nerf_forward": dict(bound="tensor", flops_per_sample_padded=36864),
+    "lnrf_nerf_backward": dict(bound="tensor", flops_per_sample_padded=73728),
+    "lnrf_adam_step": dict(bound="hbm", per_param=30),            # g16 R+W 4, p/m/v R+W 24, p16 W 2
+    "lnrf_grad_nonfinite_check": dict(bound="hbm", per_param=2),
 }
 
 
@@ -278,6 +283,7 @@ def main():
 
     # ---- per-kernel roofline (events recorded live inside the timed region above) -----------------------------------
     peaks = measured_peaks()
+    n_params = sum(p.numel() for p in model.parameters())
     m_pad = int(statistics.mean(points))
     kern = timed.summary()
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
@@ -287,7 +293,8 @@ def main():
         a = ALGO[name]
         calls_per_step = k["calls"] / args.steps
         if a["bound"] == "hbm":
-            byts = a.get("per_ray", 0) * N_RAYS + a.get("per_sample", 0) * actual + a.get("per_sample_padded", 0) * m_pad
+            byts = (a.get("per_ray", 0) * N_RAYS + a.get("per_sample", 0) * actual + a.get("per_sample_padded", 0) * m_pad +
+                    a.get("per_param", 0) * n_params)
             ach = byts / (k["mean_ms"] * 1e-3) / 1e9
             table[name] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], mean_ms=k["mean_ms"],
                                calls_per_step=calls_per_step, algorithmic_bytes=byts, traffic=traffic.get(name))

@@ -228,6 +228,65 @@ LNRF_API int lnrf_sh_encode_forward(const float* inputs, void* outputs, uint32_t
 LNRF_API int lnrf_sh_encode_backward(const float* grad, uint32_t B, uint32_t degree, const float* dy_dx,
                                      float* grad_inputs, lnrf_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * fused NeRFNetwork.forward / backward (row f-1 of SURVEY.md section 8) -- nerf/network_ff.py:51-79:
+ *     h = sigma_net(enc); sigma = trunc_exp(h[:,0]) (activation.py:5-17); d = SHEncoder(dirs) (degree 4,
+ *     shencoder/src/shencoder.cu:27-123); rgb = sigmoid(color_net(cat[d, h[:,1:], 0]))
+ * with both FFMLPs (hidden 64; sigma 32 -> 64 x num_layers_sigma -> 16; colour 32 -> 64 x num_layers_color -> 16,
+ * weights in the reference's flat layout, ffmlp.cu:632) and all of the elementwise glue in one kernel.
+ * --------------------------------------------------------------------------------------------------------- */
+/* enc [M,32] fp16 (GridEncoder output), dirs [M,3] fp32, M a multiple of 128.
+ * outputs: sigmas [M] fp32 = density_scale * exp(h0) (renderer.py:299), rgbs [M,3] fp32 (fp16-rounded values, as
+ * torch.sigmoid on the half output gives).  train != 0 additionally saves forward_buffer [ns+nc, M, 64] fp16
+ * (hidden activations: sigma net's first), color_in [M,32] fp16 (the colour net's input rows) and h0 [M] fp16. */
+LNRF_API int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigma_f16, const void* w_color_f16,
+                               uint32_t M, uint32_t num_layers_sigma, uint32_t num_layers_color, float density_scale,
+                               int train, void* forward_buffer_f16, void* color_in_f16, void* h0_f16, float* sigmas,
+                               float* rgbs, lnrf_stream_t stream);
+/* grad_sigmas [M] / grad_rgbs [M,3] fp32 (what composite_rays_train's backward writes) -> grad_enc [M,32] fp16,
+ * grad_w_sigma / grad_w_color flat fp16 (written, or added to when accumulate_wgrad != 0).  dh_scratch [M,16] fp16 and wgrad_scratch
+ * (lnrf_nerf_wgrad_scratch_bytes) may hold anything.  Gradients are rounded to fp16 where autograd would
+ * hold fp16 tensors in the reference (grad of the .float() casts, dL/dh, dL/denc). */
+LNRF_API size_t lnrf_nerf_wgrad_scratch_bytes(uint32_t num_layers_sigma, uint32_t num_layers_color);
+LNRF_API int lnrf_nerf_backward(const float* grad_sigmas, const float* grad_rgbs, const float* rgbs, const void* h0_f16,
+                                const void* enc_f16, const void* color_in_f16, const void* w_sigma_f16,
+                                const void* w_color_f16, const void* forward_buffer_f16, uint32_t M,
+                                uint32_t num_layers_sigma, uint32_t num_layers_color, float density_scale,
+                                void* grad_enc_f16, void* grad_w_sigma_f16, void* grad_w_color_f16, int accumulate_wgrad,
+                                void* dh_scratch_f16, void* wgrad_scratch, size_t wgrad_scratch_bytes,
+                                lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Adam + AMP glue in one pass (row f-4) -- replaces, per training step of `-O` (nerf/utils.py:1474-1484,
+ * main_nerf.py:223: Adam betas (0.9, 0.99) eps 1e-15 under GradScaler): embeddings.half() (grid.py:43-44),
+ * the gradient clear, the fp16 -> fp32 gradient cast, GradScaler's inf check / unscale and torch.optim.Adam.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* params;      /* [n] fp32 master parameters, updated in place */
+    float* exp_avg;     /* [n] fp32 */
+    float* exp_avg_sq;  /* [n] fp32 */
+    void* grad;         /* [n] gradient, possibly loss-scaled; CLEARED to zero by lnrf_adam_step */
+    void* params_f16;   /* [n] fp16 shadow copy rewritten from the updated parameters, or NULL */
+    uint64_t n;
+    lnrf_dtype grad_dtype;
+} lnrf_opt_tensor;
+/* tensors_host: HOST array of 1..8 descriptors (device pointers inside).  found_inf: device fp32 scalar, set to
+ * 1.0f when any gradient element is inf/nan (never cleared: GradScaler's convention). */
+LNRF_API int lnrf_grad_nonfinite_check(const lnrf_opt_tensor* tensors_host, uint32_t count, float* found_inf,
+                                       lnrf_stream_t stream);
+/* One Adam step on every tensor (torch.optim.Adam, amsgrad off).  grad_scale (device fp32 scalar or NULL): the
+ * gradients are divided by it first; found_inf (device scalar or NULL): when non-zero the parameters and moments
+ * are left untouched (the gradients are still cleared); step_count: device fp32 scalar = 1-based step number;
+ * lr_scale (device fp32 scalar or NULL): multiplies lr (a LambdaLR schedule factor that a CUDA graph can replay). */
+LNRF_API int lnrf_adam_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double lr, double beta1, double beta2,
+                            double eps, double weight_decay, const float* grad_scale, const float* found_inf,
+                            const float* step_count, const float* lr_scale, lnrf_stream_t stream);
+/* GradScaler.update() (growth / backoff of the loss scale from found_inf) fused with the step bookkeeping:
+ * step_count += 1 unless the step was skipped, found_inf re-armed to 0.  scale / growth_tracker may be NULL
+ * (no loss scaling). */
+LNRF_API int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, float* step_count,
+                             float growth_factor, float backoff_factor, int32_t growth_interval, lnrf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

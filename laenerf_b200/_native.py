@@ -14,7 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "liblaenerf_b200.so")
 _lib = None
 
-vp, u32, i32, f32, sz, u64 = C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_size_t, C.c_uint64
+vp, u32, i32, f32, f64, sz, u64 = C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_uint64
+
+
+class OptTensor(C.Structure):
+    """lnrf_opt_tensor (include/laenerf_b200.h): one parameter tensor of the fused Adam / AMP step."""
+    _fields_ = [("params", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("grad", vp), ("params_f16", vp), ("n", u64),
+                ("grad_dtype", i32)]
+
 
 # name -> (restype, argtypes); must list every symbol include/laenerf_b200.h declares (tests/test_abi.py checks)
 SIGNATURES = {
@@ -49,6 +56,12 @@ SIGNATURES = {
     "lnrf_free_splitk": (i32, []),
     "lnrf_sh_encode_forward": (i32, [vp, vp, u32, u32, vp, i32, vp]),
     "lnrf_sh_encode_backward": (i32, [vp, u32, u32, vp, vp, vp]),
+    "lnrf_nerf_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, f32, i32, vp, vp, vp, vp, vp, vp]),
+    "lnrf_nerf_wgrad_scratch_bytes": (sz, [u32, u32]),
+    "lnrf_nerf_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, f32, vp, vp, vp, i32, vp, vp, sz, vp]),
+    "lnrf_grad_nonfinite_check": (i32, [vp, u32, vp, vp]),
+    "lnrf_adam_step": (i32, [vp, u32, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp]),
+    "lnrf_amp_update": (i32, [vp, vp, vp, vp, f32, f32, i32, vp]),
 }
 
 F32, F16 = 0, 1  # lnrf_dtype

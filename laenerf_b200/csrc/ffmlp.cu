@@ -17,175 +17,9 @@
 //     with coalesced fp32 reductions into a scratch vector -- no split-K workspace, no side streams.
 //   Accumulation is fp32 everywhere (the reference accumulates in fp16); activations are rounded to fp16 exactly
 //   where the reference stores them (forward_buffer, backward chain, outputs).
-#include "common.cuh"
+#include "mlp_core.cuh"
 
 namespace lnrf {
-
-constexpr uint32_t kRows = 128;                      // rows per tile == UMMA M
-constexpr uint32_t kTileBytes = kRows * 128;         // one operand tile: 128 rows x 128 B
-constexpr uint32_t kWBytes = 64 * 128;               // one 64-row weight tile
-constexpr uint32_t kMaxLayers = 6;
-
-struct MlpShape {
-    uint32_t in_dim, out_dim, n_layers, act, out_act;
-};
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-// byte offset of 16-byte chunk c (0..7) of row r inside a SWIZZLE_128B tile (tile base 1024-byte aligned)
-__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    while (true) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).  8-row groups are 1024 B apart in every tile.
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(1024u >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor, kind::f16: D=f32 [4,6), A/B=f16 (0), a_major [15], b_major [16] (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc(uint32_t M, uint32_t N, bool a_mn, bool b_mn) {
-    return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 16 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
-}
-
-// ACT template parameter of the kernels: 0 = ReLU (every LAENeRF net), kActRuntime = decided per launch from MlpShape.
-// Keeping the 7-way switch out of the 64-element epilogue loops matters: with a runtime switch the epilogue, not
-// the tensor core, bounds the kernel (ncu source page, profiles/r1_ffmlp_fwd_stalls.txt).
-constexpr int kActRuntime = -1;
-
-__device__ __forceinline__ float act_fwd(uint32_t a, float x) {  // ffmlp/src/utils.h:424-475
-    switch (a) {
-        case 0: return fmaxf(x, 0.0f);
-        case 1: return __expf(x);
-        case 2: return __sinf(x);
-        case 3: return 1.0f / (1.0f + __expf(-x));
-        case 4: { const float y = x * 10.0f; return 0.5f * (y + sqrtf(y * y + 4.0f)) / 10.0f; }
-        case 5: return __logf(__expf(x * 10.0f) + 1.0f) / 10.0f;
-        default: return x;
-    }
-}
-__device__ __forceinline__ float act_bwd(uint32_t a, float g, float fwd) {  // utils.h:538-583 (through the stored output)
-    switch (a) {
-        case 0: return fwd > 0.0f ? g : 0.0f;
-        case 1: return g * fwd;
-        case 3: return g * (fwd * (1.0f - fwd));
-        case 4: { const float y = fwd * 10.0f; return g * (y * y / (y * y + 1.0f)); }
-        case 5: return g * (1.0f - __expf(-fwd * 10.0f));
-        default: return g;
-    }
-}
-
-// ---- asynchronous global -> shared copies (LDGSTS): all 16-byte pieces of a tile are in flight together ----
-__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// rows x K fp16 row-major (global) -> SWIZZLE_128B tile at shared address `tile`
-__device__ __forceinline__ void load_rows_async(uint32_t tile, const __half* __restrict__ src, uint32_t rows, uint32_t K, int tid) {
-    const uint32_t cpr = K >> 3, n = rows * cpr;
-    const uint4* g = reinterpret_cast<const uint4*>(src);
-    for (uint32_t c = tid; c < n; c += 128) {
-        const uint32_t r = c / cpr, cc = c - r * cpr;
-        cp_async16(tile + sw128(r, cc), g + c);
-    }
-}
-// raw copy of n16 16-byte pieces (staging area, no swizzle)
-__device__ __forceinline__ void copy_raw_async(uint32_t dst, const void* __restrict__ src, uint32_t n16, int tid) {
-    const uint4* g = reinterpret_cast<const uint4*>(src);
-    for (uint32_t c = tid; c < n16; c += 128) cp_async16(dst + c * 16u, g + c);
-}
-// shared (row-major [rows][K] fp16 at `src`) -> SWIZZLE_128B tile holding the TRANSPOSE: element (r, k) -> tile row k, column r
-__device__ __forceinline__ void transpose_to_tile(uint8_t* tile, const __half* src, uint32_t rows, uint32_t K, int tid) {
-    for (uint32_t e = tid; e < rows * K; e += 128) {
-        const uint32_t r = e / K, k = e - r * K;
-        *reinterpret_cast<__half*>(tile + sw128(k, r >> 3) + (r & 7u) * 2u) = src[e];
-    }
-}
-
-__device__ __forceinline__ uint4 pack8(const float* v) {
-    union { uint4 u; __half2 h[4]; } p;
-#pragma unroll
-    for (int j = 0; j < 4; j++) p.h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    return p.u;
-}
-__device__ __forceinline__ void unpack8(uint4 u, float* v) {
-    union { uint4 u; __half2 h[4]; } p;
-    p.u = u;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const float2 f = __half22float2(p.h[j]);
-        v[2 * j] = f.x; v[2 * j + 1] = f.y;
-    }
-}
-
-// 32 consecutive fp32 columns of this thread's TMEM lane, WITHOUT waiting (pair with tmem_wait_ld)
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // =========================================================================================================
 // forward / inference
@@ -308,11 +142,16 @@ __device__ __host__ inline uint32_t bwd_tmem_cols(uint32_t in_dim, uint32_t out_
 // {X, H_0..H_{NL-1}, dY}: with NBUF = 2 the next tile's 60-76 KB are prefetched (cp.async) during this tile's chain.
 // Every tile that serves as an M=128 MN-major A operand (H_l, G_0) is followed by another tile: the "second atom"
 // the MMA reads for D rows 64..127, which are never used.
-template <int ACT>
+//
+// GLUE = true is the colour net of NeRFNetwork.forward (nerf/network_ff.py:51-79) with the elementwise glue of its backward
+// fused in: dL/dY is built on the fly from dL/drgb and the saved sigmoid outputs (fp16 sigmoid backward), and instead of
+// dL/dinput [B,32] the kernel writes dL/dh [B,16] of the sigma net: column 0 = dL/dsigma * density_scale * exp(clamp(h0,
+// -15, 15)) (trunc_exp backward, activation.py:13-16), columns 1..15 = dL/dgeo_feat = dL/dinput[:, 16:31].
+template <int ACT, bool GLUE>
 __global__ void __launch_bounds__(128)
 k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, const __half* __restrict__ weights,
             const __half* __restrict__ fwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ wgrad, const uint32_t B,
-            const MlpShape sh, const uint32_t ntiles, const int calc_grad_inputs, const uint32_t nbuf) {
+            const MlpShape sh, const uint32_t ntiles, const int calc_grad_inputs, const uint32_t nbuf, const BwdGlue glue) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     const uint32_t NL = sh.n_layers, in_dim = sh.in_dim, out_dim = sh.out_dim;
@@ -332,7 +171,21 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
         const uint32_t base = smem_u32(sIN + buf * in_bytes);
         load_rows_async(base, inputs + r0 * in_dim, kRows, in_dim, tid);
         for (uint32_t l = 0; l < NL; l++) load_rows_async(base + (1 + l) * kTileBytes, fwd_buf + ((size_t)l * B + r0) * 64, kRows, 64, tid);
-        load_rows_async(base + (1 + NL) * kTileBytes, grad + r0 * out_dim, kRows, out_dim, tid);
+        if (!GLUE) load_rows_async(base + (1 + NL) * kTileBytes, grad + r0 * out_dim, kRows, out_dim, tid);
+    };
+    // GLUE: this thread's row of dL/dY (16 columns, 3 real) = fp16 sigmoid backward of dL/drgb, written straight into the tile
+    auto glue_dy = [&](uint32_t tile, uint32_t buf) {
+        const size_t r = (size_t)tile * kRows + row;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float g = __half2float(__float2half_rn(__ldcs(glue.grad_rgb + r * 3 + c)));  // the grad of the .float() cast
+            const float sgm = __ldg(glue.rgb + r * 3 + c);
+            v[c] = g * ((1.0f - sgm) * sgm);
+        }
+        uint8_t* t = sIN + buf * in_bytes + (1 + NL) * kTileBytes;
+        *reinterpret_cast<uint4*>(t + sw128(row, 0)) = pack8(v);
+        *reinterpret_cast<uint4*>(t + sw128(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
     };
 
     // stage the raw weights in the (still unused) first input set, request the first tile, then transpose in shared memory
@@ -342,6 +195,7 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
     cp_async_commit();
     load_inputs(blockIdx.x, 0);
     cp_async_commit();
+    if (GLUE) glue_dy(blockIdx.x, 0);
     if (warp == 0) tmem_alloc(tslot, ncols);
     if (tid == 32) { mbar_init(mbar, 1); fence_mbar_init(); }
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // the weights (first group) have landed
@@ -352,6 +206,7 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
         for (uint32_t m = 1; m < NL; m++) transpose_to_tile(sWT + (m - 1) * kWBytes, w + 64 * in_dim + (m - 1) * 4096, 64, 64, tid);
         if (calc_grad_inputs) transpose_to_tile(sWT0, w, 64, in_dim, tid);  // W_0 [64,in] -> [in][64]
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -377,6 +232,12 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
         if (nbuf == 2 && tile + gridDim.x < ntiles) {
             load_inputs(tile + gridDim.x, buf ^ 1u);
             cp_async_commit();
+            if (GLUE) glue_dy(tile + gridDim.x, buf ^ 1u);  // made visible by the fences + barriers of this tile's chain
+        }
+        float glue_gs = 0.f, glue_h0 = 0.f;
+        if (GLUE) {
+            glue_gs = __ldcs(glue.grad_sigma + r0 + row);
+            glue_h0 = __half2float(glue.h0[r0 + row]);
         }
         for (uint32_t m = NL; m >= 1; m--) {
             uint8_t* Gm = m == NL ? sDY : sG + (m & 1u) * kTileBytes;
@@ -437,7 +298,16 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
         mbar_wait(mbar, phase);  // every MMA of this tile has finished: its shared-memory tiles may be overwritten
         phase ^= 1u;
         tc_fence_after();
-        if (calc_grad_inputs) {
+        if (GLUE) {
+            float v[16], o[16];
+            tmem_ld16(taddr + 16, v);  // dL/dinput[:, 16:32] = dL/dgeo_feat (15) and the zero-pad column
+            o[0] = glue_gs * glue.density_scale * expf(fminf(fmaxf(glue_h0, -15.0f), 15.0f));
+#pragma unroll
+            for (int i = 1; i < 16; i++) o[i] = v[i - 1];
+            __half* d = glue.dh + (r0 + row) * 16;
+            *reinterpret_cast<uint4*>(d) = pack8(o);
+            *(reinterpret_cast<uint4*>(d) + 1) = pack8(o + 8);
+        } else if (calc_grad_inputs) {
             __half* gi = grad_inputs + (r0 + row) * in_dim;
             for (uint32_t q = 0; q < in_dim / 16; q++) {
                 float v[16];
@@ -451,6 +321,7 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
             __syncthreads();
             load_inputs(tile + gridDim.x, 0);
             cp_async_commit();
+            if (GLUE) glue_dy(tile + gridDim.x, 0);
         }
     }
 
@@ -482,9 +353,9 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
-__global__ void __launch_bounds__(256) k_ffmlp_wgrad_finalize(const float* __restrict__ acc, __half* __restrict__ gw, uint32_t n) {
+__global__ void __launch_bounds__(256) k_ffmlp_wgrad_finalize(const float* __restrict__ acc, __half* __restrict__ gw, uint32_t n, int accumulate) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) gw[i] = __float2half_rn(acc[i]);
+    if (i < n) gw[i] = __float2half_rn(accumulate ? __half2float(gw[i]) + acc[i] : acc[i]);
 }
 
 }  // namespace lnrf
@@ -547,6 +418,63 @@ static int ffmlp_fwd_launch(const char* who, const void* inputs, const void* wei
     return LNRF_OK;
 }
 
+namespace lnrf {
+
+int mlp_shape(const char* who, uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t num_layers, MlpShape* sh) {
+    return check_mlp(who, B, input_dim, output_dim, 64, num_layers, 0, 6, sh);
+}
+
+// One launch for the whole backward of a 64-wide net (+ the fp32 -> fp16 finalize of the weight gradients).  `glue` non-null
+// selects the colour-net variant with the NeRFNetwork glue fused in (see k_ffmlp_bwd).
+int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16, const void* weights_f16, const void* forward_buffer_f16,
+                  uint32_t B, const MlpShape& sh, int calc_grad_inputs, void* grad_inputs_f16, void* grad_weights_f16,
+                  void* wgrad_scratch, size_t wgrad_scratch_bytes, const BwdGlue* glue, int accumulate, cudaStream_t st) {
+    const uint32_t input_dim = sh.in_dim, output_dim = sh.out_dim, num_layers = sh.n_layers;
+    LNRF_REQUIRE(inputs_f16 && weights_f16 && forward_buffer_f16 && grad_weights_f16, "%s: null pointer", who);
+    LNRF_REQUIRE(glue || !calc_grad_inputs || grad_inputs_f16, "%s: calc_grad_inputs without grad_inputs", who);
+    const size_t need = lnrf_ffmlp_wgrad_scratch_bytes(input_dim, output_dim, 64, num_layers);
+    if (!wgrad_scratch || wgrad_scratch_bytes < need) {
+        set_error("%s: wgrad scratch too small (%zu < %zu)", who, wgrad_scratch_bytes, need);
+        return LNRF_ERR_SCRATCH_TOO_SMALL;
+    }
+    LNRF_REQUIRE(bwd_tmem_cols(input_dim, output_dim, num_layers) <= 512, "%s: network too deep for one TMEM allocation", who);
+    const uint32_t nparams = (uint32_t)(need / sizeof(float));
+    cudaError_t e = cudaMemsetAsync(wgrad_scratch, 0, need, st);
+    if (e != cudaSuccess) return cuda_fail(e, who);
+    if (B > 0) {
+        const uint32_t nbuf = bwd_smem_bytes(sh, 2) <= 227 * 1024 ? 2u : 1u;  // prefetch the next tile when it fits
+        const size_t smem = bwd_smem_bytes(sh, nbuf);
+        LNRF_REQUIRE(smem <= 227 * 1024, "%s: network needs %zu B of shared memory (> 227 KiB)", who, smem);
+        const int variant = glue ? 2 : (sh.act == 0 ? 0 : 1);
+        auto kern = variant == 2 ? k_ffmlp_bwd<0, true> : (variant == 0 ? k_ffmlp_bwd<0, false> : k_ffmlp_bwd<kActRuntime, false>);
+        static std::atomic<size_t> s_max_smem[3] = {{0}, {0}, {0}};
+        std::atomic<size_t>& mx = s_max_smem[variant];
+        if (smem > mx.load(std::memory_order_relaxed)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, who);
+            mx.store(smem, std::memory_order_relaxed);
+        }
+        const uint32_t ntiles = B / kRows;
+        const uint32_t per_sm_smem = (uint32_t)((227 * 1024) / (smem + 1024));
+        const uint32_t per_sm_tmem = 512u / bwd_tmem_cols(input_dim, output_dim, num_layers);
+        uint32_t per_sm = per_sm_smem < per_sm_tmem ? per_sm_smem : per_sm_tmem;
+        if (per_sm < 1) per_sm = 1;
+        const uint32_t cap = (uint32_t)kNumSMs * per_sm;
+        const uint32_t grid = ntiles < cap ? ntiles : cap;
+        BwdGlue g{};
+        if (glue) g = *glue;
+        kern<<<grid, 128, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
+                                      (const __half*)forward_buffer_f16, (__half*)grad_inputs_f16, (float*)wgrad_scratch, B, sh,
+                                      ntiles, glue ? 1 : calc_grad_inputs, nbuf, g);
+        LNRF_LAUNCH_CHECK(who);
+    }
+    k_ffmlp_wgrad_finalize<<<div_up(nparams, 256u), 256, 0, st>>>((const float*)wgrad_scratch, (__half*)grad_weights_f16, nparams, accumulate);
+    LNRF_LAUNCH_CHECK(who);
+    return LNRF_OK;
+}
+
+}  // namespace lnrf
+
 extern "C" {
 
 int lnrf_ffmlp_forward(const void* inputs_f16, const void* weights_f16, uint32_t B, uint32_t input_dim, uint32_t output_dim,
@@ -580,45 +508,10 @@ int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void
     (void)backward_buffer_f16;  // dL/dhidden never leaves the chip
     MlpShape sh;
     if (int e = check_mlp("ffmlp_backward", B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, &sh)) return e;
-    LNRF_REQUIRE(grad_f16 && inputs_f16 && weights_f16 && forward_buffer_f16 && grad_weights_f16, "ffmlp_backward: null pointer");
-    LNRF_REQUIRE(!calc_grad_inputs || grad_inputs_f16, "ffmlp_backward: calc_grad_inputs without grad_inputs");
-    const size_t need = lnrf_ffmlp_wgrad_scratch_bytes(input_dim, output_dim, hidden_dim, num_layers);
-    if (!wgrad_scratch || wgrad_scratch_bytes < need) {
-        set_error("ffmlp_backward: wgrad scratch too small (%zu < %zu)", wgrad_scratch_bytes, need);
-        return LNRF_ERR_SCRATCH_TOO_SMALL;
-    }
-    LNRF_REQUIRE(bwd_tmem_cols(input_dim, output_dim, num_layers) <= 512, "ffmlp_backward: network too deep for one TMEM allocation");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const uint32_t nparams = (uint32_t)(need / sizeof(float));
-    cudaError_t e = cudaMemsetAsync(wgrad_scratch, 0, need, st);
-    if (e != cudaSuccess) return cuda_fail(e, "ffmlp_backward: memset");
-    if (B > 0) {
-        const uint32_t nbuf = bwd_smem_bytes(sh, 2) <= 227 * 1024 ? 2u : 1u;  // prefetch the next tile when it fits
-        const size_t smem = bwd_smem_bytes(sh, nbuf);
-        LNRF_REQUIRE(smem <= 227 * 1024, "ffmlp_backward: network needs %zu B of shared memory (> 227 KiB)", smem);
-        auto kern = sh.act == 0 ? k_ffmlp_bwd<0> : k_ffmlp_bwd<kActRuntime>;
-        static std::atomic<size_t> s_max_smem[2] = {{0}, {0}};
-        std::atomic<size_t>& mx = s_max_smem[sh.act == 0 ? 0 : 1];
-        if (smem > mx.load(std::memory_order_relaxed)) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return cuda_fail(e, "ffmlp_backward: smem attribute");
-            mx.store(smem, std::memory_order_relaxed);
-        }
-        const uint32_t ntiles = B / kRows;
-        const uint32_t per_sm_smem = (uint32_t)((227 * 1024) / (smem + 1024));
-        const uint32_t per_sm_tmem = 512u / bwd_tmem_cols(input_dim, output_dim, num_layers);
-        uint32_t per_sm = per_sm_smem < per_sm_tmem ? per_sm_smem : per_sm_tmem;
-        if (per_sm < 1) per_sm = 1;
-        const uint32_t cap = (uint32_t)kNumSMs * per_sm;
-        const uint32_t grid = ntiles < cap ? ntiles : cap;
-        kern<<<grid, 128, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
-                                             (const __half*)forward_buffer_f16, (__half*)grad_inputs_f16, (float*)wgrad_scratch, B, sh,
-                                             ntiles, calc_grad_inputs, nbuf);
-        LNRF_LAUNCH_CHECK("ffmlp_backward");
-    }
-    k_ffmlp_wgrad_finalize<<<div_up(nparams, 256u), 256, 0, st>>>((const float*)wgrad_scratch, (__half*)grad_weights_f16, nparams);
-    LNRF_LAUNCH_CHECK("ffmlp_backward(finalize)");
-    return LNRF_OK;
+    LNRF_REQUIRE(grad_f16, "ffmlp_backward: null pointer");
+    return lnrf::ffmlp_bwd_run("ffmlp_backward", grad_f16, inputs_f16, weights_f16, forward_buffer_f16, B, sh, calc_grad_inputs,
+                               grad_inputs_f16, grad_weights_f16, wgrad_scratch, wgrad_scratch_bytes, nullptr, 0,
+                               reinterpret_cast<cudaStream_t>(stream));
 }
 
 int lnrf_allocate_splitk(size_t size) { (void)size; return LNRF_OK; }

@@ -1,0 +1,273 @@
+// optim.cu -- Adam + AMP glue for the hash-grid table and the MLP weights in one pass (row f-4 of SURVEY.md section 8).
+//
+// What the reference's training step does around the kernels on the 12.2 M-parameter table, every step
+// (nerf/utils.py:1474-1484 under `-O`: GradScaler + torch.optim.Adam; gridencoder/grid.py:43-44):
+//     embeddings.half()                      49 MB read + 24.5 MB write
+//     zeros_like(grad_embeddings)            24.5 MB write
+//     fp16 grad -> fp32 .grad                24.5 MB read + 49 MB write
+//     GradScaler inf check (+ unscale)       49 MB read (+ 49 MB write)
+//     Adam                                   4 x 49 MB read + 3 x 49 MB write
+// = ~610 MB of HBM traffic in 6+ launches.  Here: one non-finite check over the fp16 gradient the encoder backward
+// accumulated (24.5 MB read, normally still in L2) and ONE update kernel that unscales, applies Adam (torch's fused
+// CUDA Adam arithmetic, including its double-precision intermediate steps), writes the fp16 shadow copy the next
+// forward gathers from, and clears the gradient: g16 R+W, p32 R+W, m R+W, v R+W, p16 W = 367 MB -- HBM-bound.
+// Several tensors (table + both MLP weight vectors) are served by the same two launches.
+#include "common.cuh"
+
+namespace lnrf {
+
+constexpr int kMaxOptTensors = 8;
+constexpr uint32_t kOptBlock = 256;
+constexpr uint32_t kOptPerThread = 8;                      // elements per thread per chunk (one 16-byte fp16 vector)
+constexpr uint32_t kOptChunk = kOptBlock * kOptPerThread;  // elements per block-iteration
+
+struct OptTensor {
+    float* p;          // fp32 master parameters
+    float* m;          // exp_avg
+    float* v;          // exp_avg_sq
+    void* g;           // gradient (fp16 or fp32), cleared after use
+    __half* p16;       // fp16 shadow copy (may be null)
+    uint64_t n;
+    uint32_t g_is_f16;
+    uint32_t first_block;  // first block of the grid that works on this tensor
+};
+struct OptBatch {
+    OptTensor t[kMaxOptTensors];
+    uint32_t count;
+};
+
+__device__ __forceinline__ bool finite_h2(uint32_t w) {  // both halves of a packed half2 finite?
+    return ((w & 0x7c00u) != 0x7c00u) && ((w & 0x7c000000u) != 0x7c000000u);
+}
+
+__device__ __forceinline__ int find_tensor(const OptBatch& b, uint32_t block) {
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxOptTensors; i++)
+        if (i < (int)b.count && block >= b.t[i].first_block) k = i;
+    return k;
+}
+
+// found_inf[0] = 1.0f when any gradient element is inf/nan (never cleared here: torch's GradScaler convention)
+__global__ void __launch_bounds__(kOptBlock) k_grad_nonfinite(const OptBatch b, float* __restrict__ found_inf) {
+    const int k = find_tensor(b, blockIdx.x);
+    const OptTensor& t = b.t[k];
+    const uint32_t nblocks = (k + 1 < (int)b.count ? b.t[k + 1].first_block : gridDim.x) - t.first_block;
+    bool bad = false;
+    for (uint64_t base = (uint64_t)(blockIdx.x - t.first_block) * kOptChunk; base < t.n; base += (uint64_t)nblocks * kOptChunk) {
+        const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;
+        if (i + kOptPerThread <= t.n) {
+            if (t.g_is_f16) {
+                const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i);
+                bad |= !(finite_h2(w.x) && finite_h2(w.y) && finite_h2(w.z) && finite_h2(w.w));
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i);
+                const float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i + 4);
+                bad |= !(isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w) && isfinite(c.x) && isfinite(c.y) &&
+                         isfinite(c.z) && isfinite(c.w));
+            }
+        } else {
+            for (uint64_t j = i; j < t.n; j++) {
+                const float g = t.g_is_f16 ? __half2float(reinterpret_cast<const __half*>(t.g)[j]) : reinterpret_cast<const float*>(t.g)[j];
+                bad |= !isfinite(g);
+            }
+        }
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.0f;
+}
+
+struct AdamHyper {
+    double lr, beta1, beta2, eps, weight_decay;
+};
+
+// torch/aten fused CUDA Adam (ADAM_MODE::ORIGINAL, amsgrad = false, maximize = false), statement by statement, including
+// the places where its double hyper-parameters promote the arithmetic to double before the result is stored as float.
+struct AdamStepConsts {
+    double w1, w2;          // 1 - beta1, 1 - beta2
+    float step_size;        // (float)(lr / bias_correction1)
+    float bc2_sqrt;
+    double scale;           // GradScaler scale (1 when absent)
+    float inv_scale;        // exact reciprocal when the scale is a power of two (the GradScaler default), else 0
+    bool unscale;
+};
+__device__ __forceinline__ float adam_unscale(float g, const AdamStepConsts& c) {
+    if (!c.unscale) return g;
+    return c.inv_scale != 0.0f ? g * c.inv_scale : (float)((double)g / c.scale);  // both are torch's `grad /= scale`
+}
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamHyper& h, const AdamStepConsts& c) {
+    if (h.weight_decay != 0.0) g = (float)((double)g + h.weight_decay * (double)p);
+    m = (float)((double)m + c.w1 * (double)(g - m));                          // lerp(exp_avg, grad, 1 - beta1)
+    v = (float)(h.beta2 * (double)v + c.w2 * (double)g * (double)g);          // beta2 * v + (1 - beta2) * g * g
+    const float denom = (float)((double)(sqrtf(v) / c.bc2_sqrt) + h.eps);
+    p -= c.step_size * m / denom;
+}
+
+__global__ void __launch_bounds__(kOptBlock)
+k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
+            const float* __restrict__ step_count, const float* __restrict__ lr_scale) {
+    const int k = find_tensor(b, blockIdx.x);
+    const OptTensor& t = b.t[k];
+    const uint32_t nblocks = (k + 1 < (int)b.count ? b.t[k + 1].first_block : gridDim.x) - t.first_block;
+    const bool skip = found_inf != nullptr && *found_inf != 0.0f;  // GradScaler: the step is skipped, the gradient still cleared
+    if (lr_scale) h.lr *= (double)*lr_scale;  // LambdaLR-style schedule factor kept on the device (CUDA-graph friendly)
+    const float step = *step_count;
+    const float bc1 = (float)(1.0 - pow(h.beta1, (double)step));
+    AdamStepConsts c;
+    c.w1 = 1.0 - h.beta1;
+    c.w2 = 1.0 - h.beta2;
+    c.step_size = (float)(h.lr / (double)bc1);
+    c.bc2_sqrt = sqrtf((float)(1.0 - pow(h.beta2, (double)step)));
+    c.unscale = grad_scale != nullptr;
+    const float scale_f = c.unscale ? *grad_scale : 1.0f;
+    c.scale = (double)scale_f;
+    int e2;
+    c.inv_scale = (frexpf(scale_f, &e2) == 0.5f && e2 > -100 && e2 < 100) ? 1.0f / scale_f : 0.0f;
+
+    for (uint64_t base = (uint64_t)(blockIdx.x - t.first_block) * kOptChunk; base < t.n; base += (uint64_t)nblocks * kOptChunk) {
+        const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;
+        if (i >= t.n) continue;
+        if (i + kOptPerThread > t.n) {  // ragged tail of the tensor: scalar path
+            for (uint64_t j = i; j < t.n; j++) {
+                float g;
+                if (t.g_is_f16) {
+                    g = __half2float(reinterpret_cast<const __half*>(t.g)[j]);
+                    reinterpret_cast<__half*>(t.g)[j] = __float2half_rn(0.f);
+                } else {
+                    g = reinterpret_cast<const float*>(t.g)[j];
+                    reinterpret_cast<float*>(t.g)[j] = 0.f;
+                }
+                if (skip) continue;
+                float p = t.p[j], m = t.m[j], v = t.v[j];
+                adam_update(p, m, v, adam_unscale(g, c), h, c);
+                t.p[j] = p; t.m[j] = m; t.v[j] = v;
+                if (t.p16) t.p16[j] = __float2half_rn(p);
+            }
+            continue;
+        }
+        float g[kOptPerThread], p[kOptPerThread], m[kOptPerThread], v[kOptPerThread];
+        if (t.g_is_f16) {
+            union { uint4 u; __half2 h2[4]; } w;
+            w.u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float2 f = __half22float2(w.h2[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(t.g) + i) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            float* gp = reinterpret_cast<float*>(t.g) + i;
+            *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(gp);
+            *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(gp + 4);
+            *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(gp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (skip) continue;
+        *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(t.p + i);
+        *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(t.p + i + 4);
+        *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(t.m + i);
+        *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(t.m + i + 4);
+        *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(t.v + i);
+        *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(t.v + i + 4);
+#pragma unroll
+        for (int j = 0; j < (int)kOptPerThread; j++)
+            adam_update(p[j], m[j], v[j], adam_unscale(g[j], c), h, c);
+        *reinterpret_cast<float4*>(t.p + i) = *reinterpret_cast<const float4*>(p);
+        *reinterpret_cast<float4*>(t.p + i + 4) = *reinterpret_cast<const float4*>(p + 4);
+        *reinterpret_cast<float4*>(t.m + i) = *reinterpret_cast<const float4*>(m);
+        *reinterpret_cast<float4*>(t.m + i + 4) = *reinterpret_cast<const float4*>(m + 4);
+        *reinterpret_cast<float4*>(t.v + i) = *reinterpret_cast<const float4*>(v);
+        *reinterpret_cast<float4*>(t.v + i + 4) = *reinterpret_cast<const float4*>(v + 4);
+        if (t.p16) {
+            union { uint4 u; __half2 h2[4]; } w;
+#pragma unroll
+            for (int j = 0; j < 4; j++) w.h2[j] = __floats2half2_rn(p[2 * j], p[2 * j + 1]);
+            *reinterpret_cast<uint4*>(t.p16 + i) = w.u;
+        }
+    }
+}
+
+// GradScaler.update() (torch amp_update_scale_cuda_kernel) + the bookkeeping around it, one thread: adjust the scale,
+// advance the step number when the step was not skipped, and re-arm found_inf for the next step.
+__global__ void k_amp_update(float* scale, int* growth_tracker, float* found_inf, float* step_count, float growth_factor,
+                             float backoff_factor, int growth_interval) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (*found_inf != 0.0f) {
+        if (scale) *scale = *scale * backoff_factor;
+        if (growth_tracker) *growth_tracker = 0;
+    } else {
+        if (scale && growth_tracker) {
+            const int successful = *growth_tracker + 1;
+            if (successful == growth_interval) {
+                const float grown = *scale * growth_factor;
+                if (isfinite(grown)) *scale = grown;
+                *growth_tracker = 0;
+            } else {
+                *growth_tracker = successful;
+            }
+        }
+        *step_count += 1.0f;
+    }
+    *found_inf = 0.0f;
+}
+
+static int make_batch(const char* who, const lnrf_opt_tensor* tensors, uint32_t count, OptBatch* b, uint32_t* grid, bool need_state) {
+    LNRF_REQUIRE(tensors && count >= 1 && count <= (uint32_t)kMaxOptTensors, "%s: 1..%d tensors per call, got %u", who, kMaxOptTensors, count);
+    uint32_t blocks = 0;
+    b->count = count;
+    for (uint32_t i = 0; i < count; i++) {
+        const lnrf_opt_tensor& s = tensors[i];
+        LNRF_REQUIRE(s.grad && s.n > 0, "%s: tensor %u has no gradient / no elements", who, i);
+        LNRF_REQUIRE(!need_state || (s.params && s.exp_avg && s.exp_avg_sq), "%s: tensor %u: null params / exp_avg / exp_avg_sq", who, i);
+        LNRF_REQUIRE(s.grad_dtype == LNRF_F16 || s.grad_dtype == LNRF_F32, "%s: tensor %u: grad_dtype must be LNRF_F16 or LNRF_F32", who, i);
+        LNRF_REQUIRE(((reinterpret_cast<uintptr_t>(s.grad) | reinterpret_cast<uintptr_t>(s.params) | reinterpret_cast<uintptr_t>(s.exp_avg) |
+                       reinterpret_cast<uintptr_t>(s.exp_avg_sq) | reinterpret_cast<uintptr_t>(s.params_f16)) & 15) == 0,
+                     "%s: tensor %u: buffers must be 16-byte aligned", who, i);
+        OptTensor& t = b->t[i];
+        t.p = s.params; t.m = s.exp_avg; t.v = s.exp_avg_sq; t.g = s.grad; t.p16 = (__half*)s.params_f16; t.n = s.n;
+        t.g_is_f16 = s.grad_dtype == LNRF_F16;
+        t.first_block = blocks;
+        // enough blocks to fill the machine (8 resident blocks per SM), never more than the tensor has chunks
+        const uint64_t chunks = (s.n + kOptChunk - 1) / kOptChunk;
+        const uint64_t cap = (uint64_t)kNumSMs * 8;
+        blocks += (uint32_t)(chunks < cap ? chunks : cap);
+    }
+    *grid = blocks;
+    return LNRF_OK;
+}
+
+}  // namespace lnrf
+
+using namespace lnrf;
+
+extern "C" {
+
+int lnrf_grad_nonfinite_check(const lnrf_opt_tensor* tensors_host, uint32_t count, float* found_inf, lnrf_stream_t stream) {
+    OptBatch b;
+    uint32_t grid;
+    if (int e = make_batch("grad_nonfinite_check", tensors_host, count, &b, &grid, false)) return e;
+    LNRF_REQUIRE(found_inf, "grad_nonfinite_check: null found_inf");
+    k_grad_nonfinite<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, found_inf);
+    LNRF_LAUNCH_CHECK("grad_nonfinite_check");
+    return LNRF_OK;
+}
+
+int lnrf_adam_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, const float* grad_scale, const float* found_inf, const float* step_count,
+                   const float* lr_scale, lnrf_stream_t stream) {
+    OptBatch b;
+    uint32_t grid;
+    if (int e = make_batch("adam_step", tensors_host, count, &b, &grid, true)) return e;
+    LNRF_REQUIRE(step_count, "adam_step: null step_count (device fp32 scalar holding the 1-based step number)");
+    AdamHyper h{lr, beta1, beta2, eps, weight_decay};
+    k_adam_step<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
+    LNRF_LAUNCH_CHECK("adam_step");
+    return LNRF_OK;
+}
+
+int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, float* step_count, float growth_factor,
+                    float backoff_factor, int32_t growth_interval, lnrf_stream_t stream) {
+    LNRF_REQUIRE(found_inf && step_count, "amp_update: null found_inf / step_count");
+    k_amp_update<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scale, growth_tracker, found_inf, step_count, growth_factor,
+                                                                       backoff_factor, growth_interval);
+    LNRF_LAUNCH_CHECK("amp_update");
+    return LNRF_OK;
+}
+
+}  // extern "C"

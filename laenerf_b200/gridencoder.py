@@ -45,15 +45,20 @@ class _grid_encode(Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
     def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
-                align_corners=False, interpolation=0):
+                align_corners=False, interpolation=0, shadow_f16=None, grad_f16=None):
         inputs = inputs.contiguous().float()
         B, D = inputs.shape
         L = offsets.shape[0] - 1
         C = embeddings.shape[1]
         S = float(np.log2(per_level_scale))
         H = int(base_resolution)
+        ctx.grad_f16 = None
         if torch.is_autocast_enabled() and C % 2 == 0:  # grid.py:43-44
-            embeddings = embeddings.to(torch.half)
+            if shadow_f16 is not None:  # laenerf_b200.optim.AmpAdam keeps embeddings.half() up to date: no cast pass
+                embeddings = shadow_f16
+                ctx.grad_f16 = grad_f16
+            else:
+                embeddings = embeddings.to(torch.half)
         embeddings = embeddings.contiguous()
         off_h = _offsets_host(offsets)
         outputs = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
@@ -72,7 +77,8 @@ class _grid_encode(Function):
         inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
         B, D, C, L, S, H, gridtype, interpolation = ctx.dims
         grad = grad.contiguous().to(embeddings.dtype)
-        grad_embeddings = torch.zeros_like(embeddings)
+        # with AmpAdam the gradient accumulates straight into its persistent fp16 buffer (cleared by the optimizer kernel)
+        grad_embeddings = ctx.grad_f16 if ctx.grad_f16 is not None else torch.zeros_like(embeddings)
         grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if dy_dx is not None else None
         N.check(N.lib().lnrf_grid_encode_backward(N.ptr(grad), N.ptr(inputs), N.ptr(embeddings), N.ptr(_offsets_host(offsets)),
                                                   N.ptr(grad_embeddings), B, D, C, L, S, H, N.ptr(dy_dx), N.ptr(grad_inputs),
@@ -80,7 +86,9 @@ class _grid_encode(Function):
                                                   _dt(embeddings), N.GRID_BLC, N.stream()))
         if dy_dx is not None:
             grad_inputs = grad_inputs.to(inputs.dtype)
-        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None
+        if ctx.grad_f16 is not None:
+            grad_embeddings = None
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None, None
 
 
 grid_encode = _grid_encode.apply
@@ -118,6 +126,9 @@ class GridEncoder(nn.Module):
         self.n_params = offsets[-1] * level_dim
         self.embeddings = nn.Parameter(torch.empty(offset, level_dim))
         self.reset_parameters()
+        # set by laenerf_b200.optim.AmpAdam: fp16 shadow of the table + persistent fp16 gradient (row f-4)
+        self._shadow_f16 = None
+        self._grad_f16 = None
 
     def reset_parameters(self):
         std = 1e-4
@@ -134,7 +145,8 @@ class GridEncoder(nn.Module):
         prefix_shape = list(inputs.shape[:-1])
         inputs = inputs.view(-1, self.input_dim)
         outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
-                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id)
+                              inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id,
+                              self._shadow_f16, self._grad_f16)
         return outputs.view(prefix_shape + [self.output_dim])
 
     @torch.autocast(device_type="cuda", enabled=False)

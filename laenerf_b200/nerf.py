@@ -13,6 +13,7 @@ import torch.nn as nn
 from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
+from . import _native as N
 from . import raymarching
 from .ffmlp import FFMLP
 from .gridencoder import GridEncoder
@@ -34,6 +35,62 @@ class _trunc_exp(Function):  # activation.py:5-17
 
 
 trunc_exp = _trunc_exp.apply
+
+
+class _fused_network(Function):
+    """NeRFNetwork.forward after the hash-grid encoder (network_ff.py:57-79 + `density_scale * sigma`, renderer.py:299)
+    as ONE kernel (lnrf_nerf_forward) and its backward as two (lnrf_nerf_backward): row f-1 of SURVEY.md section 8.
+    Inputs/outputs and every fp16 rounding point are those of the module-by-module path below; the ~25 elementwise /
+    cat / cast launches between the MLP kernels are gone."""
+
+    @staticmethod
+    def forward(ctx, enc, dirs, w_sigma, w_color, ns, nc, density_scale, train, w_sigma_f16, w_color_f16, gw_sigma_f16, gw_color_f16):
+        M = enc.shape[0]
+        enc = enc.contiguous()
+        dirs = dirs.contiguous().float()
+        ws = w_sigma_f16 if w_sigma_f16 is not None else w_sigma.detach().half()
+        wc = w_color_f16 if w_color_f16 is not None else w_color.detach().half()
+        dev = enc.device
+        sigmas = torch.empty(M, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        fb = cin = h0 = None
+        if train:
+            fb = torch.empty(ns + nc, M, 64, dtype=torch.half, device=dev)
+            cin = torch.empty(M, 32, dtype=torch.half, device=dev)
+            h0 = torch.empty(M, dtype=torch.half, device=dev)
+        N.check(N.lib().lnrf_nerf_forward(N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, ns, nc, float(density_scale), int(train),
+                                          N.ptr(fb), N.ptr(cin), N.ptr(h0), N.ptr(sigmas), N.ptr(rgbs), N.stream()))
+        if train:
+            ctx.save_for_backward(enc, ws, wc, fb, cin, h0, rgbs)
+            ctx.cfg = (ns, nc, float(density_scale))
+            ctx.gw = (gw_sigma_f16, gw_color_f16)
+        return sigmas, rgbs
+
+    @staticmethod
+    def backward(ctx, grad_sigmas, grad_rgbs):
+        enc, ws, wc, fb, cin, h0, rgbs = ctx.saved_tensors
+        ns, nc, density_scale = ctx.cfg
+        M = enc.shape[0]
+        dev = enc.device
+        grad_sigmas = torch.zeros(M, dtype=torch.float32, device=dev) if grad_sigmas is None else grad_sigmas.contiguous().float()
+        grad_rgbs = torch.zeros(M, 3, dtype=torch.float32, device=dev) if grad_rgbs is None else grad_rgbs.contiguous().float()
+        grad_enc = torch.empty_like(enc)
+        persistent = ctx.gw[0] is not None
+        gws = ctx.gw[0] if persistent else torch.empty_like(ws)
+        gwc = ctx.gw[1] if persistent else torch.empty_like(wc)
+        dh = torch.empty(M, 16, dtype=torch.half, device=dev)
+        lib = N.lib()
+        nbytes = lib.lnrf_nerf_wgrad_scratch_bytes(ns, nc)
+        scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        N.check(lib.lnrf_nerf_backward(N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(rgbs), N.ptr(h0), N.ptr(enc), N.ptr(cin), N.ptr(ws),
+                                       N.ptr(wc), N.ptr(fb), M, ns, nc, density_scale, N.ptr(grad_enc), N.ptr(gws), N.ptr(gwc),
+                                       int(persistent), N.ptr(dh), N.ptr(scratch), nbytes, N.stream()))
+        if persistent:  # AmpAdam reads (and clears) the persistent fp16 buffers; autograd sees no weight gradient
+            gws = gwc = None
+        return grad_enc, None, gws, gwc, None, None, None, None, None, None, None, None
+
+
+fused_network = _fused_network.apply
 
 
 class NeRFNetwork(nn.Module):
@@ -68,6 +125,27 @@ class NeRFNetwork(nn.Module):
         self.encoder_dir = SHEncoder(input_dim=3, degree=4)
         self.in_dim_color = self.encoder_dir.output_dim + geo_feat_dim + 1  # padded to 32 (network_ff.py:43)
         self.color_net = FFMLP(input_dim=self.in_dim_color, output_dim=3, hidden_dim=hidden_dim_color, num_layers=num_layers_color)
+        # fused = True: forward()/the sigma scaling run as the fused kernels of csrc/nerfnet.cu whenever the call has the shape
+        # they are built for (fp16 autocast, hidden 64, 16+15+1 colour inputs, sample count a multiple of 128)
+        self.fused = True
+        self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
+                          self.in_dim_color == 32 and self.encoder_dir.degree == 4)
+
+    def _use_fused(self, x):
+        return (self.fused and self._fused_ok and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and x.shape[0] % 128 == 0 and
+                torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.float16)
+
+    def forward_scaled(self, x, d):
+        """(density_scale * sigma, rgb): what run_cuda feeds the compositor (renderer.py:298-299, 363-364)."""
+        if self._use_fused(x):
+            enc = self.encoder(x, bound=self.bound)
+            train = torch.is_grad_enabled() and (enc.requires_grad or self.sigma_net.weights.requires_grad)
+            sn, cn = self.sigma_net, self.color_net
+            return fused_network(enc, d, sn.weights, cn.weights, sn.num_layers, cn.num_layers, self.density_scale, train,
+                                 getattr(sn, "_shadow_f16", None), getattr(cn, "_shadow_f16", None),
+                                 getattr(sn, "_grad_f16", None), getattr(cn, "_grad_f16", None))
+        sigmas, rgbs = self(x, d)
+        return self.density_scale * sigmas, rgbs
 
     # ---- network_ff.py:51-79 -------------------------------------------------------------------------------
     def forward(self, x, d):
@@ -123,8 +201,7 @@ class NeRFNetwork(nn.Module):
             xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
                                                                     self.grid_size, nears, fars, counter, self.mean_count, perturb,
                                                                     128, force_all_rays, dt_gamma, max_steps)
-            sigmas, rgbs = self(xyzs, dirs)
-            sigmas = self.density_scale * sigmas
+            sigmas, rgbs = self.forward_scaled(xyzs, dirs)
             weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
             image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
             if not kwargs.get("distill", False):
@@ -152,8 +229,7 @@ class NeRFNetwork(nn.Module):
                 xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound,
                                                             dens_grid, self.cascade, self.grid_size, nears, fars, 128,
                                                             perturb if step == 0 else False, dt_gamma, max_steps)
-                sigmas, rgbs = self(xyzs, dirs)
-                sigmas = self.density_scale * sigmas
+                sigmas, rgbs = self.forward_scaled(xyzs, dirs)
                 raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image,
                                            T_thresh)
                 total_samples += xyzs.shape[0]
@@ -199,8 +275,7 @@ class NeRFNetwork(nn.Module):
             xyzs, dirs, deltas, edit_occ = raymarching.march_rays_distill(
                 n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, edit_bitfield, self.cascade,
                 self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
-            sigmas, rgbs = self(xyzs, dirs)
-            sigmas = self.density_scale * sigmas
+            sigmas, rgbs = self.forward_scaled(xyzs, dirs)
             raymarching.composite_rays_distill(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
                                                weights_edit_sum, depth, depth_edit, image, edit_occ, T_thresh)
             raymarching.compact_alive(rays_alive, n_alive, spare, count)
@@ -223,14 +298,21 @@ class TrainStep:
     """One NeRF training step as `Trainer.train_one_epoch` runs it under `-O` (nerf/utils.py:1474-1484):
     fp16 autocast forward, MSE on RGB, GradScaler backward, Adam(lr 1e-2, betas (0.9, 0.99), eps 1e-15)."""
 
-    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True, world_size: int = 1):
+    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True, world_size: int = 1, fused_optimizer: bool = True):
         self.model = model
         self.fp16 = fp16
         self.world_size = world_size
-        # fused=True: one multi-tensor kernel that also consumes GradScaler's scale / found_inf on the device, so the
-        # step has no host synchronisation and can be captured into a CUDA graph (GraphedTrainStep below)
-        self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
-        self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
+        self.fused_optimizer = bool(fused_optimizer) and fp16 and model.fused and model._fused_ok
+        if self.fused_optimizer:
+            # row f-4: inf check + unscale + Adam + fp16 shadow rewrite + gradient clear in two launches (optim.py)
+            from .optim import AmpAdam
+            self.optimizer = AmpAdam(model, lr=lr, betas=(0.9, 0.99), eps=1e-15, fp16=True)
+            self.scaler = None
+        else:
+            # torch path.  fused=True: one multi-tensor kernel that also consumes GradScaler's scale / found_inf on the
+            # device, so the step has no host synchronisation and can be captured into a CUDA graph (GraphedTrainStep)
+            self.optimizer = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=True)
+            self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
 
     def __call__(self, rays_o, rays_d, gt_rgb, bg_color=1, perturb=True):
         self.model.train()
@@ -239,6 +321,13 @@ class TrainStep:
             out = self.model.render(rays_o, rays_d, bg_color=bg_color, perturb=perturb, force_all_rays=False, dt_gamma=0,
                                     max_steps=1024)
             loss = torch.nn.functional.mse_loss(out["image"], gt_rgb, reduction="none").mean(-1).mean()
+        if self.fused_optimizer:
+            self.optimizer.scale(loss).backward()
+            if self.world_size > 1:  # the exchange step acts on the fp16 gradient buffers (24.5 MB instead of 49 MB)
+                from .parallel import allreduce_tensors
+                allreduce_tensors(self.optimizer.grads(), self.world_size)
+            self.optimizer.step()
+            return loss, out
         self.scaler.scale(loss).backward()
         if self.world_size > 1:  # the one exchange step of ray-sharded training
             from .parallel import allreduce_gradients

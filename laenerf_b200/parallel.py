@@ -66,6 +66,23 @@ def allreduce_gradients(params, world: int, group=None, average: bool = True):
             g.div_(world)
 
 
+def allreduce_tensors(tensors, world: int, group=None, average: bool = True):
+    """The same exchange step on explicit gradient buffers (laenerf_b200.optim.AmpAdam keeps fp16 ones: the hash-grid
+    gradient crosses NVLink as 24.5 MB instead of 49 MB).  Mean over ranks: NCCL averages inside the collective
+    (ReduceOp.AVG, no fp16 overflow from summing `world` loss-scaled gradients); other backends sum, then divide."""
+    if world <= 1 or not tensors:
+        return
+    nccl = dist.get_backend(group) == "nccl"
+    op = dist.ReduceOp.AVG if (average and nccl) else dist.ReduceOp.SUM
+    tensors = sorted(tensors, key=lambda g: -g.numel())
+    works = [dist.all_reduce(g, op=op, group=group, async_op=True) for g in tensors]
+    for w in works:
+        w.wait()
+    if average and not nccl:
+        for g in tensors:
+            g.div_(world)
+
+
 def broadcast_occupancy(model, src: int = 0, group=None):
     """Keep the occupancy state identical on every rank (the reference's update uses RNG, renderer.py:590-620)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
