@@ -69,13 +69,16 @@ k_ffmlp_fwd(const __half* __restrict__ inputs, const __half* __restrict__ weight
         for (uint32_t m = 0; m <= NL; m++) {
             uint8_t* cur = m == 0 ? X : sA + ((m - 1u) & 1u) * kTileBytes;
             uint8_t* nxt = sA + (m & 1u) * kTileBytes;
-            if (tid == 0) {
+            if (warp == 0) {  // uniformly; one elected lane issues (see umma_chain in mlp_core.cuh)
                 tc_fence_after();
                 const uint32_t K = m == 0 ? in_dim : 64u, N = m == NL ? out_dim : 64u;
                 const uint32_t idesc = make_idesc(128, N, false, false);
                 const uint64_t a = desc_sw128(smem_u32(cur), 16), b = desc_sw128(smem_u32(sW + m * kWBytes), 16);
-                for (uint32_t k = 0; k < K / 16; k++) umma_f16(tmem, a + 2 * k, b + 2 * k, idesc, k > 0);
-                umma_commit(mbar);
+                if (elect_one()) {
+                    umma_chain_k(K / 16, tmem, a, b, idesc);
+                    umma_commit(mbar);
+                }
+                __syncwarp();
             }
             if (TRAIN && m > 0) {  // save H_{m-1} (== cur) while the tensor core works: coalesced 16-byte pieces
                 uint4* dst = reinterpret_cast<uint4*>(fwd_buf + ((size_t)(m - 1) * B + r0) * 64);
@@ -353,10 +356,321 @@ k_ffmlp_bwd(const __half* __restrict__ grad, const __half* __restrict__ inputs, 
     if (warp == 0) tmem_dealloc(tmem, ncols);
 }
 
-__global__ void __launch_bounds__(256) k_ffmlp_wgrad_finalize(const float* __restrict__ acc, __half* __restrict__ gw, uint32_t n, int accumulate) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) gw[i] = __float2half_rn(accumulate ? __half2float(gw[i]) + acc[i] : acc[i]);
+// =========================================================================================================
+// backward, ReLU nets: two tiles in flight per CTA, dL/dhidden chained IN PLACE through the saved activations
+// =========================================================================================================
+// ncu (profiles/r1c) showed the kernel above at 6 % warps active / 10 % tensor pipe: one 128-thread CTA per SM (TMEM- and
+// shared-memory-bound) walking a serial chain.  This variant runs kBwdGroups = 2 warpgroups per CTA, each with its own tile
+// set {X, H_0..H_{NL-1}, dY}, 64 dgrad columns + its own weight-gradient accumulators in TMEM, mbarrier and named barrier,
+// sharing the transposed weights.  G_{m-1} = dgrad .* relu'(H_{m-1}) is written over H_{m-1} itself (dead once its mask is
+// applied and matmul m's weight gradient has consumed it -- both MMAs are covered by the commit the epilogue waits on), so
+// a tile set is NL+2 tiles and two sets fit; one group's cp.async loads overlap the other group's chain.
+constexpr uint32_t kBwdGroups = 2;
+
+__device__ __host__ inline uint32_t bwd2_group_cols(uint32_t in_dim, uint32_t out_dim, uint32_t NL) {
+    return 64 + out_dim + 64 * (NL - 1) + in_dim;
 }
+
+template <bool GLUE>
+__global__ void __launch_bounds__(128 * kBwdGroups, 1)
+k_mlp_bwd2(const __half* __restrict__ grad, const __half* __restrict__ inputs, const __half* __restrict__ weights,
+           const __half* __restrict__ fwd_buf, __half* __restrict__ grad_inputs, float* __restrict__ wgrad, const uint32_t B,
+           const MlpShape sh, const uint32_t ntiles, const int calc_grad_inputs, const BwdGlue glue) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+    const uint32_t NL = sh.n_layers, in_dim = sh.in_dim, out_dim = sh.out_dim;
+    uint8_t* sWT = sm;                         // index m-1 for m = 1..NL: [64 rows = input feature][K = n_m]
+    uint8_t* sWT0 = sWT + NL * kWBytes;        // W_0^T: [in rows][K = 64]
+    uint8_t* sSets = sWT0 + kWBytes;
+    const uint32_t set_bytes = (NL + 2) * kTileBytes;  // X, H_0..H_{NL-1}, dY  (+ one spare tile after the last set: the
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(sSets + kBwdGroups * set_bytes + kTileBytes);  //  "second atom" of dY)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbars + kBwdGroups);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, gt = tid & 127u;
+    const uint32_t row = gt;
+    uint8_t* sX = sSets + g * set_bytes;
+    uint8_t* sH = sX + kTileBytes;
+    uint8_t* sDY = sH + NL * kTileBytes;
+    uint64_t* mbar = mbars + g;
+    const uint32_t gcols = bwd2_group_cols(in_dim, out_dim, NL);
+    const uint32_t stride = gridDim.x * kBwdGroups, first = blockIdx.x * kBwdGroups + g;
+
+    // ---- streaming loads: the tile a chain step frees is exactly the one the NEXT tile of this group needs at the same step,
+    // so its rows are requested (cp.async, one commit group per step, issued even when empty) as soon as the step's MMAs have
+    // completed.  Groups complete in order and NL+1 are issued per tile, so "at most NL-1 groups pending" at the end of a step
+    // is precisely "what the next step reads has landed"; load latency never sits on the chain.
+    auto wait_loads = [&]() {
+        switch (NL) {
+            case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+            case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+            case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+            default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        }
+    };
+    // unit m of a tile: m == NL -> dY; 1 <= m < NL -> H_m; m == 0 -> H_0 and X
+    auto load_unit = [&](uint32_t tile, uint32_t m) {
+        if (tile < ntiles) {
+            const size_t r0 = (size_t)tile * kRows;
+            if (m == NL) {
+                if (!GLUE) load_rows_async_n(smem_u32(sDY), grad + r0 * out_dim, kRows, out_dim, gt, 128);
+            } else {
+                load_rows_async_n(smem_u32(sH + m * kTileBytes), fwd_buf + ((size_t)m * B + r0) * 64, kRows, 64, gt, 128);
+                if (m == 0) load_rows_async_n(smem_u32(sX), inputs + r0 * in_dim, kRows, in_dim, gt, 128);
+            }
+        }
+        cp_async_commit();
+    };
+    // GLUE: this row of dL/dY (16 columns, 3 real) = fp16 sigmoid backward of dL/drgb, as three fp16 values in two registers
+    auto glue_dy_regs = [&](uint32_t tile, uint32_t* pk) {
+        pk[0] = pk[1] = 0u;
+        if (tile < ntiles) {
+            const size_t r = (size_t)tile * kRows + row;
+            float v[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float gg = __half2float(__float2half_rn(__ldcs(glue.grad_rgb + r * 3 + c)));  // the grad of the .float() cast
+                const float sgm = __ldg(glue.rgb + r * 3 + c);
+                v[c] = gg * (1.0f - sgm) * sgm;
+            }
+            pk[0] = pack_h2(v[0], v[1]);
+            pk[1] = pack_h2(v[2], 0.0f);
+        }
+    };
+    auto glue_dy_store = [&](const uint32_t* pk) {
+        *reinterpret_cast<uint4*>(sDY + sw128(row, 0)) = make_uint4(pk[0], pk[1], 0u, 0u);
+        *reinterpret_cast<uint4*>(sDY + sw128(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    };
+
+    // stage the raw weights in group 0's (still unused) tile set, transpose them into the resident W^T tiles
+    const uint32_t nparams = 64 * (in_dim + 64 * (NL - 1) + out_dim);
+    uint8_t* stage = sSets;  // >= 64 KB, the weights are <= 22.5 KB
+    for (uint32_t c = tid; c < nparams * 2 / 16; c += 128 * kBwdGroups)
+        cp_async16(smem_u32(stage) + c * 16u, reinterpret_cast<const uint4*>(weights) + c);
+    cp_async_commit();
+    if (warp == 0) tmem_alloc(tslot, 512);
+    if (tid == 32) {
+        for (uint32_t i = 0; i < kBwdGroups; i++) mbar_init(mbars + i, 1);
+        fence_mbar_init();
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    {
+        const __half* w = reinterpret_cast<const __half*>(stage);
+        auto transpose = [&](uint8_t* tile, const __half* src, uint32_t rows, uint32_t K) {  // (r, k) -> tile row k, column r
+            for (uint32_t e = tid; e < rows * K; e += 128 * kBwdGroups) {
+                const uint32_t r = e / K, k = e - r * K;
+                *reinterpret_cast<__half*>(tile + sw128(k, r >> 3) + (r & 7u) * 2u) = src[e];
+            }
+        };
+        transpose(sWT + (NL - 1) * kWBytes, w + 64 * in_dim + (NL - 1) * 4096, out_dim, 64);  // W_NL [out,64] -> [64][out]
+        for (uint32_t m = 1; m < NL; m++) transpose(sWT + (m - 1) * kWBytes, w + 64 * in_dim + (m - 1) * 4096, 64, 64);
+        if (calc_grad_inputs) transpose(sWT0, w, 64, in_dim);  // W_0 [64,in] -> [in][64]
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();   // transposes done (the staging area may be overwritten), TMEM allocated, mbarriers initialised
+    tc_fence_after();
+    const uint32_t tmem = *tslot + g * gcols;                               // this group's columns
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3u) * 32u) << 16);
+    // group-relative TMEM columns: [0,64) dgrad accumulator; then dW_NL (out_dim), dW_{NL-1}..dW_1 (64 each), dW_0 (in_dim)
+    auto acc_col = [&](uint32_t m) -> uint32_t {
+        if (m == NL) return 64u;
+        if (m == 0) return 64u + out_dim + 64u * (NL - 1);
+        return 64u + out_dim + 64u * (NL - 1 - m);
+    };
+    uint32_t phase = 0, it = 0;
+
+    // first tile of this group: all of its units, in the order the chain consumes them
+    uint32_t dy_next[2] = {0u, 0u};
+    for (uint32_t u = 0; u <= NL; u++) load_unit(first, NL - u);
+    if (GLUE) {
+        glue_dy_regs(first, dy_next);
+        glue_dy_store(dy_next);
+    }
+    wait_loads();
+    fence_proxy_async();
+    group_barrier(g);
+
+    for (uint32_t tile = first; tile < ntiles; tile += stride, it++) {
+        const size_t r0 = (size_t)tile * kRows;
+        const uint32_t next = tile + stride;
+        float glue_gs = 0.f, glue_h0 = 0.f;
+        if (GLUE) {  // the trunc_exp backward inputs of this row, used by the epilogue at the end of the chain
+            glue_gs = __ldcs(glue.grad_sigma + r0 + row);
+            glue_h0 = __half2float(glue.h0[r0 + row]);
+        }
+        for (uint32_t m = NL; m >= 1; m--) {
+            uint8_t* Gm = m == NL ? sDY : sH + m * kTileBytes;   // G_m lives in H_m's tile (in place), dY for the output layer
+            uint8_t* Hp = sH + (m - 1) * kTileBytes;             // H_{m-1}: input of matmul m, ReLU mask, and the home of G_{m-1}
+            const uint32_t n_m = m == NL ? out_dim : 64u;
+            if ((gt >> 5) == 0) {  // the group's first warp, uniformly; one elected lane issues (see umma_chain)
+                tc_fence_after();
+                // wgrad: acc_m[feature i][neuron j] += H_{m-1}^T . G_m  (K = the 128 rows, 16 per MMA = 2048 B)
+                const uint64_t wa = desc_sw128(smem_u32(Hp), kTileBytes), wb = desc_sw128(smem_u32(Gm), kTileBytes);
+                const uint32_t widesc = make_idesc(128, n_m, true, true);
+                // dgrad: D[128,64] = G_m[128,n_m] . W_m[n_m,64]
+                const uint64_t a = desc_sw128(smem_u32(Gm), 16), b = desc_sw128(smem_u32(sWT + (m - 1) * kWBytes), 16);
+                const uint32_t idesc = make_idesc(128, 64, false, false);
+                if (elect_one()) {
+                    umma_chain<8>(tmem + acc_col(m), wa, wb, 128, 128, widesc, it > 0);
+                    if (m == NL) umma_chain<1>(tmem, a, b, 2, 2, idesc, false);   // n_m = out_dim = 16
+                    else umma_chain<4>(tmem, a, b, 2, 2, idesc, false);           // n_m = 64
+                    umma_commit(mbar);  // covers both: H_{m-1} may be overwritten once it fires
+                }
+                __syncwarp();
+            }
+            // the saved activations of this row, fetched while the tensor core works
+            uint4 hrow[8];
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) hrow[q] = *reinterpret_cast<const uint4*>(Hp + sw128(row, q));
+            mbar_wait_hot(mbar, phase);
+            phase ^= 1u;
+            tc_fence_after();
+            uint32_t r[64];
+            tmem_ld32_nowait(taddr, r);
+            tmem_ld32_nowait(taddr + 32, r + 32);
+            tmem_wait_ld();
+            const __half2 zero2 = __float2half2_rn(0.0f);
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) {
+                const uint32_t hw[4] = {hrow[q].x, hrow[q].y, hrow[q].z, hrow[q].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {  // round to fp16, then keep where the saved activation is positive
+                    const uint32_t pk = pack_h2(__uint_as_float(r[q * 8 + 2 * j]), __uint_as_float(r[q * 8 + 2 * j + 1]));
+                    o[j] = pk & __hgt2_mask(*reinterpret_cast<const __half2*>(&hw[j]), zero2);
+                }
+                *reinterpret_cast<uint4*>(Hp + sw128(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            // G_m's tile is free (both MMAs that read it have completed): stream in the next tile's rows for the same step
+            load_unit(next, m);
+            if (GLUE) {
+                if (m == NL) glue_dy_regs(next, dy_next);          // global loads issued now ...
+                else if (m == NL - 1) glue_dy_store(dy_next);      // ... consumed one step later
+            }
+            wait_loads();
+            tc_fence_before();
+            fence_proxy_async();
+            group_barrier(g);
+        }
+        // input layer: dW_0[neuron j][feature i] += G_0^T . X ; optionally dX = G_0 . W_0   (G_0 lives in H_0's tile)
+        if ((gt >> 5) == 0) {
+            tc_fence_after();
+            const uint64_t a = desc_sw128(smem_u32(sH), 16), b = desc_sw128(smem_u32(sWT0), 16);
+            const uint32_t idesc = make_idesc(128, in_dim, false, false);
+            const uint64_t wa = desc_sw128(smem_u32(sH), kTileBytes), wb = desc_sw128(smem_u32(sX), kTileBytes);
+            const uint32_t widesc = make_idesc(128, in_dim, true, true);
+            if (elect_one()) {
+                if (calc_grad_inputs) umma_chain<4>(tmem, a, b, 2, 2, idesc, false);
+                umma_chain<8>(tmem + acc_col(0), wa, wb, 128, 128, widesc, it > 0);
+                umma_commit(mbar);
+            }
+            __syncwarp();
+        }
+        mbar_wait_hot(mbar, phase);  // every MMA of this tile has finished: its shared-memory tiles may be overwritten
+        phase ^= 1u;
+        tc_fence_after();
+        if (GLUE) {
+            float v[16], o[16];
+            tmem_ld16(taddr + 16, v);  // dL/dinput[:, 16:32] = dL/dgeo_feat (15) and the zero-pad column
+            o[0] = glue_gs * glue.density_scale * expf(fminf(fmaxf(glue_h0, -15.0f), 15.0f));
+#pragma unroll
+            for (int i = 1; i < 16; i++) o[i] = v[i - 1];
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) pk[i] = pack_h2(o[2 * i], o[2 * i + 1]);
+            st_global_32B(glue.dh + (r0 + row) * 16, pk);
+        } else if (calc_grad_inputs) {
+            __half* gi = grad_inputs + (r0 + row) * in_dim;
+            for (uint32_t q = 0; q < in_dim / 16; q++) {
+                float v[16];
+                tmem_ld16(taddr + q * 16, v);
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) pk[i] = pack_h2(v[2 * i], v[2 * i + 1]);
+                st_global_32B(gi + q * 16, pk);
+            }
+        }
+        load_unit(next, 0);  // H_0 (holding G_0) and X are free: the last unit of the next tile
+        wait_loads();
+        tc_fence_before();
+        fence_proxy_async();
+        group_barrier(g);  // all TMEM reads of this tile are done and the next tile's first units are visible
+    }
+    cp_async_wait_all();
+
+    // ---- flush the weight-gradient accumulators (rows 0..63 are real; lanes 64..127 hold the ignored atom) ----
+    // No atomics: group 1 parks its sums in shared memory, group 0 adds its own and writes this CTA's slice of the partial-sum
+    // buffer with plain coalesced stores; k_wgrad_reduce adds the <= 148 slices in a fixed order (deterministic gradients).
+    cp_async_wait_all();
+    tc_fence_after();
+    __syncthreads();
+    float* park = reinterpret_cast<float*>(sSets);  // [column][64 rows] fp32, <= 45 KB of the (now idle) tile sets
+    const uint32_t wcols = gcols - 64;               // accumulator columns after the dgrad block
+    const bool other_has = blockIdx.x * kBwdGroups + 1 < ntiles;  // did group 1 process any tile?
+    if (g == 1 && it > 0 && (warp & 3u) < 2) {
+        for (uint32_t c = 0; c < wcols; c += 16) {
+            float v[16];
+            tmem_ld16(taddr + 64 + c, v);
+#pragma unroll
+            for (int j = 0; j < 16; j++) park[(c + j) * 64 + row] = v[j];
+        }
+    }
+    __syncthreads();
+    if (g == 0 && (warp & 3u) < 2) {
+        float* slice = wgrad + (size_t)blockIdx.x * nparams;
+        const uint32_t w_first = 64 * in_dim;
+        for (uint32_t m = 1; m <= NL; m++) {  // acc_m[i][j] = dW_m[j][i]; lane = i -> coalesced over i
+            const uint32_t n_m = m == NL ? out_dim : 64u;
+            float* dst = slice + w_first + (m - 1) * 4096;
+            for (uint32_t q = 0; q < n_m / 16; q++) {
+                float v[16];
+                tmem_ld16(taddr + acc_col(m) + q * 16, v);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const float o = other_has ? park[(acc_col(m) - 64 + q * 16 + j) * 64 + row] : 0.0f;
+                    dst[(q * 16 + j) * 64 + row] = v[j] + o;
+                }
+            }
+        }
+        for (uint32_t q = 0; q < in_dim / 16; q++) {  // acc_0[j][i] = dW_0[j][i]; lane = j
+            float v[16];
+            tmem_ld16(taddr + acc_col(0) + q * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float o = other_has ? park[(acc_col(0) - 64 + q * 16 + i) * 64 + row] : 0.0f;
+                slice[row * in_dim + q * 16 + i] = v[i] + o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(*tslot, 512);
+}
+
+// gw[i] = sum over slices of partial[s][i] (fixed order), rounded to fp16 (optionally added to the existing value).
+// 256 threads = 32 parameters (one 128-byte line per slice) x 8 slice lanes.
+__global__ void __launch_bounds__(256)
+k_wgrad_reduce(const float* __restrict__ partial, uint32_t nslices, __half* __restrict__ gw, uint32_t n, int accumulate) {
+    __shared__ float red[8][32];
+    const uint32_t c = threadIdx.x & 31u, l = threadIdx.x >> 5;
+    const uint32_t p = blockIdx.x * 32 + c;
+    float acc = 0.0f;
+    if (p < n) {
+#pragma unroll 5
+        for (uint32_t sidx = l; sidx < nslices; sidx += 8) acc += __ldcs(partial + (size_t)sidx * n + p);
+    }
+    red[l][c] = acc;
+    __syncthreads();
+    if (l == 0 && p < n) {
+        const float t = ((red[0][c] + red[1][c]) + (red[2][c] + red[3][c])) + ((red[4][c] + red[5][c]) + (red[6][c] + red[7][c]));
+        gw[p] = __float2half_rn(accumulate ? __half2float(gw[p]) + t : t);
+    }
+}
+
+static size_t bwd2_smem_bytes(const MlpShape& sh) {
+    return 1024 + (sh.n_layers + 1) * kWBytes + kTileBytes * (kBwdGroups * (sh.n_layers + 2) + 1) + 128;
+}
+
 
 }  // namespace lnrf
 
@@ -420,6 +734,39 @@ static int ffmlp_fwd_launch(const char* who, const void* inputs, const void* wei
 
 namespace lnrf {
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library links only cudart)
+int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, const char* who) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::atomic<encode_fn> s_encode{nullptr};
+    encode_fn enc = s_encode.load(std::memory_order_acquire);
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return cuda_fail(e, who);
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            set_error("%s: cuTensorMapEncodeTiled is not available from this driver", who);
+            return LNRF_ERR_CUDA;
+        }
+        enc = reinterpret_cast<encode_fn>(fn);
+        s_encode.store(enc, std::memory_order_release);
+    }
+    const cuuint64_t gdim[2] = {64, rows};
+    const cuuint64_t gstride[1] = {128};       // bytes between rows
+    const cuuint32_t box[2] = {64, kRows};     // one 128-row x 128-byte tile
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d)", who, (int)r);
+        return LNRF_ERR_CUDA;
+    }
+    return LNRF_OK;
+}
+
 int mlp_shape(const char* who, uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t num_layers, MlpShape* sh) {
     return check_mlp(who, B, input_dim, output_dim, 64, num_layers, 0, 6, sh);
 }
@@ -438,16 +785,43 @@ int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16,
         return LNRF_ERR_SCRATCH_TOO_SMALL;
     }
     LNRF_REQUIRE(bwd_tmem_cols(input_dim, output_dim, num_layers) <= 512, "%s: network too deep for one TMEM allocation", who);
-    const uint32_t nparams = (uint32_t)(need / sizeof(float));
-    cudaError_t e = cudaMemsetAsync(wgrad_scratch, 0, need, st);
-    if (e != cudaSuccess) return cuda_fail(e, who);
-    if (B > 0) {
+    const uint32_t nparams = (uint32_t)(need / sizeof(float) / kNumSMs);
+    cudaError_t e = cudaSuccess;
+    uint32_t nslices = 1;  // slices of partial sums the reduction adds up (the atomics path accumulates into one)
+    const bool relu2 = sh.act == 0 && kBwdGroups * bwd2_group_cols(input_dim, output_dim, num_layers) <= 512 &&
+                       bwd2_smem_bytes(sh) <= 227 * 1024 && (kBwdGroups * (num_layers + 2)) * kTileBytes >= 2 * nparams;
+    LNRF_REQUIRE(!glue || relu2, "%s: the fused colour-net backward needs a ReLU net that fits the two-tile kernel", who);
+    if (B > 0 && relu2) {
+        const size_t smem = bwd2_smem_bytes(sh);
+        auto kern = glue ? k_mlp_bwd2<true> : k_mlp_bwd2<false>;
+        static std::atomic<size_t> s_max2[2] = {{0}, {0}};
+        std::atomic<size_t>& mx = s_max2[glue ? 1 : 0];
+        if (smem > mx.load(std::memory_order_relaxed)) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, who);
+            mx.store(smem, std::memory_order_relaxed);
+        }
+        const uint32_t ntiles = B / kRows;
+        const uint32_t want = div_up(ntiles, kBwdGroups);
+        const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
+        nslices = grid;  // every CTA writes its whole slice: nothing to clear
+        BwdGlue g{};
+        if (glue) g = *glue;
+        kern<<<grid, 128 * kBwdGroups, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
+                                                   (const __half*)forward_buffer_f16, (__half*)grad_inputs_f16, (float*)wgrad_scratch, B,
+                                                   sh, ntiles, glue ? 1 : calc_grad_inputs, g);
+        LNRF_LAUNCH_CHECK(who);
+    } else {
+        e = cudaMemsetAsync(wgrad_scratch, 0, sizeof(float) * nparams, st);
+        if (e != cudaSuccess) return cuda_fail(e, who);
+    }
+    if (B > 0 && !relu2) {
         const uint32_t nbuf = bwd_smem_bytes(sh, 2) <= 227 * 1024 ? 2u : 1u;  // prefetch the next tile when it fits
         const size_t smem = bwd_smem_bytes(sh, nbuf);
         LNRF_REQUIRE(smem <= 227 * 1024, "%s: network needs %zu B of shared memory (> 227 KiB)", who, smem);
-        const int variant = glue ? 2 : (sh.act == 0 ? 0 : 1);
-        auto kern = variant == 2 ? k_ffmlp_bwd<0, true> : (variant == 0 ? k_ffmlp_bwd<0, false> : k_ffmlp_bwd<kActRuntime, false>);
-        static std::atomic<size_t> s_max_smem[3] = {{0}, {0}, {0}};
+        const int variant = sh.act == 0 ? 0 : 1;
+        auto kern = variant == 0 ? k_ffmlp_bwd<0, false> : k_ffmlp_bwd<kActRuntime, false>;
+        static std::atomic<size_t> s_max_smem[2] = {{0}, {0}};
         std::atomic<size_t>& mx = s_max_smem[variant];
         if (smem > mx.load(std::memory_order_relaxed)) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -461,14 +835,12 @@ int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16,
         if (per_sm < 1) per_sm = 1;
         const uint32_t cap = (uint32_t)kNumSMs * per_sm;
         const uint32_t grid = ntiles < cap ? ntiles : cap;
-        BwdGlue g{};
-        if (glue) g = *glue;
         kern<<<grid, 128, smem, st>>>((const __half*)grad_f16, (const __half*)inputs_f16, (const __half*)weights_f16,
                                       (const __half*)forward_buffer_f16, (__half*)grad_inputs_f16, (float*)wgrad_scratch, B, sh,
-                                      ntiles, glue ? 1 : calc_grad_inputs, nbuf, g);
+                                      ntiles, calc_grad_inputs, nbuf, BwdGlue{});
         LNRF_LAUNCH_CHECK(who);
     }
-    k_ffmlp_wgrad_finalize<<<div_up(nparams, 256u), 256, 0, st>>>((const float*)wgrad_scratch, (__half*)grad_weights_f16, nparams, accumulate);
+    k_wgrad_reduce<<<div_up(nparams, 32u), 256, 0, st>>>((const float*)wgrad_scratch, nslices, (__half*)grad_weights_f16, nparams, accumulate);
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }
@@ -496,8 +868,9 @@ int lnrf_ffmlp_inference(const void* inputs_f16, const void* weights_f16, uint32
                                    reinterpret_cast<cudaStream_t>(stream));
 }
 
+// one fp32 slice of partial weight-gradient sums per CTA of the persistent backward kernel (<= one CTA per SM)
 size_t lnrf_ffmlp_wgrad_scratch_bytes(uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers) {
-    return sizeof(float) * (size_t)hidden_dim * (input_dim + (size_t)hidden_dim * (num_layers - 1) + output_dim);
+    return sizeof(float) * (size_t)hidden_dim * (input_dim + (size_t)hidden_dim * (num_layers - 1) + output_dim) * (size_t)kNumSMs;
 }
 
 int lnrf_ffmlp_backward(const void* grad_f16, const void* inputs_f16, const void* weights_f16, const void* forward_buffer_f16,

@@ -1,6 +1,7 @@
 // mlp_core.cuh -- tcgen05 / TMEM / mbarrier / cp.async PTX wrappers and SWIZZLE_128B tile helpers shared by the
 // fused-MLP kernels (ffmlp.cu) and the fused NeRF network kernels (nerfnet.cu).  sm_100a only.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encode entry point is fetched through the runtime, no libcuda link)
 #include "common.cuh"
 
 namespace lnrf {
@@ -186,5 +187,99 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- helpers of the multi-tile-in-flight kernels (one warpgroup of 128 threads per tile, several tiles per CTA) ----
+
+__device__ __forceinline__ void group_barrier(uint32_t g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1u) : "memory"); }
+
+// mbarrier wait for the hot loop: try_wait suspends in hardware; the wall-clock bound is only consulted every 64 K polls
+__device__ __forceinline__ void mbar_wait_hot(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t polls = 0;
+    long long t0 = 0;
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++polls & 0xffffu) == 0u) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000ll) __trap();
+        }
+    }
+}
+
+// two fp32 -> packed fp16x2 with ReLU in one instruction (F2FP.RELU); `lo` lands in the low half (lower address)
+__device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+// one full 32-byte sector per thread, streaming (evict-first)
+__device__ __forceinline__ void st_global_32B(void* p, const uint32_t* r) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+// rows x K fp16 row-major (global) -> SWIZZLE_128B tile, issued by the `nthr` threads of one group / of the CTA
+__device__ __forceinline__ void load_rows_async_n(uint32_t tile, const __half* __restrict__ src, uint32_t rows, uint32_t K, uint32_t t,
+                                                  uint32_t nthr) {
+    const uint32_t cpr = K >> 3, n = rows * cpr;
+    const uint4* g = reinterpret_cast<const uint4*>(src);
+    for (uint32_t c = t; c < n; c += nthr) {
+        const uint32_t r = c / cpr, cc = c - r * cpr;
+        cp_async16(tile + sw128(r, cc), g + c);
+    }
+}
+
+// ---- MMA issue: warp-uniform control flow + elect.sync + unrolled K loop ----
+// Guarding the issue with `tid == 0` makes ptxas wrap EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (the
+// operands must be uniform registers and the branch is divergent to it): ~30 instructions and ~150-200 cycles per MMA, which
+// put 0.4 us (forward, 4 MMAs) to 1.2 us (backward, 12 MMAs) of pure issue overhead on every chain step (SASS of profiles/r1d).
+// With the whole warp taking the branch and elect.sync as the inner predicate the MMAs are emitted back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+// NK MMAs whose operand descriptors advance by (step_a, step_b) encoded units per K-slice; the first accumulates iff acc_first
+template <int NK>
+__device__ __forceinline__ void umma_chain(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t step_a, uint32_t step_b, uint32_t idesc,
+                                           bool acc_first) {
+#pragma unroll
+    for (int k = 0; k < NK; k++) umma_f16(d_tmem, a + (uint64_t)(step_a * k), b + (uint64_t)(step_b * k), idesc, (k > 0 || acc_first) ? 1u : 0u);
+}
+
+// runtime K-slice count 1..4 (K = 16..64), K-major operands
+__device__ __forceinline__ void umma_chain_k(uint32_t nk, uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc) {
+    switch (nk) {
+        case 1: umma_chain<1>(d_tmem, a, b, 2, 2, idesc, false); break;
+        case 2: umma_chain<2>(d_tmem, a, b, 2, 2, idesc, false); break;
+        case 3: umma_chain<3>(d_tmem, a, b, 2, 2, idesc, false); break;
+        default: umma_chain<4>(d_tmem, a, b, 2, 2, idesc, false); break;
+    }
+}
+
+// ---- TMA (bulk tensor copies): one elected thread moves a whole 128-row x 128-byte SWIZZLE_128B tile ----
+// [rows, 64] fp16 row-major global tensor, box = one tile; defined in ffmlp.cu
+int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, const char* who);
+
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, uint32_t smem_tile, int32_t col, int32_t row) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_tile), "r"(col), "r"(row)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory source of every committed store has been read (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace lnrf

@@ -18,134 +18,159 @@
 // net, whose dL/dinput feeds the hash-grid backward.
 #include "mlp_core.cuh"
 #include "sh_core.cuh"
+#include <string.h>
 
 namespace lnrf {
 
 constexpr uint32_t kEncDim = 32;   // hash-grid features per sample (16 levels x 2)
 constexpr uint32_t kColIn = 32;    // 16 SH + 15 geo_feat + 1 zero pad (network_ff.py:43)
 
+// ---- multi-tile-in-flight structure --------------------------------------------------------------------------------
+// A layer step of one 128-row tile is a serial chain (MMA -> commit -> TMEM load -> ReLU/pack -> shared store -> fence ->
+// barrier, ~1 us) that leaves the SM mostly idle, and shared memory (44 KB of weights per CTA) allowed only two CTAs per
+// SM (ncu r1c: 12 % warps active, 9 % tensor pipe, long-scoreboard + barrier stalls).  So ONE CTA of 512 threads per SM
+// runs kGroups = 4 independent tiles at once: warpgroup g (4 warps = the 128 TMEM lanes) owns tile slots, 64 TMEM columns,
+// one mbarrier and one named barrier; the weights are shared.  Each group's chain runs IN PLACE in a single 16 KB tile
+// (the MMA that read it has completed before the epilogue overwrites it) while the group's other tile receives the next
+// input rows (cp.async prefetch), and the activations to be saved for the backward go to global memory straight from the
+// epilogue registers as full 32-byte sectors (st.global.v8), not through a second pass over shared memory.
+constexpr uint32_t kGroups = 4;
+
 // shared memory: sigma-net weights W_0..W_{ns} then colour-net weights W_0..W_{nc} (8 KB per 64-row matrix, 2 KB for the
-// 16-row output matrices, each 1024-byte aligned), X double buffer, activation ping-pong pair.
+// 16-row output matrices, each 1024-byte aligned), then per group two 16 KB tiles, then kGroups mbarriers + the TMEM slot.
 template <bool TRAIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128 * kGroups, 1)
 k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const __half* __restrict__ w_sigma,
            const __half* __restrict__ w_color, const uint32_t M, const uint32_t ns, const uint32_t nc, const float density_scale,
-           __half* __restrict__ fwd_buf, __half* __restrict__ color_in, __half* __restrict__ h0_out, float* __restrict__ sigmas,
-           float* __restrict__ rgbs, const uint32_t ntiles) {
+           const __grid_constant__ CUtensorMap tm_fwd_buf, __half* __restrict__ color_in, __half* __restrict__ h0_out,
+           float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t ntiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     uint8_t* sWs = sm;                                  // ns matrices of 8 KB + 2 KB
     uint8_t* sWc = sWs + ns * kWBytes + 2048;           // nc matrices of 8 KB + 2 KB
-    uint8_t* sX = sWc + nc * kWBytes + 2048;
-    uint8_t* sA = sX + 2 * kTileBytes;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sA + 2 * kTileBytes);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t row = tid;
+    uint8_t* sT = sWc + nc * kWBytes + 2048;            // kGroups x 2 tiles
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(sT + kGroups * 2 * kTileBytes);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbars + kGroups);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, g = tid >> 7, gt = tid & 127u;
+    const uint32_t row = gt;  // this thread's row of its group's tile == its TMEM lane (warp % 4 selects the 32-lane quarter)
+    uint8_t* myT = sT + g * 2 * kTileBytes;
+    uint64_t* mbar = mbars + g;
+    const uint32_t stride = gridDim.x * kGroups;
+    const uint32_t first = blockIdx.x * kGroups + g;
 
-    // weights of both nets + the first tile, all in flight together; TMEM allocation overlaps the copies
-    load_rows_async(smem_u32(sWs), w_sigma, 64, kEncDim, tid);
-    for (uint32_t m = 1; m < ns; m++) load_rows_async(smem_u32(sWs + m * kWBytes), w_sigma + 64 * kEncDim + (m - 1) * 4096, 64, 64, tid);
-    load_rows_async(smem_u32(sWs + ns * kWBytes), w_sigma + 64 * kEncDim + (ns - 1) * 4096, 16, 64, tid);
-    load_rows_async(smem_u32(sWc), w_color, 64, kColIn, tid);
-    for (uint32_t m = 1; m < nc; m++) load_rows_async(smem_u32(sWc + m * kWBytes), w_color + 64 * kColIn + (m - 1) * 4096, 64, 64, tid);
-    load_rows_async(smem_u32(sWc + nc * kWBytes), w_color + 64 * kColIn + (nc - 1) * 4096, 16, 64, tid);
-    load_rows_async(smem_u32(sX), enc + (size_t)blockIdx.x * kRows * kEncDim, kRows, kEncDim, tid);
+    // weights of both nets (all 512 threads) + every group's first tile, all in flight together; TMEM allocation overlaps
+    load_rows_async_n(smem_u32(sWs), w_sigma, 64, kEncDim, tid, 128 * kGroups);
+    for (uint32_t m = 1; m < ns; m++) load_rows_async_n(smem_u32(sWs + m * kWBytes), w_sigma + 64 * kEncDim + (m - 1) * 4096, 64, 64, tid, 128 * kGroups);
+    load_rows_async_n(smem_u32(sWs + ns * kWBytes), w_sigma + 64 * kEncDim + (ns - 1) * 4096, 16, 64, tid, 128 * kGroups);
+    load_rows_async_n(smem_u32(sWc), w_color, 64, kColIn, tid, 128 * kGroups);
+    for (uint32_t m = 1; m < nc; m++) load_rows_async_n(smem_u32(sWc + m * kWBytes), w_color + 64 * kColIn + (m - 1) * 4096, 64, 64, tid, 128 * kGroups);
+    load_rows_async_n(smem_u32(sWc + nc * kWBytes), w_color + 64 * kColIn + (nc - 1) * 4096, 16, 64, tid, 128 * kGroups);
+    if (first < ntiles) load_rows_async_n(smem_u32(myT), enc + (size_t)first * kRows * kEncDim, kRows, kEncDim, gt, 128);
     cp_async_commit();
-    if (warp == 0) tmem_alloc(tslot, 64);
-    if (tid == 32) { mbar_init(mbar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc(tslot, 64 * kGroups);
+    if (tid == 32) {
+        for (uint32_t i = 0; i < kGroups; i++) mbar_init(mbars + i, 1);
+        fence_mbar_init();
+    }
+    float dx = 0.f, dy = 0.f, dz = 0.f;  // this sample's direction, fetched one tile ahead (the sigma epilogue needs it)
+    if (first < ntiles) {
+        const float* d = dirs + ((size_t)first * kRows + row) * 3;
+        dx = __ldcs(d); dy = __ldcs(d + 1); dz = __ldcs(d + 2);
+    }
+    cp_async_wait_all();
+    fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();   // weights + first tiles landed, TMEM allocated, mbarriers initialised
     tc_fence_after();
-    const uint32_t tmem = *tslot;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem = *tslot + g * 64u;                                  // this group's 64 accumulator columns
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3u) * 32u) << 16);     // + this warp's lane quarter
     uint32_t phase = 0, it = 0;
     const uint32_t nsteps = ns + 1 + nc + 1;  // matmuls per sample
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    for (uint32_t tile = first; tile < ntiles; tile += stride, it++) {
         const size_t r0 = (size_t)tile * kRows;
-        uint8_t* X = sX + (it & 1u) * kTileBytes;
-        cp_async_wait_all();
-        fence_proxy_async();
-        __syncthreads();  // X (and on the first pass the weights) landed; the previous tile is completely done
-        if (tile + gridDim.x < ntiles) {
-            load_rows_async(smem_u32(sX + ((it + 1u) & 1u) * kTileBytes), enc + (size_t)(tile + gridDim.x) * kRows * kEncDim, kRows, kEncDim, tid);
-            cp_async_commit();
+        uint8_t* T = myT + (it & 1u) * kTileBytes;   // this tile's chain buffer (its input rows are already here)
+        if (it > 0) {
+            cp_async_wait_all();
+            fence_proxy_async();
+            group_barrier(g);  // the prefetched rows landed; the previous tile of this group is completely done
         }
-        // this sample's direction: needed by the sigma epilogue, ns + 1 matmuls from now
-        const float dx = __ldcs(dirs + (r0 + row) * 3), dy = __ldcs(dirs + (r0 + row) * 3 + 1), dz = __ldcs(dirs + (r0 + row) * 3 + 2);
+        const float cx = dx, cy = dy, cz = dz;
+        if (tile + stride < ntiles) {
+            load_rows_async_n(smem_u32(myT + ((it + 1u) & 1u) * kTileBytes), enc + (size_t)(tile + stride) * kRows * kEncDim, kRows, kEncDim, gt, 128);
+            cp_async_commit();
+            const float* d = dirs + ((size_t)(tile + stride) * kRows + row) * 3;
+            dx = __ldcs(d); dy = __ldcs(d + 1); dz = __ldcs(d + 2);
+        }
 
-        // step s: 0..ns = sigma net (input X), ns+1..ns+1+nc = colour net (input = the assembled colour row)
-        // operand tiles: step 0 reads X; step s > 0 reads sA[(s-1)&1]; its epilogue writes sA[s&1]
+        // step s: 0..ns = sigma net, ns+1..ns+1+nc = colour net; every step reads T and its epilogue rewrites T in place
         for (uint32_t s = 0; s < nsteps; s++) {
             const bool sig = s <= ns;
             const uint32_t m = sig ? s : s - (ns + 1);            // layer index inside its net
-            const uint32_t nl = sig ? ns : nc;
-            const bool last = m == nl;                            // the 16-wide output layer
-            uint8_t* cur = s == 0 ? X : sA + ((s - 1u) & 1u) * kTileBytes;
-            uint8_t* nxt = sA + (s & 1u) * kTileBytes;
-            if (tid == 0) {
+            const bool last = m == (sig ? ns : nc);               // the 16-wide output layer
+            if ((gt >> 5) == 0) {  // the group's first warp, uniformly; one elected lane issues (see umma_chain)
                 tc_fence_after();
-                const uint32_t K = m == 0 ? 32u : 64u, N = last ? 16u : 64u;
-                const uint32_t idesc = make_idesc(128, N, false, false);
-                const uint64_t a = desc_sw128(smem_u32(cur), 16), b = desc_sw128(smem_u32((sig ? sWs : sWc) + m * kWBytes), 16);
-                for (uint32_t k = 0; k < K / 16; k++) umma_f16(tmem, a + 2 * k, b + 2 * k, idesc, k > 0);
-                umma_commit(mbar);
-            }
-            if (TRAIN && s > 0) {  // save the operand of this matmul while the tensor core works
-                if (s == ns + 1) {  // the colour net's input rows (64 B each)
-                    uint4* dst = reinterpret_cast<uint4*>(color_in + r0 * kColIn);
-#pragma unroll
-                    for (uint32_t i = 0; i < 4; i++) {
-                        const uint32_t c = tid + i * 128;
-                        __stcs(dst + c, *reinterpret_cast<const uint4*>(cur + sw128(c >> 2, c & 3u)));
-                    }
-                } else {  // hidden activations: sigma H_0..H_{ns-1} then colour H_0..H_{nc-1}
-                    const uint32_t slot = sig ? s - 1 : s - 2;
-                    uint4* dst = reinterpret_cast<uint4*>(fwd_buf + ((size_t)slot * M + r0) * 64);
-#pragma unroll
-                    for (uint32_t i = 0; i < 8; i++) {
-                        const uint32_t c = tid + i * 128;
-                        __stcs(dst + c, *reinterpret_cast<const uint4*>(cur + sw128(c >> 3, c & 7u)));
-                    }
+                const uint32_t idesc = make_idesc(128, last ? 16u : 64u, false, false);
+                const uint64_t a = desc_sw128(smem_u32(T), 16), b = desc_sw128(smem_u32((sig ? sWs : sWc) + m * kWBytes), 16);
+                if (elect_one()) {
+                    if (m == 0) umma_chain<2>(tmem, a, b, 2, 2, idesc, false);   // K = 32
+                    else umma_chain<4>(tmem, a, b, 2, 2, idesc, false);          // K = 64
+                    // the TMA store of the previous step's activations (issued below) reads T too: the commit that lets the
+                    // epilogue overwrite T is issued only after that read has finished (it overlaps the MMAs)
+                    if (TRAIN) tma_store_wait_read();
+                    umma_commit(mbar);
                 }
+                __syncwarp();
             }
-            mbar_wait(mbar, phase);
+            mbar_wait_hot(mbar, phase);
             phase ^= 1u;
             tc_fence_after();
             if (!last) {
-                uint32_t r[64];
+                uint32_t r[64], pk[32];
                 tmem_ld32_nowait(taddr, r);
                 tmem_ld32_nowait(taddr + 32, r + 32);
                 tmem_wait_ld();
 #pragma unroll
-                for (uint32_t q = 0; q < 8; q++) {
-                    float v[8];
+                for (int i = 0; i < 32; i++) pk[i] = pack_relu(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
 #pragma unroll
-                    for (int i = 0; i < 8; i++) v[i] = fmaxf(__uint_as_float(r[q * 8 + i]), 0.0f);
-                    *reinterpret_cast<uint4*>(nxt + sw128(row, q)) = pack8(v);
-                }
+                for (uint32_t q = 0; q < 8; q++)
+                    *reinterpret_cast<uint4*>(T + sw128(row, q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 tc_fence_before();
                 fence_proxy_async();
-                __syncthreads();
+                group_barrier(g);
+                if (TRAIN && (gt >> 5) == 0) {  // hidden activations: sigma H_0..H_{ns-1} then colour H_0..H_{nc-1}, one TMA store per tile
+                    const uint32_t slot = sig ? s : s - 1;
+                    if (elect_one()) {
+                        tma_store_tile(&tm_fwd_buf, smem_u32(T), 0, (int32_t)(slot * M + (uint32_t)r0));
+                        tma_store_commit();
+                    }
+                    __syncwarp();
+                }
             } else if (sig) {
                 // sigma epilogue: h (fp16) -> sigma = density_scale * exp(h0); colour row = [SH(dir) | h[1..15] | 0]
-                float h[16], sh[16], c2[16];
+                float h[16], sh[16];
+                uint32_t pk[16];
                 tmem_ld16(taddr, h);
                 const __half h0 = __float2half_rn(h[0]);
-                __stcs(sigmas + r0 + row, density_scale * expf(__half2float(h0)));
-                if (TRAIN) h0_out[r0 + row] = h0;
-                sh_basis(dx, dy, dz, 4, sh);
+                sh_basis(cx, cy, cz, 4, sh);
 #pragma unroll
-                for (int i = 0; i < 15; i++) c2[i] = h[i + 1];
-                c2[15] = 0.0f;
-                *reinterpret_cast<uint4*>(nxt + sw128(row, 0)) = pack8(sh);
-                *reinterpret_cast<uint4*>(nxt + sw128(row, 1)) = pack8(sh + 8);
-                *reinterpret_cast<uint4*>(nxt + sw128(row, 2)) = pack8(c2);
-                *reinterpret_cast<uint4*>(nxt + sw128(row, 3)) = pack8(c2 + 8);
+                for (int i = 0; i < 8; i++) pk[i] = pack_h2(sh[2 * i], sh[2 * i + 1]);
+#pragma unroll
+                for (int i = 0; i < 7; i++) pk[8 + i] = pack_h2(h[2 * i + 1], h[2 * i + 2]);
+                pk[15] = pack_h2(h[15], 0.0f);
+#pragma unroll
+                for (uint32_t q = 0; q < 4; q++)
+                    *reinterpret_cast<uint4*>(T + sw128(row, q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 tc_fence_before();
                 fence_proxy_async();
-                __syncthreads();
+                group_barrier(g);
+                __stcs(sigmas + r0 + row, density_scale * expf(__half2float(h0)));
+                if (TRAIN) {
+                    h0_out[r0 + row] = h0;
+                    __half* dst = color_in + (r0 + row) * kColIn;
+                    st_global_32B(dst, pk);
+                    st_global_32B(dst + 16, pk + 8);
+                }
             } else {
                 // colour epilogue: rgb = sigmoid(h[0..2]) evaluated on the fp16 output, result rounded to fp16 (torch.sigmoid on half)
                 float h[16];
@@ -161,11 +186,16 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
         }
     }
     cp_async_wait_all();
+    if (TRAIN && (gt >> 5) == 0) {
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    }
+    tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (warp == 0) tmem_dealloc(*tslot, 64 * kGroups);
 }
 
-static size_t nerf_fwd_smem(uint32_t ns, uint32_t nc) { return 1024 + (ns + nc) * kWBytes + 4096 + 4 * kTileBytes + 64; }
+static size_t nerf_fwd_smem(uint32_t ns, uint32_t nc) { return 1024 + (ns + nc) * kWBytes + 4096 + kGroups * 2 * kTileBytes + 128; }
 
 }  // namespace lnrf
 
@@ -199,14 +229,18 @@ int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigm
         if (e != cudaSuccess) return cuda_fail(e, "nerf_forward");
         mx.store(smem, std::memory_order_relaxed);
     }
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (train) {
+        LNRF_REQUIRE((uint64_t)(ns + nc) * M < (1ull << 31), "nerf_forward: forward_buffer too large for one tensor map");
+        if (int e = make_tile_tensor_map(&tm, forward_buffer_f16, (uint64_t)(ns + nc) * M, "nerf_forward")) return e;
+    }
     const uint32_t ntiles = M / kRows;
-    uint32_t per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-    const uint32_t cap = (uint32_t)kNumSMs * per_sm;
-    const uint32_t grid = ntiles < cap ? ntiles : cap;
-    kern<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    const uint32_t want = div_up(ntiles, kGroups);  // one persistent CTA per SM, kGroups tiles in flight each
+    const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
+    kern<<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale,
-        (__half*)forward_buffer_f16, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles);
+        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles);
     LNRF_LAUNCH_CHECK("nerf_forward");
     return LNRF_OK;
 }

@@ -144,27 +144,35 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
             }
             continue;
         }
+        // every load of this chunk is issued before the first store (the compiler cannot prove g / p / m / v do not alias, so
+        // the order written here is the order executed): 7 x 16 B per thread in flight
         float g[kOptPerThread], p[kOptPerThread], m[kOptPerThread], v[kOptPerThread];
+        uint4 gw = make_uint4(0u, 0u, 0u, 0u);
         if (t.g_is_f16) {
-            union { uint4 u; __half2 h2[4]; } w;
-            w.u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i);
-#pragma unroll
-            for (int j = 0; j < 4; j++) { const float2 f = __half22float2(w.h2[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(t.g) + i) = make_uint4(0u, 0u, 0u, 0u);
+            gw = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i));
         } else {
-            float* gp = reinterpret_cast<float*>(t.g) + i;
-            *reinterpret_cast<float4*>(g) = *reinterpret_cast<const float4*>(gp);
-            *reinterpret_cast<float4*>(g + 4) = *reinterpret_cast<const float4*>(gp + 4);
-            *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(gp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i);
+            *reinterpret_cast<float4*>(g) = __ldcs(gp);
+            *reinterpret_cast<float4*>(g + 4) = __ldcs(gp + 1);
         }
-        if (skip) continue;
         *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(t.p + i);
         *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(t.p + i + 4);
         *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(t.m + i);
         *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(t.m + i + 4);
         *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(t.v + i);
         *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(t.v + i + 4);
+        if (t.g_is_f16) {
+            union { uint4 u; __half2 h2[4]; } w;
+            w.u = gw;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float2 f = __half22float2(w.h2[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(t.g) + i) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            float* gp = reinterpret_cast<float*>(t.g) + i;
+            *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(gp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (skip) continue;
 #pragma unroll
         for (int j = 0; j < (int)kOptPerThread; j++)
             adam_update(p[j], m[j], v[j], adam_unscale(g[j], c), h, c);
