@@ -35,6 +35,8 @@ ALGO = {
     "lnrf_march_rays_train": dict(bound="hbm", per_ray=48, per_sample=32),
     "lnrf_grid_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
     "lnrf_grid_encode_backward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
+    "lnrf_grid_encode_forward_world": dict(bound="hbm", per_ray=0, per_sample_padded=588),   # same kernels, world-coordinate inputs
+    "lnrf_grid_encode_backward_world": dict(bound="hbm", per_ray=0, per_sample_padded=588),
     "lnrf_composite_rays_train_forward": dict(bound="hbm", per_ray=32, per_sample=24),
     "lnrf_composite_rays_train_backward": dict(bound="hbm", per_ray=44, per_sample=40),
     "lnrf_ffmlp_forward": dict(bound="tensor", flops_per_sample_padded=36864 / 2),   # mean of sigma (14336) and colour (22528) nets

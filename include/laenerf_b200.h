@@ -228,6 +228,64 @@ LNRF_API int lnrf_sh_encode_forward(const float* inputs, void* outputs, uint32_t
 LNRF_API int lnrf_sh_encode_backward(const float* grad, uint32_t B, uint32_t degree, const float* dy_dx,
                                      float* grad_inputs, lnrf_stream_t stream);
 
+/* world-coordinate variants of the hot hash-grid kernels (D = 3, C = 2, [B, L*C] layout): GridEncoder.forward's
+ * (x + bound) / (2 * bound) (gridencoder/grid.py:147) is applied inside the kernel with the same two IEEE operations.
+ * B_dev (forward, device int32 or NULL): when given, B is only the capacity and the kernel reads the row count there. */
+LNRF_API int lnrf_grid_encode_forward_world(const float* inputs_world, float bound, const void* embeddings,
+                                            const int32_t* offsets_host, void* outputs, uint32_t B, const int32_t* B_dev,
+                                            uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                            uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream);
+LNRF_API int lnrf_grid_encode_backward_world(const void* grad, const float* inputs_world, float bound,
+                                             const int32_t* offsets_host, void* grad_embeddings, uint32_t B, uint32_t L,
+                                             float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
+                                             lnrf_dtype emb_dtype, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * device-driven inference rounds (row f-3) -- the loop of NeRFRenderer.run_cuda / run_cuda_distill
+ * (nerf/renderer.py:335-387, 425-470) without a device->host synchronisation per round.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t* ctl;                 /* device int32[16] control block: [0] n_alive [1] n_step [2] steps marched [3] rows of the
+                                     round (n_alive*n_step padded past 128) [4] n_rays [5] max_steps [6] finished [7] rounds
+                                     [9] sample slots marched so far */
+    uint32_t n_rays, max_steps;
+    /* rays and marching (raymarching.march_rays arguments) */
+    const float *rays_o, *rays_d, *nears, *fars;       /* [n_rays,3] x2, [n_rays] x2 */
+    const uint8_t* density_bitfield;
+    const uint8_t* edit_bitfield;                      /* NULL: plain render; else run_cuda_distill */
+    float bound, dt_gamma, T_thresh;
+    uint32_t cascade, grid_size;
+    const float* first_round_noises;                   /* [n_rays] or NULL (perturb only applies to the first round) */
+    /* network (NeRFNetwork.forward, see lnrf_nerf_forward) */
+    const void* embeddings_f16;
+    const int32_t* offsets_host;
+    uint32_t num_levels, base_resolution, gridtype, interpolation;
+    int align_corners;
+    float level_scale_log2;                            /* S of lnrf_grid_encode_forward */
+    const void *w_sigma_f16, *w_color_f16;
+    uint32_t num_layers_sigma, num_layers_color;
+    float density_scale;
+    /* state: two rays_alive buffers [n_rays] (round r reads [r & 1]), rays_t [n_rays] */
+    int32_t* rays_alive[2];
+    float* rays_t;
+    /* per-round sample buffers, n_rays + 128 rows each */
+    float *xyzs, *dirs, *deltas;                       /* [rows,3], [rows,3], [rows,2] */
+    uint8_t* edit_occ;                                 /* [rows] (distillation) or NULL */
+    void* enc_f16;                                     /* [rows,32] */
+    float *sigmas, *rgbs;                              /* [rows], [rows,3] */
+    /* per-ray accumulators [n_rays] (image [n_rays,3]); cleared by lnrf_render_begin */
+    float *weights_sum, *depth, *image, *weights_edit_sum, *depth_edit;
+    void* scratch;                                     /* lnrf_render_scratch_bytes(n_rays), zero-filled before first use */
+    size_t scratch_bytes;
+} lnrf_render_desc;
+LNRF_API size_t lnrf_render_scratch_bytes(uint32_t n_rays);
+/* rays_alive[0] = 0..n_rays-1, rays_t = nears, accumulators = 0, control block = first round. */
+LNRF_API int lnrf_render_begin(const lnrf_render_desc* desc_host, lnrf_stream_t stream);
+/* Queues rounds first_round .. first_round + n_rounds - 1 (march -> encode -> network -> composite -> compact each).
+ * Rounds after the frame has finished are no-ops; read ctl[6] (finished) between calls. */
+LNRF_API int lnrf_render_rounds(const lnrf_render_desc* desc_host, uint32_t first_round, uint32_t n_rounds,
+                                lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * fused NeRFNetwork.forward / backward (row f-1 of SURVEY.md section 8) -- nerf/network_ff.py:51-79:
  *     h = sigma_net(enc); sigma = trunc_exp(h[:,0]) (activation.py:5-17); d = SHEncoder(dirs) (degree 4,

@@ -56,6 +56,11 @@ SIGNATURES = {
     "lnrf_free_splitk": (i32, []),
     "lnrf_sh_encode_forward": (i32, [vp, vp, u32, u32, vp, i32, vp]),
     "lnrf_sh_encode_backward": (i32, [vp, u32, u32, vp, vp, vp]),
+    "lnrf_grid_encode_forward_world": (i32, [vp, f32, vp, vp, vp, u32, vp, u32, f32, u32, u32, i32, u32, i32, vp]),
+    "lnrf_grid_encode_backward_world": (i32, [vp, vp, f32, vp, vp, u32, u32, f32, u32, u32, i32, u32, i32, vp]),
+    "lnrf_render_scratch_bytes": (sz, [u32]),
+    "lnrf_render_begin": (i32, [vp, vp]),
+    "lnrf_render_rounds": (i32, [vp, u32, u32, vp]),
     "lnrf_nerf_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "lnrf_nerf_wgrad_scratch_bytes": (sz, [u32, u32]),
     "lnrf_nerf_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, f32, vp, vp, vp, i32, vp, vp, sz, vp]),
@@ -63,6 +68,27 @@ SIGNATURES = {
     "lnrf_adam_step": (i32, [vp, u32, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp]),
     "lnrf_amp_update": (i32, [vp, vp, vp, vp, f32, f32, i32, vp]),
 }
+
+class RenderDesc(C.Structure):
+    """lnrf_render_desc (include/laenerf_b200.h): everything one device-driven inference frame needs."""
+    _fields_ = [
+        ("ctl", vp), ("n_rays", u32), ("max_steps", u32),
+        ("rays_o", vp), ("rays_d", vp), ("nears", vp), ("fars", vp),
+        ("density_bitfield", vp), ("edit_bitfield", vp),
+        ("bound", f32), ("dt_gamma", f32), ("T_thresh", f32),
+        ("cascade", u32), ("grid_size", u32),
+        ("first_round_noises", vp),
+        ("embeddings_f16", vp), ("offsets_host", vp),
+        ("num_levels", u32), ("base_resolution", u32), ("gridtype", u32), ("interpolation", u32),
+        ("align_corners", i32), ("level_scale_log2", f32),
+        ("w_sigma_f16", vp), ("w_color_f16", vp),
+        ("num_layers_sigma", u32), ("num_layers_color", u32), ("density_scale", f32),
+        ("rays_alive", vp * 2), ("rays_t", vp),
+        ("xyzs", vp), ("dirs", vp), ("deltas", vp), ("edit_occ", vp), ("enc_f16", vp), ("sigmas", vp), ("rgbs", vp),
+        ("weights_sum", vp), ("depth", vp), ("image", vp), ("weights_edit_sum", vp), ("depth_edit", vp),
+        ("scratch", vp), ("scratch_bytes", sz),
+    ]
+
 
 F32, F16 = 0, 1  # lnrf_dtype
 GRID_LBC, GRID_BLC = 0, 1  # lnrf_grid_layout

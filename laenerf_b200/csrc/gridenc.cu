@@ -132,14 +132,21 @@ constexpr int kGridThreads = 256;
 template <typename T, bool SMOOTH>
 __global__ void __launch_bounds__(kGridThreads)
 k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* __restrict__ emb,
-                typename Vec2<T>::type* __restrict__ outputs, const uint32_t B, const uint32_t L, const float S,
+                typename Vec2<T>::type* __restrict__ outputs, uint32_t B, const uint32_t L, const float S,
                 const uint32_t H, const uint32_t gridtype, const bool align_corners, const GridOffsets off,
-                const uint32_t ntiles) {
+                uint32_t ntiles, const float in_bound, const int* __restrict__ B_dev) {
     using T2 = typename Vec2<T>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ Level s_lv[kMaxLevels];
     __shared__ float s_in[kTile * 3];
     T2* s_out = reinterpret_cast<T2*>(s_raw);
+    if (B_dev) {  // device-driven inference round (row f-3): the sample count lives in the render control block
+        B = (uint32_t)*B_dev;
+        ntiles = div_up(B, (uint32_t)kTile);
+    }
+    // torch evaluates `t / python_scalar` as t * (1 / scalar) with the reciprocal rounded to fp32 (div_true_kernel_cuda), and that
+    // is what the reference's grid.py:147 runs; the same two roundings here
+    const float in_inv = in_bound > 0.0f ? __fdiv_rn(1.0f, __fmul_rn(2.0f, in_bound)) : 0.0f;
     const uint32_t LP = L | 1u;  // odd row pitch: conflict-free transposition
     const int tid = threadIdx.x;
     if (tid < (int)L) s_lv[tid] = make_level<3>(tid, S, H, off, gridtype, align_corners);
@@ -148,7 +155,12 @@ k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* 
         const size_t b0 = (size_t)tile * kTile;
         const uint32_t rows = (uint32_t)min((size_t)kTile, (size_t)B - b0);
         __syncthreads();  // previous tile's copy-out finished with s_out / s_in (also publishes s_lv)
-        for (uint32_t i = tid; i < rows * 3; i += kGridThreads) s_in[i] = __ldcs(inputs + b0 * 3 + i);
+        // in_bound > 0: the caller passes world coordinates and GridEncoder.forward's (x + bound) / (2 * bound) (grid.py:147) is
+        // applied here with the same two roundings instead of two elementwise passes over [B, 3]
+        for (uint32_t i = tid; i < rows * 3; i += kGridThreads) {
+            const float x = __ldcs(inputs + b0 * 3 + i);
+            s_in[i] = in_bound > 0.0f ? __fmul_rn(__fadd_rn(x, in_bound), in_inv) : x;
+        }
         __syncthreads();
         const uint32_t nitems = L * kTile;
 #pragma unroll 2
@@ -207,12 +219,15 @@ __global__ void __launch_bounds__(kGridThreads)
 k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __restrict__ inputs,
                 typename Vec2<T>::type* __restrict__ grad_emb, const uint32_t B, const uint32_t L, const float S,
                 const uint32_t H, const uint32_t gridtype, const bool align_corners, const GridOffsets off,
-                const uint32_t ntiles) {
+                const uint32_t ntiles, const float in_bound) {
     using T2 = typename Vec2<T>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ Level s_lv[kMaxLevels];
     __shared__ float s_in[kTile * 3];
     T2* s_g = reinterpret_cast<T2*>(s_raw);
+    // torch evaluates `t / python_scalar` as t * (1 / scalar) with the reciprocal rounded to fp32 (div_true_kernel_cuda), and that
+    // is what the reference's grid.py:147 runs; the same two roundings here
+    const float in_inv = in_bound > 0.0f ? __fdiv_rn(1.0f, __fmul_rn(2.0f, in_bound)) : 0.0f;
     const uint32_t LP = L | 1u;
     const int tid = threadIdx.x;
     if (tid < (int)L) s_lv[tid] = make_level<3>(tid, S, H, off, gridtype, align_corners);
@@ -221,7 +236,10 @@ k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __
         const size_t b0 = (size_t)tile * kTile;
         const uint32_t rows = (uint32_t)min((size_t)kTile, (size_t)B - b0);
         __syncthreads();
-        for (uint32_t i = tid; i < rows * 3; i += kGridThreads) s_in[i] = __ldcs(inputs + b0 * 3 + i);
+        for (uint32_t i = tid; i < rows * 3; i += kGridThreads) {
+            const float x = __ldcs(inputs + b0 * 3 + i);
+            s_in[i] = in_bound > 0.0f ? __fmul_rn(__fadd_rn(x, in_bound), in_inv) : x;
+        }
         const T2* g = grad + b0 * L;
         for (uint32_t j = tid; j < rows * L; j += kGridThreads) {
             const uint32_t s = j / L, l = j - s * L;
@@ -522,20 +540,25 @@ static void launch_bwd_generic(bool smooth, dim3 g, cudaStream_t st, const T* gr
 template <typename T>
 static int grid_forward_t(const float* inputs, const T* emb, const GridOffsets& off, T* outputs, uint32_t B, uint32_t D, uint32_t C,
                           uint32_t L, float S, uint32_t H, T* dy_dx, uint32_t gridtype, bool ac, uint32_t interp, int layout,
-                          cudaStream_t st) {
+                          cudaStream_t st, float in_bound = 0.0f, const int* B_dev = nullptr) {
     using T2 = typename Vec2<T>::type;
     const bool smooth = interp == 1;
-    if (D == 3 && C == 2 && !dy_dx && layout == LNRF_GRID_BLC && (reinterpret_cast<uintptr_t>(emb) % sizeof(T2)) == 0 &&
-        (reinterpret_cast<uintptr_t>(outputs) % sizeof(T2)) == 0) {
-        const uint32_t ntiles = div_up(B, (uint32_t)kTile);
+    const bool hot = D == 3 && C == 2 && !dy_dx && layout == LNRF_GRID_BLC && (reinterpret_cast<uintptr_t>(emb) % sizeof(T2)) == 0 &&
+                     (reinterpret_cast<uintptr_t>(outputs) % sizeof(T2)) == 0;
+    if ((in_bound > 0.0f || B_dev) && !hot) {
+        set_error("grid_encode_forward: in_bound / device-side B need the D=3, C=2, [B, L*C] kernel");
+        return LNRF_ERR_UNSUPPORTED;
+    }
+    if (hot) {
+        const uint32_t ntiles = div_up(B, (uint32_t)kTile);  // with B_dev: B is the capacity, the kernel re-derives both
         const uint32_t grid = ntiles < (uint32_t)kNumSMs * 8u ? ntiles : (uint32_t)kNumSMs * 8u;
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
         if (smooth)
             k_grid_fwd_tile<T, true><<<grid, kGridThreads, smem, st>>>(inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs),
-                                                                      B, L, S, H, gridtype, ac, off, ntiles);
+                                                                      B, L, S, H, gridtype, ac, off, ntiles, in_bound, B_dev);
         else
             k_grid_fwd_tile<T, false><<<grid, kGridThreads, smem, st>>>(inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs),
-                                                                       B, L, S, H, gridtype, ac, off, ntiles);
+                                                                       B, L, S, H, gridtype, ac, off, ntiles, in_bound, B_dev);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);
 #define CALL_(DD, CC) launch_fwd_generic<T, DD, CC>(smooth, g, st, inputs, emb, outputs, B, L, S, H, dy_dx, gridtype, ac, off, layout)
@@ -549,20 +572,25 @@ static int grid_forward_t(const float* inputs, const T* emb, const GridOffsets& 
 template <typename T>
 static int grid_backward_t(const T* grad, const float* inputs, const GridOffsets& off, T* grad_emb, uint32_t B, uint32_t D, uint32_t C,
                            uint32_t L, float S, uint32_t H, const T* dy_dx, T* grad_inputs, uint32_t gridtype, bool ac, uint32_t interp,
-                           int layout, cudaStream_t st) {
+                           int layout, cudaStream_t st, float in_bound = 0.0f) {
     using T2 = typename Vec2<T>::type;
     const bool smooth = interp == 1;
-    if (D == 3 && C == 2 && layout == LNRF_GRID_BLC && (reinterpret_cast<uintptr_t>(grad_emb) % sizeof(T2)) == 0 &&
-        (reinterpret_cast<uintptr_t>(grad) % sizeof(T2)) == 0) {
+    const bool hot = D == 3 && C == 2 && layout == LNRF_GRID_BLC && (reinterpret_cast<uintptr_t>(grad_emb) % sizeof(T2)) == 0 &&
+                     (reinterpret_cast<uintptr_t>(grad) % sizeof(T2)) == 0;
+    if (in_bound > 0.0f && (!hot || dy_dx)) {
+        set_error("grid_encode_backward: in_bound needs the D=3, C=2, [B, L*C] kernel without input gradients");
+        return LNRF_ERR_UNSUPPORTED;
+    }
+    if (hot) {
         const uint32_t ntiles = div_up(B, (uint32_t)kTile);
         const uint32_t grid = ntiles < (uint32_t)kNumSMs * 8u ? ntiles : (uint32_t)kNumSMs * 8u;
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
         if (smooth)
             k_grid_bwd_tile<T, true><<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb),
-                                                                      B, L, S, H, gridtype, ac, off, ntiles);
+                                                                      B, L, S, H, gridtype, ac, off, ntiles, in_bound);
         else
             k_grid_bwd_tile<T, false><<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb),
-                                                                       B, L, S, H, gridtype, ac, off, ntiles);
+                                                                       B, L, S, H, gridtype, ac, off, ntiles, in_bound);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);
 #define CALL_(DD, CC) launch_bwd_generic<T, DD, CC>(smooth, g, st, grad, inputs, grad_emb, B, L, S, H, gridtype, ac, off, layout)
@@ -606,6 +634,40 @@ int lnrf_grid_encode_forward(const float* inputs, const void* embeddings, const 
         return grid_forward_t<float>(inputs, (const float*)embeddings, off, (float*)outputs, B, D, C, L, S, H, (float*)dy_dx, gridtype,
                                      align_corners != 0, interp, (int)out_layout, S_(stream));
     set_error("grid_encode_forward: unsupported embedding dtype %d", (int)emb_dtype);
+    return LNRF_ERR_UNSUPPORTED;
+}
+
+int lnrf_grid_encode_forward_world(const float* inputs_world, float bound, const void* embeddings, const int32_t* offsets_host,
+                                   void* outputs, uint32_t B, const int32_t* B_dev, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                   int align_corners, uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream) {
+    GridOffsets off;
+    if (int e = check_grid_args("grid_encode_forward_world", offsets_host, 3, 2, L, gridtype, interp, &off)) return e;
+    if (B == 0) return LNRF_OK;
+    LNRF_REQUIRE(inputs_world && embeddings && outputs && bound > 0.0f, "grid_encode_forward_world: null pointer / bound <= 0");
+    if (emb_dtype == LNRF_F16)
+        return grid_forward_t<__half>(inputs_world, (const __half*)embeddings, off, (__half*)outputs, B, 3, 2, L, S, H, nullptr, gridtype,
+                                      align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound, B_dev);
+    if (emb_dtype == LNRF_F32)
+        return grid_forward_t<float>(inputs_world, (const float*)embeddings, off, (float*)outputs, B, 3, 2, L, S, H, nullptr, gridtype,
+                                     align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound, B_dev);
+    set_error("grid_encode_forward_world: unsupported embedding dtype %d", (int)emb_dtype);
+    return LNRF_ERR_UNSUPPORTED;
+}
+
+int lnrf_grid_encode_backward_world(const void* grad, const float* inputs_world, float bound, const int32_t* offsets_host,
+                                    void* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                    int align_corners, uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream) {
+    GridOffsets off;
+    if (int e = check_grid_args("grid_encode_backward_world", offsets_host, 3, 2, L, gridtype, interp, &off)) return e;
+    if (B == 0) return LNRF_OK;
+    LNRF_REQUIRE(grad && inputs_world && grad_embeddings && bound > 0.0f, "grid_encode_backward_world: null pointer / bound <= 0");
+    if (emb_dtype == LNRF_F16)
+        return grid_backward_t<__half>((const __half*)grad, inputs_world, off, (__half*)grad_embeddings, B, 3, 2, L, S, H, nullptr, nullptr,
+                                       gridtype, align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound);
+    if (emb_dtype == LNRF_F32)
+        return grid_backward_t<float>((const float*)grad, inputs_world, off, (float*)grad_embeddings, B, 3, 2, L, S, H, nullptr, nullptr,
+                                      gridtype, align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound);
+    set_error("grid_encode_backward_world: unsupported embedding dtype %d", (int)emb_dtype);
     return LNRF_ERR_UNSUPPORTED;
 }
 

@@ -76,7 +76,7 @@ LNRF_HD uint32_t morton3d_invert(uint32_t x) {
 
 // Per-launch constants (identical for every ray).
 struct MarchParams {
-    float bound, neg_bound, dt_gamma, dt_min, dt_max, rH, Hf, H3, Cm1, half_H, Hm1;
+    float bound, neg_bound, rbound, dt_gamma, dt_min, dt_max, rH, Hf, H3, Cm1, half_H, Hm1;
     uint32_t max_steps;
     int dt_const;  // dt_gamma == 0 (every shipped LAENeRF config): dt is the same for every t ...
     float dt0;     // ... namely clamp(0, dt_min, dt_max) (== dt_min unless max_steps is so small that dt_min > dt_max)
@@ -86,6 +86,7 @@ LNRF_HD MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_
     MarchParams p;
     p.bound = bound;
     p.neg_bound = -bound;
+    p.rbound = f_div(1.0f, bound);  // the reference divides per visit (1 / mip_bound); the quotient only takes these values
     p.dt_gamma = dt_gamma;
     p.dt_min = f_div(3.4641015529632568f, (float)max_steps);                      // 2*SQRT3()/max_steps
     p.dt_max = f_div(f_mul(3.4641015529632568f, (float)(1u << (C - 1))), (float)H);  // 2*SQRT3()*(1<<(C-1))/H
@@ -128,12 +129,20 @@ LNRF_HD Probe march_probe(const MarchParams& p, const Ray& r, float t, float dt)
     q.x = f_clamp(f_fma(t, r.dx, r.ox), p.neg_bound, p.bound);
     q.y = f_clamp(f_fma(t, r.dy, r.oy), p.neg_bound, p.bound);
     q.z = f_clamp(f_fma(t, r.dz, r.oz), p.neg_bound, p.bound);
-    const float mx = fmaxf(fabsf(q.x), fmaxf(fabsf(q.y), fabsf(q.z)));
-    const int l1 = (int)fminf(p.Cm1, fmaxf(0.0f, (float)frexp_exponent(mx)));
-    const int l2 = (int)fminf(p.Cm1, fmaxf(0.0f, (float)frexp_exponent(f_mul(f_mul(dt, p.Hf), 0.5f))));
-    const int level = l1 > l2 ? l1 : l2;
-    const float mip_bound = fminf(u2f((uint32_t)(127 + level) << 23), p.bound);
-    const float mip_rbound = f_div(1.0f, mip_bound);
+    // cascade level (raymarching.cu:42-54).  With a single cascade (bound <= 1: every synthetic scene) both frexp terms clamp
+    // to 0, so the branch -- uniform over the launch -- skips them.  1 / mip_bound is exact without a division: mip_bound is
+    // 2^level (reciprocal = the power of two with the negated exponent) unless the box itself is smaller (then 1 / bound).
+    int level = 0;
+    if (p.Cm1 > 0.0f) {
+        const float mx = fmaxf(fabsf(q.x), fmaxf(fabsf(q.y), fabsf(q.z)));
+        const int l1 = (int)fminf(p.Cm1, fmaxf(0.0f, (float)frexp_exponent(mx)));
+        const int l2 = (int)fminf(p.Cm1, fmaxf(0.0f, (float)frexp_exponent(f_mul(f_mul(dt, p.Hf), 0.5f))));
+        level = l1 > l2 ? l1 : l2;
+    }
+    const float pow2 = u2f((uint32_t)(127 + level) << 23);
+    const bool boxed = p.bound < pow2;
+    const float mip_bound = boxed ? p.bound : pow2;
+    const float mip_rbound = boxed ? p.rbound : u2f((uint32_t)(127 - level) << 23);
     const int nx = (int)f_clamp(f_mul(f_fma(q.x, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
     const int ny = (int)f_clamp(f_mul(f_fma(q.y, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);
     const int nz = (int)f_clamp(f_mul(f_fma(q.z, mip_rbound, 1.0f), p.half_H), 0.0f, p.Hm1);

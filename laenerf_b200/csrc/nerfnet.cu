@@ -18,6 +18,7 @@
 // net, whose dL/dinput feeds the hash-grid backward.
 #include "mlp_core.cuh"
 #include "sh_core.cuh"
+#include "render_core.cuh"
 #include <string.h>
 
 namespace lnrf {
@@ -43,8 +44,12 @@ __global__ void __launch_bounds__(128 * kGroups, 1)
 k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const __half* __restrict__ w_sigma,
            const __half* __restrict__ w_color, const uint32_t M, const uint32_t ns, const uint32_t nc, const float density_scale,
            const __grid_constant__ CUtensorMap tm_fwd_buf, __half* __restrict__ color_in, __half* __restrict__ h0_out,
-           float* __restrict__ sigmas, float* __restrict__ rgbs, const uint32_t ntiles) {
+           float* __restrict__ sigmas, float* __restrict__ rgbs, uint32_t ntiles, const int* __restrict__ M_dev) {
     extern __shared__ uint8_t smem_raw[];
+    if (M_dev) {  // device-driven inference round (row f-3): the sample count lives in the render control block
+        ntiles = (uint32_t)*M_dev / kRows;
+        if (ntiles == 0u) return;
+    }
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     uint8_t* sWs = sm;                                  // ns matrices of 8 KB + 2 KB
     uint8_t* sWc = sWs + ns * kWBytes + 2048;           // nc matrices of 8 KB + 2 KB
@@ -197,6 +202,30 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
 
 static size_t nerf_fwd_smem(uint32_t ns, uint32_t nc) { return 1024 + (ns + nc) * kWBytes + 4096 + kGroups * 2 * kTileBytes + 128; }
 
+int nerf_forward_dev_launch(const void* enc_f16, const float* dirs, const void* w_sigma_f16, const void* w_color_f16, uint32_t M_cap,
+                            const int32_t* M_dev, uint32_t ns, uint32_t nc, float density_scale, float* sigmas, float* rgbs,
+                            cudaStream_t st) {
+    LNRF_REQUIRE(ns >= 2 && nc >= 2 && ns <= kMaxLayers && nc <= kMaxLayers, "render_rounds: num_layers outside [2, %u]", kMaxLayers);
+    if (M_cap == 0) return LNRF_OK;
+    LNRF_REQUIRE(enc_f16 && dirs && w_sigma_f16 && w_color_f16 && sigmas && rgbs && M_dev, "render_rounds(network): null pointer");
+    const size_t smem = nerf_fwd_smem(ns, nc);
+    LNRF_REQUIRE(smem <= 227 * 1024, "render_rounds: networks need %zu B of shared memory (> 227 KiB)", smem);
+    static std::atomic<size_t> s_max{0};
+    if (smem > s_max.load(std::memory_order_relaxed)) {
+        cudaError_t e = cudaFuncSetAttribute(k_nerf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "render_rounds(network)");
+        s_max.store(smem, std::memory_order_relaxed);
+    }
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    const uint32_t want = div_up(div_up(M_cap, kRows), kGroups);
+    const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
+    k_nerf_fwd<false><<<grid, 128 * kGroups, smem, st>>>((const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M_cap,
+                                                         ns, nc, density_scale, tm, nullptr, nullptr, sigmas, rgbs, 0u, M_dev);
+    LNRF_LAUNCH_CHECK("render_rounds(network)");
+    return LNRF_OK;
+}
+
 }  // namespace lnrf
 
 using namespace lnrf;
@@ -240,7 +269,7 @@ int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigm
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     kern<<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale,
-        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles);
+        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles, nullptr);
     LNRF_LAUNCH_CHECK("nerf_forward");
     return LNRF_OK;
 }

@@ -11,6 +11,11 @@
 //   * compositing: warp per ray; transmittance is a multiplicative warp scan, colour/depth are warp reductions.
 #include "common.cuh"
 #include "march_core.cuh"
+#include "render_core.cuh"
+
+extern "C" {
+static int check_march_common(uint32_t C, uint32_t H, uint32_t max_steps, const char* who);
+}
 
 namespace lnrf {
 
@@ -553,60 +558,113 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
 // inference / distillation march (group of 8 lanes per alive ray, fixed n_step slots per ray)
 // =========================================================================================================
 
+// Device-side round control (row f-3 of SURVEY.md section 8): the inference loop of NeRFRenderer.run_cuda
+// (nerf/renderer.py:353-379) sizes every round on the host from `n_alive` -- one device->host synchronisation per round,
+// 100+ rounds per frame.  With a control block in device memory the kernels read the round's geometry themselves, the
+// compaction kernel computes the next round's, and the host only looks at it every few rounds.
+//   ctl[0] n_alive   ctl[1] n_step = clamp(n_rays / n_alive, 1, 8)   ctl[2] steps marched so far (renderer.py: `step`)
+//   ctl[3] rows = n_alive * n_step rounded up PAST the next multiple of 128 (raymarching.py:318-320)
+//   ctl[4] n_rays    ctl[5] max_steps    ctl[6] finished (n_alive == 0 or step >= max_steps)    ctl[7] rounds executed
+//   ctl[8] survivors of the running compaction (internal)    ctl[9] sample slots marched so far
+enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, kCtlMaxSteps = 5, kCtlFinished = 6, kCtlRounds = 7 };
+
+__device__ __forceinline__ void ctl_set_round(int* ctl, uint32_t n_alive) {
+    const uint32_t n_rays = (uint32_t)ctl[kCtlRays];
+    const bool fin = n_alive == 0u || (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps];
+    uint32_t n_step = n_alive ? n_rays / n_alive : 1u;
+    n_step = n_step > 8u ? 8u : (n_step < 1u ? 1u : n_step);
+    uint32_t rows = n_alive * n_step;
+    rows += 128u - rows % 128u;
+    ctl[kCtlAlive] = fin ? 0 : (int)n_alive;
+    ctl[kCtlStep] = (int)n_step;
+    ctl[kCtlRows] = fin ? 0 : (int)rows;
+    ctl[kCtlFinished] = fin ? 1 : 0;
+}
+
+// group of G lanes per alive ray (8 covers the <= 8 samples per ray of a round; see march_infer_dev_launch for the first round)
 constexpr int kInferGroup = 8;
 
-template <bool DISTILL>
+template <bool DISTILL, int G>
 __global__ void __launch_bounds__(256)
-k_march_infer(const uint32_t n_alive, const uint32_t n_step, const int* __restrict__ rays_alive,
+k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
               const float* __restrict__ rays_t, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
               const MarchParams p, const uint8_t* __restrict__ grid, const uint8_t* __restrict__ edit_grid,
               const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
               float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, const float* __restrict__ noises,
-              const uint32_t M_rows, const uint32_t n_groups) {
-    constexpr int G = kInferGroup;
+              uint32_t M_rows, uint32_t n_groups, const int* __restrict__ ctl, const int g_lo, const int g_hi) {
     const Group<G> grp;
-    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    const bool active = g < n_alive;
-    Ray r = Ray{};
-    float t = 0.f, far = 0.f;
-    if (active) {
-        const int index = __ldg(rays_alive + g);
-        r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
-        far = fars[index];
-        const float t_in = rays_t[index];
-        t = f_fma(f_clamp(f_mul(t_in, p.dt_gamma), p.dt_min, p.dt_max), noises[g], t_in);  // raymarching.cu:746
+    if (ctl) {  // device-driven round: geometry from the control block; this instantiation serves n_step in [g_lo, g_hi]
+        n_alive = (uint32_t)ctl[kCtlAlive];
+        n_step = (uint32_t)ctl[kCtlStep];
+        M_rows = (uint32_t)ctl[kCtlRows];
+        if (M_rows == 0u || (int)n_step < g_lo || (int)n_step > g_hi) return;
+        n_groups = div_up(M_rows, n_step);
     }
-    const size_t row0 = (size_t)g * n_step;
-    const uint32_t cnt = march_group<G, true>(
-        grp, p, r, grid, t, far, n_step, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
-            const size_t row = row0 + rank;
-            xyzs[row * 3] = q.x; xyzs[row * 3 + 1] = q.y; xyzs[row * 3 + 2] = q.z;
-            dirs[row * 3] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz;
-            reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, f_add(f_add(s, dt), -prev_after));
-            if (DISTILL) edit_occ[row] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
-        });
-    if (g >= n_groups) return;
-    // zero-fill the slots this ray did not use, and whole padding groups (torch.zeros in raymarching.py:334-336)
-    const size_t zlo = row0 + (active ? cnt : 0u);
-    size_t zhi = row0 + n_step;
-    if (zhi > M_rows) zhi = M_rows;
-    for (size_t i = zlo * 3 + grp.gl; i < zhi * 3; i += G) { xyzs[i] = 0.f; dirs[i] = 0.f; }
-    for (size_t i = zlo * 2 + grp.gl; i < zhi * 2; i += G) deltas[i] = 0.f;
-    if (DISTILL)
-        for (size_t i = zlo + grp.gl; i < zhi; i += G) edit_occ[i] = 0;
+    const uint32_t groups_per_pass = gridDim.x * (blockDim.x / G);
+    const uint32_t passes = div_up(n_groups, groups_per_pass);
+    for (uint32_t pass = 0; pass < passes; pass++) {  // uniform trip count: march_group uses full-warp votes
+        const uint32_t g = pass * groups_per_pass + (blockIdx.x * blockDim.x + threadIdx.x) / G;
+        const bool active = g < n_alive;
+        Ray r = Ray{};
+        float t = 0.f, far = 0.f;
+        if (active) {
+            const int index = __ldg(rays_alive + g);
+            r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+            far = fars[index];
+            const float t_in = rays_t[index];
+            const float noise = noises ? noises[g] : 0.0f;
+            t = f_fma(f_clamp(f_mul(t_in, p.dt_gamma), p.dt_min, p.dt_max), noise, t_in);  // raymarching.cu:746
+        }
+        const size_t row0 = (size_t)g * n_step;
+        const uint32_t cnt = march_group<G, true>(
+            grp, p, r, grid, t, far, n_step, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
+                const size_t row = row0 + rank;
+                xyzs[row * 3] = q.x; xyzs[row * 3 + 1] = q.y; xyzs[row * 3 + 2] = q.z;
+                dirs[row * 3] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz;
+                reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, f_add(f_add(s, dt), -prev_after));
+                if (DISTILL) edit_occ[row] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
+            });
+        if (g >= n_groups) continue;
+        // zero-fill the slots this ray did not use, and whole padding groups (torch.zeros in raymarching.py:334-336)
+        const size_t zlo = row0 + (active ? cnt : 0u);
+        size_t zhi = row0 + n_step;
+        if (zhi > M_rows) zhi = M_rows;
+        for (size_t i = zlo * 3 + grp.gl; i < zhi * 3; i += G) { xyzs[i] = 0.f; dirs[i] = 0.f; }
+        for (size_t i = zlo * 2 + grp.gl; i < zhi * 2; i += G) deltas[i] = 0.f;
+        if (DISTILL)
+            for (size_t i = zlo + grp.gl; i < zhi; i += G) edit_occ[i] = 0;
+    }
 }
 
 // raymarching.cu:948-1035 and :1037-1142.  Thread per alive ray: at most n_step <= 8 samples, and the reference's
 // sequential float order (T = 1 - weight_sum; t += delta) is kept so that rays_t and the kill pattern are exact.
+template <bool DISTILL>
+__device__ __forceinline__ void composite_infer_ray(const uint32_t n, const uint32_t n_step, const float T_thresh, int* __restrict__ rays_alive,
+                  float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                  const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ weights_edit_sum,
+                  float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
+                  float* __restrict__ image);
+
 template <bool DISTILL>
 __global__ void __launch_bounds__(256)
 k_composite_infer(const uint32_t n_alive, const uint32_t n_step, const float T_thresh, int* __restrict__ rays_alive,
                   float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                   const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ weights_edit_sum,
                   float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
+                  float* __restrict__ image, const int* __restrict__ ctl) {
+    uint32_t na = n_alive, ns = n_step;
+    if (ctl) { na = (uint32_t)ctl[kCtlAlive]; ns = (uint32_t)ctl[kCtlStep]; }
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < na; n += gridDim.x * blockDim.x)
+        composite_infer_ray<DISTILL>(n, ns, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, weights_edit_sum, depth,
+                                     depth_edit, edit_occ, image);
+}
+
+template <bool DISTILL>
+__device__ __forceinline__ void composite_infer_ray(const uint32_t n, const uint32_t n_step, const float T_thresh, int* __restrict__ rays_alive,
+                  float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                  const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ weights_edit_sum,
+                  float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
                   float* __restrict__ image) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_alive) return;
     const int index = rays_alive[n];
     const float* ps = sigmas + (size_t)n * n_step;
     const float* pc = rgbs + (size_t)n * n_step * 3;
@@ -650,11 +708,15 @@ k_composite_infer(const uint32_t n_alive, const uint32_t n_step, const float T_t
 // scratch[0] = finished-block counter, scratch[1 + b] = look-back word of block b (flag << 32 | count).  The block
 // that finishes last re-zeroes everything, so the scratch is ready for the next launch on the same stream.
 __global__ void __launch_bounds__(1024)
-k_compact_alive(const int* __restrict__ rays_alive, const uint32_t n_alive, int* __restrict__ out, int* __restrict__ n_out,
-                unsigned long long* __restrict__ scratch) {
+k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __restrict__ out, int* __restrict__ n_out,
+                unsigned long long* __restrict__ scratch, int* __restrict__ ctl) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_excl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (ctl) n_alive = (uint32_t)ctl[kCtlAlive];  // device-driven round: the grid covers the ray capacity
+    // blocks past the last alive entry hold nothing and are not part of anyone's look-back: they only check out below
+    const uint32_t active_blocks = n_alive ? div_up(n_alive, 1024u) : 1u;
+    const bool idle_block = blockIdx.x >= active_blocks;
     const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
     const int v = i < n_alive ? rays_alive[i] : -1;
     const bool keep = v >= 0;
@@ -662,7 +724,7 @@ k_compact_alive(const int* __restrict__ rays_alive, const uint32_t n_alive, int*
     if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
     __syncthreads();
     unsigned long long* status = scratch + 1;
-    if (warp == 0) {
+    if (warp == 0 && !idle_block) {
         uint32_t c = s_warp[lane], incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -698,11 +760,14 @@ k_compact_alive(const int* __restrict__ rays_alive, const uint32_t n_alive, int*
         if (lane == 0) {
             st_relaxed_u64(status + b, (2ull << 32) | (unsigned long long)(excl + agg));
             s_excl = excl;
-            if (b == gridDim.x - 1) *n_out = (int)(excl + agg);
+            if (b == active_blocks - 1) {
+                if (n_out) *n_out = (int)(excl + agg);
+                if (ctl) ctl[kCtlRounds + 1] = (int)(excl + agg);  // parked; the last block out publishes the next round
+            }
         }
     }
     __syncthreads();
-    if (keep) out[s_excl + s_warp[warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = v;
+    if (keep && !idle_block) out[s_excl + s_warp[warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = v;
     // last block out cleans up
     __syncthreads();
     __shared__ bool s_last;
@@ -713,7 +778,115 @@ k_compact_alive(const int* __restrict__ rays_alive, const uint32_t n_alive, int*
     __syncthreads();
     if (s_last) {
         for (uint32_t k = threadIdx.x; k < gridDim.x + 1u; k += 1024u) scratch[k] = 0ull;
+        if (ctl && threadIdx.x == 0) {  // every block has read ctl[kCtlAlive] and written its survivors: set up the next round
+            __threadfence();
+            if (!ctl[kCtlFinished]) {
+                ctl[kCtlSteps] += ctl[kCtlStep];
+                ctl[kCtlRounds] += 1;
+                ctl[kCtlRounds + 2] += ctl[kCtlRows];  // sample slots marched so far (what the host loop sums up)
+                ctl_set_round(ctl, (uint32_t)((volatile int*)ctl)[kCtlRounds + 1]);
+            }
+        }
     }
+}
+
+// start of a device-driven render: rays_alive = 0..n_rays-1, rays_t = nears, accumulators cleared, first round published
+__global__ void __launch_bounds__(256)
+k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_steps, int* __restrict__ rays_alive,
+               float* __restrict__ rays_t, const float* __restrict__ nears, float* __restrict__ weights_sum,
+               float* __restrict__ depth, float* __restrict__ image, float* __restrict__ weights_edit_sum,
+               float* __restrict__ depth_edit) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x) {
+        rays_alive[i] = (int)i;
+        rays_t[i] = nears[i];
+        weights_sum[i] = 0.f; depth[i] = 0.f;
+        image[(size_t)i * 3] = 0.f; image[(size_t)i * 3 + 1] = 0.f; image[(size_t)i * 3 + 2] = 0.f;
+        if (weights_edit_sum) { weights_edit_sum[i] = 0.f; depth_edit[i] = 0.f; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl[kCtlRays] = (int)n_rays;
+        ctl[kCtlMaxSteps] = (int)max_steps;
+        ctl[kCtlSteps] = 0;
+        ctl[kCtlRounds] = 0;
+        ctl[kCtlRounds + 1] = 0;
+        ctl[kCtlRounds + 2] = 0;
+        ctl_set_round(ctl, n_rays);
+    }
+}
+
+
+// ---- host launchers of the device-driven rounds (declared in render_core.cuh) ----
+int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, int32_t* rays_alive, float* rays_t, const float* nears,
+                        float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, cudaStream_t st) {
+    LNRF_REQUIRE(ctl && (n_rays == 0 || (rays_alive && rays_t && nears && weights_sum && depth && image)), "render_begin: null pointer");
+    const uint32_t blocks = n_rays ? (div_up(n_rays, 256u) < (uint32_t)kNumSMs * 8u ? div_up(n_rays, 256u) : (uint32_t)kNumSMs * 8u) : 1u;
+    k_render_begin<<<blocks, 256, 0, st>>>(ctl, n_rays, max_steps, rays_alive, rays_t, nears, weights_sum, depth, image, weights_edit_sum,
+                                           depth_edit);
+    LNRF_LAUNCH_CHECK("render_begin");
+    return LNRF_OK;
+}
+
+int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
+                           const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                           uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars, float* xyzs, float* dirs,
+                           float* deltas, uint8_t* edit_occ, const float* noises, bool first, cudaStream_t st) {
+    const char* who = distill ? "render_rounds(march_distill)" : "render_rounds(march)";
+    if (int e = check_march_common(C, H, max_steps, who)) return e;
+    if (n_rays_cap == 0) return LNRF_OK;
+    LNRF_REQUIRE(ctl && rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && dirs && deltas, "%s: null pointer", who);
+    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    // the grid covers the ray capacity (a round has at most n_rays_cap + 128 groups); blocks past the round's groups read the
+    // control block and leave (cheaper than a grid-stride loop over a persistent grid: 97 vs 115 us per steady-state round)
+    const uint32_t cap_blocks = 0xffffffffu;
+#define LNRF_MARCH_DEV_(DD, GG, LO, HI)                                                                                               \
+    {                                                                                                                                 \
+        const uint32_t want = div_up(n_rays_cap + 128u, 256u / GG);                                                                   \
+        k_march_infer<DD, GG><<<want < cap_blocks ? want : cap_blocks, 256, 0, st>>>(0u, 1u, rays_alive, rays_t, rays_o, rays_d, p, grid, \
+                                                                                      edit_grid, fars, xyzs, dirs, deltas, edit_occ,   \
+                                                                                      noises, 0u, 0u, ctl, LO, HI);                    \
+        LNRF_LAUNCH_CHECK(who);                                                                                                       \
+    }
+    // Group width, measured per round on the 640 000-ray lego frame (profiles/r1g_render.txt): first round (every ray walks
+    // from `near` through ~440 empty sequence members, one voxel ~ 4.6 members) 4 lanes 2.08 ms, 8 lanes 2.22 ms, 32 lanes
+    // 3.69 ms -- a window wider than a voxel only adds resolve iterations and idle probes; later rounds (rays continue inside
+    // or next to occupied cells, 2-3 samples wanted) 8 lanes 97 us, 4 lanes 150-200 us -- a second window costs more than
+    // four idle lanes.
+    if (first) {
+        if (distill) LNRF_MARCH_DEV_(true, 4, 1, 8) else LNRF_MARCH_DEV_(false, 4, 1, 8)
+    } else {
+        if (distill) LNRF_MARCH_DEV_(true, 8, 1, 8) else LNRF_MARCH_DEV_(false, 8, 1, 8)
+    }
+#undef LNRF_MARCH_DEV_
+    return LNRF_OK;
+}
+
+int composite_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, float T_thresh, int32_t* rays_alive, float* rays_t,
+                               const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* weights_edit_sum,
+                               float* depth, float* depth_edit, const uint8_t* edit_occ, float* image, cudaStream_t st) {
+    if (n_rays_cap == 0) return LNRF_OK;
+    const uint32_t want = div_up(n_rays_cap, 256u), cap_blocks = (uint32_t)kNumSMs * 8u;
+    const uint32_t blocks = want < cap_blocks ? want : cap_blocks;
+    if (distill)
+        k_composite_infer<true><<<blocks, 256, 0, st>>>(0u, 1u, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
+                                                        weights_edit_sum, depth, depth_edit, edit_occ, image, ctl);
+    else
+        k_composite_infer<false><<<blocks, 256, 0, st>>>(0u, 1u, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, nullptr,
+                                                         depth, nullptr, nullptr, image, ctl);
+    LNRF_LAUNCH_CHECK("render_rounds(composite)");
+    return LNRF_OK;
+}
+
+int compact_alive_dev_launch(int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, int32_t* out, void* scratch,
+                             size_t scratch_bytes, cudaStream_t st) {
+    if (n_rays_cap == 0) return LNRF_OK;
+    if (!scratch || scratch_bytes < lnrf_compact_alive_scratch_bytes(n_rays_cap)) {
+        set_error("render_rounds: compaction scratch too small (%zu < %zu)", scratch_bytes, lnrf_compact_alive_scratch_bytes(n_rays_cap));
+        return LNRF_ERR_SCRATCH_TOO_SMALL;
+    }
+    k_compact_alive<<<div_up(n_rays_cap, 1024u), 1024, 0, st>>>(rays_alive, n_rays_cap, out, nullptr,
+                                                                reinterpret_cast<unsigned long long*>(scratch), ctl);
+    LNRF_LAUNCH_CHECK("render_rounds(compact)");
+    return LNRF_OK;
 }
 
 }  // namespace lnrf
@@ -870,13 +1043,12 @@ static int march_infer_launch(bool distill, uint32_t n_alive, uint32_t n_step, c
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "%s: deltas must be 8-byte aligned", who);
     const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
     const uint32_t n_groups = div_up(M_rows, n_step);
-    const uint32_t blocks = div_up(n_groups, 256u / kInferGroup);
-    if (distill)
-        k_march_infer<true><<<blocks, 256, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, p, grid, edit_grid, fars,
-                                                    xyzs, dirs, deltas, edit_occ, noises, M_rows, n_groups);
-    else
-        k_march_infer<false><<<blocks, 256, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, p, grid, nullptr, fars,
-                                                     xyzs, dirs, deltas, nullptr, noises, M_rows, n_groups);
+#define LNRF_MARCH_INFER_(DD, GG)                                                                                                        \
+    k_march_infer<DD, GG><<<div_up(n_groups, 256u / GG), 256, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, p, grid,   \
+                                                                       edit_grid, fars, xyzs, dirs, deltas, edit_occ, noises, M_rows,  \
+                                                                       n_groups, nullptr, 0, 0)
+    if (distill) LNRF_MARCH_INFER_(true, 8); else LNRF_MARCH_INFER_(false, 8);
+#undef LNRF_MARCH_INFER_
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }
@@ -907,7 +1079,8 @@ int lnrf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32
     LNRF_REQUIRE(rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, "composite_rays: null pointer");
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays: deltas must be 8-byte aligned");
     k_composite_infer<false><<<div_up(n_alive, 256u), 256, 0, S(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
-                                                                           deltas, weights_sum, nullptr, depth, nullptr, nullptr, image);
+                                                                           deltas, weights_sum, nullptr, depth, nullptr, nullptr, image,
+                                                                           nullptr);
     LNRF_LAUNCH_CHECK("composite_rays");
     return LNRF_OK;
 }
@@ -923,7 +1096,7 @@ int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, float T_thres
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays_distill: deltas must be 8-byte aligned");
     k_composite_infer<true><<<div_up(n_alive, 256u), 256, 0, S(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs,
                                                                           deltas, weights_sum, weights_edit_sum, depth, depth_edit,
-                                                                          edit_occ, image);
+                                                                          edit_occ, image, nullptr);
     LNRF_LAUNCH_CHECK("composite_rays_distill");
     return LNRF_OK;
 }
@@ -944,7 +1117,7 @@ int lnrf_compact_alive(const int32_t* rays_alive, uint32_t n_alive, int32_t* out
         return LNRF_ERR_SCRATCH_TOO_SMALL;
     }
     k_compact_alive<<<div_up(n_alive, 1024u), 1024, 0, S(stream)>>>(rays_alive, n_alive, out, n_out,
-                                                                   reinterpret_cast<unsigned long long*>(scratch));
+                                                                   reinterpret_cast<unsigned long long*>(scratch), nullptr);
     LNRF_LAUNCH_CHECK("compact_alive");
     return LNRF_OK;
 }

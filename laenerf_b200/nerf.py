@@ -6,8 +6,10 @@ a re-implementation of the reference's trainer, GUI, datasets or checkpointing (
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torch.autograd import Function
@@ -128,6 +130,7 @@ class NeRFNetwork(nn.Module):
         # fused = True: forward()/the sigma scaling run as the fused kernels of csrc/nerfnet.cu whenever the call has the shape
         # they are built for (fp16 autocast, hidden 64, 16+15+1 colour inputs, sample count a multiple of 128)
         self.fused = True
+        self.device_loop = True  # row f-3: inference rounds driven from the device (falls back to the host loop when not fused)
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
                           self.in_dim_color == 32 and self.encoder_dir.degree == 4)
 
@@ -180,6 +183,77 @@ class NeRFNetwork(nn.Module):
             self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
         self.local_step = 0
 
+    # ---- row f-3: the inference loop of run_cuda / run_cuda_distill driven from the device -----------------------------
+    def _render_rounds_device(self, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
+                              rounds_per_call: int = 8):
+        """renderer.py:335-387 (and :425-470 with an edit grid) without a host synchronisation per round: the kernels read
+        n_alive / n_step from a control block in device memory that the compaction kernel updates (csrc/render.cu); the
+        host queues `rounds_per_call` rounds at a time and only then looks at the `finished` flag.  Same kernels, same
+        order, same per-round geometry as the host loop -- the results are bit-identical to it."""
+        from .gridencoder import _offsets_host
+        n_rays = rays_o.shape[0]
+        dev = rays_o.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        rows = n_rays + 128
+        distill = edit_bitfield is not None
+        enc, sn, cn = self.encoder, self.sigma_net, self.color_net
+        emb = enc._shadow_f16 if enc._shadow_f16 is not None else enc.embeddings.detach().half()
+        ws = sn._shadow_f16 if getattr(sn, "_shadow_f16", None) is not None else sn.weights.detach().half()
+        wc = cn._shadow_f16 if getattr(cn, "_shadow_f16", None) is not None else cn.weights.detach().half()
+        t = dict(
+            ctl=torch.zeros(16, dtype=torch.int32, device=dev),
+            alive0=torch.empty(n_rays, dtype=torch.int32, device=dev), alive1=torch.empty(n_rays, dtype=torch.int32, device=dev),
+            rays_t=torch.empty(n_rays, **f32), xyzs=torch.empty(rows, 3, **f32), dirs=torch.empty(rows, 3, **f32),
+            deltas=torch.empty(rows, 2, **f32), enc=torch.empty(rows, 32, dtype=torch.half, device=dev),
+            sigmas=torch.empty(rows, **f32), rgbs=torch.empty(rows, 3, **f32),
+            weights_sum=torch.empty(n_rays, **f32), depth=torch.empty(n_rays, **f32), image=torch.empty(n_rays, 3, **f32),
+            noises=torch.rand(n_rays, **f32) if perturb else None,
+            edit_occ=torch.empty(rows, dtype=torch.uint8, device=dev) if distill else None,
+            wes=torch.empty(n_rays, **f32) if distill else None, de=torch.empty(n_rays, **f32) if distill else None,
+        )
+        lib = N.lib()
+        nbytes = lib.lnrf_render_scratch_bytes(n_rays)
+        t["scratch"] = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+        off_h = _offsets_host(enc.offsets)
+        d = N.RenderDesc()
+        d.ctl, d.n_rays, d.max_steps = t["ctl"].data_ptr(), n_rays, int(max_steps)
+        d.rays_o, d.rays_d, d.nears, d.fars = rays_o.data_ptr(), rays_d.data_ptr(), nears.data_ptr(), fars.data_ptr()
+        d.density_bitfield = dens_grid.data_ptr()
+        d.edit_bitfield = edit_bitfield.data_ptr() if distill else None
+        d.bound, d.dt_gamma, d.T_thresh = float(self.bound), float(dt_gamma), float(T_thresh)
+        d.cascade, d.grid_size = int(self.cascade), int(self.grid_size)
+        d.first_round_noises = N.ptr(t["noises"])
+        d.embeddings_f16, d.offsets_host = emb.data_ptr(), off_h.data_ptr()
+        d.num_levels, d.base_resolution = int(enc.num_levels), int(enc.base_resolution)
+        d.gridtype, d.interpolation, d.align_corners = int(enc.gridtype_id), int(enc.interp_id), int(bool(enc.align_corners))
+        d.level_scale_log2 = float(np.log2(enc.per_level_scale))
+        d.w_sigma_f16, d.w_color_f16 = ws.data_ptr(), wc.data_ptr()
+        d.num_layers_sigma, d.num_layers_color, d.density_scale = int(sn.num_layers), int(cn.num_layers), float(self.density_scale)
+        d.rays_alive[0], d.rays_alive[1], d.rays_t = t["alive0"].data_ptr(), t["alive1"].data_ptr(), t["rays_t"].data_ptr()
+        d.xyzs, d.dirs, d.deltas = t["xyzs"].data_ptr(), t["dirs"].data_ptr(), t["deltas"].data_ptr()
+        d.edit_occ, d.enc_f16 = N.ptr(t["edit_occ"]), t["enc"].data_ptr()
+        d.sigmas, d.rgbs = t["sigmas"].data_ptr(), t["rgbs"].data_ptr()
+        d.weights_sum, d.depth, d.image = t["weights_sum"].data_ptr(), t["depth"].data_ptr(), t["image"].data_ptr()
+        d.weights_edit_sum, d.depth_edit = N.ptr(t["wes"]), N.ptr(t["de"])
+        d.scratch, d.scratch_bytes = t["scratch"].data_ptr(), nbytes
+        st = N.stream()
+        N.check(lib.lnrf_render_begin(C.byref(d), st))
+        launched = 0
+        max_rounds = int(max_steps)  # n_step >= 1: the reference loop cannot run more rounds than this
+        while launched < max_rounds:
+            k = min(rounds_per_call, max_rounds - launched)
+            N.check(lib.lnrf_render_rounds(C.byref(d), launched, k, st))
+            launched += k
+            ctl = t["ctl"].tolist()  # the one synchronisation per `rounds_per_call` rounds
+            if ctl[6]:
+                break
+        t["rounds"], t["steps"], t["slots"] = ctl[7], ctl[2], ctl[9]
+        return t
+
+    def _device_loop_ok(self, rays_o):
+        return (self.fused and self._fused_ok and rays_o.is_cuda and rays_o.shape[0] > 0 and torch.is_autocast_enabled() and
+                torch.get_autocast_dtype("cuda") == torch.float16 and not torch.is_grad_enabled())
+
     # ---- renderer.py:259-392 ---------------------------------------------------------------------------------
     def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
                  T_thresh=1e-4, scale_depth=True, edit_grid=None, **kwargs):
@@ -211,6 +285,18 @@ class NeRFNetwork(nn.Module):
             results["weights_sum"] = weights_sum
             results["nears"] = nears
             results["num_points"] = xyzs.shape[0]
+        elif self.device_loop and self._device_loop_ok(rays_o):
+            t = self._render_rounds_device(rays_o, rays_d, nears, fars, dens_grid, None, dt_gamma, perturb, max_steps, T_thresh)
+            weights_sum, depth, image = t["weights_sum"], t["depth"], t["image"]
+            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+            if scale_depth:
+                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+            else:
+                results["t"] = weights_sum
+            image = image.view(*prefix, 3)
+            depth = depth.view(*prefix)
+            results["num_points"] = t["slots"]
+            results["rounds"] = t["rounds"]
         else:
             weights_sum = torch.zeros(n_rays, dtype=torch.float32, device=device)
             depth = torch.zeros(n_rays, dtype=torch.float32, device=device)
@@ -262,6 +348,13 @@ class NeRFNetwork(nn.Module):
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer, self.min_near)
         if bg_color is None:
             bg_color = 1
+        if self.device_loop and self._device_loop_ok(rays_o):
+            t = self._render_rounds_device(rays_o, rays_d, nears, fars, self.density_bitfield, edit_bitfield, dt_gamma, perturb, max_steps,
+                                           T_thresh)
+            weights_sum, weights_edit_sum, depth, depth_edit = t["weights_sum"], t["wes"], t["depth"], t["de"]
+            image = t["image"] + (1 - weights_sum).unsqueeze(-1) * bg_color
+            return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum,
+                    "weights_edit_sum": weights_edit_sum, "depth_edit": depth_edit, "x_term": rays_o + depth_edit.unsqueeze(-1) * rays_d}
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
         weights_sum, weights_edit_sum, depth, depth_edit, image = z(n_rays), z(n_rays), z(n_rays), z(n_rays), z(n_rays, 3)
         n_alive = n_rays

@@ -258,3 +258,48 @@ def test_whole_training_steps_against_the_reference_extensions(dev):
         assert int(ours.step_counter[(ours.local_step - 1) % 16, 0]) == int(ref.step_counter[(ref.local_step - 1) % 16, 0])
     assert np.allclose(lo, lr, rtol=2e-2), (lo, lr)
     assert lo[-1] < lo[0] and lr[-1] < lr[0]
+
+
+def test_device_driven_render_equals_host_loop(dev):
+    """Row f-3: the inference rounds driven from the device (csrc/render.cu) against the host loop of run_cuda -- same kernels,
+    same per-round geometry, so image / depth / weights are bit-identical; also through the distillation variant."""
+    m = _model(dev, True, 41)
+    _, ro, rd, _ = scene_rays("lego", 6000, 23)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    m.eval()
+    outs = []
+    for loop in (True, False):
+        m.device_loop = loop
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            outs.append(m.render(ro, rd, perturb=False, bg_color=1))
+    a, b = outs
+    assert a["rounds"] > 3 and a["num_points"] == b["num_points"]
+    assert torch.equal(a["image"], b["image"])
+    assert torch.allclose(a["depth"], b["depth"], rtol=0, atol=0, equal_nan=True)  # rays that miss the box: 0 / (far - near = 0)
+    # distillation render with a synthetic edit grid (every other byte of the density bitfield)
+    edit = m.density_bitfield.clone()
+    edit[::2] = 0
+    outs = []
+    for loop in (True, False):
+        m.device_loop = loop
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            outs.append(m.run_cuda_distill(ro, rd, edit, perturb=False))
+    a, b = outs
+    for k in ("image", "depth", "weights_sum", "weights_edit_sum", "depth_edit"):
+        assert torch.allclose(a[k], b[k], rtol=0, atol=0, equal_nan=True), k
+    assert float(a["weights_edit_sum"].sum()) > 0
+    m.device_loop = True
+
+
+def test_grid_encoder_world_coordinates_equal_prenormalised_inputs(dev):
+    from laenerf_b200.gridencoder import GridEncoder, grid_encode
+    enc = GridEncoder(desired_resolution=4096).to(dev)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    x = torch.rand(5000, 3, device=dev) * 4 - 2
+    for bound in (1, 2, 16):
+        with torch.autocast("cuda", dtype=torch.float16):
+            y = enc(x.clamp(-bound, bound), bound=bound)
+            ref = grid_encode((x.clamp(-bound, bound) + bound) / (2 * bound), enc.embeddings, enc.offsets, enc.per_level_scale,
+                              enc.base_resolution, False, enc.gridtype_id, enc.align_corners, enc.interp_id)
+        assert torch.equal(y, ref)
