@@ -315,6 +315,30 @@ LNRF_API int lnrf_nerf_backward(const float* grad_sigmas, const float* grad_rgbs
                                 lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * occupancy-grid maintenance (row f-2) -- NeRFRenderer.update_extra_state, nerf/renderer.py:556-649
+ * --------------------------------------------------------------------------------------------------------- */
+/* Jittered query points of one cascade: xyz = (2 c / (H-1) - 1) * (bound_c - hgs) + (u * 2 - 1) * hgs, hgs = bound_c / H
+ * (renderer.py:585-597, torch's rounding sequence), indices = morton3D(c).  coords [N,3] int32 cell coordinates, or
+ * NULL for the full grid in meshgrid('ij') order (N == H^3); uniforms [N,3] fp32 in [0,1) (torch.rand). */
+LNRF_API int lnrf_occupancy_points(const int32_t* coords, const float* uniforms, uint32_t N, uint32_t H,
+                                   float cascade_bound, float* xyzs, int32_t* indices, lnrf_stream_t stream);
+/* tmp_grid_cascade[indices[i]] = sigmas[i] (renderer.py:601, 641). */
+LNRF_API int lnrf_occupancy_scatter(const float* sigmas, const int32_t* indices, uint32_t N, float* tmp_grid_cascade,
+                                    lnrf_stream_t stream);
+LNRF_API int lnrf_occupancy_fill(float* grid, uint32_t n, float value, lnrf_stream_t stream);
+/* density_grid = max(density_grid * decay, tmp_grid) where both >= 0 (renderer.py:625-626); tmp_grid is reset to -1;
+ * mean_out[0] = mean(clamp(density_grid, 0)) (:627), mean_out[1] = min(mean, density_thresh) (:632), both on the device. */
+LNRF_API size_t lnrf_occupancy_scratch_bytes(void);
+LNRF_API int lnrf_occupancy_ema(float* density_grid, float* tmp_grid, uint32_t n, float decay, float density_thresh,
+                                float* mean_out, void* scratch, size_t scratch_bytes, lnrf_stream_t stream);
+/* packbits (raymarching.cu:267-300) with the threshold read from device memory; N = number of output bytes. */
+LNRF_API int lnrf_packbits_dev(const float* grid, uint32_t N, const float* thresh_dev, uint8_t* bitfield,
+                               lnrf_stream_t stream);
+/* sigma net only (NeRFNetwork.density, network_ff.py:81-95): sigmas [M] = density_scale * exp(h0); M a multiple of 128. */
+LNRF_API int lnrf_nerf_density(const void* enc_f16, const void* w_sigma_f16, uint32_t M, uint32_t num_layers_sigma,
+                               float density_scale, float* sigmas, lnrf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Adam + AMP glue in one pass (row f-4) -- replaces, per training step of `-O` (nerf/utils.py:1474-1484,
  * main_nerf.py:223: Adam betas (0.9, 0.99) eps 1e-15 under GradScaler): embeddings.half() (grid.py:43-44),
  * the gradient clear, the fp16 -> fp32 gradient cast, GradScaler's inf check / unscale and torch.optim.Adam.

@@ -61,6 +61,13 @@ SIGNATURES = {
     "lnrf_render_scratch_bytes": (sz, [u32]),
     "lnrf_render_begin": (i32, [vp, vp]),
     "lnrf_render_rounds": (i32, [vp, u32, u32, vp]),
+    "lnrf_occupancy_points": (i32, [vp, vp, u32, u32, f32, vp, vp, vp]),
+    "lnrf_occupancy_scatter": (i32, [vp, vp, u32, vp, vp]),
+    "lnrf_occupancy_fill": (i32, [vp, u32, f32, vp]),
+    "lnrf_occupancy_scratch_bytes": (sz, []),
+    "lnrf_occupancy_ema": (i32, [vp, vp, u32, f32, f32, vp, vp, sz, vp]),
+    "lnrf_packbits_dev": (i32, [vp, u32, vp, vp, vp]),
+    "lnrf_nerf_density": (i32, [vp, vp, u32, u32, f32, vp, vp]),
     "lnrf_nerf_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "lnrf_nerf_wgrad_scratch_bytes": (sz, [u32, u32]),
     "lnrf_nerf_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, f32, vp, vp, vp, i32, vp, vp, sz, vp]),

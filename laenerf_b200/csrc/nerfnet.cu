@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(128 * kGroups, 1)
 k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const __half* __restrict__ w_sigma,
            const __half* __restrict__ w_color, const uint32_t M, const uint32_t ns, const uint32_t nc, const float density_scale,
            const __grid_constant__ CUtensorMap tm_fwd_buf, __half* __restrict__ color_in, __half* __restrict__ h0_out,
-           float* __restrict__ sigmas, float* __restrict__ rgbs, uint32_t ntiles, const int* __restrict__ M_dev) {
+           float* __restrict__ sigmas, float* __restrict__ rgbs, uint32_t ntiles, const int* __restrict__ M_dev,
+           const uint32_t sigma_only) {
     extern __shared__ uint8_t smem_raw[];
     if (M_dev) {  // device-driven inference round (row f-3): the sample count lives in the render control block
         ntiles = (uint32_t)*M_dev / kRows;
@@ -67,9 +68,11 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
     load_rows_async_n(smem_u32(sWs), w_sigma, 64, kEncDim, tid, 128 * kGroups);
     for (uint32_t m = 1; m < ns; m++) load_rows_async_n(smem_u32(sWs + m * kWBytes), w_sigma + 64 * kEncDim + (m - 1) * 4096, 64, 64, tid, 128 * kGroups);
     load_rows_async_n(smem_u32(sWs + ns * kWBytes), w_sigma + 64 * kEncDim + (ns - 1) * 4096, 16, 64, tid, 128 * kGroups);
-    load_rows_async_n(smem_u32(sWc), w_color, 64, kColIn, tid, 128 * kGroups);
-    for (uint32_t m = 1; m < nc; m++) load_rows_async_n(smem_u32(sWc + m * kWBytes), w_color + 64 * kColIn + (m - 1) * 4096, 64, 64, tid, 128 * kGroups);
-    load_rows_async_n(smem_u32(sWc + nc * kWBytes), w_color + 64 * kColIn + (nc - 1) * 4096, 16, 64, tid, 128 * kGroups);
+    if (!sigma_only) {
+        load_rows_async_n(smem_u32(sWc), w_color, 64, kColIn, tid, 128 * kGroups);
+        for (uint32_t m = 1; m < nc; m++) load_rows_async_n(smem_u32(sWc + m * kWBytes), w_color + 64 * kColIn + (m - 1) * 4096, 64, 64, tid, 128 * kGroups);
+        load_rows_async_n(smem_u32(sWc + nc * kWBytes), w_color + 64 * kColIn + (nc - 1) * 4096, 16, 64, tid, 128 * kGroups);
+    }
     if (first < ntiles) load_rows_async_n(smem_u32(myT), enc + (size_t)first * kRows * kEncDim, kRows, kEncDim, gt, 128);
     cp_async_commit();
     if (warp == 0) tmem_alloc(tslot, 64 * kGroups);
@@ -78,7 +81,7 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
         fence_mbar_init();
     }
     float dx = 0.f, dy = 0.f, dz = 0.f;  // this sample's direction, fetched one tile ahead (the sigma epilogue needs it)
-    if (first < ntiles) {
+    if (first < ntiles && !sigma_only) {
         const float* d = dirs + ((size_t)first * kRows + row) * 3;
         dx = __ldcs(d); dy = __ldcs(d + 1); dz = __ldcs(d + 2);
     }
@@ -90,7 +93,7 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
     const uint32_t tmem = *tslot + g * 64u;                                  // this group's 64 accumulator columns
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3u) * 32u) << 16);     // + this warp's lane quarter
     uint32_t phase = 0, it = 0;
-    const uint32_t nsteps = ns + 1 + nc + 1;  // matmuls per sample
+    const uint32_t nsteps = sigma_only ? ns + 1 : ns + 1 + nc + 1;  // matmuls per sample (density(): the sigma net alone)
 
     for (uint32_t tile = first; tile < ntiles; tile += stride, it++) {
         const size_t r0 = (size_t)tile * kRows;
@@ -104,8 +107,10 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
         if (tile + stride < ntiles) {
             load_rows_async_n(smem_u32(myT + ((it + 1u) & 1u) * kTileBytes), enc + (size_t)(tile + stride) * kRows * kEncDim, kRows, kEncDim, gt, 128);
             cp_async_commit();
-            const float* d = dirs + ((size_t)(tile + stride) * kRows + row) * 3;
-            dx = __ldcs(d); dy = __ldcs(d + 1); dz = __ldcs(d + 2);
+            if (!sigma_only) {
+                const float* d = dirs + ((size_t)(tile + stride) * kRows + row) * 3;
+                dx = __ldcs(d); dy = __ldcs(d + 1); dz = __ldcs(d + 2);
+            }
         }
 
         // step s: 0..ns = sigma net, ns+1..ns+1+nc = colour net; every step reads T and its epilogue rewrites T in place
@@ -157,6 +162,11 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
                 uint32_t pk[16];
                 tmem_ld16(taddr, h);
                 const __half h0 = __float2half_rn(h[0]);
+                if (sigma_only) {
+                    __stcs(sigmas + r0 + row, density_scale * expf(__half2float(h0)));
+                    tc_fence_before();
+                    continue;
+                }
                 sh_basis(cx, cy, cz, 4, sh);
 #pragma unroll
                 for (int i = 0; i < 8; i++) pk[i] = pack_h2(sh[2 * i], sh[2 * i + 1]);
@@ -221,7 +231,7 @@ int nerf_forward_dev_launch(const void* enc_f16, const float* dirs, const void* 
     const uint32_t want = div_up(div_up(M_cap, kRows), kGroups);
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     k_nerf_fwd<false><<<grid, 128 * kGroups, smem, st>>>((const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M_cap,
-                                                         ns, nc, density_scale, tm, nullptr, nullptr, sigmas, rgbs, 0u, M_dev);
+                                                         ns, nc, density_scale, tm, nullptr, nullptr, sigmas, rgbs, 0u, M_dev, 0u);
     LNRF_LAUNCH_CHECK("render_rounds(network)");
     return LNRF_OK;
 }
@@ -269,8 +279,34 @@ int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigm
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     kern<<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale,
-        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles, nullptr);
+        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles, nullptr, 0u);
     LNRF_LAUNCH_CHECK("nerf_forward");
+    return LNRF_OK;
+}
+
+int lnrf_nerf_density(const void* enc_f16, const void* w_sigma_f16, uint32_t M, uint32_t num_layers_sigma, float density_scale,
+                      float* sigmas, lnrf_stream_t stream) {
+    const uint32_t ns = num_layers_sigma;
+    LNRF_REQUIRE(M % 128 == 0, "nerf_density: the sample count must be 128 * m, but got %u", M);
+    LNRF_REQUIRE(ns >= 2 && ns <= kMaxLayers, "nerf_density: num_layers outside [2, %u]", kMaxLayers);
+    if (M == 0) return LNRF_OK;
+    LNRF_REQUIRE(enc_f16 && w_sigma_f16 && sigmas, "nerf_density: null pointer");
+    const size_t smem = nerf_fwd_smem(ns, 2);  // the colour-net slots stay empty
+    static std::atomic<size_t> s_max{0};
+    if (smem > s_max.load(std::memory_order_relaxed)) {
+        cudaError_t e = cudaFuncSetAttribute(k_nerf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "nerf_density");
+        s_max.store(smem, std::memory_order_relaxed);
+    }
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    const uint32_t ntiles = M / kRows;
+    const uint32_t want = div_up(ntiles, kGroups);
+    const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
+    k_nerf_fwd<false><<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __half*)enc_f16, nullptr, (const __half*)w_sigma_f16, nullptr, M, ns, 0u, density_scale, tm, nullptr, nullptr, sigmas, nullptr,
+        ntiles, nullptr, 1u);
+    LNRF_LAUNCH_CHECK("nerf_density");
     return LNRF_OK;
 }
 

@@ -114,7 +114,8 @@ class NeRFNetwork(nn.Module):
         self.register_buffer("density_grid", torch.zeros([self.cascade, grid_size ** 3]))
         self.register_buffer("density_bitfield", torch.zeros(self.cascade * grid_size ** 3 // 8, dtype=torch.uint8))
         self.register_buffer("step_counter", torch.zeros(16, 2, dtype=torch.int32))
-        self.mean_density = 0
+        self._mean_host, self._mean_dev = 0.0, None  # behind the mean_density property
+        self._tmp_grid = self._occ_scratch = self._occ_mean = None
         self.iter_density = 0
         self.mean_count = 0
         self.local_step = 0
@@ -175,6 +176,85 @@ class NeRFNetwork(nn.Module):
         self.mean_density = float(self.density_grid.clamp(min=0).mean().item())
         t = min(self.mean_density, self.density_thresh) if thresh is None else thresh
         raymarching.packbits(self.density_grid, t, self.density_bitfield)
+
+    # ---- renderer.py:556-649 (row f-2) ----------------------------------------------------------------------------
+    def _density_scaled(self, xyzs):
+        """density_scale * sigma of `xyzs` ([M,3] world coordinates): the fused encode + sigma-net path when available."""
+        M = xyzs.shape[0]
+        if self.fused and self._fused_ok and xyzs.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.float16:
+            from .gridencoder import _offsets_host
+            enc, sn = self.encoder, self.sigma_net
+            emb = enc._shadow_f16 if enc._shadow_f16 is not None else enc.embeddings.detach().half()
+            ws = sn._shadow_f16 if getattr(sn, "_shadow_f16", None) is not None else sn.weights.detach().half()
+            Mp = (M + 127) // 128 * 128
+            if Mp != M:
+                xyzs = torch.cat([xyzs, torch.zeros(Mp - M, 3, dtype=xyzs.dtype, device=xyzs.device)], 0)
+            feat = torch.empty(Mp, 32, dtype=torch.half, device=xyzs.device)
+            sig = torch.empty(Mp, dtype=torch.float32, device=xyzs.device)
+            lib, st = N.lib(), N.stream()
+            N.check(lib.lnrf_grid_encode_forward_world(N.ptr(xyzs), float(self.bound), N.ptr(emb), N.ptr(_offsets_host(enc.offsets)), N.ptr(feat),
+                                                       Mp, None, int(enc.num_levels), float(np.log2(enc.per_level_scale)),
+                                                       int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
+                                                       int(enc.interp_id), N.F16, st))
+            N.check(lib.lnrf_nerf_density(N.ptr(feat), N.ptr(ws), Mp, int(sn.num_layers), float(self.density_scale), N.ptr(sig), st))
+            return sig[:M]
+        sig = self.density(xyzs)["sigma"].reshape(-1).detach().float()
+        return sig * self.density_scale
+
+    @property
+    def mean_density(self):
+        """mean(clamp(density_grid, 0)) of the last update; kept on the device, read (one sync) only when somebody asks."""
+        if self._mean_dev is not None:
+            self._mean_host = float(self._mean_dev[0].item())
+            self._mean_dev = None
+        return self._mean_host
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_host, self._mean_dev = float(v), None
+
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128):
+        """NeRFRenderer.update_extra_state (renderer.py:556-649): re-sample the density grid (all cells for the first 16
+        updates, then H^3/4 random + H^3/4 occupied cells per cascade), EMA-max it into `density_grid`, rebuild the
+        bitfield from min(mean density, density_thresh), refresh `mean_count`.  The random numbers are drawn with the
+        reference's torch calls in the reference's order; everything else runs in csrc/occupancy.cu, and nothing on the
+        path waits for the device (the reference's mean().item() becomes a device-side threshold)."""
+        H, Cc = self.grid_size, self.cascade
+        dev = self.density_bitfield.device
+        lib, st = N.lib(), N.stream()
+        if self._tmp_grid is None or self._tmp_grid.device != dev:
+            self._tmp_grid = -torch.ones_like(self.density_grid)
+            self._occ_scratch = torch.empty(lib.lnrf_occupancy_scratch_bytes() // 4, dtype=torch.float32, device=dev)
+            self._occ_mean = torch.zeros(2, dtype=torch.float32, device=dev)
+        tmp = self._tmp_grid
+        for cas in range(Cc):
+            bound_c = min(2 ** cas, self.bound)
+            if self.iter_density < 16:  # full update
+                n = H ** 3
+                coords = None
+                indices = torch.empty(n, dtype=torch.int32, device=dev)
+            else:  # partial update: random cells + random occupied cells
+                n4 = H ** 3 // 4
+                coords = torch.randint(0, H, (n4, 3), device=dev)
+                occ_indices = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                rand_mask = torch.randint(0, occ_indices.shape[0], [n4], dtype=torch.long, device=dev)
+                occ_coords = raymarching.morton3D_invert(occ_indices[rand_mask])
+                coords = torch.cat([coords.int(), occ_coords], dim=0).contiguous()
+                n = coords.shape[0]
+                indices = torch.empty(n, dtype=torch.int32, device=dev)
+            u = torch.rand(n, 3, device=dev)  # rand_like(cas_xyzs)
+            xyzs = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            N.check(lib.lnrf_occupancy_points(N.ptr(coords), N.ptr(u), n, H, float(bound_c), N.ptr(xyzs), N.ptr(indices), st))
+            sig = self._density_scaled(xyzs).contiguous()
+            N.check(lib.lnrf_occupancy_scatter(N.ptr(sig), N.ptr(indices), n, N.ptr(tmp[cas]), st))
+        N.check(lib.lnrf_occupancy_ema(N.ptr(self.density_grid), N.ptr(tmp), self.density_grid.numel(), float(decay), float(self.density_thresh),
+                                       N.ptr(self._occ_mean), N.ptr(self._occ_scratch), self._occ_scratch.numel() * 4, st))
+        self._mean_dev = self._occ_mean
+        self.iter_density += 1
+        N.check(lib.lnrf_packbits_dev(N.ptr(self.density_grid), self.density_bitfield.numel(), N.ptr(self._occ_mean[1:]),
+                                      N.ptr(self.density_bitfield), st))
+        self.update_mean_count()
 
     def update_mean_count(self):
         """The step-counter part of update_extra_state (renderer.py:643-647)."""

@@ -303,3 +303,91 @@ def test_grid_encoder_world_coordinates_equal_prenormalised_inputs(dev):
             ref = grid_encode((x.clamp(-bound, bound) + bound) / (2 * bound), enc.embeddings, enc.offsets, enc.per_level_scale,
                               enc.base_resolution, False, enc.gridtype_id, enc.align_corners, enc.interp_id)
         assert torch.equal(y, ref)
+
+
+def _update_extra_state_torch(m, decay=0.95):
+    """Plain-torch restatement of NeRFRenderer.update_extra_state (renderer.py:556-649) on the module path of the package:
+    the comparison target for the fused row f-2 path (same RNG calls in the same order)."""
+    from laenerf_b200 import raymarching
+    H, dev = m.grid_size, m.density_bitfield.device
+    tmp_grid = -torch.ones_like(m.density_grid)
+    if m.iter_density < 16:
+        ar = torch.arange(H, dtype=torch.int32, device=dev)
+        xx, yy, zz = torch.meshgrid(ar, ar, ar, indexing="ij")
+        coords = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+        indices = raymarching.morton3D(coords).long()
+        xyzs = 2 * coords.float() / (H - 1) - 1
+        for cas in range(m.cascade):
+            bound = min(2 ** cas, m.bound)
+            hgs = bound / H
+            cas_xyzs = xyzs * (bound - hgs)
+            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * hgs
+            sigmas = m.density(cas_xyzs)["sigma"].reshape(-1).detach().float()
+            sigmas *= m.density_scale
+            tmp_grid[cas, indices] = sigmas
+    else:
+        n4 = H ** 3 // 4
+        for cas in range(m.cascade):
+            coords = torch.randint(0, H, (n4, 3), device=dev)
+            indices = raymarching.morton3D(coords).long()
+            occ_indices = torch.nonzero(m.density_grid[cas] > 0).squeeze(-1)
+            rand_mask = torch.randint(0, occ_indices.shape[0], [n4], dtype=torch.long, device=dev)
+            occ_indices = occ_indices[rand_mask]
+            occ_coords = raymarching.morton3D_invert(occ_indices)
+            indices = torch.cat([indices, occ_indices], dim=0)
+            coords = torch.cat([coords, occ_coords], dim=0)
+            xyzs = 2 * coords.float() / (H - 1) - 1
+            bound = min(2 ** cas, m.bound)
+            hgs = bound / H
+            cas_xyzs = xyzs * (bound - hgs)
+            cas_xyzs += (torch.rand_like(cas_xyzs) * 2 - 1) * hgs
+            sigmas = m.density(cas_xyzs)["sigma"].reshape(-1).detach().float()
+            sigmas *= m.density_scale
+            tmp_grid[cas, indices] = sigmas
+    valid = (m.density_grid >= 0) & (tmp_grid >= 0)
+    m.density_grid[valid] = torch.maximum(m.density_grid[valid] * decay, tmp_grid[valid])
+    m.mean_density = torch.mean(m.density_grid.clamp(min=0)).item()
+    m.iter_density += 1
+    raymarching.packbits(m.density_grid, min(m.mean_density, m.density_thresh), m.density_bitfield)
+
+
+@pytest.mark.parametrize("bound", [1, 2])
+def test_update_extra_state_matches_torch_restatement(dev, bound):
+    """Row f-2: the fused occupancy update against the torch restatement of the reference's, same seed."""
+    from laenerf_b200.nerf import NeRFNetwork
+    torch.manual_seed(7)
+    a = NeRFNetwork(bound=bound, density_thresh=0.01).to(dev)
+    with torch.no_grad():
+        a.encoder.embeddings.uniform_(-0.5, 0.5)
+    b = NeRFNetwork(bound=bound, density_thresh=0.01).to(dev)
+    b.load_state_dict(a.state_dict())
+    b.fused = False
+    nbits = a.density_bitfield.numel() * 8
+
+    def bit_mismatch():
+        x = (a.density_bitfield ^ b.density_bitfield).int()
+        return sum(int(((x >> k) & 1).sum()) for k in range(8)) / nbits
+
+    for it in range(2):  # two full updates (the second exercises the EMA-max)
+        with torch.autocast("cuda", dtype=torch.float16):
+            torch.manual_seed(100 + it)
+            a.update_extra_state()
+            torch.manual_seed(100 + it)
+            _update_extra_state_torch(b)
+        assert torch.equal(a.density_grid, b.density_grid), float((a.density_grid - b.density_grid).abs().max())  # same RNG, same roundings
+        assert abs(a.mean_density - b.mean_density) <= 1e-3 * abs(b.mean_density) + 1e-6
+        assert bit_mismatch() < 1e-3
+    assert a.iter_density == 2 and int(a.density_bitfield.count_nonzero()) > 0
+    # partial update: duplicates make the indexed assignment order-dependent in torch too, so the check is statistical
+    a.iter_density = b.iter_density = 16
+    with torch.autocast("cuda", dtype=torch.float16):
+        torch.manual_seed(300)
+        a.update_extra_state()
+        torch.manual_seed(300)
+        _update_extra_state_torch(b)
+    changed_a, changed_b = (a._tmp_grid == -1).all(), True
+    assert changed_a and changed_b  # the scratch grid is re-armed for the next update
+    assert abs(a.mean_density - b.mean_density) <= 2e-2 * abs(b.mean_density) + 1e-6
+    # ~9 % of the cells are drawn more than once (1 M draws over 2 M cells) and either draw may win the assignment
+    assert (a.density_grid - b.density_grid).abs().gt(1e-3 + 5e-3 * b.density_grid.abs()).float().mean() < 0.10
+    assert bit_mismatch() < 0.02
