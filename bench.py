@@ -246,10 +246,13 @@ def main():
     model.update_mean_count()
 
     # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
-    gstep, graph_note = None, "cuda graph (one capture per sample-buffer size)"
+    lookahead = os.environ.get("LNRF_LOOKAHEAD", "0") == "1"
+    gstep, graph_note = None, ("cuda graph (one capture per sample-buffer size)" +
+                               ("; look-ahead: the parameter-independent near/far + march of batch k runs on a second stream beside "
+                                "the network/backward/Adam of batch k-1 -- every step still marches one batch and trains on one" if lookahead else ""))
     if os.environ.get("LNRF_NO_GRAPH", "0") != "1":
         try:
-            gstep = GraphedTrainStep(step, N_RAYS)
+            gstep = GraphedTrainStep(step, N_RAYS, lookahead=lookahead)
             gstep.capture(*dev_batches[0])
             for i in range(3):
                 gstep(*dev_batches[i % n_batches])
@@ -266,6 +269,18 @@ def main():
     if gstep is not None:  # replays do not pass through the C ABI: count the launches the captured step contains
         launches = eager_launches  # same step, same number of steps, counted when it was issued through the C ABI
     clk = clocks.stop() if rank == 0 else None
+    seq_ms = None
+    if gstep is not None and lookahead:  # the same graph without the cross-step overlap, for reference
+        try:
+            model.update_mean_count()
+            g2 = GraphedTrainStep(step, N_RAYS, lookahead=False)
+            g2.capture(*dev_batches[0])
+            for i in range(3):
+                g2(*dev_batches[i % n_batches])
+            seq_ms = timed_loop(lambda i: g2(*dev_batches[i % n_batches]), args.steps) / args.steps
+            del g2
+        except Exception as e:
+            seq_ms = f"failed: {type(e).__name__}: {e}"[:200]
     ms_per_step = ms / args.steps
     value = world * N_RAYS * args.steps / (ms * 1e-3)
 
@@ -370,6 +385,7 @@ def main():
                    "parallelism": f"ray-sharded dp{world}" if world > 1 else "single GPU"},
         "clocks": clk,
         "step_mode": graph_note,
+        "graph_sequential_ms_per_step": seq_ms,
         "eager": {"ms_per_step": eager_ms / args.steps, "value": world * N_RAYS * args.steps / (eager_ms * 1e-3), "unit": "rays/s",
                   "note": "same step issued launch by launch from Python (the drop-in modules without graph capture)"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

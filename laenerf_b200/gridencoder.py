@@ -7,6 +7,8 @@ layout, so the reference's two permute copies (grid.py:57, 75) do not exist here
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -18,18 +20,23 @@ from . import _native as N
 _gridtype_to_id = {"hash": 0, "tiled": 1}
 _interp_to_id = {"linear": 0, "smoothstep": 1}
 
-_host_offsets = {}  # (data_ptr, numel) of the device offsets tensor -> pinned int32 host copy
+_host_offsets = {}  # id(device offsets tensor) -> (weakref to it, its _version, int32 host copy)
 
 
 def _offsets_host(offsets: torch.Tensor) -> torch.Tensor:
-    """The C ABI takes the L+1 level offsets from the host (they are launch geometry, not data)."""
+    """The C ABI takes the L+1 level offsets from the host (they are launch geometry, not data).  The cache entry is tied
+    to the tensor OBJECT (weak reference): a freed tensor whose address is reused by another model must not hit it."""
     if not offsets.is_cuda:
         return offsets.contiguous().to(torch.int32)
-    key = (offsets.data_ptr(), offsets.numel(), offsets._version)
-    h = _host_offsets.get(key)
-    if h is None:
-        h = offsets.detach().to("cpu", torch.int32).contiguous()
-        _host_offsets[key] = h
+    key = id(offsets)
+    hit = _host_offsets.get(key)
+    if hit is not None and hit[0]() is offsets and hit[1] == offsets._version:
+        return hit[2]
+    h = offsets.detach().to("cpu", torch.int32).contiguous()
+    if len(_host_offsets) > 64:  # drop entries whose tensor is gone
+        for k in [k for k, v in _host_offsets.items() if v[0]() is None]:
+            del _host_offsets[k]
+    _host_offsets[key] = (weakref.ref(offsets), offsets._version, h)
     return h
 
 

@@ -334,6 +334,37 @@ class NeRFNetwork(nn.Module):
         return (self.fused and self._fused_ok and rays_o.is_cuda and rays_o.shape[0] > 0 and torch.is_autocast_enabled() and
                 torch.get_autocast_dtype("cuda") == torch.float16 and not torch.is_grad_enabled())
 
+    # ---- the training branch of run_cuda (renderer.py:284-333) in two halves: everything that depends only on the rays
+    # (near/far + occupancy-grid march) and everything that depends on the parameters (network, compositing).  run_cuda runs
+    # them back to back; GraphedTrainStep(lookahead=True) runs the first half of the NEXT batch beside the second half of
+    # the current one.
+    def _march_train_from(self, rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps):
+        counter = self.step_counter[self.local_step % 16]
+        counter.zero_()
+        self.local_step += 1
+        xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
+                                                                self.grid_size, nears, fars, counter, self.mean_count, perturb,
+                                                                128, force_all_rays, dt_gamma, max_steps)
+        return dict(xyzs=xyzs, dirs=dirs, deltas=deltas, rays=rays, nears=nears, fars=fars)
+
+    def march_train(self, rays_o, rays_d, perturb=True, force_all_rays=False, dt_gamma=0, max_steps=1024, edit_grid=None):
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train, self.min_near)
+        dens_grid = edit_grid if edit_grid is not None else self.density_bitfield
+        return self._march_train_from(rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps)
+
+    def shade_train(self, marched, bg_color=1, T_thresh=1e-4, prefix=None, scale_depth=True):
+        xyzs, dirs, deltas, rays, nears, fars = (marched[k] for k in ("xyzs", "dirs", "deltas", "rays", "nears", "fars"))
+        prefix = (rays.shape[0],) if prefix is None else prefix
+        sigmas, rgbs = self.forward_scaled(xyzs, dirs)
+        weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        if scale_depth:
+            depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum, "nears": nears,
+                "num_points": xyzs.shape[0]}
+
     # ---- renderer.py:259-392 ---------------------------------------------------------------------------------
     def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
                  T_thresh=1e-4, scale_depth=True, edit_grid=None, **kwargs):
@@ -349,22 +380,9 @@ class NeRFNetwork(nn.Module):
             bg_color = 1
         results = {}
         if self.training:
-            counter = self.step_counter[self.local_step % 16]
-            counter.zero_()
-            self.local_step += 1
-            xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
-                                                                    self.grid_size, nears, fars, counter, self.mean_count, perturb,
-                                                                    128, force_all_rays, dt_gamma, max_steps)
-            sigmas, rgbs = self.forward_scaled(xyzs, dirs)
-            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
-            image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-            if not kwargs.get("distill", False):
-                depth = torch.clamp(depth - nears, min=0) / (fars - nears)
-            image = image.view(*prefix, 3)
-            depth = depth.view(*prefix)
-            results["weights_sum"] = weights_sum
-            results["nears"] = nears
-            results["num_points"] = xyzs.shape[0]
+            marched = self._march_train_from(rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps)
+            results = self.shade_train(marched, bg_color, T_thresh, prefix, scale_depth=not kwargs.get("distill", False))
+            depth, image = results["depth"], results["image"]
         elif self.device_loop and self._device_loop_ok(rays_o):
             t = self._render_rounds_device(rays_o, rays_d, nears, fars, dens_grid, None, dt_gamma, perturb, max_steps, T_thresh)
             weights_sum, depth, image = t["weights_sum"], t["depth"], t["image"]
@@ -488,11 +506,18 @@ class TrainStep:
             self.scaler = torch.amp.GradScaler("cuda", enabled=fp16)
 
     def __call__(self, rays_o, rays_d, gt_rgb, bg_color=1, perturb=True):
+        return self.train_on(self.march(rays_o, rays_d, perturb), gt_rgb, bg_color)
+
+    def march(self, rays_o, rays_d, perturb=True):
+        """The parameter-independent half of the step (near/far + occupancy march); see NeRFNetwork.march_train."""
+        self.model.train()
+        return self.model.march_train(rays_o, rays_d, perturb=perturb, force_all_rays=False, dt_gamma=0, max_steps=1024)
+
+    def train_on(self, marched, gt_rgb, bg_color=1):
         self.model.train()
         self.optimizer.zero_grad(set_to_none=True)
         with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
-            out = self.model.render(rays_o, rays_d, bg_color=bg_color, perturb=perturb, force_all_rays=False, dt_gamma=0,
-                                    max_steps=1024)
+            out = self.model.shade_train(marched, bg_color)
             loss = torch.nn.functional.mse_loss(out["image"], gt_rgb, reduction="none").mean(-1).mean()
         if self.fused_optimizer:
             self.optimizer.scale(loss).backward()
@@ -512,20 +537,27 @@ class TrainStep:
 
 class GraphedTrainStep:
     """The same training step replayed from ONE CUDA graph (march -> encode -> MLPs -> composite -> loss -> backward
-    -> Adam, ~100 launches): the 4096-ray step is launch-bound when issued from Python ("hard
-    parts"), so the steady state is captured once per sample-buffer size and replayed.  Inputs are copied into static
-    device buffers; `loss` / `out` are views of graph-owned memory that the next replay overwrites."""
+    -> Adam): the 4096-ray step is launch-bound when issued from Python ("hard parts"), so the
+    steady state is captured once per sample-buffer size and replayed.  Inputs are copied into static device buffers;
+    `loss` / `out` are views of graph-owned memory that the next replay overwrites.
 
-    def __init__(self, step: TrainStep, n_rays: int, bg_color=1, perturb=True):
+    lookahead=True software-pipelines consecutive steps: near/far + the occupancy march depend only on the rays, never
+    on the parameters, and the march is latency-bound (one warp per ray, ~38 % of the warp slots of the GPU for 75 us),
+    so the graph marches the batch handed to call k on a second stream WHILE the network / compositing / backward / Adam
+    of the batch handed to call k-1 run on the first.  Every call still consumes one batch and performs one full
+    optimizer step; the returned loss is the previous call's batch (one-step delay, `flush()` trains the last one)."""
+
+    def __init__(self, step: TrainStep, n_rays: int, bg_color=1, perturb=True, lookahead: bool = False):
         self.step, self.model = step, step.model
         dev = next(self.model.parameters()).device
         self.ro = torch.zeros(n_rays, 3, device=dev)
         self.rd = torch.zeros(n_rays, 3, device=dev)
         self.gt = torch.zeros(n_rays, 3, device=dev)
-        self.bg_color, self.perturb = bg_color, perturb
+        self.bg_color, self.perturb, self.lookahead = bg_color, perturb, bool(lookahead)
         self.graph = None
         self.captured_mean_count = 0
         self.loss = self.out = None
+        self.cur = self.gt_cur = None  # lookahead: the marched batch (and its targets) the next replay trains on
 
     def _load(self, rays_o, rays_d, gt_rgb):
         self.ro.copy_(rays_o, non_blocking=True)
@@ -545,9 +577,26 @@ class GraphedTrainStep:
                 self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
         torch.cuda.current_stream().wait_stream(side)
         m.local_step = 0  # the captured march always counts into step_counter[0]; rotated after each replay
+        if self.lookahead:
+            # prime the pipeline: march the capture batch eagerly into persistent buffers
+            self.cur = {k: v.clone() for k, v in self.step.march(self.ro, self.rd, self.perturb).items()}
+            self.gt_cur = self.gt.clone()
+            m.local_step = 0
+            self._side = torch.cuda.Stream()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss, self.out = self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
+            if self.lookahead:
+                main = torch.cuda.current_stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):  # branch 1: march the batch that was just loaded
+                    nxt = self.step.march(self.ro, self.rd, self.perturb)
+                self.loss, self.out = self.step.train_on(self.cur, self.gt_cur, self.bg_color)  # branch 2: train on the previous one
+                main.wait_stream(self._side)
+                for k, v in nxt.items():  # hand over: 7 MB of device-to-device copies after the join
+                    self.cur[k].copy_(v)
+                self.gt_cur.copy_(self.gt)
+            else:
+                self.loss, self.out = self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
         self.captured_mean_count = m.mean_count
         m.local_step = 0
         self._replays = 0
@@ -560,6 +609,8 @@ class GraphedTrainStep:
     def __call__(self, rays_o, rays_d, gt_rgb):
         if self.graph is None:
             self.capture(rays_o, rays_d, gt_rgb)
+            if self.lookahead:  # the capture batch is in flight; its loss arrives with the next call
+                return None, None
         self._load(rays_o, rays_d, gt_rgb)
         self.graph.replay()
         m = self.model
@@ -569,3 +620,9 @@ class GraphedTrainStep:
         self._replays += 1
         m.local_step = min(16, self._replays)
         return self.loss, self.out
+
+    def flush(self):
+        """lookahead: train on the batch that is still in flight (eagerly); returns its (loss, out)."""
+        if not self.lookahead or self.cur is None:
+            return None, None
+        return self.step.train_on(self.cur, self.gt_cur, self.bg_color)

@@ -391,3 +391,28 @@ def test_update_extra_state_matches_torch_restatement(dev, bound):
     # ~9 % of the cells are drawn more than once (1 M draws over 2 M cells) and either draw may win the assignment
     assert (a.density_grid - b.density_grid).abs().gt(1e-3 + 5e-3 * b.density_grid.abs()).float().mean() < 0.10
     assert bit_mismatch() < 0.02
+
+
+def test_lookahead_graph_trains_the_same_sequence(dev):
+    """GraphedTrainStep(lookahead=True) marches batch k beside the training of batch k-1: same batches, same updates, the
+    loss simply arrives one call later."""
+    from laenerf_b200.nerf import GraphedTrainStep, TrainStep
+    batches = []
+    for k in range(6):
+        _, ro, rd, _ = scene_rays("lego", 4096, 50 + k)
+        batches.append((torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev),
+                        torch.rand(4096, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(k))))
+    runs = []
+    for look in (False, True):
+        m = _model(dev, True, 61)
+        g = GraphedTrainStep(TrainStep(m), 4096, perturb=False, lookahead=look)
+        g.capture(*batches[0], warmup=1)
+        if look:
+            losses = [g(*b)[0] for b in batches[1:]]            # call k trains on batch k-1 (batch 0 was primed by capture)
+            losses = [float(x) for x in losses] + [float(g.flush()[0])]
+        else:
+            losses = [float(g(*b)[0]) for b in batches]
+        runs.append(losses)
+    seq, pipe = runs
+    assert len(seq) == len(pipe) == 6 and all(np.isfinite(seq)) and all(np.isfinite(pipe))
+    assert np.allclose(seq, pipe, rtol=2e-2), (seq, pipe)
