@@ -172,6 +172,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -246,7 +248,9 @@ def main():
     model.update_mean_count()
 
     # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
-    lookahead = os.environ.get("LNRF_LOOKAHEAD", "0") == "1"
+    # look-ahead pays when there is an exchange step to hide the march behind (measured at N = 2: 0.623 -> 0.590 ms); on one GPU
+    # the march only competes with Adam for the same SMs (0.522 -> 0.553 ms), so it is off there
+    lookahead = os.environ.get("LNRF_LOOKAHEAD", "1" if world > 1 else "0") == "1"
     gstep, graph_note = None, ("cuda graph (one capture per sample-buffer size)" +
                                ("; look-ahead: the parameter-independent near/far + march of batch k runs on a second stream beside "
                                 "the network/backward/Adam of batch k-1 -- every step still marches one batch and trains on one" if lookahead else ""))
@@ -269,6 +273,13 @@ def main():
     if gstep is not None:  # replays do not pass through the C ABI: count the launches the captured step contains
         launches = eager_launches  # same step, same number of steps, counted when it was issued through the C ABI
     clk = clocks.stop() if rank == 0 else None
+    in_sync = None
+    if world > 1 and step.fused_optimizer:  # every rank must hold the same fp16 table after the sharded optimizer steps
+        chk = model.encoder._shadow_f16.float().abs().sum().double().reshape(1)
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        in_sync = bool(lo_.item() == hi_.item())
     seq_ms = None
     if gstep is not None and lookahead:  # the same graph without the cross-step overlap, for reference
         try:
@@ -311,7 +322,7 @@ def main():
         calls_per_step = k["calls"] / args.steps
         if a["bound"] == "hbm":
             byts = (a.get("per_ray", 0) * N_RAYS + a.get("per_sample", 0) * actual + a.get("per_sample_padded", 0) * m_pad +
-                    a.get("per_param", 0) * n_params)
+                    a.get("per_param", 0) * (n_params // world))  # sharded optimizer: each rank updates 1/world of the table
             ach = byts / (k["mean_ms"] * 1e-3) / 1e9
             table[name] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], mean_ms=k["mean_ms"],
                                calls_per_step=calls_per_step, algorithmic_bytes=byts, traffic=traffic.get(name))
@@ -360,8 +371,7 @@ def main():
         model.train()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------------------
@@ -382,10 +392,17 @@ def main():
                    "samples_per_ray": actual / N_RAYS, "scene_occupancy": sc.occupancy_fraction(),
                    "l2": "no explicit flush: one step touches ~245 MB (fp32 table + grads + Adam moments + fp16 copies) > 126 MB L2",
                    "occupancy_update": "excluded (row f-2 of SURVEY.md section 8: fixed procedural occupancy grid)",
-                   "parallelism": f"ray-sharded dp{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"ray-sharded dp{world}: reduce-scatter of the fp16 hash-grid gradient, Adam on a 1/{world} table slice per "
+                                   f"rank, all-gather of the fp16 table (ZeRO-1 style)") if world > 1 else "single GPU"},
         "clocks": clk,
         "step_mode": graph_note,
         "graph_sequential_ms_per_step": seq_ms,
+        "replicas_in_sync": in_sync,
+        "exchange": (None if world == 1 or not step.fused_optimizer else
+                     ("one fused kernel over NVLink peer memory (torch symmetric memory): average of the ranks' fp16 gradients + Adam on "
+                      "a 1/N slice + store of the new fp16 values into every rank's table" if step.optimizer.p2p is not None else
+                      "NCCL reduce-scatter + Adam on a 1/N slice + NCCL all-gather (symmetric memory unavailable: " +
+                      str(getattr(step.optimizer, "p2p_error", "disabled")) + ")")),
         "eager": {"ms_per_step": eager_ms / args.steps, "value": world * N_RAYS * args.steps / (eager_ms * 1e-3), "unit": "rays/s",
                   "note": "same step issued launch by launch from Python (the drop-in modules without graph capture)"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -397,8 +414,19 @@ def main():
         "train_msamples_per_s": world * actual * args.steps / (ms * 1e-3) / 1e6,
     }
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Multi-rank runs leave without tearing NCCL down: destroy_process_group() with captured collectives still alive in
+    CUDA graphs was observed to hang until the launcher's timeout (2-GPU run of round 1).  All collectives are complete
+    (every rank passed the final barrier + synchronize), so the processes simply exit."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -363,6 +363,19 @@ LNRF_API int lnrf_grad_nonfinite_check(const lnrf_opt_tensor* tensors_host, uint
 LNRF_API int lnrf_adam_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double lr, double beta1, double beta2,
                             double eps, double weight_decay, const float* grad_scale, const float* found_inf,
                             const float* step_count, const float* lr_scale, lnrf_stream_t stream);
+/* Ray-sharded training: gradient exchange + Adam + parameter broadcast in ONE kernel over NVLink
+ * peer memory.  grad_peers / shadow_peers / flag_peers: HOST arrays of `world` pointers, entry r = rank r's full fp16
+ * gradient vector, full fp16 shadow vector and non-finite flag (all peer-mapped into this process, e.g. torch symmetric
+ * memory).  This rank owns elements [lo, lo + n): it averages the `world` gradients of that slice, applies Adam to its fp32
+ * master / moment slices and stores the new fp16 values into every rank's shadow.  When any flag is non-zero nothing is
+ * updated and *found_inf_out = 1.  The caller synchronises the ranks before (gradients and flags complete) and after
+ * (shadows visible; gradients may be cleared) the call. */
+LNRF_API int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* const* shadow_peers_host,
+                                    const float* const* flag_peers_host, uint32_t world, uint64_t lo, uint64_t n,
+                                    float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard, double lr,
+                                    double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
+                                    float* found_inf_out, const float* step_count, const float* lr_scale,
+                                    lnrf_stream_t stream);
 /* GradScaler.update() (growth / backoff of the loss scale from found_inf) fused with the step bookkeeping:
  * step_count += 1 unless the step was skipped, found_inf re-armed to 0.  scale / growth_tracker may be NULL
  * (no loss scaling). */

@@ -191,6 +191,91 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Ray-sharded training: gradient exchange + Adam + parameter broadcast as ONE kernel over NVLink peer memory
+// ---------------------------------------------------------------------------------------------------------------------
+// Every rank holds its full local fp16 gradient and the full fp16 shadow table in symmetric (peer-mapped) memory.  Rank r
+// owns elements [lo, lo + n) of the flat parameter vector: for each of them it LOADS the gradient from all R ranks (its own
+// and R-1 over NVLink), averages in fp32, applies Adam to its fp32 master slice and STORES the new fp16 value into all R
+// shadow tables.  Per rank that moves (R-1)/R x 24.5 MB in and (R-1)/R x 24.5 MB out over NVLink -- the bytes of an
+// all-reduce -- while the 367 MB HBM pass of Adam shrinks R-fold, and no intermediate buffer or collective launch exists.
+// The skip-on-inf decision is global and identical everywhere: every rank checked its own gradient beforehand and
+// published a flag next to it; the kernel reads all R flags.  (Averaging finite fp16 values in fp32 cannot overflow.)
+// Synchronisation is the caller's: a cross-rank barrier before (gradients + flags complete) and after (shadows written,
+// gradients may be cleared) the launch.
+constexpr int kMaxPeers = 8;   // one NVSwitch domain of 8 GPUs; also bounds the registers that hold the in-flight peer loads
+struct PeerPtrs {
+    const __half* grad[kMaxPeers];
+    __half* shadow[kMaxPeers];
+    const float* flag[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(kOptBlock)
+k_adam_step_p2p(const PeerPtrs peers, const uint32_t R, const uint64_t lo, const uint64_t n, float* __restrict__ master,
+                float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, AdamHyper h, const float* __restrict__ grad_scale,
+                float* __restrict__ found_inf_out, const float* __restrict__ step_count, const float* __restrict__ lr_scale) {
+    bool skip = false;
+    for (uint32_t r = 0; r < R; r++) skip |= (*peers.flag[r] != 0.0f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *found_inf_out = skip ? 1.0f : 0.0f;
+    if (skip) return;  // GradScaler: nothing is updated; the gradients are cleared by the caller after the closing barrier
+    if (lr_scale) h.lr *= (double)*lr_scale;
+    const float step = *step_count;
+    const float bc1 = (float)(1.0 - pow(h.beta1, (double)step));
+    AdamStepConsts c;
+    c.w1 = 1.0 - h.beta1;
+    c.w2 = 1.0 - h.beta2;
+    c.step_size = (float)(h.lr / (double)bc1);
+    c.bc2_sqrt = sqrtf((float)(1.0 - pow(h.beta2, (double)step)));
+    c.unscale = grad_scale != nullptr;
+    const float scale_f = c.unscale ? *grad_scale : 1.0f;
+    c.scale = (double)scale_f;
+    int e2;
+    c.inv_scale = (frexpf(scale_f, &e2) == 0.5f && e2 > -100 && e2 < 100) ? 1.0f / scale_f : 0.0f;
+    const float inv_R = 1.0f / (float)R;
+
+    for (uint64_t base = (uint64_t)blockIdx.x * kOptChunk; base < n; base += (uint64_t)gridDim.x * kOptChunk) {
+        const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;  // n is a multiple of 8: no ragged tail
+        if (i >= n) continue;
+        float g[kOptPerThread], p[kOptPerThread], m[kOptPerThread], v[kOptPerThread];
+#pragma unroll
+        for (int j = 0; j < (int)kOptPerThread; j++) g[j] = 0.0f;
+        // all loads first: R gradient vectors (R-1 of them remote) + the local fp32 state
+        uint4 gw[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; r++)
+            if (r < (int)R) gw[r] = *reinterpret_cast<const uint4*>(peers.grad[r] + lo + i);
+        *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(master + i);
+        *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(master + i + 4);
+        *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(exp_avg + i);
+        *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(exp_avg + i + 4);
+        *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(exp_avg_sq + i);
+        *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(exp_avg_sq + i + 4);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; r++) {
+            if (r < (int)R) {
+                union { uint4 u; __half2 h2[4]; } w;
+                w.u = gw[r];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const float2 f = __half22float2(w.h2[j]); g[2 * j] += f.x; g[2 * j + 1] += f.y; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < (int)kOptPerThread; j++) adam_update(p[j], m[j], v[j], adam_unscale(g[j] * inv_R, c), h, c);
+        *reinterpret_cast<float4*>(master + i) = *reinterpret_cast<const float4*>(p);
+        *reinterpret_cast<float4*>(master + i + 4) = *reinterpret_cast<const float4*>(p + 4);
+        *reinterpret_cast<float4*>(exp_avg + i) = *reinterpret_cast<const float4*>(m);
+        *reinterpret_cast<float4*>(exp_avg + i + 4) = *reinterpret_cast<const float4*>(m + 4);
+        *reinterpret_cast<float4*>(exp_avg_sq + i) = *reinterpret_cast<const float4*>(v);
+        *reinterpret_cast<float4*>(exp_avg_sq + i + 4) = *reinterpret_cast<const float4*>(v + 4);
+        union { uint4 u; __half2 h2[4]; } o;
+#pragma unroll
+        for (int j = 0; j < 4; j++) o.h2[j] = __floats2half2_rn(p[2 * j], p[2 * j + 1]);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; r++)
+            if (r < (int)R) *reinterpret_cast<uint4*>(peers.shadow[r] + lo + i) = o.u;
+    }
+}
+
 // GradScaler.update() (torch amp_update_scale_cuda_kernel) + the bookkeeping around it, one thread: adjust the scale,
 // advance the step number when the step was not skipped, and re-arm found_inf for the next step.
 __global__ void k_amp_update(float* scale, int* growth_tracker, float* found_inf, float* step_count, float growth_factor,
@@ -275,6 +360,31 @@ int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, flo
     k_amp_update<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(scale, growth_tracker, found_inf, step_count, growth_factor,
                                                                        backoff_factor, growth_interval);
     LNRF_LAUNCH_CHECK("amp_update");
+    return LNRF_OK;
+}
+
+int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* const* shadow_peers_host, const float* const* flag_peers_host,
+                           uint32_t world, uint64_t lo, uint64_t n, float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
+                           double lr, double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
+                           float* found_inf_out, const float* step_count, const float* lr_scale, lnrf_stream_t stream) {
+    LNRF_REQUIRE(world >= 1 && world <= (uint32_t)kMaxPeers, "adam_step_sharded: 1..%d ranks, got %u", kMaxPeers, world);
+    LNRF_REQUIRE(grad_peers_host && shadow_peers_host && flag_peers_host && master_shard && exp_avg_shard && exp_avg_sq_shard &&
+                     found_inf_out && step_count,
+                 "adam_step_sharded: null pointer");
+    LNRF_REQUIRE(n % 8 == 0 && lo % 8 == 0, "adam_step_sharded: slice offset / length must be multiples of 8 elements");
+    if (n == 0) return LNRF_OK;
+    PeerPtrs pp{};
+    for (uint32_t r = 0; r < world; r++) {
+        LNRF_REQUIRE(grad_peers_host[r] && shadow_peers_host[r] && flag_peers_host[r], "adam_step_sharded: null peer pointer (rank %u)", r);
+        pp.grad[r] = (const __half*)grad_peers_host[r];
+        pp.shadow[r] = (__half*)shadow_peers_host[r];
+        pp.flag[r] = flag_peers_host[r];
+    }
+    AdamHyper h{lr, beta1, beta2, eps, weight_decay};
+    const uint64_t chunks = (n + kOptChunk - 1) / kOptChunk, cap = (uint64_t)kNumSMs * 8;
+    k_adam_step_p2p<<<(uint32_t)(chunks < cap ? chunks : cap), kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        pp, world, lo, n, master_shard, exp_avg_shard, exp_avg_sq_shard, h, grad_scale, found_inf_out, step_count, lr_scale);
+    LNRF_LAUNCH_CHECK("adam_step_sharded");
     return LNRF_OK;
 }
 

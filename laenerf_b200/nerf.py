@@ -497,7 +497,12 @@ class TrainStep:
         if self.fused_optimizer:
             # row f-4: inf check + unscale + Adam + fp16 shadow rewrite + gradient clear in two launches (optim.py)
             from .optim import AmpAdam
-            self.optimizer = AmpAdam(model, lr=lr, betas=(0.9, 0.99), eps=1e-15, fp16=True)
+            rank = 0
+            if world_size > 1:
+                import torch.distributed as dist
+                rank = dist.get_rank()
+            # world_size > 1: reduce-scatter + per-rank Adam on a 1/N table slice + all-gather of the fp16 shadow (optim.py)
+            self.optimizer = AmpAdam(model, lr=lr, betas=(0.9, 0.99), eps=1e-15, fp16=True, world_size=world_size, rank=rank)
             self.scaler = None
         else:
             # torch path.  fused=True: one multi-tensor kernel that also consumes GradScaler's scale / found_inf on the
@@ -514,25 +519,30 @@ class TrainStep:
         return self.model.march_train(rays_o, rays_d, perturb=perturb, force_all_rays=False, dt_gamma=0, max_steps=1024)
 
     def train_on(self, marched, gt_rgb, bg_color=1):
+        loss, out = self.forward_backward(marched, gt_rgb, bg_color)
+        self.reduce_and_step()
+        return loss, out
+
+    def forward_backward(self, marched, gt_rgb, bg_color=1):
+        """Network + compositing + loss + backward of one marched batch: gradients are left in the optimizer's buffers."""
         self.model.train()
         self.optimizer.zero_grad(set_to_none=True)
         with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
             out = self.model.shade_train(marched, bg_color)
             loss = torch.nn.functional.mse_loss(out["image"], gt_rgb, reduction="none").mean(-1).mean()
+        (self.optimizer if self.fused_optimizer else self.scaler).scale(loss).backward()
+        return loss, out
+
+    def reduce_and_step(self):
+        """The exchange step of ray-sharded training followed by the identical Adam step on every rank."""
         if self.fused_optimizer:
-            self.optimizer.scale(loss).backward()
-            if self.world_size > 1:  # the exchange step acts on the fp16 gradient buffers (24.5 MB instead of 49 MB)
-                from .parallel import allreduce_tensors
-                allreduce_tensors(self.optimizer.grads(), self.world_size)
-            self.optimizer.step()
-            return loss, out
-        self.scaler.scale(loss).backward()
-        if self.world_size > 1:  # the one exchange step of ray-sharded training
+            self.optimizer.step()  # includes the exchange when world_size > 1 (AmpAdam._exchange_gradients)
+            return
+        if self.world_size > 1:
             from .parallel import allreduce_gradients
             allreduce_gradients([p for g in self.optimizer.param_groups for p in g["params"]], self.world_size)
         self.scaler.step(self.optimizer)
         self.scaler.update()
-        return loss, out
 
 
 class GraphedTrainStep:
@@ -543,9 +553,10 @@ class GraphedTrainStep:
 
     lookahead=True software-pipelines consecutive steps: near/far + the occupancy march depend only on the rays, never
     on the parameters, and the march is latency-bound (one warp per ray, ~38 % of the warp slots of the GPU for 75 us),
-    so the graph marches the batch handed to call k on a second stream WHILE the network / compositing / backward / Adam
-    of the batch handed to call k-1 run on the first.  Every call still consumes one batch and performs one full
-    optimizer step; the returned loss is the previous call's batch (one-step delay, `flush()` trains the last one)."""
+    so the graph marches the batch handed to call k on a second stream WHILE the gradient all-reduce and Adam of the batch
+    handed to call k-1 run on the first (forking earlier, beside the persistent MLP kernels that need a whole SM's shared
+    memory, measured slower than no overlap).  Every call still consumes one batch and performs one full optimizer step;
+    the returned loss is the previous call's batch (one-step delay, `flush()` trains the last one)."""
 
     def __init__(self, step: TrainStep, n_rays: int, bg_color=1, perturb=True, lookahead: bool = False):
         self.step, self.model = step, step.model
@@ -587,10 +598,13 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             if self.lookahead:
                 main = torch.cuda.current_stream()
+                # train on the previous batch up to the end of the backward, then fork: the gradient exchange (NVLink) and Adam
+                # (HBM) of this batch on one branch, the march of the batch that was just loaded (latency-bound) on the other
+                self.loss, self.out = self.step.forward_backward(self.cur, self.gt_cur, self.bg_color)
                 self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):  # branch 1: march the batch that was just loaded
+                with torch.cuda.stream(self._side):
                     nxt = self.step.march(self.ro, self.rd, self.perturb)
-                self.loss, self.out = self.step.train_on(self.cur, self.gt_cur, self.bg_color)  # branch 2: train on the previous one
+                self.step.reduce_and_step()
                 main.wait_stream(self._side)
                 for k, v in nxt.items():  # hand over: 7 MB of device-to-device copies after the join
                     self.cur[k].copy_(v)

@@ -13,10 +13,18 @@ and runs `lnrf_grad_nonfinite_check` + `lnrf_adam_step` + `lnrf_amp_update` (csr
 unscale, skip-on-inf, scale growth/backoff and torch's Adam arithmetic, with no host synchronisation, so the whole
 training step stays capturable in a CUDA graph.  `state_dict()` uses torch.optim.Adam's layout so checkpoints
 interchange with the reference's optimizer.
+
+Ray-sharded training (world_size > 1): the exchange step and the optimizer are fused ZeRO-1 style.
+Instead of all-reduce(24.5 MB) followed by the full 367 MB Adam pass on every rank, the hash-table gradient is
+REDUCE-SCATTERED (mean over ranks, fp16), every rank runs Adam on its 1/N slice of the table only (fp32 master, moments and
+the slice of the fp16 shadow), and the updated fp16 shadow slices are ALL-GATHERED -- the same NVLink bytes as the
+all-reduce, but the HBM-bound optimizer pass shrinks N-fold, which more than pays for the exchange.  The two small MLP
+gradient vectors share one flat buffer and one all-reduce; the skip-on-inf decision is agreed with a one-float MAX.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -25,11 +33,13 @@ from . import _native as N
 
 class AmpAdam:
     def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, fp16=True, init_scale=2.0 ** 16,
-                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, world_size=1, rank=0, group=None):
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.fp16 = bool(fp16)
         self.growth_factor, self.backoff_factor, self.growth_interval = float(growth_factor), float(backoff_factor), int(growth_interval)
+        self.world, self.rank, self.group = int(world_size), int(rank), group
+        self.sharded = self.world > 1 and self.fp16
         # (owner module, parameter) in torch.optim order of NeRFNetwork.get_params (network_ff.py:139-153)
         self.owners = [(model.encoder, model.encoder.embeddings), (model.sigma_net, model.sigma_net.weights),
                        (model.color_net, model.color_net.weights)]
@@ -37,19 +47,86 @@ class AmpAdam:
         if dev.type != "cuda":
             raise RuntimeError("AmpAdam: the model must live on a CUDA device (there is no CPU path)")
         self.state = []
-        for owner, p in self.owners:
-            st = {"exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
-            if self.fp16:
-                owner._shadow_f16 = p.data.half()
-                owner._grad_f16 = torch.zeros_like(owner._shadow_f16)
-            else:
-                owner._shadow_f16 = owner._grad_f16 = None
-            self.state.append(st)
+        if self.sharded:
+            self._init_sharded(dev)
+        else:
+            for owner, p in self.owners:
+                st = {"exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
+                if self.fp16:
+                    owner._shadow_f16 = p.data.half()
+                    owner._grad_f16 = torch.zeros_like(owner._shadow_f16)
+                else:
+                    owner._shadow_f16 = owner._grad_f16 = None
+                self.state.append(st)
         self.step_count = torch.ones(1, dtype=torch.float32, device=dev)       # 1-based number of the NEXT update
         self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scale = torch.full((1,), float(init_scale), dtype=torch.float32, device=dev) if self.fp16 else None
         self._growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev) if self.fp16 else None
         self.lr_scale = torch.ones(1, dtype=torch.float32, device=dev)  # schedule factor (LambdaLR), read on the device
+
+    def _init_sharded(self, dev):
+        """One flat parameter vector [table | sigma-net weights | colour-net weights | pad] whose [lo, hi) slice this rank owns:
+        the fp32 master and the Adam moments exist for that slice only; the fp16 shadow and the fp16 gradient exist in full on
+        every rank and the modules' `_shadow_f16` / `_grad_f16` are views of them.  With torch symmetric memory the two flat
+        fp16 vectors are peer-mapped and the whole exchange is one kernel (lnrf_adam_step_sharded); otherwise NCCL
+        reduce-scatter / all-gather move the same bytes."""
+        sizes = [p.numel() for _, p in self.owners]
+        T = sum(sizes)
+        unit = self.world * 8  # every slice a multiple of 8 elements: 16-byte fp16 vectors
+        self.P, self.P_pad = T, (T + unit - 1) // unit * unit
+        self.Sz = self.P_pad // self.world
+        self.lo, self.hi = self.rank * self.Sz, (self.rank + 1) * self.Sz
+        flat32 = torch.zeros(self.P_pad, dtype=torch.float32, device=dev)
+        off = 0
+        for (_, p), n in zip(self.owners, sizes):
+            flat32[off:off + n] = p.data.reshape(-1)
+            off += n
+        self.p2p = None
+        if os.environ.get("LNRF_P2P", "1") == "1":
+            try:
+                self.p2p = self._init_symmetric(dev)
+            except Exception as e:  # never silently: bench.py reports which exchange path ran
+                self.p2p_error = f"{type(e).__name__}: {e}"[:300]
+                self.p2p = None
+        if self.p2p is None:
+            self.shadow_flat = torch.empty(self.P_pad, dtype=torch.half, device=dev)
+            self.grad_flat = torch.zeros(self.P_pad, dtype=torch.half, device=dev)
+            self.grad_shard = torch.zeros(self.Sz, dtype=torch.half, device=dev)
+        self.shadow_flat.copy_(flat32)
+        self.master_shard = flat32[self.lo:self.hi].clone()
+        del flat32
+        off = 0
+        for (owner, p), n in zip(self.owners, sizes):
+            owner._shadow_f16 = self.shadow_flat[off:off + n].view_as(p)
+            owner._grad_f16 = self.grad_flat[off:off + n].view_as(p)
+            off += n
+        # ONE state entry in sharded mode: the moments of this rank's slice of the flat vector
+        self.state.append({"exp_avg": torch.zeros(self.Sz, dtype=torch.float32, device=dev),
+                           "exp_avg_sq": torch.zeros(self.Sz, dtype=torch.float32, device=dev)})
+        self._sizes = sizes
+
+    def _init_symmetric(self, dev):
+        """Peer-mapped gradient / shadow / flag buffers (torch.distributed._symmetric_memory): returns the handles and the
+        per-rank device pointers the fused kernel dereferences over NVLink."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        bufs, hdls = {}, {}
+        for name, numel, dt in (("grad", self.P_pad, torch.half), ("shadow", self.P_pad, torch.half), ("flag", 32, torch.float32)):
+            t = symm.empty(numel, dtype=dt, device=dev)
+            hdls[name] = symm.rendezvous(t, group)
+            bufs[name] = t
+        self.grad_flat, self.shadow_flat, self.flag_buf = bufs["grad"], bufs["shadow"], bufs["flag"]
+        self.grad_flat.zero_()
+        self.flag_buf.zero_()
+        ptrs = {k: [int(x) for x in hdls[k].buffer_ptrs] for k in hdls}
+        if any(len(v) != self.world or not all(v) for v in ptrs.values()):
+            raise RuntimeError(f"symmetric memory rendezvous returned {ptrs}")
+        mk = lambda v: (C.c_void_p * self.world)(*v)
+        self._peer_arrays = (mk(ptrs["grad"]), mk(ptrs["shadow"]), mk(ptrs["flag"]))
+        torch.cuda.synchronize()
+        hdls["grad"].barrier(channel=0)
+        return hdls
 
     # ---- GradScaler surface -------------------------------------------------------------------------------------
     def scale(self, loss):
@@ -90,8 +167,54 @@ class AmpAdam:
             arr[i].grad_dtype = N.F16 if g.dtype == torch.float16 else N.F32
         return arr, keep
 
+    def _one(self, params, st, grad, shadow, n):
+        arr = (N.OptTensor * 1)()
+        arr[0].params, arr[0].exp_avg, arr[0].exp_avg_sq = N.ptr(params), N.ptr(st["exp_avg"]) if st else None, N.ptr(st["exp_avg_sq"]) if st else None
+        arr[0].grad, arr[0].params_f16, arr[0].n, arr[0].grad_dtype = grad.data_ptr(), N.ptr(shadow), n, N.F16
+        return arr
+
+    @torch.no_grad()
+    def _step_sharded(self):
+        """world_size > 1: exchange + Adam on this rank's slice + broadcast of the new fp16 values (see the module docstring)."""
+        import torch.distributed as dist
+        lib, st = N.lib(), N.stream()
+        hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay)
+        if self.p2p is not None:
+            # own gradient checked locally, flag published beside it; barrier; ONE kernel averages the R gradients of the slice
+            # over NVLink, updates, and writes the new fp16 slice into every rank's table; barrier; clear the local gradient
+            self.flag_buf.zero_()
+            N.check(lib.lnrf_grad_nonfinite_check(C.cast(self._one(None, None, self.grad_flat, None, self.P_pad), C.c_void_p), 1,
+                                                  N.ptr(self.flag_buf), st))
+            self.p2p["grad"].barrier(channel=0)
+            g, sh, fl = self._peer_arrays
+            N.check(lib.lnrf_adam_step_sharded(C.cast(g, C.c_void_p), C.cast(sh, C.c_void_p), C.cast(fl, C.c_void_p), self.world, self.lo,
+                                               self.Sz, N.ptr(self.master_shard), N.ptr(self.state[0]["exp_avg"]),
+                                               N.ptr(self.state[0]["exp_avg_sq"]), *hyper, N.ptr(self._scale), N.ptr(self.found_inf),
+                                               N.ptr(self.step_count), N.ptr(self.lr_scale), st))
+            self.p2p["grad"].barrier(channel=1)
+            self.grad_flat.zero_()
+        else:
+            nccl = dist.get_backend(self.group) == "nccl"
+            if nccl:  # mean inside the collective (pre-scaled sum: no fp16 overflow from adding `world` loss-scaled gradients)
+                dist.reduce_scatter_tensor(self.grad_shard, self.grad_flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:     # gloo (CPU tests of the host logic): sum, slice, divide
+                dist.all_reduce(self.grad_flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.grad_shard.copy_(self.grad_flat[self.lo:self.hi])
+                self.grad_shard.div_(self.world)
+            self.grad_flat.zero_()
+            arr = self._one(self.master_shard, self.state[0], self.grad_shard, self.shadow_flat[self.lo:self.hi], self.Sz)
+            N.check(lib.lnrf_grad_nonfinite_check(C.cast(arr, C.c_void_p), 1, N.ptr(self.found_inf), st))
+            dist.all_reduce(self.found_inf, op=dist.ReduceOp.MAX, group=self.group)  # an inf may sit in another rank's slice only
+            N.check(lib.lnrf_adam_step(C.cast(arr, C.c_void_p), 1, *hyper, N.ptr(self._scale), N.ptr(self.found_inf), N.ptr(self.step_count),
+                                       N.ptr(self.lr_scale), st))
+            dist.all_gather_into_tensor(self.shadow_flat, self.shadow_flat[self.lo:self.hi], group=self.group)
+        N.check(lib.lnrf_amp_update(N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf), N.ptr(self.step_count),
+                                    self.growth_factor, self.backoff_factor, self.growth_interval, st))
+
     @torch.no_grad()
     def step(self):
+        if self.sharded:
+            return self._step_sharded()
         lib = N.lib()
         arr, keep = self._descriptors()
         n = len(self.owners)
@@ -104,11 +227,41 @@ class AmpAdam:
                                     self.growth_factor, self.backoff_factor, self.growth_interval, st))
         del keep
 
+    def _gather_flat(self, shard):
+        import torch.distributed as dist
+        full = torch.empty(self.P_pad, dtype=shard.dtype, device=shard.device)
+        dist.all_gather_into_tensor(full, shard.contiguous(), group=self.group)
+        return full
+
+    def _split_flat(self, full):
+        out, off = [], 0
+        for (_, p), n in zip(self.owners, self._sizes):
+            out.append(full[off:off + n].view_as(p))
+            off += n
+        return out
+
+    @torch.no_grad()
+    def gather_master(self):
+        """Sharded mode (collective): bring the fp32 masters of every slice back into the modules' parameters (checkpoints)."""
+        if not self.sharded:
+            return
+        for (_, p), t in zip(self.owners, self._split_flat(self._gather_flat(self.master_shard))):
+            p.data.copy_(t)
+
     def sync_shadows(self):
-        """Re-derive the fp16 shadows after the fp32 parameters were changed from outside (load_state_dict, manual edits)."""
-        if self.fp16:
-            for owner, p in self.owners:
-                owner._shadow_f16.copy_(p.data)
+        """Re-derive the fp16 shadows (and, sharded, this rank's master slice) after the fp32 parameters were changed from
+        outside (load_state_dict, manual edits)."""
+        if not self.fp16:
+            return
+        for owner, p in self.owners:
+            owner._shadow_f16.copy_(p.data)
+        if self.sharded:
+            flat = torch.zeros(self.P_pad, dtype=torch.float32, device=self.master_shard.device)
+            off = 0
+            for (_, p), n in zip(self.owners, self._sizes):
+                flat[off:off + n] = p.data.reshape(-1)
+                off += n
+            self.master_shard.copy_(flat[self.lo:self.hi])
 
     def detach(self):
         """Give the modules back to the plain torch path (drops the shadows and persistent gradient buffers)."""
@@ -119,18 +272,31 @@ class AmpAdam:
     def state_dict(self):
         step = float(self.step_count.item()) - 1.0
         state = {i: {"step": torch.tensor(step), "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]} for i, st in enumerate(self.state)}
+        if self.sharded:  # collective: every rank must call it; the moments are gathered back into the per-parameter layout
+            ea = self._split_flat(self._gather_flat(self.state[0]["exp_avg"]))
+            es = self._split_flat(self._gather_flat(self.state[0]["exp_avg_sq"]))
+            state = {i: {"step": torch.tensor(step), "exp_avg": ea[i], "exp_avg_sq": es[i]} for i in range(len(self.owners))}
         group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
-                 "maximize": False, "params": list(range(len(self.state)))}
+                 "maximize": False, "params": list(range(len(self.owners)))}
         scaler = {"scale": self.get_scale(), "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
                   "growth_interval": self.growth_interval, "_growth_tracker": int(self._growth_tracker.item()) if self.fp16 else 0}
         return {"state": state, "param_groups": [group], "scaler": scaler}
 
     def load_state_dict(self, sd):
-        for i, st in enumerate(self.state):
-            src = sd["state"][i]
-            st["exp_avg"].copy_(src["exp_avg"])
-            st["exp_avg_sq"].copy_(src["exp_avg_sq"])
-        steps = [float(sd["state"][i]["step"]) for i in range(len(self.state))]
+        if self.sharded:
+            for k in ("exp_avg", "exp_avg_sq"):
+                flat = torch.zeros(self.P_pad, dtype=torch.float32, device=self.master_shard.device)
+                off = 0
+                for i, n in enumerate(self._sizes):
+                    flat[off:off + n] = sd["state"][i][k].reshape(-1)
+                    off += n
+                self.state[0][k].copy_(flat[self.lo:self.hi])
+        else:
+            for i, st in enumerate(self.state):
+                src = sd["state"][i]
+                st["exp_avg"].copy_(src["exp_avg"])
+                st["exp_avg_sq"].copy_(src["exp_avg_sq"])
+        steps = [float(sd["state"][i]["step"]) for i in range(len(self.owners))]
         self.step_count.fill_(steps[0] + 1.0)
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(map(float, g["betas"])), float(g["eps"]), float(g["weight_decay"])
