@@ -39,6 +39,9 @@ ALGO = {
     "lnrf_grid_encode_backward_world": dict(bound="hbm", per_ray=0, per_sample_padded=588),
     "lnrf_composite_rays_train_forward": dict(bound="hbm", per_ray=32, per_sample=24),
     "lnrf_composite_rays_train_backward": dict(bound="hbm", per_ray=44, per_sample=40),
+    # row f-5: composite + blend + depth normalisation + MSE in one launch (gt 12 + image_raw 12 + nears/fars 8 B/ray on top)
+    "lnrf_composite_loss_train_forward": dict(bound="hbm", per_ray=64, per_sample=24),
+    "lnrf_composite_loss_train_backward": dict(bound="hbm", per_ray=60, per_sample=40),
     "lnrf_ffmlp_forward": dict(bound="tensor", flops_per_sample_padded=36864 / 2),   # mean of sigma (14336) and colour (22528) nets
     "lnrf_ffmlp_backward": dict(bound="tensor", flops_per_sample_padded=73728 / 2),
     "lnrf_sh_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=12 + 64),

@@ -112,6 +112,31 @@ LNRF_API int lnrf_composite_rays_train_backward(const float* grad_weights_sum, c
                                                 uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
                                                 float* grad_rgbs, int zero_fill, lnrf_stream_t stream);
 
+/* Row f-5 of SURVEY.md section 8: the tail of the training step behind the network as one launch each way --
+ * composite_rays_train (raymarching.h:14-15) + `image + (1 - weights_sum) * bg_color` (nerf/renderer.py:326) +
+ * `clamp(depth - nears, min=0) / (fars - nears)` (:328) + the trainer's MSE `criterion(pred, gt).mean(-1).mean()`
+ * (nerf/utils.py:592,633).  The reference runs ~12 elementwise / reduction launches here and as many backward.
+ *   gt_rgb [N,3]; bg_rgb [N,3] per-pixel background or NULL -> bg_scalar; nears/fars [N] or both NULL (depth unscaled).
+ *   outputs: weights_sum, depth [N], image [N,3] (blended), image_raw [N,3] (the composite, kept for the backward),
+ *   loss [1] (deterministic: per-block partial sums added in index order by the last block).
+ *   scratch: lnrf_composite_loss_scratch_bytes(N) bytes, zero before first use (the kernel re-arms it). */
+LNRF_API size_t lnrf_composite_loss_scratch_bytes(uint32_t N);
+LNRF_API int lnrf_composite_loss_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                               const int32_t* rays, const float* gt_rgb, const float* bg_rgb,
+                                               float bg_scalar, const float* nears, const float* fars, uint32_t M,
+                                               uint32_t N, float T_thresh, float* weights_sum, float* depth,
+                                               float* image, float* image_raw, float* loss, void* scratch,
+                                               size_t scratch_bytes, lnrf_stream_t stream);
+/* grad_loss [1] on the DEVICE (dL_total/dloss: the AMP loss scale, never read by the host).  dL/dimage and
+ * dL/dweights_sum are formed inside the kernel; grad_sigmas [M] / grad_rgbs [M,3] are written completely (the
+ * zero_fill contract of lnrf_composite_rays_train_backward: needs the canonical `rays` layout). */
+LNRF_API int lnrf_composite_loss_train_backward(const float* grad_loss, const float* sigmas, const float* rgbs,
+                                                const float* deltas, const int32_t* rays, const float* gt_rgb,
+                                                const float* bg_rgb, float bg_scalar, const float* weights_sum,
+                                                const float* image, const float* image_raw, uint32_t M, uint32_t N,
+                                                float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                                lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * inference / distillation march + compositing -- replaces raymarching.cu:929-945, 1145-1159
  * --------------------------------------------------------------------------------------------------------- */

@@ -38,6 +38,9 @@ SIGNATURES = {
     "lnrf_march_rays_train": (i32, [vp, vp, vp, f32, f32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "lnrf_composite_rays_train_forward": (i32, [vp, vp, vp, vp, u32, u32, f32, vp, vp, vp, vp]),
     "lnrf_composite_rays_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, f32, vp, vp, i32, vp]),
+    "lnrf_composite_loss_scratch_bytes": (sz, [u32]),
+    "lnrf_composite_loss_train_forward": (i32, [vp, vp, vp, vp, vp, vp, f32, vp, vp, u32, u32, f32, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "lnrf_composite_loss_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, u32, u32, f32, vp, vp, vp]),
     "lnrf_march_rays": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
     "lnrf_march_rays_distill": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
     "lnrf_composite_rays": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

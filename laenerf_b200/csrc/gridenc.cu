@@ -79,6 +79,38 @@ __device__ __forceinline__ uint32_t grid_index(const Level& lv, const uint32_t* 
     return index < lv.hs ? index : index % lv.hs;
 }
 
+// The 8 corner indices of a 3-D cell (same values as 8 grid_index<3> calls).  `lv` is warp-uniform in the tile kernels, so the
+// branch is taken once per item instead of once per corner: hashed power-of-two tables need two multiplies and eight xor/and
+// (uint32 wrap-around: (y + 1) * P == y * P + P); dense levels are base + stride sums, in range whenever the far corner is.
+__device__ __forceinline__ void corner_indices3(const Level& lv, const uint32_t* pg, uint32_t* idx) {
+    if (lv.hashed && lv.mask) {
+        const uint32_t x0 = pg[0], x1 = pg[0] + 1u;
+        const uint32_t y0 = pg[1] * kPrime1, y1 = y0 + kPrime1;
+        const uint32_t z0 = pg[2] * kPrime2, z1 = z0 + kPrime2;
+        const uint32_t a00 = y0 ^ z0, a10 = y1 ^ z0, a01 = y0 ^ z1, a11 = y1 ^ z1;
+        idx[0] = (x0 ^ a00) & lv.mask; idx[1] = (x1 ^ a00) & lv.mask;
+        idx[2] = (x0 ^ a10) & lv.mask; idx[3] = (x1 ^ a10) & lv.mask;
+        idx[4] = (x0 ^ a01) & lv.mask; idx[5] = (x1 ^ a01) & lv.mask;
+        idx[6] = (x0 ^ a11) & lv.mask; idx[7] = (x1 ^ a11) & lv.mask;
+    } else if (!lv.hashed) {
+        const uint32_t b = pg[0] + pg[1] * lv.str1 + pg[2] * lv.str2;
+        idx[0] = b; idx[1] = b + 1u;
+        idx[2] = b + lv.str1; idx[3] = idx[2] + 1u;
+        idx[4] = b + lv.str2; idx[5] = idx[4] + 1u;
+        idx[6] = idx[4] + lv.str1; idx[7] = idx[6] + 1u;
+        if (idx[7] >= lv.hs) {  // only when a caller hands in a table smaller than the level (index % hashmap_size, gridencoder.cu:83)
+#pragma unroll
+            for (int c = 0; c < 8; c++) idx[c] = lv.mask ? (idx[c] & lv.mask) : (idx[c] < lv.hs ? idx[c] : idx[c] % lv.hs);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t pgl[3] = {pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1)};
+            idx[c] = grid_index<3>(lv, pgl);
+        }
+    }
+}
+
 template <typename T> struct Vec2;
 template <> struct Vec2<__half> { using type = __half2; };
 template <> struct Vec2<float> { using type = float2; };
@@ -99,6 +131,27 @@ __device__ __forceinline__ void red2(__half2* p, float2 v) {
 }
 __device__ __forceinline__ void red2(float2* p, float2 v) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+// Two table entries that share an aligned 8-byte (16-byte for fp32) slot in ONE reduction (REDG.E.ADD.F16x4): the x / x+1 corners of
+// a cell are such a pair whenever the first index is even -- always adjacent on dense levels, and on hashed levels exactly when
+// pg[0] is even (x ^ h and (x + 1) ^ h then differ in bit 0 only).  Same per-lane fp16 adds as two separate reductions.
+__device__ __forceinline__ void red4(__half2* p, float2 a, float2 b) {
+    const __half2 ha = __floats2half2_rn(a.x, a.y), hb = __floats2half2_rn(b.x, b.y);
+    asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(p), "r"(*reinterpret_cast<const uint32_t*>(&ha)),
+                 "r"(*reinterpret_cast<const uint32_t*>(&hb)) : "memory");
+}
+__device__ __forceinline__ void red4(float2* p, float2 a, float2 b) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+__device__ __forceinline__ void ld2x2(const __half2* p, float2& a, float2& b) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+}
+__device__ __forceinline__ void ld2x2(const float2* p, float2& a, float2& b) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    a = make_float2(v.x, v.y);
+    b = make_float2(v.z, v.w);
 }
 __device__ __forceinline__ void red1(__half* p, float v) { atomicAdd(p, __float2half_rn(v)); }
 __device__ __forceinline__ void red1(float* p, float v) { atomicAdd(p, v); }
@@ -129,7 +182,7 @@ __device__ __forceinline__ void cell_of(const Level& lv, const float* x, bool al
 constexpr int kTile = 128;
 constexpr int kGridThreads = 256;
 
-template <typename T, bool SMOOTH>
+template <typename T, bool SMOOTH, bool PAIR>
 __global__ void __launch_bounds__(kGridThreads)
 k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* __restrict__ emb,
                 typename Vec2<T>::type* __restrict__ outputs, uint32_t B, const uint32_t L, const float S,
@@ -177,14 +230,25 @@ k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* 
                 cell_of<3, SMOOTH>(lv, x, align_corners, pg, pos, nullptr);
                 const T2* grid = emb + lv.base;
                 uint32_t idx[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const uint32_t pgl[3] = {pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1)};
-                    idx[c] = grid_index<3>(lv, pgl);
-                }
+                corner_indices3(lv, pg, idx);
                 float2 v[8];
+                if (PAIR && (reinterpret_cast<uintptr_t>(grid) & (2 * sizeof(T2) - 1)) == 0 && !(lv.hs & 1u)) {
+                    // x / x+1 corners that share an aligned slot (see red4) come in with ONE load, without a divergent branch:
+                    // every lane loads the aligned slot of its x corner; only lanes whose x+1 corner lives elsewhere issue the
+                    // second (predicated) load.  Level sizes are even (multiples of 8 entries in grid.py:114), so the slot stays inside the level.
 #pragma unroll
-                for (int c = 0; c < 8; c++) v[c] = ld2(grid + idx[c]);
+                    for (int c = 0; c < 8; c += 2) {
+                        float2 lo, hi;
+                        ld2x2(grid + (idx[c] & ~1u), lo, hi);
+                        const bool odd = idx[c] & 1u;
+                        v[c] = odd ? hi : lo;
+                        v[c + 1] = hi;
+                        if (odd || idx[c + 1] != idx[c] + 1u) v[c + 1] = ld2(grid + idx[c + 1]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) v[c] = ld2(grid + idx[c]);
+                }
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const float w = ((c & 1) ? pos[0] : 1.0f - pos[0]) * ((c & 2) ? pos[1] : 1.0f - pos[1]) *
@@ -214,7 +278,7 @@ k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* 
 // levels (level 0 has 4920 entries for 2.3e5 samples x 8 corners) -- the reference issues every one of them.
 constexpr int kRun = 8;
 
-template <typename T, bool SMOOTH>
+template <typename T, bool SMOOTH, bool PAIR>
 __global__ void __launch_bounds__(kGridThreads)
 k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __restrict__ inputs,
                 typename Vec2<T>::type* __restrict__ grad_emb, const uint32_t B, const uint32_t L, const float S,
@@ -255,10 +319,18 @@ k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __
             uint32_t idx[8];
             float2 acc[8];
             bool open = false;
+            const bool slot_ok = PAIR && (reinterpret_cast<uintptr_t>(gg) & (2 * sizeof(T2) - 1)) == 0;
             auto flush = [&]() {
 #pragma unroll
-                for (int c = 0; c < 8; c++)
-                    if (acc[c].x != 0.f || acc[c].y != 0.f) red2(gg + idx[c], acc[c]);
+                for (int c = 0; c < 8; c += 2) {
+                    const bool nz0 = acc[c].x != 0.f || acc[c].y != 0.f, nz1 = acc[c + 1].x != 0.f || acc[c + 1].y != 0.f;
+                    if (slot_ok && !(idx[c] & 1u) && idx[c + 1] == idx[c] + 1u) {
+                        if (nz0 || nz1) red4(gg + idx[c], acc[c], acc[c + 1]);
+                    } else {
+                        if (nz0) red2(gg + idx[c], acc[c]);
+                        if (nz1) red2(gg + idx[c + 1], acc[c + 1]);
+                    }
+                }
             };
 #pragma unroll 1
             for (uint32_t j = 0; j < (uint32_t)kRun; j++) {
@@ -276,12 +348,9 @@ k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __
                     if (open) flush();
                     open = true;
                     cell[0] = pg[0]; cell[1] = pg[1]; cell[2] = pg[2];
+                    corner_indices3(lv, pg, idx);
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        const uint32_t pgl[3] = {pg[0] + (c & 1), pg[1] + ((c >> 1) & 1), pg[2] + ((c >> 2) & 1)};
-                        idx[c] = grid_index<3>(lv, pgl);
-                        acc[c] = make_float2(0.f, 0.f);
-                    }
+                    for (int c = 0; c < 8; c++) acc[c] = make_float2(0.f, 0.f);
                 }
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -501,6 +570,15 @@ using namespace lnrf;
 
 static inline cudaStream_t S_(lnrf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// x-pair merged table accesses (bit 0: forward gathers, bit 1: backward reductions); LNRF_GRID_PAIR overrides for A/B measurement
+static int pair_mode() {
+    static const int mode = [] {
+        const char* e = getenv("LNRF_GRID_PAIR");
+        return e ? atoi(e) : 3;
+    }();
+    return mode;
+}
+
 static int check_grid_args(const char* who, const int32_t* offsets_host, uint32_t D, uint32_t C, uint32_t L, uint32_t gridtype,
                            uint32_t interp, GridOffsets* off) {
     LNRF_REQUIRE(offsets_host, "%s: offsets_host is null", who);
@@ -553,12 +631,10 @@ static int grid_forward_t(const float* inputs, const T* emb, const GridOffsets& 
         const uint32_t ntiles = div_up(B, (uint32_t)kTile);  // with B_dev: B is the capacity, the kernel re-derives both
         const uint32_t grid = ntiles < (uint32_t)kNumSMs * 8u ? ntiles : (uint32_t)kNumSMs * 8u;
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
-        if (smooth)
-            k_grid_fwd_tile<T, true><<<grid, kGridThreads, smem, st>>>(inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs),
-                                                                      B, L, S, H, gridtype, ac, off, ntiles, in_bound, B_dev);
-        else
-            k_grid_fwd_tile<T, false><<<grid, kGridThreads, smem, st>>>(inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs),
-                                                                       B, L, S, H, gridtype, ac, off, ntiles, in_bound, B_dev);
+        auto kern = smooth ? (pair_mode() & 1 ? k_grid_fwd_tile<T, true, true> : k_grid_fwd_tile<T, true, false>)
+                           : (pair_mode() & 1 ? k_grid_fwd_tile<T, false, true> : k_grid_fwd_tile<T, false, false>);
+        kern<<<grid, kGridThreads, smem, st>>>(inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs), B, L, S, H, gridtype,
+                                               ac, off, ntiles, in_bound, B_dev);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);
 #define CALL_(DD, CC) launch_fwd_generic<T, DD, CC>(smooth, g, st, inputs, emb, outputs, B, L, S, H, dy_dx, gridtype, ac, off, layout)
@@ -585,12 +661,10 @@ static int grid_backward_t(const T* grad, const float* inputs, const GridOffsets
         const uint32_t ntiles = div_up(B, (uint32_t)kTile);
         const uint32_t grid = ntiles < (uint32_t)kNumSMs * 8u ? ntiles : (uint32_t)kNumSMs * 8u;
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
-        if (smooth)
-            k_grid_bwd_tile<T, true><<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb),
-                                                                      B, L, S, H, gridtype, ac, off, ntiles, in_bound);
-        else
-            k_grid_bwd_tile<T, false><<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb),
-                                                                       B, L, S, H, gridtype, ac, off, ntiles, in_bound);
+        auto kern = smooth ? (pair_mode() & 2 ? k_grid_bwd_tile<T, true, true> : k_grid_bwd_tile<T, true, false>)
+                           : (pair_mode() & 2 ? k_grid_bwd_tile<T, false, true> : k_grid_bwd_tile<T, false, false>);
+        kern<<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb), B, L, S, H, gridtype,
+                                               ac, off, ntiles, in_bound);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);
 #define CALL_(DD, CC) launch_bwd_generic<T, DD, CC>(smooth, g, st, grad, inputs, grad_emb, B, L, S, H, gridtype, ac, off, layout)

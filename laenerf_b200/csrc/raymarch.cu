@@ -397,16 +397,14 @@ k_march_train_tail(unsigned long long* __restrict__ scratch, uint32_t nblocks, f
 // training compositing (warp per ray)
 // =========================================================================================================
 
-// raymarching.cu:500-577
-__global__ void __launch_bounds__(256)
-k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
-                      const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
-                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
-                   num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+// raymarching.cu:500-577, one warp per ray: returns the (warp-reduced) sums in every lane
+struct RaySums {
+    float r, g, b, ws, d;
+};
+
+__device__ __forceinline__ RaySums composite_ray_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                     const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps,
+                                                     uint32_t M, float T_thresh, int lane) {
     float r = 0, g = 0, b = 0, ws = 0, d = 0;
     if (num_steps != 0 && offset + num_steps <= M) {
         const float* ps = sigmas + offset;
@@ -448,12 +446,102 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
         }
         r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
     }
+    return RaySums{r, g, b, ws, d};
+}
+
+__global__ void __launch_bounds__(256)
+k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh,
+                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                   num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+    const RaySums a = composite_ray_fwd(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane);
     if (lane == 0) {
-        weights_sum[index] = ws;
-        depth[index] = d;
-        image[(size_t)index * 3] = r;
-        image[(size_t)index * 3 + 1] = g;
-        image[(size_t)index * 3 + 2] = b;
+        weights_sum[index] = a.ws;
+        depth[index] = a.d;
+        image[(size_t)index * 3] = a.r;
+        image[(size_t)index * 3 + 1] = a.g;
+        image[(size_t)index * 3 + 2] = a.b;
+    }
+}
+
+// Row f-5: the tail of the training step after the network -- compositing, background blend
+// (renderer.py:326), depth normalisation (:328) and the trainer's MSE (nerf/utils.py:592 `criterion(pred, gt).mean(-1)`,
+// :633 `.mean()`) -- as ONE launch.  The reference spends ~12 elementwise / reduction launches here (and as many in the
+// backward).  The loss is reduced deterministically: per-block partials, then the last block out adds them in index order.
+struct LossArgs {
+    const float* gt;         // [N,3] target colours
+    const float* bg;         // [N,3] per-pixel background or null -> bg_scalar (bg_color = 1 in the trainer's default)
+    float bg_scalar;
+    const float* nears;      // null: depth is left unscaled
+    const float* fars;
+    float* image_raw;        // [N,3] composite before the blend, saved for the backward
+    float* partial;          // [gridDim.x]
+    unsigned int* ticket;    // zero before first use; the kernel re-arms it
+    float* loss;             // [1]
+    const float* grad_loss;  // backward only: dL_total/dloss on the device (the AMP loss scale)
+};
+
+__global__ void __launch_bounds__(256)
+k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                     const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
+                     float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    __shared__ float s_err[8];
+    __shared__ bool s_last;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float err = 0.f;
+    if (n < N) {
+        const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                       num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+        const RaySums a = composite_ray_fwd(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane);
+        if (lane == 0) {
+            const size_t i3 = (size_t)index * 3;
+            const float raw[3] = {a.r, a.g, a.b};
+            const float omw = __fadd_rn(1.0f, -a.ws);
+            float e = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float bgc = la.bg ? __ldg(la.bg + i3 + c) : la.bg_scalar;
+                const float v = __fadd_rn(raw[c], __fmul_rn(omw, bgc));  // image + (1 - weights_sum) * bg_color
+                la.image_raw[i3 + c] = raw[c];
+                image[i3 + c] = v;
+                const float df = __fadd_rn(v, -__ldg(la.gt + i3 + c));
+                e = __fadd_rn(e, __fmul_rn(df, df));
+            }
+            err = e;
+            weights_sum[index] = a.ws;
+            float dpt = a.d;
+            if (la.nears) {  // clamp(depth - nears, min=0) / (fars - nears)
+                const float nr = __ldg(la.nears + index);
+                dpt = __fdiv_rn(fmaxf(__fadd_rn(dpt, -nr), 0.0f), __fadd_rn(__ldg(la.fars + index), -nr));
+            }
+            depth[index] = dpt;
+        }
+    }
+    if (lane == 0) s_err[warp] = err;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) s += s_err[w];
+        la.partial[blockIdx.x] = s;
+        __threadfence();
+        s_last = atomicAdd(la.ticket, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (s_last && warp == 0) {
+        __threadfence();
+        float s = 0.f;
+        for (uint32_t i = lane; i < gridDim.x; i += 32) s += __ldcg(la.partial + i);
+        s = warp_sum(s);
+        if (lane == 0) {
+            la.loss[0] = s / (3.0f * (float)N);
+            *la.ticket = 0u;
+        }
     }
 }
 
@@ -462,12 +550,16 @@ __device__ __forceinline__ void warp_zero_range(float* __restrict__ p, size_t lo
 }
 
 // raymarching.cu:601-682
-template <bool ZERO_FILL>
+// LOSS (row f-5): dL/dimage and dL/dweights_sum are not read but formed here from the blended image, the targets and the
+// device-side scalar dL/dloss: g = dloss * 2 (image - gt) / (3 N), gws = -sum_c g_c bg_c; `image` is then the blended image and
+// la.image_raw the composite the C_final - C_acc term needs.
+template <bool ZERO_FILL, bool LOSS>
 __global__ void __launch_bounds__(256)
 k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
                       const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
                       const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
-                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs,
+                      const LossArgs la) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -491,10 +583,22 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
     }
     if (num_steps == 0 || !fits) return;
 
-    const float gws = grad_weights_sum[index];
-    const float gr = grad_image[(size_t)index * 3], gg = grad_image[(size_t)index * 3 + 1], gb = grad_image[(size_t)index * 3 + 2];
+    float gws, gr, gg, gb, r_final, g_final, b_final;
+    const size_t i3 = (size_t)index * 3;
+    if (LOSS) {
+        const float gsc = __ldg(la.grad_loss) * (2.0f / (3.0f * (float)N));
+        gr = gsc * (image[i3] - __ldg(la.gt + i3));
+        gg = gsc * (image[i3 + 1] - __ldg(la.gt + i3 + 1));
+        gb = gsc * (image[i3 + 2] - __ldg(la.gt + i3 + 2));
+        gws = la.bg ? -(gr * __ldg(la.bg + i3) + gg * __ldg(la.bg + i3 + 1) + gb * __ldg(la.bg + i3 + 2))
+                    : -(gr + gg + gb) * la.bg_scalar;
+        r_final = la.image_raw[i3]; g_final = la.image_raw[i3 + 1]; b_final = la.image_raw[i3 + 2];
+    } else {
+        gws = grad_weights_sum[index];
+        gr = grad_image[i3]; gg = grad_image[i3 + 1]; gb = grad_image[i3 + 2];
+        r_final = image[i3]; g_final = image[i3 + 1]; b_final = image[i3 + 2];
+    }
     const float ws_final = weights_sum[index];
-    const float r_final = image[(size_t)index * 3], g_final = image[(size_t)index * 3 + 1], b_final = image[(size_t)index * 3 + 2];
     const float* ps = sigmas + offset;
     const float* pc = rgbs + (size_t)offset * 3;
     const float2* pl = reinterpret_cast<const float2*>(deltas) + offset;
@@ -1019,12 +1123,53 @@ int lnrf_composite_rays_train_backward(const float* grad_weights_sum, const floa
     LNRF_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs), "composite_rays_train_backward: null sample buffer");
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_rays_train_backward: deltas must be 8-byte aligned");
     if (zero_fill)
-        k_composite_train_bwd<true><<<div_up(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
-                                                                          weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+        k_composite_train_bwd<true, false><<<div_up(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
+                                                                                 weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs,
+                                                                                 LossArgs{});
     else
-        k_composite_train_bwd<false><<<div_up(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
-                                                                           weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+        k_composite_train_bwd<false, false><<<div_up(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
+                                                                                  weights_sum, image, M, N, T_thresh, grad_sigmas,
+                                                                                  grad_rgbs, LossArgs{});
     LNRF_LAUNCH_CHECK("composite_rays_train_backward");
+    return LNRF_OK;
+}
+
+size_t lnrf_composite_loss_scratch_bytes(uint32_t N) { return ((size_t)div_up(N, 8u) + 4u) * sizeof(float); }
+
+int lnrf_composite_loss_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
+                                      const float* gt_rgb, const float* bg_rgb, float bg_scalar, const float* nears,
+                                      const float* fars, uint32_t M, uint32_t N, float T_thresh, float* weights_sum, float* depth,
+                                      float* image, float* image_raw, float* loss, void* scratch, size_t scratch_bytes,
+                                      lnrf_stream_t stream) {
+    LNRF_REQUIRE(N > 0, "composite_loss_train_forward: the mean over zero rays is undefined");
+    LNRF_REQUIRE(rays && gt_rgb && weights_sum && depth && image && image_raw && loss && scratch, "composite_loss_train_forward: null pointer");
+    LNRF_REQUIRE((nears == nullptr) == (fars == nullptr), "composite_loss_train_forward: nears and fars go together");
+    LNRF_REQUIRE(M == 0 || (sigmas && rgbs && deltas), "composite_loss_train_forward: null sample buffer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_loss_train_forward: deltas must be 8-byte aligned");
+    LNRF_REQUIRE(scratch_bytes >= lnrf_composite_loss_scratch_bytes(N), "composite_loss_train_forward: scratch too small");
+    LossArgs la{};
+    la.gt = gt_rgb; la.bg = bg_rgb; la.bg_scalar = bg_scalar; la.nears = nears; la.fars = fars; la.image_raw = image_raw;
+    la.ticket = reinterpret_cast<unsigned int*>(scratch);
+    la.partial = reinterpret_cast<float*>(scratch) + 4;
+    la.loss = loss;
+    k_composite_loss_fwd<<<div_up(N, 8u), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
+    LNRF_LAUNCH_CHECK("composite_loss_train_forward");
+    return LNRF_OK;
+}
+
+int lnrf_composite_loss_train_backward(const float* grad_loss, const float* sigmas, const float* rgbs, const float* deltas,
+                                       const int32_t* rays, const float* gt_rgb, const float* bg_rgb, float bg_scalar,
+                                       const float* weights_sum, const float* image, const float* image_raw, uint32_t M, uint32_t N,
+                                       float T_thresh, float* grad_sigmas, float* grad_rgbs, lnrf_stream_t stream) {
+    if (N == 0) return LNRF_OK;
+    LNRF_REQUIRE(grad_loss && rays && gt_rgb && weights_sum && image && image_raw, "composite_loss_train_backward: null pointer");
+    LNRF_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs), "composite_loss_train_backward: null sample buffer");
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_loss_train_backward: deltas must be 8-byte aligned");
+    LossArgs la{};
+    la.gt = gt_rgb; la.bg = bg_rgb; la.bg_scalar = bg_scalar; la.image_raw = const_cast<float*>(image_raw); la.grad_loss = grad_loss;
+    k_composite_train_bwd<true, true><<<div_up(N, 8u), 256, 0, S(stream)>>>(nullptr, nullptr, sigmas, rgbs, deltas, rays, weights_sum,
+                                                                            image, M, N, T_thresh, grad_sigmas, grad_rgbs, la);
+    LNRF_LAUNCH_CHECK("composite_loss_train_backward");
     return LNRF_OK;
 }
 

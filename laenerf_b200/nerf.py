@@ -365,6 +365,18 @@ class NeRFNetwork(nn.Module):
         return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum, "nears": nears,
                 "num_points": xyzs.shape[0]}
 
+    def shade_loss_train(self, marched, gt_rgb, bg_color=1, T_thresh=1e-4, prefix=None, scale_depth=True):
+        """shade_train + the trainer's MSE (nerf/utils.py:592,633) with the whole tail behind the network -- compositing,
+        background blend, depth normalisation, loss -- as one launch each way (row f-5, raymarching.composite_loss_train).
+        Returns (loss, results) with the same `results` dict as shade_train."""
+        xyzs, dirs, deltas, rays, nears, fars = (marched[k] for k in ("xyzs", "dirs", "deltas", "rays", "nears", "fars"))
+        prefix = (rays.shape[0],) if prefix is None else prefix
+        sigmas, rgbs = self.forward_scaled(xyzs, dirs)
+        loss, weights_sum, depth, image = raymarching.composite_loss_train(
+            sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears if scale_depth else None, fars if scale_depth else None, T_thresh)
+        return loss, {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum, "nears": nears,
+                      "num_points": xyzs.shape[0]}
+
     # ---- renderer.py:259-392 ---------------------------------------------------------------------------------
     def run_cuda(self, rays_o, rays_d, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False, max_steps=1024,
                  T_thresh=1e-4, scale_depth=True, edit_grid=None, **kwargs):
@@ -489,10 +501,12 @@ class TrainStep:
     """One NeRF training step as `Trainer.train_one_epoch` runs it under `-O` (nerf/utils.py:1474-1484):
     fp16 autocast forward, MSE on RGB, GradScaler backward, Adam(lr 1e-2, betas (0.9, 0.99), eps 1e-15)."""
 
-    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True, world_size: int = 1, fused_optimizer: bool = True):
+    def __init__(self, model: NeRFNetwork, lr: float = 1e-2, fp16: bool = True, world_size: int = 1, fused_optimizer: bool = True,
+                 fused_loss: bool = True):
         self.model = model
         self.fp16 = fp16
         self.world_size = world_size
+        self.fused_loss = bool(fused_loss)
         self.fused_optimizer = bool(fused_optimizer) and fp16 and model.fused and model._fused_ok
         if self.fused_optimizer:
             # row f-4: inf check + unscale + Adam + fp16 shadow rewrite + gradient clear in two launches (optim.py)
@@ -527,6 +541,13 @@ class TrainStep:
         """Network + compositing + loss + backward of one marched batch: gradients are left in the optimizer's buffers."""
         self.model.train()
         self.optimizer.zero_grad(set_to_none=True)
+        if self.fused_loss and self.fused_optimizer:
+            # row f-5: composite + blend + MSE in one launch; the AMP scale enters the backward as a device scalar, so
+            # `scale(loss).backward()` costs no launch of its own
+            with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
+                loss, out = self.model.shade_loss_train(marched, gt_rgb, bg_color)
+            torch.autograd.backward(loss, grad_tensors=self.optimizer._scale.view(()))
+            return loss, out
         with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
             out = self.model.shade_train(marched, bg_color)
             loss = torch.nn.functional.mse_loss(out["image"], gt_rgb, reduction="none").mean(-1).mean()

@@ -19,7 +19,7 @@ from . import _native as N
 __all__ = [
     "near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert", "packbits", "march_rays_train",
     "composite_rays_train", "march_rays", "march_rays_distill", "composite_rays", "composite_rays_distill",
-    "compact_alive",
+    "compact_alive", "composite_loss_train",
 ]
 
 _scratch = {}  # (device index, stream, kind) -> zero-initialised int64 scratch the kernels keep zeroed
@@ -183,6 +183,62 @@ class _composite_rays_train(Function):
 
 
 composite_rays_train = _composite_rays_train.apply
+
+
+class _composite_loss_train(Function):
+    """Row f-5 (fused tier, no reference twin): composite_rays_train + background blend + depth normalisation + the trainer's
+    MSE loss in ONE launch, and the whole backward of that tail in one more (include/laenerf_b200.h).  What it replaces:
+    renderer.py:324-329 and nerf/utils.py:592,633 -- about a dozen elementwise / reduction launches each way.
+    Returns (loss, weights_sum, depth, image); only `loss` is differentiable (w.r.t. sigmas and rgbs)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears, fars, T_thresh=1e-4):
+        sigmas, rgbs, deltas = sigmas.contiguous(), rgbs.contiguous(), deltas.contiguous()
+        M, n = sigmas.shape[0], rays.shape[0]
+        dev = sigmas.device
+        gt_rgb = _cuda(gt_rgb).contiguous().view(n, 3)
+        if torch.is_tensor(bg_color) and bg_color.numel() == 3 * n:
+            bg, bg_scalar = _cuda(bg_color).contiguous().view(n, 3), 0.0
+        elif torch.is_tensor(bg_color):
+            if bg_color.numel() != 1:
+                raise RuntimeError("composite_loss_train: bg_color must be a scalar or one colour per ray")
+            bg, bg_scalar = None, float(bg_color)
+        else:
+            bg, bg_scalar = None, float(bg_color)
+        weights_sum = torch.empty(n, dtype=torch.float32, device=dev)
+        depth = torch.empty(n, dtype=torch.float32, device=dev)
+        image = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        image_raw = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        lib = N.lib()
+        nbytes = lib.lnrf_composite_loss_scratch_bytes(n)
+        scratch = _get_scratch("composite_loss", nbytes, dev)
+        N.check(lib.lnrf_composite_loss_train_forward(N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(rays), N.ptr(gt_rgb), N.ptr(bg),
+                                                      bg_scalar, N.ptr(nears), N.ptr(fars), M, n, float(T_thresh), N.ptr(weights_sum),
+                                                      N.ptr(depth), N.ptr(image), N.ptr(image_raw), N.ptr(loss), N.ptr(scratch),
+                                                      nbytes, N.stream()))
+        ctx.save_for_backward(sigmas, rgbs, deltas, rays, gt_rgb, bg, weights_sum, image, image_raw)
+        ctx.dims = [M, n, T_thresh, bg_scalar]
+        ctx.mark_non_differentiable(weights_sum, depth, image)
+        return loss, weights_sum, depth, image
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad_loss, *_):
+        sigmas, rgbs, deltas, rays, gt_rgb, bg, weights_sum, image, image_raw = ctx.saved_tensors
+        M, n, T_thresh, bg_scalar = ctx.dims
+        grad_loss = grad_loss.to(device=sigmas.device, dtype=torch.float32).contiguous()
+        grad_sigmas = torch.empty_like(sigmas)  # the kernel writes every element (zero_fill contract)
+        grad_rgbs = torch.empty_like(rgbs)
+        N.check(N.lib().lnrf_composite_loss_train_backward(N.ptr(grad_loss), N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(rays),
+                                                           N.ptr(gt_rgb), N.ptr(bg), bg_scalar, N.ptr(weights_sum), N.ptr(image),
+                                                           N.ptr(image_raw), M, n, float(T_thresh), N.ptr(grad_sigmas),
+                                                           N.ptr(grad_rgbs), N.stream()))
+        return grad_sigmas, grad_rgbs, None, None, None, None, None, None, None
+
+
+composite_loss_train = _composite_loss_train.apply
 
 
 def _march_infer(distill, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, density_bitfield, edit_bitfield, C, H,

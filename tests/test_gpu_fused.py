@@ -416,3 +416,77 @@ def test_lookahead_graph_trains_the_same_sequence(dev):
     seq, pipe = runs
     assert len(seq) == len(pipe) == 6 and all(np.isfinite(seq)) and all(np.isfinite(pipe))
     assert np.allclose(seq, pipe, rtol=2e-2), (seq, pipe)
+
+
+@pytest.mark.parametrize("bg_kind,scale_depth", [("scalar", True), ("per_ray", True), ("scalar", False)])
+def test_composite_loss_tail_matches_module_tier_and_torch_autograd(dev, bg_kind, scale_depth):
+    """Row f-5: composite + blend + depth normalisation + MSE in one launch each way against composite_rays_train followed by
+    the torch expressions of renderer.py:324-329 / nerf/utils.py:592,633 and torch autograd (fp32; differences are summation
+    order only)."""
+    from laenerf_b200 import raymarching
+    from laenerf_b200.nerf import NeRFNetwork
+    sc = scene("lego")
+    m = NeRFNetwork(bound=sc.bound, min_near=sc.min_near).to(dev)
+    m.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+    m.train()
+    n = 1500  # ragged: not a multiple of the 8 rays a block composites
+    _, ro, rd, _ = scene_rays("lego", n, 23)
+    torch.manual_seed(5)
+    mr = m.march_train(torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev), perturb=True)
+    M = mr["xyzs"].shape[0]
+    g = torch.Generator(device=dev).manual_seed(3)
+    sig0 = torch.rand(M, device=dev, generator=g) * 40.0  # large enough that some rays hit the T_thresh early-out
+    rgb0 = torch.rand(M, 3, device=dev, generator=g)
+    gt = torch.rand(n, 3, device=dev, generator=g)
+    bg = torch.rand(n, 3, device=dev, generator=g) if bg_kind == "per_ray" else 1
+    scale = torch.tensor(1024.0, device=dev)
+
+    sa, ra = sig0.clone().requires_grad_(True), rgb0.clone().requires_grad_(True)
+    ws, depth, image = raymarching.composite_rays_train(sa, ra, mr["deltas"], mr["rays"], 1e-4)
+    image = image + (1 - ws).unsqueeze(-1) * bg
+    if scale_depth:
+        depth = torch.clamp(depth - mr["nears"], min=0) / (mr["fars"] - mr["nears"])
+    loss_a = torch.nn.functional.mse_loss(image, gt, reduction="none").mean(-1).mean()
+    (loss_a * scale).backward()
+
+    sb, rb = sig0.clone().requires_grad_(True), rgb0.clone().requires_grad_(True)
+    loss_b, ws_b, depth_b, image_b = raymarching.composite_loss_train(sb, rb, mr["deltas"], mr["rays"], gt, bg,
+                                                                      mr["nears"] if scale_depth else None,
+                                                                      mr["fars"] if scale_depth else None, 1e-4)
+    torch.autograd.backward(loss_b, grad_tensors=scale)
+    torch.cuda.synchronize()
+    assert torch.equal(ws, ws_b)  # same kernel body
+    assert float((image - image_b).abs().max()) <= 1e-6 and float((depth - depth_b).abs().max()) <= 1e-6
+    assert abs(float(loss_a) - float(loss_b)) <= 2e-6 * abs(float(loss_a))
+    for x, y in ((sa.grad, sb.grad), (ra.grad, rb.grad)):
+        tol = 1e-5 * float(x.abs().max())
+        assert float((x - y).abs().max()) <= tol, (float((x - y).abs().max()), tol)
+    assert float(sb.grad.abs().max()) > 0 and not ws_b.requires_grad and not image_b.requires_grad
+    # deterministic: a second launch reproduces the loss bit for bit (fixed-order reduction, re-armed ticket)
+    loss_c = raymarching.composite_loss_train(sb.detach(), rb.detach(), mr["deltas"], mr["rays"], gt, bg, None, None, 1e-4)[0]
+    loss_d = raymarching.composite_loss_train(sb.detach(), rb.detach(), mr["deltas"], mr["rays"], gt, bg, None, None, 1e-4)[0]
+    assert float(loss_c) == float(loss_d) == float(loss_b)
+
+
+def test_train_step_fused_loss_equals_unfused_loss_path(dev):
+    """TrainStep(fused_loss=True) and (fused_loss=False) from the same state: same sample counts, losses equal to fp32
+    summation order on the first step and close afterwards (hash-grid atomics reorder fp16 additions)."""
+    from laenerf_b200.nerf import TrainStep
+    a, b = _model(dev, True, 41), _model(dev, True, 41)
+    b.load_state_dict(a.state_dict())
+    sa, sb = TrainStep(a, fused_loss=True), TrainStep(b, fused_loss=False)
+    _, ro, rd, _ = scene_rays("lego", 2048, 29)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    gt = torch.rand(2048, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(4))
+    la, lb = [], []
+    for it in range(5):
+        torch.manual_seed(300 + it)
+        l, oa = sa(ro, rd, gt)
+        la.append(float(l))
+        torch.manual_seed(300 + it)
+        l, ob = sb(ro, rd, gt)
+        lb.append(float(l))
+        assert oa["num_points"] == ob["num_points"]
+    assert abs(la[0] - lb[0]) <= 1e-5 * abs(lb[0]), (la, lb)
+    assert np.allclose(la, lb, rtol=1e-2), (la, lb)
+    assert la[-1] < la[0]
