@@ -572,11 +572,8 @@ static inline cudaStream_t S_(lnrf_stream_t s) { return reinterpret_cast<cudaStr
 
 // x-pair merged table accesses (bit 0: forward gathers, bit 1: backward reductions); LNRF_GRID_PAIR overrides for A/B measurement
 static int pair_mode() {
-    static const int mode = [] {
-        const char* e = getenv("LNRF_GRID_PAIR");
-        return e ? atoi(e) : 3;
-    }();
-    return mode;
+    const char* e = getenv("LNRF_GRID_PAIR");  // read per call: tests flip it inside one process
+    return e ? atoi(e) : 3;
 }
 
 static int check_grid_args(const char* who, const int32_t* offsets_host, uint32_t D, uint32_t C, uint32_t L, uint32_t gridtype,

@@ -80,6 +80,7 @@ struct MarchParams {
     uint32_t max_steps;
     int dt_const;  // dt_gamma == 0 (every shipped LAENeRF config): dt is the same for every t ...
     float dt0;     // ... namely clamp(0, dt_min, dt_max) (== dt_min unless max_steps is so small that dt_min > dt_max)
+    int jump;      // closed-form windows are resolved with the jump table (march_jump + pointer doubling) instead of the serial loop
 };
 
 LNRF_HD MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H) {
@@ -99,6 +100,7 @@ LNRF_HD MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_
     p.max_steps = max_steps;
     p.dt_const = (dt_gamma == 0.0f) ? 1 : 0;
     p.dt0 = f_clamp(0.0f, p.dt_min, p.dt_max);
+    p.jump = p.dt_const;
     return p;
 }
 
@@ -164,8 +166,18 @@ LNRF_HD Probe march_probe(const MarchParams& p, const Ray& r, float t, float dt)
 // sum stays inside the binade.  Then s_k = t + k*q*u EXACTLY, which each lane evaluates with one fma.  Anything
 // else (binade crossing, ties, tiny or non-positive t) takes the sequential path, which is the definition.
 // ---------------------------------------------------------------------------------------------------------
+// What a closed-form window knows about itself: every member is (mt + k*qi) * u inside binade `e` (u = ulp of the binade).
+struct WindowInfo {
+    int closed;      // 0: the sequential path produced this window (march_jump is not applicable)
+    uint32_t e;      // biased exponent of every member
+    uint32_t mt;     // mantissa field of the first member
+    uint32_t qi;     // step in ulps (1 <= qi <= 2^18)
+    float rq;        // ~ 1 / qi
+};
+
 template <int G>
-LNRF_HD float march_window(const MarchParams& p, float t, int lane, float* next) {
+LNRF_HD float march_window(const MarchParams& p, float t, int lane, float* next, WindowInfo* wi = nullptr) {
+    if (wi) wi->closed = 0;
     if (p.dt_const) {
         const float dt = p.dt0;
         const uint32_t bt = f2u(t);
@@ -178,6 +190,13 @@ LNRF_HD float march_window(const MarchParams& p, float t, int lane, float* next)
                 const float end = f_fma(f_mul((float)G, q), u, t);
                 if ((f2u(end) >> 23) == e) {
                     *next = end;
+                    if (wi) {
+                        wi->closed = 1;
+                        wi->e = e;
+                        wi->mt = bt & 0x7fffffu;
+                        wi->qi = (uint32_t)q;
+                        wi->rq = f_div(1.0f, q);
+                    }
                     return f_fma(f_mul((float)lane, q), u, t);
                 }
             }
@@ -200,6 +219,29 @@ LNRF_HD float march_window(const MarchParams& p, float t, int lane, float* next)
         *next = s;
         return mine;
     }
+}
+
+// Successor of member v of a closed-form window whose cell is empty: the reference runs `do { t += dt; } while (t < tt)`
+// (raymarching.cu:396-398), i.e. it visits the first member j > v with s_j >= tt.  All members are (mt + j*qi) ulps of one
+// binade, so the comparison is integer arithmetic on the mantissa fields: j = ceil((mtt - mt) / qi).  Returns G when no member
+// of this window qualifies (tt in a later binade, or past the last member).  The float quotient is only a first guess; the
+// result is fixed up with exact integer products, so host and device agree whatever the rounding of rq.
+LNRF_HD int march_jump(const WindowInfo& w, int v, float tt, int G) {
+    const uint32_t btt = f2u(tt);
+    const uint32_t et = btt >> 23;  // tt >= s_v > 0: sign bit clear
+    if (et > w.e) return G;
+    if (et < w.e) return v + 1;     // not reachable for tt >= s_v; keeps the function total
+    const uint32_t mtt = btt & 0x7fffffu;
+    if (mtt <= w.mt) return v + 1;
+    const uint32_t a = mtt - w.mt;
+    const float f = f_mul((float)a, w.rq);
+    if (f > 40.0f) return G;
+    uint32_t j = (uint32_t)f;
+    if (j * w.qi < a) j++;
+    if (j * w.qi < a) j++;
+    if (j > 0u && (j - 1u) * w.qi >= a) j--;
+    const int ji = (int)j;
+    return ji <= v ? v + 1 : (ji < G ? ji : G);
 }
 
 }  // namespace lnrf

@@ -69,6 +69,116 @@ static uint32_t emulate_group(const MarchParams& p, const Ray& r, const uint8_t*
     return cnt;
 }
 
+// The jump-table resolve of raymarch.cu (march_group, closed-form windows): every lane computes its successor with
+// march_jump, the orbit of the first visited lane is found by pointer doubling (log2 G rounds of "shuffles"), and far / sample
+// budget / pending-skip bookkeeping is applied to the resulting masks.  Windows that are not closed-form take the serial
+// resolve above.  Emulated lane by lane with exactly the device's data flow.
+template <int G>
+static uint32_t emulate_group_jump(const MarchParams& p, const Ray& r, const uint8_t* grid, float t, float far, uint32_t max_emit,
+                                   float* tl, uint64_t* jump_windows) {
+    uint32_t cnt = 0;
+    float pend = -INFINITY;
+    bool alive = true;
+    constexpr int LOG = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
+    while (alive) {
+        float s[G], nxt = 0.f;
+        Probe q[G];
+        bool valid[G], occ[G];
+        WindowInfo wi;
+        for (int l = 0; l < G; l++) {
+            s[l] = march_window<G>(p, t, l, &nxt, &wi);
+            const float dt = p.dt_const ? p.dt0 : march_dt(p, s[l]);
+            valid[l] = s[l] < far;
+            occ[l] = false;
+            q[l].tt = 0.f;
+            if (valid[l]) {
+                q[l] = march_probe(p, r, s[l], dt);
+                occ[l] = (grid[q[l].index >> 3] >> (q[l].index & 7u)) & 1u;
+            }
+        }
+        int v0 = G;
+        for (int l = 0; l < G; l++)
+            if (s[l] >= pend) { v0 = l; break; }
+        uint32_t vis = 0;
+        if (wi.closed) {
+            if (jump_windows) (*jump_windows)++;
+            uint32_t occm = 0, valm = 0;
+            int nx[G];
+            uint32_t orb[G];
+            for (int l = 0; l < G; l++) {
+                occm |= (uint32_t)occ[l] << l;
+                valm |= (uint32_t)valid[l] << l;
+                nx[l] = !valid[l] ? G : (occ[l] ? l + 1 : march_jump(wi, l, q[l].tt, G));
+                orb[l] = 1u << l;
+            }
+            for (int rd = 0; rd < LOG; rd++) {
+                int n2[G];
+                uint32_t o2[G];
+                for (int l = 0; l < G; l++) {
+                    const int src = nx[l] < G ? nx[l] : G - 1;
+                    n2[l] = nx[src];
+                    o2[l] = orb[src];
+                }
+                for (int l = 0; l < G; l++)
+                    if (nx[l] < G) { orb[l] |= o2[l]; nx[l] = n2[l]; }
+            }
+            if (v0 < G) {
+                pend = -INFINITY;
+                const uint32_t visited = orb[v0];
+                const uint32_t inval = visited & ~valm, visv = visited & valm;
+                uint32_t emitm = visv & occm;
+                const uint32_t room = max_emit - cnt;
+                uint32_t ne = 0;
+                for (int l = 0; l < G; l++) ne += (emitm >> l) & 1u;
+                if (emitm != 0u && ne >= room) {
+                    uint32_t keep = 0, k = 0;
+                    for (int l = 0; l < G; l++)
+                        if ((emitm >> l) & 1u) { if (k < room) keep |= 1u << l; k++; }
+                    emitm = keep;
+                    alive = false;
+                } else if (inval) {
+                    alive = false;
+                } else {
+                    int last = 0;
+                    for (int l = 0; l < G; l++)
+                        if ((visv >> l) & 1u) last = l;
+                    if (!((occm >> last) & 1u)) pend = q[last].tt;
+                }
+                vis = emitm;
+            }
+        } else {
+            int v = v0;
+            if (v < G) pend = -INFINITY;
+            bool res = v < G;
+            uint32_t nvis = 0;
+            while (res) {
+                if (!valid[v]) { alive = false; res = false; }
+                else if (occ[v]) {
+                    int run = 0;
+                    while (v + run < G && occ[v + run]) run++;
+                    const int room = (int)(max_emit - cnt) - (int)nvis;
+                    if (run >= room) { run = room; alive = false; res = false; }
+                    for (int k = 0; k < run; k++) vis |= 1u << (v + k);
+                    nvis += run;
+                    v += run;
+                    if (v >= G) res = false;
+                } else {
+                    const float tt = q[v].tt;
+                    int j = G;
+                    for (int l = v + 1; l < G; l++)
+                        if (s[l] >= tt) { j = l; break; }
+                    if (j < G) v = j;
+                    else { pend = tt; v = G; res = false; }
+                }
+            }
+        }
+        for (int l = 0; l < G; l++)
+            if ((vis >> l) & 1u) tl[cnt++] = s[l];
+        t = nxt;
+    }
+    return cnt;
+}
+
 extern "C" {
 
 // returns the number of mismatching members over `windows` consecutive windows starting at t
@@ -92,7 +202,12 @@ uint64_t mch_check_window(float t, float dt_gamma, uint32_t max_steps, uint32_t 
     return bad;
 }
 
-// Emulated group march of N rays; counts[n] and, concatenated in ray order, the visited t values (ts, capacity cap).
+static uint64_t g_jump_windows = 0;
+uint64_t mch_jump_windows() { return g_jump_windows; }  // how many windows the jump-table resolve handled so far
+static uint32_t g_max_emit = 0;
+void mch_set_max_emit(uint32_t m) { g_max_emit = m; }   // 0: max_steps (training); else the per-call sample budget (inference rounds)
+
+// Emulated group march of N rays (G > 0: serial resolve, G < 0: jump-table resolve with |G| lanes); counts[n] and, concatenated in ray order, the visited t values (ts, capacity cap).
 // Returns the total number of samples.
 uint64_t mch_group_march(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars,
@@ -100,12 +215,17 @@ uint64_t mch_group_march(const float* rays_o, const float* rays_d, const uint8_t
     const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
     std::vector<float> tl(max_steps);
     uint64_t total = 0;
+    const uint32_t max_emit = g_max_emit ? g_max_emit : max_steps;
     for (uint32_t n = 0; n < N; n++) {
         const Ray r = make_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
         const float near = nears[n];
         const float t0 = f_fma(f_clamp(f_mul(near, p.dt_gamma), p.dt_min, p.dt_max), noises[n], near);
-        const uint32_t c = (G == 32) ? emulate_group<32>(p, r, grid, t0, fars[n], max_steps, tl.data())
-                                     : emulate_group<8>(p, r, grid, t0, fars[n], max_steps, tl.data());
+        uint32_t c;
+        if (G == 32) c = emulate_group<32>(p, r, grid, t0, fars[n], max_emit, tl.data());
+        else if (G == 8) c = emulate_group<8>(p, r, grid, t0, fars[n], max_emit, tl.data());
+        else if (G == -32) c = emulate_group_jump<32>(p, r, grid, t0, fars[n], max_emit, tl.data(), &g_jump_windows);
+        else if (G == -8) c = emulate_group_jump<8>(p, r, grid, t0, fars[n], max_emit, tl.data(), &g_jump_windows);
+        else c = emulate_group_jump<4>(p, r, grid, t0, fars[n], max_emit, tl.data(), &g_jump_windows);
         counts[n] = c;
         for (uint32_t k = 0; k < c && total + k < cap; k++) ts[total + k] = tl[k];
         total += c;

@@ -15,6 +15,16 @@
 
 extern "C" {
 static int check_march_common(uint32_t C, uint32_t H, uint32_t max_steps, const char* who);
+
+}
+
+// LNRF_MARCH_JUMP=0 keeps the serial window resolve (A/B measurement; results are identical either way)
+static lnrf::MarchParams march_params_env(float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H) {
+    const char* e = getenv("LNRF_MARCH_JUMP");  // read per call: tests flip it inside one process
+    const int jump = e ? atoi(e) : 1;
+    lnrf::MarchParams p = lnrf::make_march_params(bound, dt_gamma, max_steps, C, H);
+    if (!jump) p.jump = 0;
+    return p;
 }
 
 namespace lnrf {
@@ -129,6 +139,9 @@ struct Group {
     static constexpr unsigned kMask = (G == 32) ? 0xffffffffu : ((1u << (G & 31)) - 1u);
     __device__ __forceinline__ unsigned ballot(bool pred) const { return (__ballot_sync(kFull, pred) >> gshift) & kMask; }
     __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(kFull, v, gshift + src); }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(kFull, v, gshift + src); }
+    __device__ __forceinline__ unsigned shfl(unsigned v, int src) const { return __shfl_sync(kFull, v, gshift + src); }
+    static constexpr int kLog = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : (G == 4) ? 2 : 1;
 };
 
 __device__ __forceinline__ unsigned low_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
@@ -146,7 +159,8 @@ __device__ __forceinline__ uint32_t march_group(const Group<G>& grp, const March
     float last_after = t;
     while (__any_sync(kFull, alive)) {
         float nxt;
-        const float s = march_window<G>(p, t, grp.gl, &nxt);
+        WindowInfo wi;
+        const float s = march_window<G>(p, t, grp.gl, &nxt, &wi);
         const float dt = p.dt_const ? p.dt0 : march_dt(p, s);
         const bool valid = alive && (s < far);
         Probe q;
@@ -160,36 +174,72 @@ __device__ __forceinline__ uint32_t march_group(const Group<G>& grp, const March
         const unsigned reach = grp.ballot(s >= pend);
         unsigned vis = 0;
         int v = reach ? (__ffs(reach) - 1) : G;
-        if (v < G) pend = -INFINITY;
-        bool res = alive && (v < G);
-        while (__any_sync(kFull, res)) {
-            const int vv = v < G ? v : (G - 1);
-            const float tt = grp.shfl(q.tt, vv);
-            const unsigned ge = grp.ballot(s >= tt);
-            if (res) {
-                if (!((valm >> v) & 1u)) {  // t >= far at a visited member: the ray is finished
+        if (p.jump && __all_sync(kFull, !alive || wi.closed)) {
+            // ---- jump-table resolve (every group of the warp holds a closed-form window; tests/test_march_core.py checks this
+            // data flow lane by lane against the sequential marcher).  Successor of a lane: the next lane when its cell is
+            // occupied (t += dt), the first member >= the voxel exit when it is empty, nothing when t >= far (the ray ends
+            // there).  Pointer doubling then gives every lane its whole orbit in log2(G) shuffle rounds; the orbit of the first
+            // visited lane is what the reference visits.  No data-dependent loop, no divergence.
+            int nx = !valid ? G : (occ ? grp.gl + 1 : march_jump(wi, grp.gl, q.tt, G));
+            unsigned orb = 1u << grp.gl;
+#pragma unroll
+            for (int rd = 0; rd < Group<G>::kLog; rd++) {
+                const int src = nx < G ? nx : G - 1;
+                const int n2 = grp.shfl(nx, src);
+                const unsigned o2 = grp.shfl(orb, src);
+                if (nx < G) { orb |= o2; nx = n2; }
+            }
+            const unsigned visited = grp.shfl(orb, v < G ? v : 0);
+            const unsigned inval = visited & ~valm, visv = visited & valm;
+            const unsigned emitm = visv & occm;
+            const uint32_t room = max_emit - cnt;
+            const int last = visv ? (31 - __clz(visv)) : 0;
+            const float tt_last = grp.shfl(q.tt, last);
+            // the first `room` samples when the budget ends the ray inside this window (num_steps < max_steps, raymarching.cu:359)
+            const unsigned keep = grp.ballot(((emitm >> grp.gl) & 1u) && (uint32_t)__popc(emitm & low_bits(grp.gl)) < room);
+            if (alive && v < G) {
+                pend = -INFINITY;
+                if (emitm != 0u && (uint32_t)__popc(emitm) >= room) {
+                    vis = keep;
                     alive = false;
-                    res = false;
-                } else if ((occm >> v) & 1u) {  // occupied: every following occupied lane is visited too (t += dt)
-                    const unsigned rest = (~occm & Group<G>::kMask) >> v;
-                    int run = rest ? (__ffs(rest) - 1) : (G - v);
-                    const int room = (int)(max_emit - cnt) - __popc(vis);
-                    if (run >= room) {  // reached the sample budget (num_steps < max_steps, raymarching.cu:359)
-                        run = room;
+                } else {
+                    vis = emitm;
+                    if (inval) alive = false;                              // a visited member has t >= far
+                    else if (!((occm >> last) & 1u)) pend = tt_last;       // the last skip runs past this window
+                }
+            }
+        } else {
+            if (v < G) pend = -INFINITY;
+            bool res = alive && (v < G);
+            while (__any_sync(kFull, res)) {
+                const int vv = v < G ? v : (G - 1);
+                const float tt = grp.shfl(q.tt, vv);
+                const unsigned ge = grp.ballot(s >= tt);
+                if (res) {
+                    if (!((valm >> v) & 1u)) {  // t >= far at a visited member: the ray is finished
                         alive = false;
                         res = false;
-                    }
-                    vis |= low_bits(run) << v;
-                    v += run;
-                    if (v >= G) res = false;
-                } else {  // empty: do { t += dt } while (t < tt)  ==> first later member with s >= tt
-                    const unsigned m = ge & ~low_bits(v + 1) & Group<G>::kMask;
-                    if (m) {
-                        v = __ffs(m) - 1;
-                    } else {
-                        pend = tt;
-                        v = G;
-                        res = false;
+                    } else if ((occm >> v) & 1u) {  // occupied: every following occupied lane is visited too (t += dt)
+                        const unsigned rest = (~occm & Group<G>::kMask) >> v;
+                        int run = rest ? (__ffs(rest) - 1) : (G - v);
+                        const int room = (int)(max_emit - cnt) - __popc(vis);
+                        if (run >= room) {  // reached the sample budget (num_steps < max_steps, raymarching.cu:359)
+                            run = room;
+                            alive = false;
+                            res = false;
+                        }
+                        vis |= low_bits(run) << v;
+                        v += run;
+                        if (v >= G) res = false;
+                    } else {  // empty: do { t += dt } while (t < tt)  ==> first later member with s >= tt
+                        const unsigned m = ge & ~low_bits(v + 1) & Group<G>::kMask;
+                        if (m) {
+                            v = __ffs(m) - 1;
+                        } else {
+                            pend = tt;
+                            v = G;
+                            res = false;
+                        }
                     }
                 }
             }
@@ -938,7 +988,7 @@ int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap
     if (int e = check_march_common(C, H, max_steps, who)) return e;
     if (n_rays_cap == 0) return LNRF_OK;
     LNRF_REQUIRE(ctl && rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && dirs && deltas, "%s: null pointer", who);
-    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    const MarchParams p = march_params_env(bound, dt_gamma, max_steps, C, H);
     // the grid covers the ray capacity (a round has at most n_rays_cap + 128 groups); blocks past the round's groups read the
     // control block and leave (cheaper than a grid-stride loop over a persistent grid: 97 vs 115 us per steady-state round)
     const uint32_t cap_blocks = 0xffffffffu;
@@ -1073,7 +1123,7 @@ int lnrf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
         set_error("march_rays_train: scratch too small (%zu < %zu)", scratch_bytes, lnrf_march_rays_train_scratch_bytes(N));
         return LNRF_ERR_SCRATCH_TOO_SMALL;
     }
-    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    const MarchParams p = march_params_env(bound, dt_gamma, max_steps, C, H);
     unsigned long long* sc = reinterpret_cast<unsigned long long*>(scratch);
     uint32_t nblocks;
     if ((size_t)max_steps * 4 * sizeof(float) <= 96 * 1024) {
@@ -1186,7 +1236,7 @@ static int march_infer_launch(bool distill, uint32_t n_alive, uint32_t n_step, c
     LNRF_REQUIRE(xyzs && dirs && deltas && (!distill || (edit_occ && edit_grid)), "%s: null output", who);
     LNRF_REQUIRE(n_alive == 0 || (rays_alive && rays_t && rays_o && rays_d && grid && fars && noises), "%s: null input", who);
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "%s: deltas must be 8-byte aligned", who);
-    const MarchParams p = make_march_params(bound, dt_gamma, max_steps, C, H);
+    const MarchParams p = march_params_env(bound, dt_gamma, max_steps, C, H);
     const uint32_t n_groups = div_up(M_rows, n_step);
 #define LNRF_MARCH_INFER_(DD, GG)                                                                                                        \
     k_march_infer<DD, GG><<<div_up(n_groups, 256u / GG), 256, 0, st>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, p, grid,   \

@@ -130,3 +130,74 @@ def test_ffmlp_inference_equals_training_forward(ours_backend):
             assert np.allclose(fb[l], h, rtol=4e-3, atol=4e-3)
         y = h @ w[off:].reshape(16, 64).T
         assert np.allclose(out, y, rtol=1e-2, atol=1e-2)
+
+
+class _env:
+    def __init__(self, key, value):
+        self.key, self.value = key, str(value)
+
+    def __enter__(self):
+        import os
+        self.old = os.environ.get(self.key)
+        os.environ[self.key] = self.value
+
+    def __exit__(self, *a):
+        import os
+        if self.old is None:
+            os.environ.pop(self.key, None)
+        else:
+            os.environ[self.key] = self.old
+
+
+@pytest.mark.parametrize("name", ["march_lego", "march_flower", "march_bonsai", "infer_lego", "distill_flower"])
+def test_jump_table_resolve_is_bit_identical_to_the_serial_resolve(name, ours_backend):
+    """LNRF_MARCH_JUMP=0 (serial ballot loop per window) and the default jump-table resolve (march_jump + pointer doubling)
+    must produce the same bits for every marcher (training 32 lanes, inference / distill 4 and 8 lanes)."""
+    if name not in CASES:
+        pytest.skip(f"no case {name}")
+    with _env("LNRF_MARCH_JUMP", 0):
+        a = run_case(name, ours_backend)
+    with _env("LNRF_MARCH_JUMP", 1):
+        b = run_case(name, ours_backend)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def test_march_budget_and_far_edges_serial_vs_jump(ours_backend, oracle_backend):
+    """Rays that end on the sample budget inside a window (tiny max_steps) and at `far`, against the sequential oracle, with the
+    jump-table resolve on and off."""
+    sc, ro, rd, rng = scene_rays("lego", 700, 37)
+    nears, fars = oracle_backend.near_far(ro, rd, sc.aabb, sc.min_near)
+    noises = rng.random(700, dtype=np.float32)
+    full = np.full_like(sc.density_bitfield, 255)
+    for grid in (sc.density_bitfield, full):
+        for max_steps in (7, 48, 333, 1024):
+            want = oracle_backend.march_train(ro, rd, grid, sc.bound, 0.0, max_steps, 1, 128, 700 * max_steps, nears, fars, noises)
+            for jump in (0, 1):
+                with _env("LNRF_MARCH_JUMP", jump):
+                    got = ours_backend.march_train(ro, rd, grid, sc.bound, 0.0, max_steps, 1, 128, 700 * max_steps, nears, fars, noises)
+                for a, b, nm in zip(got, want, ("xyzs", "dirs", "deltas", "rays", "counter")):
+                    assert np.array_equal(a, b), (nm, max_steps, jump)
+
+
+def test_paired_table_access_equals_unpaired(ours_backend):
+    """LNRF_GRID_PAIR: x / x+1 corners in one 8-byte gather / one REDG.F16x4 (default) against one access per corner.  The
+    forward is the same arithmetic on the same values (bit-equal); the backward differs by the order of fp16 atomic adds only."""
+    from cases import grid_config
+    rng = np.random.default_rng(38)
+    offsets, pls = grid_config(16, 2, 3, 16, 19, 2048)
+    x = rng.random((4096 + 77, 3), dtype=np.float32)
+    x[:1000] = np.linspace(0.2, 0.6, 1000, dtype=np.float32)[:, None] * np.array([1.0, 0.7, 0.3], np.float32) + 0.1  # ray-like runs
+    emb = rng.uniform(-1, 1, size=(int(offsets[-1]), 2)).astype(np.float16).astype(np.float32)
+    g = (rng.standard_normal((x.shape[0], 32)) * 0.05).astype(np.float16).astype(np.float32)
+    for half in (True, False):
+        with _env("LNRF_GRID_PAIR", 0):
+            f0 = ours_backend.grid_fwd(x, emb, offsets, pls, 16, half=half)
+            b0 = ours_backend.grid_bwd(g, x, offsets, 2, pls, 16, half=half)
+        with _env("LNRF_GRID_PAIR", 3):
+            f1 = ours_backend.grid_fwd(x, emb, offsets, pls, 16, half=half)
+            b1 = ours_backend.grid_bwd(g, x, offsets, 2, pls, 16, half=half)
+        assert np.array_equal(f0, f1), half
+        assert np.abs(b0).max() > 0
+        assert np.allclose(b0, b1, rtol=2e-2, atol=2e-3) if half else np.allclose(b0, b1, rtol=1e-4, atol=1e-5), half

@@ -60,3 +60,38 @@ def test_group_resolve_equals_sequential_march(host, oracle_backend, name, n, dt
     ray_of = np.repeat(np.arange(n), counts)
     x = np.clip((ro[ray_of].astype(np.float64) + t[:, None].astype(np.float64) * rd[ray_of].astype(np.float64)), -sc.bound, sc.bound)
     assert np.allclose(x, xyzs[:total], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,n,dt_gamma,max_steps", [("lego", 384, 0.0, None), ("flower", 192, 0.0, None), ("bonsai", 192, 0.0, None),
+                                                        ("flower", 96, 1.0 / 128, None), ("lego", 256, 0.0, 48), ("lego", 256, 0.0, 7),
+                                                        ("bonsai", 128, 0.0, 12)])
+@pytest.mark.parametrize("G", [4, 8, 32])
+def test_jump_table_resolve_equals_sequential_march(host, oracle_backend, name, n, dt_gamma, max_steps, G):
+    """The pointer-doubling resolve of closed-form windows (march_jump + orbit doubling, raymarch.cu march_group) against the
+    sequential oracle: identical counts and visited t values, including rays that end on the sample budget (small max_steps)
+    and at `far`; windows that are not closed-form (binade crossings, dt_gamma > 0) take the serial resolve."""
+    host.mch_jump_windows.restype = C.c_uint64
+    sc, ro, rd, rng = scene_rays(name, n, 33)
+    ms = sc.max_steps if max_steps is None else max_steps
+    nears, fars = oracle_backend.near_far(ro, rd, sc.aabb, sc.min_near)
+    noises = rng.random(n, dtype=np.float32)
+    M = n * ms
+    xyzs, dirs, deltas, rays, counter = oracle_backend.march_train(ro, rd, sc.density_bitfield, sc.bound, dt_gamma, ms, sc.cascade, 128,
+                                                                   M, nears, fars, noises)
+    counts = np.zeros(n, np.uint32)
+    ts = np.zeros(int(counter[0]) + 16, np.float32)
+    grid = np.ascontiguousarray(sc.density_bitfield)
+    before = host.mch_jump_windows()
+    total = host.mch_group_march(ro.ctypes.data, rd.ctypes.data, grid.ctypes.data, sc.bound, dt_gamma, ms, n, sc.cascade, 128,
+                                 nears.ctypes.data, fars.ctypes.data, noises.ctypes.data, -G, counts.ctypes.data, ts.ctypes.data,
+                                 ts.shape[0])
+    assert total == int(counter[0])
+    assert np.array_equal(counts.astype(np.int32), rays[:, 2])
+    if dt_gamma == 0.0:
+        assert host.mch_jump_windows() > before  # the new path really ran
+    if max_steps is not None:
+        assert int(counts.max()) == ms  # some ray did end on the budget
+    t = ts[:total]
+    ray_of = np.repeat(np.arange(n), counts)
+    x = np.clip((ro[ray_of].astype(np.float64) + t[:, None].astype(np.float64) * rd[ray_of].astype(np.float64)), -sc.bound, sc.bound)
+    assert np.allclose(x, xyzs[:total], rtol=0, atol=1e-6 * max(1.0, sc.bound))
