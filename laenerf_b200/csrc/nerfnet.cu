@@ -210,6 +210,20 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
     if (warp == 0) tmem_dealloc(*tslot, 64 * kGroups);
 }
 
+// ONE high-water mark per kernel instantiation, shared by every entry point that launches it: the attribute is per function, so
+// separate marks let a later, smaller request (lnrf_nerf_density) lower it under an earlier, larger one (the render loop).
+static int ensure_nerf_fwd_smem(bool train, size_t smem, const char* who) {
+    static std::atomic<size_t> s_max_smem[2] = {{0}, {0}};
+    std::atomic<size_t>& mx = s_max_smem[train ? 1 : 0];
+    if (smem > mx.load(std::memory_order_relaxed)) {
+        cudaError_t e = train ? cudaFuncSetAttribute(k_nerf_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(k_nerf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, who);
+        mx.store(smem, std::memory_order_relaxed);
+    }
+    return LNRF_OK;
+}
+
 static size_t nerf_fwd_smem(uint32_t ns, uint32_t nc) { return 1024 + (ns + nc) * kWBytes + 4096 + kGroups * 2 * kTileBytes + 128; }
 
 int nerf_forward_dev_launch(const void* enc_f16, const float* dirs, const void* w_sigma_f16, const void* w_color_f16, uint32_t M_cap,
@@ -220,12 +234,7 @@ int nerf_forward_dev_launch(const void* enc_f16, const float* dirs, const void* 
     LNRF_REQUIRE(enc_f16 && dirs && w_sigma_f16 && w_color_f16 && sigmas && rgbs && M_dev, "render_rounds(network): null pointer");
     const size_t smem = nerf_fwd_smem(ns, nc);
     LNRF_REQUIRE(smem <= 227 * 1024, "render_rounds: networks need %zu B of shared memory (> 227 KiB)", smem);
-    static std::atomic<size_t> s_max{0};
-    if (smem > s_max.load(std::memory_order_relaxed)) {
-        cudaError_t e = cudaFuncSetAttribute(k_nerf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "render_rounds(network)");
-        s_max.store(smem, std::memory_order_relaxed);
-    }
+    if (int e = ensure_nerf_fwd_smem(false, smem, "render_rounds(network)")) return e;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     const uint32_t want = div_up(div_up(M_cap, kRows), kGroups);
@@ -261,13 +270,7 @@ int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigm
     const size_t smem = nerf_fwd_smem(ns, nc);
     LNRF_REQUIRE(smem <= 227 * 1024, "nerf_forward: networks need %zu B of shared memory (> 227 KiB)", smem);
     auto kern = train ? k_nerf_fwd<true> : k_nerf_fwd<false>;
-    static std::atomic<size_t> s_max_smem[2] = {{0}, {0}};
-    std::atomic<size_t>& mx = s_max_smem[train ? 1 : 0];
-    if (smem > mx.load(std::memory_order_relaxed)) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "nerf_forward");
-        mx.store(smem, std::memory_order_relaxed);
-    }
+    if (int e = ensure_nerf_fwd_smem(train != 0, smem, "nerf_forward")) return e;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     if (train) {
@@ -292,12 +295,7 @@ int lnrf_nerf_density(const void* enc_f16, const void* w_sigma_f16, uint32_t M, 
     if (M == 0) return LNRF_OK;
     LNRF_REQUIRE(enc_f16 && w_sigma_f16 && sigmas, "nerf_density: null pointer");
     const size_t smem = nerf_fwd_smem(ns, 2);  // the colour-net slots stay empty
-    static std::atomic<size_t> s_max{0};
-    if (smem > s_max.load(std::memory_order_relaxed)) {
-        cudaError_t e = cudaFuncSetAttribute(k_nerf_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "nerf_density");
-        s_max.store(smem, std::memory_order_relaxed);
-    }
+    if (int e = ensure_nerf_fwd_smem(false, smem, "nerf_density")) return e;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     const uint32_t ntiles = M / kRows;

@@ -102,6 +102,20 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     p -= c.step_size * m / denom;
 }
 
+// STREAM: the fp32 master / moment vectors (147 MB each way, touched once per step) go through the cache with the streaming
+// (evict-first) hint so that the 49 MB the NEXT step gathers from and reduces into -- the fp16 shadow this kernel writes and the
+// gradient buffer it clears -- stay resident in the 126 MB L2.
+template <bool STREAM>
+__device__ __forceinline__ float4 ld_state(const float* p) {
+    return STREAM ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+}
+template <bool STREAM>
+__device__ __forceinline__ void st_state(float* p, float4 v) {
+    if (STREAM) __stcs(reinterpret_cast<float4*>(p), v);
+    else *reinterpret_cast<float4*>(p) = v;
+}
+
+template <bool STREAM>
 __global__ void __launch_bounds__(kOptBlock)
 k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale, const float* __restrict__ found_inf,
             const float* __restrict__ step_count, const float* __restrict__ lr_scale) {
@@ -149,18 +163,18 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
         float g[kOptPerThread], p[kOptPerThread], m[kOptPerThread], v[kOptPerThread];
         uint4 gw = make_uint4(0u, 0u, 0u, 0u);
         if (t.g_is_f16) {
-            gw = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i));
+            gw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i);
         } else {
             const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i);
             *reinterpret_cast<float4*>(g) = __ldcs(gp);
             *reinterpret_cast<float4*>(g + 4) = __ldcs(gp + 1);
         }
-        *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(t.p + i);
-        *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(t.p + i + 4);
-        *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(t.m + i);
-        *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(t.m + i + 4);
-        *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(t.v + i);
-        *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(t.v + i + 4);
+        *reinterpret_cast<float4*>(p) = ld_state<STREAM>(t.p + i);
+        *reinterpret_cast<float4*>(p + 4) = ld_state<STREAM>(t.p + i + 4);
+        *reinterpret_cast<float4*>(m) = ld_state<STREAM>(t.m + i);
+        *reinterpret_cast<float4*>(m + 4) = ld_state<STREAM>(t.m + i + 4);
+        *reinterpret_cast<float4*>(v) = ld_state<STREAM>(t.v + i);
+        *reinterpret_cast<float4*>(v + 4) = ld_state<STREAM>(t.v + i + 4);
         if (t.g_is_f16) {
             union { uint4 u; __half2 h2[4]; } w;
             w.u = gw;
@@ -176,12 +190,12 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
 #pragma unroll
         for (int j = 0; j < (int)kOptPerThread; j++)
             adam_update(p[j], m[j], v[j], adam_unscale(g[j], c), h, c);
-        *reinterpret_cast<float4*>(t.p + i) = *reinterpret_cast<const float4*>(p);
-        *reinterpret_cast<float4*>(t.p + i + 4) = *reinterpret_cast<const float4*>(p + 4);
-        *reinterpret_cast<float4*>(t.m + i) = *reinterpret_cast<const float4*>(m);
-        *reinterpret_cast<float4*>(t.m + i + 4) = *reinterpret_cast<const float4*>(m + 4);
-        *reinterpret_cast<float4*>(t.v + i) = *reinterpret_cast<const float4*>(v);
-        *reinterpret_cast<float4*>(t.v + i + 4) = *reinterpret_cast<const float4*>(v + 4);
+        st_state<STREAM>(t.p + i, *reinterpret_cast<const float4*>(p));
+        st_state<STREAM>(t.p + i + 4, *reinterpret_cast<const float4*>(p + 4));
+        st_state<STREAM>(t.m + i, *reinterpret_cast<const float4*>(m));
+        st_state<STREAM>(t.m + i + 4, *reinterpret_cast<const float4*>(m + 4));
+        st_state<STREAM>(t.v + i, *reinterpret_cast<const float4*>(v));
+        st_state<STREAM>(t.v + i + 4, *reinterpret_cast<const float4*>(v + 4));
         if (t.p16) {
             union { uint4 u; __half2 h2[4]; } w;
 #pragma unroll
@@ -318,7 +332,8 @@ static int make_batch(const char* who, const lnrf_opt_tensor* tensors, uint32_t 
         t.first_block = blocks;
         // enough blocks to fill the machine (8 resident blocks per SM), never more than the tensor has chunks
         const uint64_t chunks = (s.n + kOptChunk - 1) / kOptChunk;
-        const uint64_t cap = (uint64_t)kNumSMs * 8;
+        const char* ec = getenv("LNRF_ADAM_BLOCKS_PER_SM");  // A/B switch
+        const uint64_t cap = (uint64_t)kNumSMs * (uint64_t)(ec && atoi(ec) > 0 ? atoi(ec) : 8);
         blocks += (uint32_t)(chunks < cap ? chunks : cap);
     }
     *grid = blocks;
@@ -349,7 +364,11 @@ int lnrf_adam_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double l
     if (int e = make_batch("adam_step", tensors_host, count, &b, &grid, true)) return e;
     LNRF_REQUIRE(step_count, "adam_step: null step_count (device fp32 scalar holding the 1-based step number)");
     AdamHyper h{lr, beta1, beta2, eps, weight_decay};
-    k_adam_step<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
+    const char* es = getenv("LNRF_ADAM_STREAM");  // A/B switch (default on)
+    if (!es || atoi(es) != 0)
+        k_adam_step<true><<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
+    else
+        k_adam_step<false><<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
     LNRF_LAUNCH_CHECK("adam_step");
     return LNRF_OK;
 }

@@ -174,7 +174,7 @@ __device__ __forceinline__ uint32_t march_group(const Group<G>& grp, const March
         const unsigned reach = grp.ballot(s >= pend);
         unsigned vis = 0;
         int v = reach ? (__ffs(reach) - 1) : G;
-        if (p.jump && __all_sync(kFull, !alive || wi.closed)) {
+        if (G == 32 && p.jump && __all_sync(kFull, !alive || wi.closed)) {  // narrow groups: the serial loop is shorter than log2(G) rounds + bookkeeping (measured: 20.7 vs 61.9 ms per 800x800 frame)
             // ---- jump-table resolve (every group of the warp holds a closed-form window; tests/test_march_core.py checks this
             // data flow lane by lane against the sequential marcher).  Successor of a lane: the next lane when its cell is
             // occupied (t += dt), the first member >= the voxel exit when it is empty, nothing when t >= far (the ray ends
@@ -295,6 +295,8 @@ __device__ __forceinline__ void warp_write_flat(float* __restrict__ base, size_t
     if (done + lane < nflt) st_cs(base + first + done + lane, f(done + (uint32_t)lane));
 }
 
+constexpr uint32_t kDirectSumBlocks = 2048;  // <= this many blocks: every block sums its predecessors' aggregates directly
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
@@ -326,15 +328,60 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
     if (lane == 0) s_cnt[warp] = count;
     __syncthreads();
 
-    // ---- slot assignment: in-block prefix + decoupled look-back over blocks (status = flag<<32 | value) ----
-    // scratch[0] = 1 + first sample row no ray wrote, scratch[1] = incoming counter[0], scratch[2..] = look-back words
+    // ---- slot assignment: in-block prefix + prefix over blocks (status = flag<<32 | value) ----
+    // scratch[0] = 1 + first sample row no ray wrote, scratch[1] = incoming counter[0], scratch[2..] = status words
     unsigned long long* status = scratch + 2;
-    if (warp == 0) {
+    const uint32_t b = blockIdx.x;
+    if (gridDim.x <= kDirectSumBlocks) {
+        // Small grids (the 4096-ray training batch is 1024 blocks, all resident at once and all done marching at about the same
+        // time): a look-back chain would resolve 32 blocks per L2 round trip, one hop after the other.  Instead every block
+        // publishes its aggregate and adds up the aggregates of ALL its predecessors directly -- b loads spread over the block's
+        // threads, no chain.  Integer sums: the result does not depend on the order.  Block 0 folds the incoming counter into its
+        // aggregate, so nobody else reads counter[0] (the last block overwrites it).  Waiting only ever targets lower block ids.
+        __shared__ uint32_t s_part[WARPS];
+        if (threadIdx.x == 0) {
+            uint32_t agg = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) agg += s_cnt[w];
+            if (b == 0) {
+                const uint32_t c0 = (uint32_t)counter[0];  // slots continue from the incoming counter, like the reference's atomicAdd
+                scratch[1] = (unsigned long long)c0;
+                if (c0 > M) scratch[0] = 1ull;  // nothing can be written at all: everything is zero-fill
+                agg += c0;
+            }
+            st_relaxed_u64(status + b, (1ull << 32) | agg);
+        }
+        uint32_t part = 0;
+        for (uint32_t j = threadIdx.x; j < b; j += WARPS * 32) {
+            unsigned long long st;
+            do {
+                st = ld_relaxed_u64(status + j);
+            } while ((st >> 32) == 0ull);
+            part += (uint32_t)st;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(kFull, part, o);
+        if (lane == 0) s_part[warp] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t excl = 0, agg = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) { excl += s_part[w]; agg += s_cnt[w]; }
+            if (b == 0) excl = (uint32_t)scratch[1];  // block 0's own rays start at the incoming counter
+            s_excl = excl;
+            if (b == gridDim.x - 1) {
+                const uint32_t total_end = excl + agg;
+                counter[0] = (int)total_end;
+                counter[1] += (int)N;
+                if (total_end <= M) scratch[0] = (unsigned long long)total_end + 1ull;  // first row nobody wrote
+            }
+        }
+    } else if (warp == 0) {
+        // large grids: decoupled look-back (blocks complete in waves, inclusive prefixes are found within a window or two)
         uint32_t agg = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++) agg += s_cnt[w];
         uint32_t excl = 0;
-        const uint32_t b = blockIdx.x;
         if (b == 0) {
             excl = (uint32_t)counter[0];  // slots continue from the incoming counter, like the reference's atomicAdd
             if (lane == 0) {

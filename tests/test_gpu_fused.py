@@ -408,8 +408,9 @@ def test_lookahead_graph_trains_the_same_sequence(dev):
         g = GraphedTrainStep(TrainStep(m), 4096, perturb=False, lookahead=look)
         g.capture(*batches[0], warmup=1)
         if look:
-            losses = [g(*b)[0] for b in batches[1:]]            # call k trains on batch k-1 (batch 0 was primed by capture)
-            losses = [float(x) for x in losses] + [float(g.flush()[0])]
+            # call k trains on batch k-1 (batch 0 was primed by capture); the loss is a view of graph-owned memory that the next
+            # replay overwrites, so it is read before the next call
+            losses = [float(g(*b)[0]) for b in batches[1:]] + [float(g.flush()[0])]
         else:
             losses = [float(g(*b)[0]) for b in batches]
         runs.append(losses)
@@ -456,7 +457,9 @@ def test_composite_loss_tail_matches_module_tier_and_torch_autograd(dev, bg_kind
     torch.autograd.backward(loss_b, grad_tensors=scale)
     torch.cuda.synchronize()
     assert torch.equal(ws, ws_b)  # same kernel body
-    assert float((image - image_b).abs().max()) <= 1e-6 and float((depth - depth_b).abs().max()) <= 1e-6
+    assert float((image - image_b).abs().max()) <= 1e-6
+    # rays that miss the box have far == near: 0 / 0 on both paths (renderer.py:328 does the same)
+    assert torch.allclose(depth, depth_b, rtol=0, atol=1e-6, equal_nan=True) and torch.equal(depth.isnan(), depth_b.isnan())
     assert abs(float(loss_a) - float(loss_b)) <= 2e-6 * abs(float(loss_a))
     for x, y in ((sa.grad, sb.grad), (ra.grad, rb.grad)):
         tol = 1e-5 * float(x.abs().max())
