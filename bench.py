@@ -176,7 +176,7 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner included) stays off stdout: rank 0 prints ONE JSON line
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -186,7 +186,7 @@ def main():
     import torch.distributed as dist
     from laenerf_b200 import _native
     from laenerf_b200.nerf import GraphedTrainStep, NeRFNetwork, TrainStep
-    from laenerf_b200.parallel import gather_image, init_distributed, shard_range
+    from laenerf_b200.parallel import gather_tiles, init_distributed, tile_shard_indices
     from laenerf_b200.scene import get_rays_np, make_scene
 
     if not torch.cuda.is_available():
@@ -344,11 +344,13 @@ def main():
                         timing="CUDA events around each C-ABI launch during the eager pass of the same step (graph replays cannot be bracketed)")
 
     # ---- render: one full 800x800 view, tile-sharded over ranks (no collective but the final gather) -------------------
+    # (at N = 1 the rays are in plain row-major order, as the reference renders them)
     render = None
     if not args.no_render:
         ro, rd, _ = get_rays_np(sc.poses[0], sc.intrinsics, sc.H, sc.W)
-        lo, hi = shard_range(ro.shape[0], rank, world)
-        ro_d, rd_d = torch.from_numpy(ro[lo:hi]).to(dev), torch.from_numpy(rd[lo:hi]).to(dev)
+        # N > 1: 32 x 32 pixel tiles dealt round-robin over the ranks (contiguous row ranges leave the object to the middle ranks)
+        mine = tile_shard_indices(sc.H, sc.W, rank, world).numpy() if world > 1 else np.arange(sc.H * sc.W)
+        ro_d, rd_d = torch.from_numpy(ro[mine]).to(dev), torch.from_numpy(rd[mine]).to(dev)
         model.eval()
         frames, samples = 0, 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -358,7 +360,7 @@ def main():
             e0.record()
             for _ in range(2):
                 out = model.render(ro_d, rd_d, perturb=False, bg_color=1)
-                img = gather_image(out["image"], ro.shape[0], rank, world)
+                img = gather_tiles(out["image"], sc.H, sc.W, rank, world)
                 samples += out["num_points"]
                 frames += 1
             e1.record()

@@ -256,6 +256,46 @@ class NeRFNetwork(nn.Module):
                                       N.ptr(self.density_bitfield), st))
         self.update_mean_count()
 
+    @torch.no_grad()
+    def mark_untrained_grid(self, poses, intrinsic, S=64, filter_close_point=False):
+        """NeRFRenderer.mark_untrained_grid (renderer.py:483-554, the other half of row f-2): cells of every cascade that no
+        training camera sees (or that lie closer than `min_near` to one) get density -1, so update_extra_state never revives
+        them.  Same predicate per (cell, camera) as the reference; evaluated for all H^3 cells of a cascade at once in Morton
+        order (one `morton3D` call instead of the reference's 8 x 8 x 8 Python block loop), cameras in chunks of S."""
+        if isinstance(poses, np.ndarray):
+            poses = torch.from_numpy(poses)
+        dev = self.density_bitfield.device
+        H = self.grid_size
+        fx, fy, cx, cy = (float(v) for v in intrinsic)
+        poses = poses.to(dev).float()
+        ar = torch.arange(H, dtype=torch.int32, device=dev)
+        coords = torch.stack(torch.meshgrid(ar, ar, ar, indexing="ij"), dim=-1).reshape(-1, 3).contiguous()  # [H^3, 3] in [0, H)
+        indices = raymarching.morton3D(coords).long()
+        world = 2 * coords.float() / (H - 1) - 1  # [-1, 1]
+        count = torch.zeros_like(self.density_grid)
+        too_close = torch.zeros_like(self.density_grid)
+        chunk = max(1, min(int(S), 16))  # [chunk, H^3, 3] fp32 temporaries
+        for cas in range(self.cascade):
+            bound = min(2 ** cas, self.bound)
+            half_grid_size = bound / H
+            cas_world = (world * (bound - half_grid_size)).unsqueeze(0)
+            seen = torch.zeros(H ** 3, dtype=torch.float32, device=dev)
+            close = torch.zeros(H ** 3, dtype=torch.float32, device=dev)
+            for head in range(0, poses.shape[0], chunk):
+                P = poses[head:head + chunk]
+                cam = (cas_world - P[:, :3, 3].unsqueeze(1)) @ P[:, :3, :3]  # world -> camera (poses are c2w)
+                z = cam[:, :, 2]
+                inside = (z > 0) & (cam[:, :, 0].abs() < cx / fx * z + half_grid_size * 2) & (cam[:, :, 1].abs() < cy / fy * z + half_grid_size * 2)
+                seen += inside.sum(0)
+                close += ((z < self.min_near) & inside).sum(0)
+                if filter_close_point:
+                    close += (cam.norm(dim=-1) < self.min_near).sum(0)
+            count[cas, indices] = seen
+            too_close[cas, indices] = close
+        count = count * (too_close == 0)
+        self.density_grid[count == 0] = -1
+        return int((count == 0).sum().item())
+
     def update_mean_count(self):
         """The step-counter part of update_extra_state (renderer.py:643-647)."""
         total_step = min(16, self.local_step)

@@ -5,7 +5,9 @@ section 8(e) defines what the hot path needs:
   * training = data parallel over RAYS: every rank marches/encodes/composites its own ray batch against replicated
     parameters and a replicated occupancy bitfield; the one exchange step is the sum of the hash-grid gradient and
     of the two flat MLP weight gradients, followed by the identical Adam step on every rank;
-  * rendering = contiguous ray ranges (image tiles) per rank, no collective except the final gather.
+  * rendering = image tiles per rank, no collective except the final gather.  Tiles are small (32 x 32 pixels) and dealt
+    round-robin: contiguous row ranges put the object in the middle ranks and empty sky in the others (measured on the
+    lego-shape frame: the first 80 000 of 640 000 rays need 1 round and 0.8 ms, the whole frame 91 rounds and 19 ms).
 """
 from __future__ import annotations
 
@@ -38,6 +40,39 @@ def shard_range(n: int, rank: int, world: int):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def tile_shard_indices(H: int, W: int, rank: int, world: int, tile: int = 32) -> torch.Tensor:
+    """Flat pixel (= ray) indices of the image tiles `rank` renders: tile t, counted row-major over the
+    ceil(H/tile) x ceil(W/tile) tile grid, belongs to rank t % world.  Pixels stay tile-major (row-major inside a tile), so
+    neighbouring lanes still march neighbouring rays.  Every rank can compute every other rank's list: the final gather needs
+    no index exchange."""
+    ty, tx = (H + tile - 1) // tile, (W + tile - 1) // tile
+    t = torch.arange(ty * tx)
+    mine = t[t % world == rank]
+    y0, x0 = (mine // tx) * tile, (mine % tx) * tile
+    dy, dx = torch.meshgrid(torch.arange(tile), torch.arange(tile), indexing="ij")
+    yy = y0[:, None, None] + dy[None]
+    xx = x0[:, None, None] + dx[None]
+    ok = (yy < H) & (xx < W)
+    return (yy * W + xx)[ok].reshape(-1)
+
+
+def gather_tiles(local: torch.Tensor, H: int, W: int, rank: int, world: int, tile: int = 32, group=None):
+    """Final gather of a tile-sharded render: `local` holds this rank's pixels in tile_shard_indices order; returns the full
+    [H*W, ...] image on every rank (one all_gather of equal-sized padded pieces, then a scatter by the known index lists)."""
+    if world <= 1:
+        return local
+    idx = [tile_shard_indices(H, W, r, world, tile) for r in range(world)]
+    maxlen = max(i.numel() for i in idx)
+    pad = torch.zeros((maxlen,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    full = torch.empty((H * W,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for o, i in zip(outs, idx):
+        full[i.to(local.device)] = o[: i.numel()]
+    return full
 
 
 def allreduce_gradients(params, world: int, group=None, average: bool = True):
@@ -91,7 +126,7 @@ def broadcast_occupancy(model, src: int = 0, group=None):
 
 
 def gather_image(local: torch.Tensor, n_total: int, rank: int, world: int, group=None):
-    """Final gather of a tile-sharded render: `local` is this rank's [hi-lo, ...] slice; returns the full
+    """Final gather of a range-sharded render (contiguous ray ranges): `local` is this rank's [hi-lo, ...] slice; returns the full
     [n_total, ...] tensor on every rank (what nerf/utils.py:1560-1566 does with all_gather)."""
     if world <= 1:
         return local

@@ -19,7 +19,7 @@ def _free_port():
 
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
-    from laenerf_b200.parallel import allreduce_gradients, gather_image, init_distributed, shard_range
+    from laenerf_b200.parallel import allreduce_gradients, gather_image, gather_tiles, init_distributed, shard_range, tile_shard_indices
     r, w, _ = init_distributed("gloo")
     assert (r, w) == (rank, world)
     # gradient exchange: one "hash-grid" sized tensor (>= 2^20 elements -> own all-reduce) and two small MLP tensors
@@ -36,7 +36,12 @@ def _worker(rank, world, port, out):
     full = torch.arange(n * 3, dtype=torch.float32).view(n, 3)
     lo, hi = shard_range(n, r, w)
     img = gather_image(full[lo:hi].clone(), n, r, w)
-    out[rank] = (ok_grad, bool(torch.equal(img, full)), (lo, hi))
+    # round-robin image tiles (ragged 50 x 70 image, 16-pixel tiles): the gather restores pixel order on every rank
+    Hh, Ww = 50, 70
+    pix = torch.arange(Hh * Ww * 3, dtype=torch.float32).view(Hh * Ww, 3)
+    mine = tile_shard_indices(Hh, Ww, r, w, tile=16)
+    img2 = gather_tiles(pix[mine].clone(), Hh, Ww, r, w, tile=16)
+    out[rank] = (ok_grad, bool(torch.equal(img, full)) and bool(torch.equal(img2, pix)), (lo, hi))
     dist.destroy_process_group()
 
 
@@ -59,3 +64,15 @@ def test_shard_range_covers_everything_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_tile_shards_partition_the_image_and_balance():
+    from laenerf_b200.parallel import tile_shard_indices
+    for H, W, tile in ((800, 800, 32), (378, 504, 32), (519, 779, 16), (5, 7, 4)):
+        for w in (1, 2, 4, 8):
+            parts = [tile_shard_indices(H, W, r, w, tile) for r in range(w)]
+            allidx = torch.cat(parts)
+            assert allidx.numel() == H * W and torch.equal(torch.sort(allidx).values, torch.arange(H * W))
+            if H * W > 10000:
+                sizes = [p.numel() for p in parts]
+                assert max(sizes) - min(sizes) <= 2 * tile * tile * ((W + tile - 1) // tile)
