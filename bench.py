@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 N_RAYS = 4096
+_OUT = sys.stdout
 WORKLOAD = "lego-shape 800x800 hash-grid NeRF training step (16 levels, 2^19 table, 4096 rays/GPU, cuda_ray, fp16 autocast, Adam)"
 
 # algorithmic bytes / FLOPs per unit (restated in DESIGN.md section 7)
@@ -160,7 +161,7 @@ def run_reference(args, rank, world):
                                             "frequency encodings) restated for CPU in oracle/cpu_renderer.py; bounded sample"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def main():
@@ -175,6 +176,12 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    # ONE JSON line on stdout, whatever the libraries print (NCCL writes its version banner to fd 1): keep the real stdout aside
+    # and point fd 1 at stderr for the rest of the process
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner included) stays off stdout: rank 0 prints ONE JSON line
     if args.impl == "reference":
@@ -352,27 +359,55 @@ def main():
         mine = tile_shard_indices(sc.H, sc.W, rank, world).numpy() if world > 1 else np.arange(sc.H * sc.W)
         ro_d, rd_d = torch.from_numpy(ro[mine]).to(dev), torch.from_numpy(rd[mine]).to(dev)
         model.eval()
+        model.render_schedule = os.environ.get("LNRF_RENDER_SCHEDULE", "fast")  # "reference": run_cuda's n_step rule, bit for bit
+        # real samples of this rank's rays (the slots of a round include the zero padding the API mandates, and the fast schedule
+        # pads more): counted once, outside the timed region, by the one-shot marcher on the same rays without a sample budget
+        from laenerf_b200 import raymarching as _rm
+        real = 0
+        with torch.no_grad():
+            for c0 in range(0, ro_d.shape[0], 65536):
+                o_, d_ = ro_d[c0:c0 + 65536].contiguous(), rd_d[c0:c0 + 65536].contiguous()
+                ne_, fa_ = _rm.near_far_from_aabb(o_, d_, model.aabb_infer, model.min_near)
+                cnt_ = torch.zeros(2, dtype=torch.int32, device=dev)
+                _rm.march_rays_train(o_, d_, model.bound, model.density_bitfield, model.cascade, model.grid_size, ne_, fa_, cnt_, -1, False,
+                                     128, True, 0, 1024)
+                real += int(cnt_[0].item())
         frames, samples = 0, 0
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        e0, e1 = ev(), ev()
+        marks = []
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            model.render(ro_d, rd_d, perturb=False, bg_color=1)  # warm-up frame
+            for _ in range(2):  # warm-up frames, final gather included (the first collective of a shape pays NCCL's lazy set-up)
+                gather_tiles(model.render(ro_d, rd_d, perturb=False, bg_color=1)["image"], sc.H, sc.W, rank, world)
             barrier()
             e0.record()
-            for _ in range(2):
+            for _ in range(3):
+                a, b, c = ev(), ev(), ev()
+                a.record()
                 out = model.render(ro_d, rd_d, perturb=False, bg_color=1)
+                b.record()
                 img = gather_tiles(out["image"], sc.H, sc.W, rank, world)
+                c.record()
+                marks.append((a, b, c))
                 samples += out["num_points"]
                 frames += 1
             e1.record()
             barrier()
-        tt = torch.tensor([e0.elapsed_time(e1), float(samples)], device=dev)
+        loop_ms = sum(a.elapsed_time(b) for a, b, _ in marks) / frames
+        gather_ms = sum(b.elapsed_time(c) for _, b, c in marks) / frames
+        tt = torch.tensor([e0.elapsed_time(e1), float(samples), loop_ms, gather_ms, float(real)], device=dev, dtype=torch.float64)
         if world > 1:
             tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            tt = torch.stack([tmax[0], tsum[1]])
-        rms, rs = float(tt[0].item()), float(tt[1].item())
-        render = dict(value=rs / (rms * 1e-3) / 1e6, unit="Msamples/s", ms_per_frame=rms / frames, rays_per_frame=int(ro.shape[0]),
-                      sample_slots_per_frame=rs / frames, rays_per_s=ro.shape[0] * frames / (rms * 1e-3), image_shape=list(img.shape))
+            tt = torch.stack([tmax[0], tsum[1], tmax[2], tmax[3], tsum[4]])
+        rms, rs, real_all = float(tt[0].item()), float(tt[1].item()), float(tt[4].item())
+        render = dict(value=real_all * frames / (rms * 1e-3) / 1e6, unit="Msamples/s", ms_per_frame=rms / frames, rays_per_frame=int(ro.shape[0]),
+                      samples_per_frame=real_all, sample_slots_per_frame=rs / frames, slots_msamples_per_s=rs / (rms * 1e-3) / 1e6,
+                      note="value counts REAL samples (occupied-cell samples of the frame's rays); slots include the zero padding of every round",
+                      rays_per_s=ro.shape[0] * frames / (rms * 1e-3), image_shape=list(img.shape),
+                      rounds=out.get("rounds"), schedule=model.render_schedule, render_loop_ms=float(tt[2].item()), gather_ms=float(tt[3].item()),
+                      sharding=("32x32-pixel tiles dealt round-robin over the ranks; all_gather + scatter by the known index lists"
+                                if world > 1 else "single GPU, row-major rays"))
         model.train()
 
     if rank != 0:
@@ -418,7 +453,7 @@ def main():
         "cpu_baseline": cpu,
         "train_msamples_per_s": world * actual * args.steps / (ms * 1e-3) / 1e6,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     _finish(world)
 
 

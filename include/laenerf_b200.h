@@ -293,7 +293,7 @@ typedef struct {
     /* state: two rays_alive buffers [n_rays] (round r reads [r & 1]), rays_t [n_rays] */
     int32_t* rays_alive[2];
     float* rays_t;
-    /* per-round sample buffers, n_rays + 128 rows each */
+    /* per-round sample buffers, n_rays + 128 rows each (or sample_rows, see below) */
     float *xyzs, *dirs, *deltas;                       /* [rows,3], [rows,3], [rows,2] */
     uint8_t* edit_occ;                                 /* [rows] (distillation) or NULL */
     void* enc_f16;                                     /* [rows,32] */
@@ -302,6 +302,13 @@ typedef struct {
     float *weights_sum, *depth, *image, *weights_edit_sum, *depth_edit;
     void* scratch;                                     /* lnrf_render_scratch_bytes(n_rays), zero-filled before first use */
     size_t scratch_bytes;
+    /* Round schedule.  sample_rows = 0: the reference's, n_step = clamp(n_rays / n_alive, 1, 8) (renderer.py:357), sample buffers
+     * of n_rays + 128 rows.  sample_rows > n_rays + 128: the buffers hold that many rows and every round after the first
+     * uses n_step = clamp((sample_rows - 128) / n_alive, 1, samples_per_round): the first round (n_step = 1) weeds out the rays that miss,
+     * the survivors then take up to samples_per_round samples per round -- several times fewer rounds per frame.  Same per-sample arithmetic; sample
+     * positions can differ in the last ulp where a round boundary moves (composite_rays re-sums t from deltas). */
+    uint32_t sample_rows;
+    uint32_t samples_per_round;   /* cap on n_step after the first round when sample_rows is in force (0: 8; at most 64) */
 } lnrf_render_desc;
 LNRF_API size_t lnrf_render_scratch_bytes(uint32_t n_rays);
 /* rays_alive[0] = 0..n_rays-1, rays_t = nears, accumulators = 0, control block = first round. */

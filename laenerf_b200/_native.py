@@ -98,6 +98,7 @@ class RenderDesc(C.Structure):
         ("xyzs", vp), ("dirs", vp), ("deltas", vp), ("edit_occ", vp), ("enc_f16", vp), ("sigmas", vp), ("rgbs", vp),
         ("weights_sum", vp), ("depth", vp), ("image", vp), ("weights_edit_sum", vp), ("depth_edit", vp),
         ("scratch", vp), ("scratch_bytes", sz),
+        ("sample_rows", u32), ("samples_per_round", u32),
     ]
 
 

@@ -767,13 +767,18 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
 //   ctl[3] rows = n_alive * n_step rounded up PAST the next multiple of 128 (raymarching.py:318-320)
 //   ctl[4] n_rays    ctl[5] max_steps    ctl[6] finished (n_alive == 0 or step >= max_steps)    ctl[7] rounds executed
 //   ctl[8] survivors of the running compaction (internal)    ctl[9] sample slots marched so far
-enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, kCtlMaxSteps = 5, kCtlFinished = 6, kCtlRounds = 7 };
+//   ctl[10] row budget of the rounds after the first (n_rays: the reference schedule; more: see lnrf_render_desc.sample_rows)
+//   ctl[11] most samples a ray takes per round after the first (8: the reference schedule)
+enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, kCtlMaxSteps = 5, kCtlFinished = 6, kCtlRounds = 7,
+       kCtlBudget = 10, kCtlStepCap = 11 };
 
 __device__ __forceinline__ void ctl_set_round(int* ctl, uint32_t n_alive) {
     const uint32_t n_rays = (uint32_t)ctl[kCtlRays];
     const bool fin = n_alive == 0u || (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps];
-    uint32_t n_step = n_alive ? n_rays / n_alive : 1u;
-    n_step = n_step > 8u ? 8u : (n_step < 1u ? 1u : n_step);
+    const uint32_t budget = ctl[kCtlRounds] > 0 ? (uint32_t)ctl[kCtlBudget] : n_rays;
+    uint32_t n_step = n_alive ? budget / n_alive : 1u;
+    const uint32_t step_cap = ctl[kCtlRounds] > 0 ? (uint32_t)ctl[kCtlStepCap] : 8u;
+    n_step = n_step > step_cap ? step_cap : (n_step < 1u ? 1u : n_step);
     uint32_t rows = n_alive * n_step;
     rows += 128u - rows % 128u;
     ctl[kCtlAlive] = fin ? 0 : (int)n_alive;
@@ -993,7 +998,8 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
 
 // start of a device-driven render: rays_alive = 0..n_rays-1, rays_t = nears, accumulators cleared, first round published
 __global__ void __launch_bounds__(256)
-k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_steps, int* __restrict__ rays_alive,
+k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_steps, const uint32_t row_budget, const uint32_t step_cap,
+               int* __restrict__ rays_alive,
                float* __restrict__ rays_t, const float* __restrict__ nears, float* __restrict__ weights_sum,
                float* __restrict__ depth, float* __restrict__ image, float* __restrict__ weights_edit_sum,
                float* __restrict__ depth_edit) {
@@ -1011,17 +1017,22 @@ k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_
         ctl[kCtlRounds] = 0;
         ctl[kCtlRounds + 1] = 0;
         ctl[kCtlRounds + 2] = 0;
+        ctl[kCtlBudget] = (int)row_budget;
+        ctl[kCtlStepCap] = (int)step_cap;
         ctl_set_round(ctl, n_rays);
     }
 }
 
 
 // ---- host launchers of the device-driven rounds (declared in render_core.cuh) ----
-int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, int32_t* rays_alive, float* rays_t, const float* nears,
+int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, uint32_t row_budget, uint32_t step_cap, int32_t* rays_alive, float* rays_t,
+                        const float* nears,
                         float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, cudaStream_t st) {
     LNRF_REQUIRE(ctl && (n_rays == 0 || (rays_alive && rays_t && nears && weights_sum && depth && image)), "render_begin: null pointer");
     const uint32_t blocks = n_rays ? (div_up(n_rays, 256u) < (uint32_t)kNumSMs * 8u ? div_up(n_rays, 256u) : (uint32_t)kNumSMs * 8u) : 1u;
-    k_render_begin<<<blocks, 256, 0, st>>>(ctl, n_rays, max_steps, rays_alive, rays_t, nears, weights_sum, depth, image, weights_edit_sum,
+    LNRF_REQUIRE(row_budget >= n_rays, "render_begin: the row budget (%u) must cover one sample per ray (%u)", row_budget, n_rays);
+    LNRF_REQUIRE(step_cap >= 1 && step_cap <= 64, "render_begin: samples per ray per round must be in [1, 64], got %u", step_cap);
+    k_render_begin<<<blocks, 256, 0, st>>>(ctl, n_rays, max_steps, row_budget, step_cap, rays_alive, rays_t, nears, weights_sum, depth, image, weights_edit_sum,
                                            depth_edit);
     LNRF_LAUNCH_CHECK("render_begin");
     return LNRF_OK;
@@ -1053,9 +1064,9 @@ int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap
     // or next to occupied cells, 2-3 samples wanted) 8 lanes 97 us, 4 lanes 150-200 us -- a second window costs more than
     // four idle lanes.
     if (first) {
-        if (distill) LNRF_MARCH_DEV_(true, 4, 1, 8) else LNRF_MARCH_DEV_(false, 4, 1, 8)
+        if (distill) LNRF_MARCH_DEV_(true, 4, 1, 64) else LNRF_MARCH_DEV_(false, 4, 1, 64)
     } else {
-        if (distill) LNRF_MARCH_DEV_(true, 8, 1, 8) else LNRF_MARCH_DEV_(false, 8, 1, 8)
+        if (distill) LNRF_MARCH_DEV_(true, 8, 1, 64) else LNRF_MARCH_DEV_(false, 8, 1, 64)
     }
 #undef LNRF_MARCH_DEV_
     return LNRF_OK;

@@ -11,13 +11,18 @@
 
 using namespace lnrf;
 
+// rows the sample buffers hold beyond the 128-row padding (the row budget of a round: n_alive * n_step never exceeds it)
+static uint32_t sample_row_budget(const lnrf_render_desc* d) {
+    return d->sample_rows > d->n_rays + 128u ? d->sample_rows - 128u : d->n_rays;
+}
+
 extern "C" {
 
 size_t lnrf_render_scratch_bytes(uint32_t n_rays) { return lnrf_compact_alive_scratch_bytes(n_rays); }
 
 int lnrf_render_begin(const lnrf_render_desc* d, lnrf_stream_t stream) {
     LNRF_REQUIRE(d && d->ctl, "render_begin: null descriptor / control block");
-    return render_begin_launch(d->ctl, d->n_rays, d->max_steps, d->rays_alive[0], d->rays_t, d->nears, d->weights_sum, d->depth, d->image,
+    return render_begin_launch(d->ctl, d->n_rays, d->max_steps, sample_row_budget(d), d->sample_rows > d->n_rays + 128u && d->samples_per_round ? d->samples_per_round : 8u, d->rays_alive[0], d->rays_t, d->nears, d->weights_sum, d->depth, d->image,
                                d->weights_edit_sum, d->depth_edit, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -27,7 +32,8 @@ int lnrf_render_rounds(const lnrf_render_desc* d, uint32_t first_round, uint32_t
     const bool distill = d->edit_bitfield != nullptr;
     LNRF_REQUIRE(!distill || (d->edit_occ && d->weights_edit_sum && d->depth_edit), "render_rounds: distillation needs edit_occ / weights_edit_sum / depth_edit");
     LNRF_REQUIRE(d->rays_alive[0] && d->rays_alive[1] && d->enc_f16 && d->sigmas && d->rgbs, "render_rounds: null buffer");
-    const uint32_t cap = d->n_rays;
+    const uint32_t cap = d->n_rays;                  // ray capacity (march groups, composite, compaction)
+    const uint32_t row_cap = sample_row_budget(d);   // sample-row capacity (encoder, network)
     const int32_t* rows_dev = d->ctl + 3;  // kCtlRows
     for (uint32_t r = first_round; r < first_round + n_rounds; r++) {
         int32_t* cur = d->rays_alive[r & 1u];
@@ -37,11 +43,11 @@ int lnrf_render_rounds(const lnrf_render_desc* d, uint32_t first_round, uint32_t
                                            d->cascade, d->grid_size, d->density_bitfield, d->edit_bitfield, d->fars, d->xyzs, d->dirs,
                                            d->deltas, d->edit_occ, noises, /*first=*/r == 0, st))
             return e;
-        if (int e = lnrf_grid_encode_forward_world(d->xyzs, d->bound, d->embeddings_f16, d->offsets_host, d->enc_f16, cap + 128u, rows_dev,
+        if (int e = lnrf_grid_encode_forward_world(d->xyzs, d->bound, d->embeddings_f16, d->offsets_host, d->enc_f16, row_cap + 128u, rows_dev,
                                                    d->num_levels, d->level_scale_log2, d->base_resolution, d->gridtype, d->align_corners,
                                                    d->interpolation, LNRF_F16, stream))
             return e;
-        if (int e = nerf_forward_dev_launch(d->enc_f16, d->dirs, d->w_sigma_f16, d->w_color_f16, cap + 128u, rows_dev, d->num_layers_sigma,
+        if (int e = nerf_forward_dev_launch(d->enc_f16, d->dirs, d->w_sigma_f16, d->w_color_f16, row_cap + 128u, rows_dev, d->num_layers_sigma,
                                             d->num_layers_color, d->density_scale, d->sigmas, d->rgbs, st))
             return e;
         if (int e = composite_infer_dev_launch(distill, d->ctl, cap, d->T_thresh, cur, d->rays_t, d->sigmas, d->rgbs, d->deltas, d->weights_sum,

@@ -7,7 +7,8 @@ namespace lnrf {
 
 constexpr int kRenderCtlInts = 16;
 
-int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, int32_t* rays_alive, float* rays_t, const float* nears,
+int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, uint32_t row_budget, uint32_t step_cap, int32_t* rays_alive, float* rays_t,
+                        const float* nears,
                         float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, cudaStream_t st);
 // one march over the rays of the current round (grids sized by the ray capacity; geometry read from ctl)
 int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,

@@ -132,6 +132,10 @@ class NeRFNetwork(nn.Module):
         # they are built for (fp16 autocast, hidden 64, 16+15+1 colour inputs, sample count a multiple of 128)
         self.fused = True
         self.device_loop = True  # row f-3: inference rounds driven from the device (falls back to the host loop when not fused)
+        # round schedule of the device loop: "reference" reproduces run_cuda's n_step rule bit for bit; "fast" spends 8x the
+        # sample-buffer memory on ~5x fewer rounds (same per-sample arithmetic; see _render_rounds_device)
+        self.render_schedule = "reference"
+        self.render_samples_per_round = 32  # "fast" only: cap on the samples a ray takes per round after the first
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
                           self.in_dim_color == 32 and self.encoder_dir.degree == 4)
 
@@ -314,7 +318,12 @@ class NeRFNetwork(nn.Module):
         n_rays = rays_o.shape[0]
         dev = rays_o.device
         f32 = dict(dtype=torch.float32, device=dev)
-        rows = n_rays + 128
+        # "reference": n_step = clamp(n_rays / n_alive, 1, 8), buffers of n_rays + 128 rows (renderer.py:357) -- bit-identical to the
+        # host loop.  "fast": buffers of 8 n_rays + 128 rows; the first round (n_step = 1) weeds out the rays that miss, every later
+        # round takes up to render_samples_per_round samples per ray -- several times fewer rounds, each of which costs ~90 us of
+        # latency whatever its size
+        fast = self.render_schedule == "fast"
+        rows = (8 * n_rays if fast else n_rays) + 128
         distill = edit_bitfield is not None
         enc, sn, cn = self.encoder, self.sigma_net, self.color_net
         emb = enc._shadow_f16 if enc._shadow_f16 is not None else enc.embeddings.detach().half()
@@ -356,6 +365,8 @@ class NeRFNetwork(nn.Module):
         d.weights_sum, d.depth, d.image = t["weights_sum"].data_ptr(), t["depth"].data_ptr(), t["image"].data_ptr()
         d.weights_edit_sum, d.depth_edit = N.ptr(t["wes"]), N.ptr(t["de"])
         d.scratch, d.scratch_bytes = t["scratch"].data_ptr(), nbytes
+        d.sample_rows = rows if fast else 0
+        d.samples_per_round = int(self.render_samples_per_round) if fast else 0
         st = N.stream()
         N.check(lib.lnrf_render_begin(C.byref(d), st))
         launched = 0

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=6)
 ap.add_argument("--render-rays", type=int, default=0, help="also profile one render of this many rays")
+ap.add_argument("--render-shard", type=int, default=0, help="render rank 0's share of a frame tile-sharded over this many ranks")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -40,9 +41,14 @@ torch.cuda.synchronize()
 torch.cuda.profiler.start()
 for i in range(args.steps):
     step(ro, rd, gt)
-if args.render_rays > 0:
+if args.render_rays > 0 or args.render_shard > 0:
     fo, fd, _ = get_rays_np(sc.poses[1], sc.intrinsics, sc.H, sc.W)
-    fo, fd = torch.from_numpy(fo[: args.render_rays]).to(dev), torch.from_numpy(fd[: args.render_rays]).to(dev)
+    if args.render_shard > 0:
+        from laenerf_b200.parallel import tile_shard_indices
+        mine = tile_shard_indices(sc.H, sc.W, 0, args.render_shard).numpy()
+        fo, fd = torch.from_numpy(fo[mine]).to(dev), torch.from_numpy(fd[mine]).to(dev)
+    else:
+        fo, fd = torch.from_numpy(fo[: args.render_rays]).to(dev), torch.from_numpy(fd[: args.render_rays]).to(dev)
     model.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         model.render(fo, fd, perturb=False)

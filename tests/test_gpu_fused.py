@@ -493,3 +493,36 @@ def test_train_step_fused_loss_equals_unfused_loss_path(dev):
     assert abs(la[0] - lb[0]) <= 1e-5 * abs(lb[0]), (la, lb)
     assert np.allclose(la, lb, rtol=1e-2), (la, lb)
     assert la[-1] < la[0]
+
+
+def test_fast_render_schedule_matches_reference_schedule(dev):
+    """render_schedule = "fast" (8 samples per ray per round after the first) against the reference's n_step rule: far fewer
+    rounds, the same image up to the last-ulp drift of t at moved round boundaries (PSNR between the two > 50 dB; the
+    north-star bar is 0.05 dB against ground truth), through the plain and the distillation render."""
+    m = _model(dev, True, 43)
+    _, ro, rd, _ = scene_rays("lego", 8192, 27)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    m.eval()
+    outs = {}
+    for sched in ("reference", "fast"):
+        m.render_schedule = sched
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            outs[sched] = m.render(ro, rd, perturb=False, bg_color=1)
+    a, b = outs["reference"], outs["fast"]
+    assert b["rounds"] * 3 < a["rounds"] * 2, (a["rounds"], b["rounds"])
+    mse = float((a["image"] - b["image"]).square().mean())
+    assert mse < 1e-5, mse  # PSNR between the schedules > 50 dB
+    assert float(((a["image"] - b["image"]).abs().amax(-1) > 1e-3).float().mean()) < 0.01  # a boundary sample moved on < 1 % of the rays
+    assert float((a["weights_sum"] - b["weights_sum"]).abs().max() if "weights_sum" in a else 0.0) < 1e-2
+    ok = ~(a["depth"].isnan() | b["depth"].isnan())
+    assert float((a["depth"][ok] - b["depth"][ok]).abs().mean()) < 1e-3
+    edit = m.density_bitfield.clone()
+    edit[::2] = 0
+    d = {}
+    for sched in ("reference", "fast"):
+        m.render_schedule = sched
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            d[sched] = m.run_cuda_distill(ro, rd, edit, perturb=False)
+    for k in ("image", "weights_sum", "weights_edit_sum", "depth_edit"):
+        assert float((d["reference"][k] - d["fast"][k]).abs().mean()) < 2e-3, k
+    m.render_schedule = "reference"
