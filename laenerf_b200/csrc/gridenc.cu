@@ -570,6 +570,14 @@ using namespace lnrf;
 
 static inline cudaStream_t S_(lnrf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// CTAs for `ntiles` tiles: at most kNumSMs * per_sm (LNRF_GRID_CAP = "fwd,bwd" blocks per SM overrides the default for A/B runs)
+static uint32_t tile_grid(uint32_t ntiles, int which) {
+    int per_sm[2] = {16, 16};  // one tile per CTA up to 2368 CTAs: the block scheduler balances better than a 2-vs-1 tile split (-5 us per step)
+    if (const char* e = getenv("LNRF_GRID_CAP")) sscanf(e, "%d,%d", &per_sm[0], &per_sm[1]);
+    const uint32_t cap = (uint32_t)kNumSMs * (uint32_t)(per_sm[which] > 0 ? per_sm[which] : 16);
+    return ntiles < cap ? ntiles : cap;
+}
+
 // x-pair merged table accesses (bit 0: forward gathers, bit 1: backward reductions); LNRF_GRID_PAIR overrides for A/B measurement.
 // Default 2: the merged reductions cut the L2 atomic operations of the backward by ~20 % (118.8 -> 99.7 us at 228k samples); the
 // merged forward gathers measured no gain (the forward is issue-bound, not sector-bound: 50.9 us unmerged vs 53-55 us merged).
@@ -628,7 +636,7 @@ static int grid_forward_t(const float* inputs, const T* emb, const GridOffsets& 
     }
     if (hot) {
         const uint32_t ntiles = div_up(B, (uint32_t)kTile);  // with B_dev: B is the capacity, the kernel re-derives both
-        const uint32_t grid = ntiles < (uint32_t)kNumSMs * 8u ? ntiles : (uint32_t)kNumSMs * 8u;
+        const uint32_t grid = tile_grid(ntiles, 0);
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
         auto kern = smooth ? (pair_mode() & 1 ? k_grid_fwd_tile<T, true, true> : k_grid_fwd_tile<T, true, false>)
                            : (pair_mode() & 1 ? k_grid_fwd_tile<T, false, true> : k_grid_fwd_tile<T, false, false>);
@@ -658,7 +666,7 @@ static int grid_backward_t(const T* grad, const float* inputs, const GridOffsets
     }
     if (hot) {
         const uint32_t ntiles = div_up(B, (uint32_t)kTile);
-        const uint32_t grid = ntiles < (uint32_t)kNumSMs * 8u ? ntiles : (uint32_t)kNumSMs * 8u;
+        const uint32_t grid = tile_grid(ntiles, 1);
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
         auto kern = smooth ? (pair_mode() & 2 ? k_grid_bwd_tile<T, true, true> : k_grid_bwd_tile<T, true, false>)
                            : (pair_mode() & 2 ? k_grid_bwd_tile<T, false, true> : k_grid_bwd_tile<T, false, false>);

@@ -58,21 +58,41 @@ def tile_shard_indices(H: int, W: int, rank: int, world: int, tile: int = 32) ->
     return (yy * W + xx)[ok].reshape(-1)
 
 
+_tile_plans = {}  # (H, W, world, tile, device) -> (maxlen, inverse permutation on the device)
+
+
+def _tile_plan(H: int, W: int, world: int, tile: int, device):
+    """Where every pixel of the full image sits in the rank-major buffer an all_gather of equal-sized padded pieces produces:
+    computed once per image geometry and kept on the device (the gather itself is then one collective + one index_select)."""
+    key = (H, W, world, tile, str(device))
+    plan = _tile_plans.get(key)
+    if plan is None:
+        idx = [tile_shard_indices(H, W, r, world, tile) for r in range(world)]
+        maxlen = max(i.numel() for i in idx)
+        inv = torch.empty(H * W, dtype=torch.long)
+        for r, i in enumerate(idx):
+            inv[i] = r * maxlen + torch.arange(i.numel())
+        plan = (maxlen, inv.to(device))
+        _tile_plans[key] = plan
+    return plan
+
+
 def gather_tiles(local: torch.Tensor, H: int, W: int, rank: int, world: int, tile: int = 32, group=None):
     """Final gather of a tile-sharded render: `local` holds this rank's pixels in tile_shard_indices order; returns the full
-    [H*W, ...] image on every rank (one all_gather of equal-sized padded pieces, then a scatter by the known index lists)."""
+    [H*W, ...] image on every rank: one all_gather of equal-sized padded pieces into a flat buffer, then one index_select with
+    the cached inverse permutation."""
     if world <= 1:
         return local
-    idx = [tile_shard_indices(H, W, r, world, tile) for r in range(world)]
-    maxlen = max(i.numel() for i in idx)
-    pad = torch.zeros((maxlen,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad, group=group)
-    full = torch.empty((H * W,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for o, i in zip(outs, idx):
-        full[i.to(local.device)] = o[: i.numel()]
-    return full
+    maxlen, inv = _tile_plan(H, W, world, tile, local.device)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == maxlen:
+        piece = local.contiguous()
+    else:
+        piece = torch.zeros((maxlen,) + tail, dtype=local.dtype, device=local.device)
+        piece[: local.shape[0]] = local
+    flat = torch.empty((world * maxlen,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(flat, piece, group=group)
+    return flat.index_select(0, inv)
 
 
 def allreduce_gradients(params, world: int, group=None, average: bool = True):
