@@ -221,11 +221,14 @@ class _composite_loss_train(Function):
         ctx.save_for_backward(sigmas, rgbs, deltas, rays, gt_rgb, bg, weights_sum, image, image_raw)
         ctx.dims = [M, n, T_thresh, bg_scalar]
         ctx.mark_non_differentiable(weights_sum, depth, image)
+        ctx.set_materialize_grads(False)  # no zero tensors (three fill launches per step) for the outputs nobody differentiates
         return loss, weights_sum, depth, image
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, grad_loss, *_):
+        if grad_loss is None:
+            return (None,) * 9
         sigmas, rgbs, deltas, rays, gt_rgb, bg, weights_sum, image, image_raw = ctx.saved_tensors
         M, n, T_thresh, bg_scalar = ctx.dims
         grad_loss = grad_loss.to(device=sigmas.device, dtype=torch.float32).contiguous()
