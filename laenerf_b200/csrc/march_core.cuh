@@ -81,6 +81,7 @@ struct MarchParams {
     int dt_const;  // dt_gamma == 0 (every shipped LAENeRF config): dt is the same for every t ...
     float dt0;     // ... namely clamp(0, dt_min, dt_max) (== dt_min unless max_steps is so small that dt_min > dt_max)
     int jump;      // closed-form windows are resolved with the jump table (march_jump + pointer doubling) instead of the serial loop
+    int fast_forward;  // a pending skip moves the group straight to the member it lands on (march_fast_forward)
 };
 
 LNRF_HD MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H) {
@@ -101,6 +102,7 @@ LNRF_HD MarchParams make_march_params(float bound, float dt_gamma, uint32_t max_
     p.dt_const = (dt_gamma == 0.0f) ? 1 : 0;
     p.dt0 = f_clamp(0.0f, p.dt_min, p.dt_max);
     p.jump = p.dt_const;
+    p.fast_forward = p.dt_const && C > 1;  // a cascade-0 voxel spans < 5 members: nothing to skip over
     return p;
 }
 
@@ -219,6 +221,36 @@ LNRF_HD float march_window(const MarchParams& p, float t, int lane, float* next,
         *next = s;
         return mine;
     }
+}
+
+// Fast-forward over members nobody visits.  When a skip target `pend` lies beyond the current position -- an empty voxel of an
+// outer cascade spans dozens of members (bound 16: 0.125 / dt = 37), so a skip used to cost one idle window after the other --
+// the group moves straight to the first member >= pend: inside a binade member k is (mt + k*qi) ulps, so that member is
+// k = ceil((m_pend - mt) / qi), capped at the last member of the binade (the crossing itself stays with the sequential adds of
+// march_window).  Same lattice argument as the closed-form window: t + k*qi*u is EXACTLY the k-th sequential sum.  Returns t
+// unchanged when nothing is pending, when the target is within the next G members anyway, or when the closed form does not apply.
+LNRF_HD float march_fast_forward(const MarchParams& p, float t, float pend, int G) {
+    // cheap filter first (returning t is always valid): only a target at least two windows ahead is worth the integer divisions
+    if (!p.dt_const || !(pend > f_fma((float)(2 * G), p.dt0, t))) return t;
+    const uint32_t bt = f2u(t);
+    const uint32_t e = bt >> 23;
+    if (e < 64u || e > 200u) return t;
+    const float u = u2f((e - 23u) << 23);
+    const float r = f_mul(p.dt0, u2f((277u - e) << 23));
+    const float q = rintf(r);
+    if (!(r < 262144.0f && q >= 1.0f && fabsf(f_add(r, -q)) != 0.5f)) return t;
+    const uint32_t qi = (uint32_t)q, mt = bt & 0x7fffffu;
+    const uint32_t kmax = (0x7fffffu - mt) / qi;  // members 0..kmax stay inside the binade
+    const uint32_t bp = f2u(pend);
+    const uint32_t ep = bp >> 23;                 // pend > t > 0: sign clear; inf / NaN have ep = 255
+    uint32_t k = kmax;
+    if (ep == e) {
+        const uint32_t a = (bp & 0x7fffffu) - mt;
+        const uint32_t kk = (a + qi - 1u) / qi;
+        k = kk < kmax ? kk : kmax;
+    }
+    if (k < (uint32_t)G) return t;
+    return f_fma((float)(k * qi), u, t);
 }
 
 // Successor of member v of a closed-form window whose cell is empty: the reference runs `do { t += dt; } while (t < tt)`

@@ -13,6 +13,8 @@
 
 using namespace lnrf;
 
+static int g_fast_forward = 1;  // mch_set_fast_forward(0): emulate without the skip over unvisited members
+
 template <int G>
 static uint32_t emulate_group(const MarchParams& p, const Ray& r, const uint8_t* grid, float t, float far, uint32_t max_emit,
                               float* tl) {
@@ -20,6 +22,7 @@ static uint32_t emulate_group(const MarchParams& p, const Ray& r, const uint8_t*
     float pend = -INFINITY;
     bool alive = true;
     while (alive) {
+        if (g_fast_forward) t = march_fast_forward(p, t, pend, G);
         float s[G], nxt = 0.f;
         Probe q[G];
         bool valid[G], occ[G];
@@ -81,6 +84,7 @@ static uint32_t emulate_group_jump(const MarchParams& p, const Ray& r, const uin
     bool alive = true;
     constexpr int LOG = (G == 32) ? 5 : (G == 16) ? 4 : (G == 8) ? 3 : 2;
     while (alive) {
+        if (g_fast_forward) t = march_fast_forward(p, t, pend, G);
         float s[G], nxt = 0.f;
         Probe q[G];
         bool valid[G], occ[G];
@@ -204,6 +208,7 @@ uint64_t mch_check_window(float t, float dt_gamma, uint32_t max_steps, uint32_t 
 
 static uint64_t g_jump_windows = 0;
 uint64_t mch_jump_windows() { return g_jump_windows; }  // how many windows the jump-table resolve handled so far
+void mch_set_fast_forward(int on) { g_fast_forward = on; }
 static uint32_t g_max_emit = 0;
 void mch_set_max_emit(uint32_t m) { g_max_emit = m; }   // 0: max_steps (training); else the per-call sample budget (inference rounds)
 

@@ -24,6 +24,8 @@ static lnrf::MarchParams march_params_env(float bound, float dt_gamma, uint32_t 
     const int jump = e ? atoi(e) : 1;
     lnrf::MarchParams p = lnrf::make_march_params(bound, dt_gamma, max_steps, C, H);
     if (!jump) p.jump = 0;
+    const char* f = getenv("LNRF_MARCH_FF");  // 0: no fast-forward over pending skips (A/B; identical results)
+    if (f && atoi(f) == 0) p.fast_forward = 0;
     return p;
 }
 
@@ -158,6 +160,7 @@ __device__ __forceinline__ uint32_t march_group(const Group<G>& grp, const March
     float pend = -INFINITY;  // target of a skip that ran past the previous window
     float last_after = t;
     while (__any_sync(kFull, alive)) {
+        if (p.fast_forward) t = march_fast_forward(p, t, pend, G);  // straight to the member a pending skip lands on (group-uniform)
         float nxt;
         WindowInfo wi;
         const float s = march_window<G>(p, t, grp.gl, &nxt, &wi);

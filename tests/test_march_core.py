@@ -95,3 +95,33 @@ def test_jump_table_resolve_equals_sequential_march(host, oracle_backend, name, 
     ray_of = np.repeat(np.arange(n), counts)
     x = np.clip((ro[ray_of].astype(np.float64) + t[:, None].astype(np.float64) * rd[ray_of].astype(np.float64)), -sc.bound, sc.bound)
     assert np.allclose(x, xyzs[:total], rtol=0, atol=1e-6 * max(1.0, sc.bound))
+
+
+@pytest.mark.parametrize("G", [4, 8, 32])
+def test_fast_forward_over_pending_skips_changes_nothing_but_the_window_count(host, oracle_backend, G):
+    """march_fast_forward: on the 5-cascade bonsai shape an empty outer-cascade voxel spans ~37 members, so a pending skip used to
+    cost several idle windows; with the fast-forward the emulated march needs far fewer windows and still reproduces the
+    sequential oracle (counts and visited t) exactly."""
+    host.mch_jump_windows.restype = C.c_uint64
+    sc, ro, rd, rng = scene_rays("bonsai", 160, 35)
+    nears, fars = oracle_backend.near_far(ro, rd, sc.aabb, sc.min_near)
+    noises = rng.random(160, dtype=np.float32)
+    want = oracle_backend.march_train(ro, rd, sc.density_bitfield, sc.bound, 0.0, sc.max_steps, sc.cascade, 128, 160 * sc.max_steps,
+                                      nears, fars, noises)
+    grid = np.ascontiguousarray(sc.density_bitfield)
+    windows, results = [], []
+    for on in (0, 1):
+        host.mch_set_fast_forward(on)
+        counts = np.zeros(160, np.uint32)
+        ts = np.zeros(int(want[4][0]) + 16, np.float32)
+        before = host.mch_jump_windows()
+        total = host.mch_group_march(ro.ctypes.data, rd.ctypes.data, grid.ctypes.data, sc.bound, 0.0, sc.max_steps, 160, sc.cascade, 128,
+                                     nears.ctypes.data, fars.ctypes.data, noises.ctypes.data, -G, counts.ctypes.data, ts.ctypes.data,
+                                     ts.shape[0])
+        windows.append(host.mch_jump_windows() - before)
+        results.append((total, counts.copy(), ts[:total].copy()))
+    host.mch_set_fast_forward(1)
+    for total, counts, ts in results:
+        assert total == int(want[4][0]) and np.array_equal(counts.astype(np.int32), want[3][:, 2])
+    assert np.array_equal(results[0][2], results[1][2])
+    assert windows[1] * (2 if G < 32 else 1) < windows[0], windows  # a 32-member window already spans most of a 37-member voxel
