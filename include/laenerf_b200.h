@@ -105,7 +105,8 @@ LNRF_API int lnrf_composite_rays_train_forward(const float* sigmas, const float*
 /* composite_rays_train_backward (raymarching.h:15).  grad_sigmas [M], grad_rgbs [M,3]: ZERO-IN when
  * zero_fill == 0 (reference contract, raymarching.py:283-284).  With zero_fill != 0 the kernel itself clears
  * every element no ray covers; this requires the canonical `rays` layout lnrf_march_rays_train produces
- * (ray ranges ascending and contiguous) and is what the Python shim uses. */
+ * (ray ranges ascending and contiguous); the fused training tail uses it, the drop-in `composite_rays_train` wrapper keeps
+ * `torch.zeros` + zero_fill == 0 because callers may hand it `rays` in any order. */
 LNRF_API int lnrf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
                                                 const float* sigmas, const float* rgbs, const float* deltas,
                                                 const int32_t* rays, const float* weights_sum, const float* image,

@@ -633,13 +633,19 @@ k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__
         s_last = atomicAdd(la.ticket, 1u) == gridDim.x - 1u;
     }
     __syncthreads();
-    if (s_last && warp == 0) {
+    if (s_last) {  // the last block out: fixed-order sum of the partials (thread-strided, then warps, then the 8 warp sums)
         __threadfence();
         float s = 0.f;
-        for (uint32_t i = lane; i < gridDim.x; i += 32) s += __ldcg(la.partial + i);
+        for (uint32_t i = threadIdx.x; i < gridDim.x; i += 256) s += __ldcg(la.partial + i);
         s = warp_sum(s);
-        if (lane == 0) {
-            la.loss[0] = s / (3.0f * (float)N);
+        __syncthreads();  // s_err is being reused
+        if (lane == 0) s_err[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += s_err[w];
+            la.loss[0] = tot / (3.0f * (float)N);
             *la.ticket = 0u;
         }
     }

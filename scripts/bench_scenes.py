@@ -113,6 +113,10 @@ def edit_case():
     o = out["o"]
     mask = o["weights_edit_sum"] > 0.05
     x_term, d = o["x_term"][mask].contiguous(), rd[mask].contiguous()
+    masked = int(x_term.shape[0])
+    # the reference's fp16 regularisers overflow beyond ~75k points (sum of (1 - max w) in half, style_encoder.py:185-189): one
+    # iteration trains on a view's worth of at most 49 152 masked points here
+    x_term, d = x_term[:49152].contiguous(), d[:49152].contiguous()
     K = int(x_term.shape[0])
     params = SimpleNamespace(bound=sc.bound, num_palette_bases=8, style_weight=0.0, weight_loss_uniform=1e-6, weight_loss_non_uniform=1e-6,
                              offset_loss=1e-6, palette_loss_valid=1e-3, palette_loss_distinct=1e-3)
@@ -126,7 +130,7 @@ def edit_case():
         losses.append(st(x_term, d, target)[0])
     ms_style = timed(it, 20, warm=5)
     l = [float(x) for x in losses]
-    return dict(scene="flower", image=[sc.H, sc.W], rays=int(ro.shape[0]), distill_ms_per_view=ms_distill, masked_points=K,
+    return dict(scene="flower", image=[sc.H, sc.W], rays=int(ro.shape[0]), distill_ms_per_view=ms_distill, masked_points_of_view=masked, points_per_style_step=K,
                 style_step_ms=ms_style, style_points_per_s=K / ms_style * 1e3, loss_first=l[0], loss_last=l[-1],
                 note="run_cuda_distill (march_rays_distill / composite_rays_distill rounds) + StyleTrainStep (hash grid fwd/bwd, SH-3, two FFMLP nets, "
                      "palette mix, MSE + regularisers, GradScaler, torch Adam)")
