@@ -80,12 +80,17 @@ struct AdamHyper {
     double lr, beta1, beta2, eps, weight_decay;
 };
 
-// torch/aten fused CUDA Adam (ADAM_MODE::ORIGINAL, amsgrad = false, maximize = false), statement by statement, including
-// the places where its double hyper-parameters promote the arithmetic to double before the result is stored as float.
+// torch/aten fused CUDA Adam (ADAM_MODE::ORIGINAL, amsgrad = false, maximize = false), statement by statement.  torch's kernel
+// keeps its hyper-parameters in double, which promotes every statement to double and back: 8 float<->double conversions per
+// element, all on the XU pipe (16 lanes/clk/SM) -- ncu showed this kernel at 58 % XU utilisation and 62 % issue, i.e. bound by
+// the conversions rather than by HBM (profiles/r1k).  The same statements in fp32 with fused multiply-adds agree with torch's
+// fused and foreach kernels to 2e-6 over several steps (tests/test_gpu_fused.py::test_adam_step_matches_torch_adam: the
+// double intermediates only protect the last bit of each statement) and leave sqrt + two reciprocals on the XU pipe.
 struct AdamStepConsts {
-    double w1, w2;          // 1 - beta1, 1 - beta2
+    float w1, w2, beta2;    // 1 - beta1, 1 - beta2 (formed in double on the way in), beta2
     float step_size;        // (float)(lr / bias_correction1)
-    float bc2_sqrt;
+    float inv_bc2_sqrt;     // 1 / sqrt(bias_correction2)
+    float eps, weight_decay;
     double scale;           // GradScaler scale (1 when absent)
     float inv_scale;        // exact reciprocal when the scale is a power of two (the GradScaler default), else 0
     bool unscale;
@@ -94,17 +99,47 @@ __device__ __forceinline__ float adam_unscale(float g, const AdamStepConsts& c) 
     if (!c.unscale) return g;
     return c.inv_scale != 0.0f ? g * c.inv_scale : (float)((double)g / c.scale);  // both are torch's `grad /= scale`
 }
-__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamHyper& h, const AdamStepConsts& c) {
-    if (h.weight_decay != 0.0) g = (float)((double)g + h.weight_decay * (double)p);
-    m = (float)((double)m + c.w1 * (double)(g - m));                          // lerp(exp_avg, grad, 1 - beta1)
-    v = (float)(h.beta2 * (double)v + c.w2 * (double)g * (double)g);          // beta2 * v + (1 - beta2) * g * g
-    const float denom = (float)((double)(sqrtf(v) / c.bc2_sqrt) + h.eps);
-    p -= c.step_size * m / denom;
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamHyper&, const AdamStepConsts& c) {
+    if (c.weight_decay != 0.0f) g = fmaf(c.weight_decay, p, g);
+    m = fmaf(c.w1, g - m, m);                          // lerp(exp_avg, grad, 1 - beta1)
+    v = fmaf(c.w2 * g, g, c.beta2 * v);                // beta2 * v + (1 - beta2) * g * g
+    // sqrt.approx / div.approx (one MUFU each, <= 2 ulp; sqrt.approx(0) = 0): the update is lr-sized, so 2.4e-7 relative on it is
+    // far inside the 2e-6 agreement with torch asserted by the tests, and the IEEE fix-up paths were a tenth of the kernel's issue slots
+    float sq;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+    const float denom = fmaf(sq, c.inv_bc2_sqrt, c.eps);
+    p -= __fdividef(c.step_size * m, denom);
 }
 
 // STREAM: the fp32 master / moment vectors (147 MB each way, touched once per step) go through the cache with the streaming
 // (evict-first) hint so that the 49 MB the NEXT step gathers from and reduces into -- the fp16 shadow this kernel writes and the
 // gradient buffer it clears -- stay resident in the 126 MB L2.
+// The per-step constants (two double pow() among them: ~400 double-precision instructions) are formed by ONE thread of the block
+// and broadcast through shared memory -- every thread computing them cost as much as ten elements of its actual work.
+__device__ __forceinline__ AdamStepConsts adam_step_consts(const AdamHyper& h, const float* grad_scale, const float* step_count) {
+    __shared__ AdamStepConsts s_c;
+    if (threadIdx.x == 0) {
+        AdamStepConsts c;
+        const double step = (double)*step_count;
+        const float bc1 = (float)(1.0 - pow(h.beta1, step));
+        c.w1 = (float)(1.0 - h.beta1);
+        c.w2 = (float)(1.0 - h.beta2);
+        c.beta2 = (float)h.beta2;
+        c.eps = (float)h.eps;
+        c.weight_decay = (float)h.weight_decay;
+        c.step_size = (float)(h.lr / (double)bc1);
+        c.inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(h.beta2, step)));
+        c.unscale = grad_scale != nullptr;
+        const float scale_f = c.unscale ? *grad_scale : 1.0f;
+        c.scale = (double)scale_f;
+        int e2;
+        c.inv_scale = (frexpf(scale_f, &e2) == 0.5f && e2 > -100 && e2 < 100) ? 1.0f / scale_f : 0.0f;
+        s_c = c;
+    }
+    __syncthreads();
+    return s_c;
+}
+
 template <bool STREAM>
 __device__ __forceinline__ float4 ld_state(const float* p) {
     return STREAM ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
@@ -124,18 +159,7 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
     const uint32_t nblocks = (k + 1 < (int)b.count ? b.t[k + 1].first_block : gridDim.x) - t.first_block;
     const bool skip = found_inf != nullptr && *found_inf != 0.0f;  // GradScaler: the step is skipped, the gradient still cleared
     if (lr_scale) h.lr *= (double)*lr_scale;  // LambdaLR-style schedule factor kept on the device (CUDA-graph friendly)
-    const float step = *step_count;
-    const float bc1 = (float)(1.0 - pow(h.beta1, (double)step));
-    AdamStepConsts c;
-    c.w1 = 1.0 - h.beta1;
-    c.w2 = 1.0 - h.beta2;
-    c.step_size = (float)(h.lr / (double)bc1);
-    c.bc2_sqrt = sqrtf((float)(1.0 - pow(h.beta2, (double)step)));
-    c.unscale = grad_scale != nullptr;
-    const float scale_f = c.unscale ? *grad_scale : 1.0f;
-    c.scale = (double)scale_f;
-    int e2;
-    c.inv_scale = (frexpf(scale_f, &e2) == 0.5f && e2 > -100 && e2 < 100) ? 1.0f / scale_f : 0.0f;
+    const AdamStepConsts c = adam_step_consts(h, grad_scale, step_count);
 
     for (uint64_t base = (uint64_t)(blockIdx.x - t.first_block) * kOptChunk; base < t.n; base += (uint64_t)nblocks * kOptChunk) {
         const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;
@@ -233,18 +257,7 @@ k_adam_step_p2p(const PeerPtrs peers, const uint32_t R, const uint64_t lo, const
     if (blockIdx.x == 0 && threadIdx.x == 0) *found_inf_out = skip ? 1.0f : 0.0f;
     if (skip) return;  // GradScaler: nothing is updated; the gradients are cleared by the caller after the closing barrier
     if (lr_scale) h.lr *= (double)*lr_scale;
-    const float step = *step_count;
-    const float bc1 = (float)(1.0 - pow(h.beta1, (double)step));
-    AdamStepConsts c;
-    c.w1 = 1.0 - h.beta1;
-    c.w2 = 1.0 - h.beta2;
-    c.step_size = (float)(h.lr / (double)bc1);
-    c.bc2_sqrt = sqrtf((float)(1.0 - pow(h.beta2, (double)step)));
-    c.unscale = grad_scale != nullptr;
-    const float scale_f = c.unscale ? *grad_scale : 1.0f;
-    c.scale = (double)scale_f;
-    int e2;
-    c.inv_scale = (frexpf(scale_f, &e2) == 0.5f && e2 > -100 && e2 < 100) ? 1.0f / scale_f : 0.0f;
+    const AdamStepConsts c = adam_step_consts(h, grad_scale, step_count);
     const float inv_R = 1.0f / (float)R;
 
     for (uint64_t base = (uint64_t)blockIdx.x * kOptChunk; base < n; base += (uint64_t)gridDim.x * kOptChunk) {
