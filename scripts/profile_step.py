@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=6)
 ap.add_argument("--render-rays", type=int, default=0, help="also profile one render of this many rays")
 ap.add_argument("--render-shard", type=int, default=0, help="render rank 0's share of a frame tile-sharded over this many ranks")
+ap.add_argument("--render-schedule", default="fast", choices=["fast", "reference"])
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -50,6 +51,7 @@ if args.render_rays > 0 or args.render_shard > 0:
     else:
         fo, fd = torch.from_numpy(fo[: args.render_rays]).to(dev), torch.from_numpy(fd[: args.render_rays]).to(dev)
     model.eval()
+    model.render_schedule = args.render_schedule
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         model.render(fo, fd, perturb=False)
 torch.cuda.synchronize()
