@@ -258,9 +258,11 @@ def main():
     model.update_mean_count()
 
     # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
-    # look-ahead pays when there is an exchange step to hide the march behind (measured at N = 2: 0.623 -> 0.590 ms); on one GPU
-    # the march only competes with Adam for the same SMs (0.522 -> 0.553 ms), so it is off there
-    lookahead = os.environ.get("LNRF_LOOKAHEAD", "1" if world > 1 else "0") == "1"
+    # look-ahead (march of batch k+1 beside the exchange + Adam of batch k) paid while the exchange was an NCCL all-reduce (N = 2:
+    # 0.623 -> 0.590 ms); with the fused peer-memory kernel it measures within +-1 % of the plain graph at N = 2 / 4 / 8
+    # (profiles/r1k_bench_n*.json, r1l_bench_n8.json: 0.484 / 0.468 / 0.474 vs 0.480 / 0.462 / 0.479 ms), and on one GPU the march only
+    # competes with Adam for the same SMs -- so it is off unless asked for
+    lookahead = os.environ.get("LNRF_LOOKAHEAD", "0") == "1"
     gstep, graph_note = None, ("cuda graph (one capture per sample-buffer size)" +
                                ("; look-ahead: the parameter-independent near/far + march of batch k runs on a second stream beside "
                                 "the network/backward/Adam of batch k-1 -- every step still marches one batch and trains on one" if lookahead else ""))
