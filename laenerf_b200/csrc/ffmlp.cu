@@ -649,11 +649,19 @@ k_mlp_bwd2(const __half* __restrict__ grad, const __half* __restrict__ inputs, c
 
 // gw[i] = sum over slices of partial[s][i] (fixed order), rounded to fp16 (optionally added to the existing value).
 // 256 threads = 32 parameters (one 128-byte line per slice) x 8 slice lanes.
+// One launch serves up to two networks (blocks [0, ceil(a.n/32)) reduce `a`, the rest `b`): the fused NeRF backward finishes
+// the colour net's and the sigma net's weight gradients together instead of with a launch each.
 __global__ void __launch_bounds__(256)
-k_wgrad_reduce(const float* __restrict__ partial, uint32_t nslices, __half* __restrict__ gw, uint32_t n, int accumulate) {
+k_wgrad_reduce(const WgradPending a, const WgradPending b) {
     __shared__ float red[8][32];
+    const uint32_t blocks_a = (a.n + 31u) / 32u;
+    const bool first = blockIdx.x < blocks_a;
+    const float* __restrict__ partial = first ? a.partial : b.partial;
+    __half* __restrict__ gw = first ? a.gw : b.gw;
+    const uint32_t nslices = first ? a.nslices : b.nslices, n = first ? a.n : b.n;
+    const int accumulate = first ? a.accumulate : b.accumulate;
     const uint32_t c = threadIdx.x & 31u, l = threadIdx.x >> 5;
-    const uint32_t p = blockIdx.x * 32 + c;
+    const uint32_t p = (first ? blockIdx.x : blockIdx.x - blocks_a) * 32 + c;
     float acc = 0.0f;
     if (p < n) {
 #pragma unroll 5
@@ -775,7 +783,8 @@ int mlp_shape(const char* who, uint32_t B, uint32_t input_dim, uint32_t output_d
 // selects the colour-net variant with the NeRFNetwork glue fused in (see k_ffmlp_bwd).
 int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16, const void* weights_f16, const void* forward_buffer_f16,
                   uint32_t B, const MlpShape& sh, int calc_grad_inputs, void* grad_inputs_f16, void* grad_weights_f16,
-                  void* wgrad_scratch, size_t wgrad_scratch_bytes, const BwdGlue* glue, int accumulate, cudaStream_t st) {
+                  void* wgrad_scratch, size_t wgrad_scratch_bytes, const BwdGlue* glue, int accumulate, cudaStream_t st,
+                  WgradPending* defer) {
     const uint32_t input_dim = sh.in_dim, output_dim = sh.out_dim, num_layers = sh.n_layers;
     LNRF_REQUIRE(inputs_f16 && weights_f16 && forward_buffer_f16 && grad_weights_f16, "%s: null pointer", who);
     LNRF_REQUIRE(glue || !calc_grad_inputs || grad_inputs_f16, "%s: calc_grad_inputs without grad_inputs", who);
@@ -840,7 +849,18 @@ int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16,
                                       ntiles, calc_grad_inputs, nbuf, BwdGlue{});
         LNRF_LAUNCH_CHECK(who);
     }
-    k_wgrad_reduce<<<div_up(nparams, 32u), 256, 0, st>>>((const float*)wgrad_scratch, nslices, (__half*)grad_weights_f16, nparams, accumulate);
+    if (defer) {  // the caller reduces several networks' partial sums in one launch (wgrad_reduce_pair)
+        *defer = WgradPending{(const float*)wgrad_scratch, nslices, (__half*)grad_weights_f16, nparams, accumulate};
+        return LNRF_OK;
+    }
+    k_wgrad_reduce<<<div_up(nparams, 32u), 256, 0, st>>>(WgradPending{(const float*)wgrad_scratch, nslices, (__half*)grad_weights_f16, nparams, accumulate},
+                                                         WgradPending{nullptr, 0, nullptr, 0, 0});
+    LNRF_LAUNCH_CHECK(who);
+    return LNRF_OK;
+}
+
+int wgrad_reduce_pair(const char* who, const WgradPending& a, const WgradPending& b, cudaStream_t st) {
+    k_wgrad_reduce<<<div_up(a.n, 32u) + div_up(b.n, 32u), 256, 0, st>>>(a, b);
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }

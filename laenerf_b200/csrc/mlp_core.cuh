@@ -27,9 +27,20 @@ struct BwdGlue {
 
 // host-side launchers shared between ffmlp.cu and nerfnet.cu
 int mlp_shape(const char* who, uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t num_layers, MlpShape* sh);
+// partial weight-gradient sums of one network waiting for their fixed-order reduction (k_wgrad_reduce)
+struct WgradPending {
+    const float* partial;  // [nslices][n] fp32
+    uint32_t nslices;
+    __half* gw;            // [n] fp16 gradient (written, or added to when accumulate != 0)
+    uint32_t n;
+    int accumulate;
+};
+// defer != nullptr: the reduction is not launched; *defer describes it for wgrad_reduce_pair
 int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16, const void* weights_f16, const void* forward_buffer_f16,
                   uint32_t B, const MlpShape& sh, int calc_grad_inputs, void* grad_inputs_f16, void* grad_weights_f16,
-                  void* wgrad_scratch, size_t wgrad_scratch_bytes, const BwdGlue* glue, int accumulate, cudaStream_t st);
+                  void* wgrad_scratch, size_t wgrad_scratch_bytes, const BwdGlue* glue, int accumulate, cudaStream_t st,
+                  WgradPending* defer = nullptr);
+int wgrad_reduce_pair(const char* who, const WgradPending& a, const WgradPending& b, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers

@@ -326,13 +326,16 @@ int lnrf_nerf_backward(const float* grad_sigmas, const float* grad_rgbs, const f
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     BwdGlue g{grad_rgbs, rgbs, grad_sigmas, (const __half*)h0_f16, density_scale, (__half*)dh_scratch_f16};
     const __half* fb = (const __half*)forward_buffer_f16;
-    // colour net: dL/drgb -> dL/dh (glue fused), dW_color
+    // colour net: dL/drgb -> dL/dh (glue fused), dW_color; sigma net: dL/dh -> dL/denc, dW_sigma.  Nothing reads the weight
+    // gradients before the optimizer, so both fixed-order reductions of the per-CTA partial sums run as ONE launch at the end.
+    WgradPending pc{}, ps{};
     if (int e = ffmlp_bwd_run("nerf_backward(color)", nullptr, color_in_f16, w_color_f16, fb + (size_t)ns * M * 64, M, shc, 1, nullptr,
-                              grad_w_color_f16, (uint8_t*)wgrad_scratch + need_s, need_c, &g, accumulate_wgrad, st))
+                              grad_w_color_f16, (uint8_t*)wgrad_scratch + need_s, need_c, &g, accumulate_wgrad, st, &pc))
         return e;
-    // sigma net: dL/dh -> dL/denc, dW_sigma
-    return ffmlp_bwd_run("nerf_backward(sigma)", dh_scratch_f16, enc_f16, w_sigma_f16, fb, M, shs, 1, grad_enc_f16, grad_w_sigma_f16,
-                         wgrad_scratch, need_s, nullptr, accumulate_wgrad, st);
+    if (int e = ffmlp_bwd_run("nerf_backward(sigma)", dh_scratch_f16, enc_f16, w_sigma_f16, fb, M, shs, 1, grad_enc_f16, grad_w_sigma_f16,
+                              wgrad_scratch, need_s, nullptr, accumulate_wgrad, st, &ps))
+        return e;
+    return wgrad_reduce_pair("nerf_backward(wgrad)", ps, pc, st);
 }
 
 }  // extern "C"
