@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU check of the ray-sharded step and the tile-sharded render (tight timeout: a hang must not burn the budget)
+# N-GPU check of the ray-sharded step and the tile-sharded render (tight timeout: a hang must not burn the budget).  gpurun --gpus N -- bash scripts/gpu_multi.sh N
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-8}

@@ -1,5 +1,5 @@
 #!/bin/bash
-# final round-1 evidence: bench, ncu launch lists (train step, render frame), ncu --set full of the hot kernels
+# evidence pass: bench, ncu launch list of the training step, ncu --set full of the hot kernels (scripts/summarize_ncu.py turns them into profiles/)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "== bench (default)"; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"; head -c 200 gpurun_out/bench.json; echo; tail -3 gpurun_out/bench.err

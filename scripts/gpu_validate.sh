@@ -1,4 +1,5 @@
 #!/bin/bash
+# GPU-box validation pass: all -m gpu tests, smoke(), bench.py (default) and the reference arm.  gpurun -- bash scripts/gpu_validate.sh
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "== all gpu tests"; timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"; grep "^FAILED\|^ERROR\|passed\|failed" gpurun_out/pytest_gpu.log | head -30
