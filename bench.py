@@ -440,6 +440,11 @@ def main():
         "step_mode": graph_note,
         "graph_sequential_ms_per_step": seq_ms,
         "replicas_in_sync": in_sync,
+        "exchange_sync": (None if world == 1 or not step.fused_optimizer or step.optimizer.p2p is None else
+                          ("inside the kernels (signal + poll on peer-mapped flag words)" if step.optimizer.inkernel_sync else
+                           "two symmetric-memory barrier launches around the kernel")),
+        "exchange_timing_us": (step.optimizer.exchange_timing() if world > 1 and step.fused_optimizer and os.environ.get("LNRF_TIME_EXCHANGE") == "1"
+                               else None),
         "exchange": (None if world == 1 or not step.fused_optimizer else
                      ("one fused kernel over NVLink peer memory (torch symmetric memory): average of the ranks' fp16 gradients + Adam on "
                       "a 1/N slice + store of the new fp16 values into every rank's table" if step.optimizer.p2p is not None else

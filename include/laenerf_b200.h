@@ -409,6 +409,21 @@ LNRF_API int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* co
                                     double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
                                     float* found_inf_out, const float* step_count, const float* lr_scale,
                                     lnrf_stream_t stream);
+/* The same with the rank synchronisation inside the kernels instead of two barrier launches around it.  flag_peers: each
+ * rank's peer-mapped buffer of >= 32 fp32 words -- word 0 is the non-finite flag, words 8..15 / 16..23 are written by ranks
+ * 0..7 ("my gradient is complete" / "my stores into your table are complete", as epoch numbers); all zero before the first
+ * step.  sync_state: two LOCAL device uint32 words (completed epoch, block ticket), zero before the first step.  The kernel
+ * waits for every rank's gradient before reading it and announces the end of its stores; lnrf_exchange_finish -- the next
+ * launch on the stream -- waits for every rank's announcement, then clears this rank's gradient (n elements).  Waits trap
+ * after ~4 s instead of hanging. */
+LNRF_API int lnrf_adam_step_sharded_sync(const void* const* grad_peers_host, void* const* shadow_peers_host,
+                                         const float* const* flag_peers_host, uint32_t world, uint32_t rank, uint64_t lo,
+                                         uint64_t n, float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
+                                         double lr, double beta1, double beta2, double eps, double weight_decay,
+                                         const float* grad_scale, float* found_inf_out, const float* step_count,
+                                         const float* lr_scale, uint32_t* sync_state, lnrf_stream_t stream);
+LNRF_API int lnrf_exchange_finish(const float* my_flags, uint32_t world, const uint32_t* sync_state, void* grad_f16,
+                                  uint64_t n, lnrf_stream_t stream);
 /* GradScaler.update() (growth / backoff of the loss scale from found_inf) fused with the step bookkeeping:
  * step_count += 1 unless the step was skipped, found_inf re-armed to 0.  scale / growth_tracker may be NULL
  * (no loss scaling). */

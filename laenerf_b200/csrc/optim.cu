@@ -248,19 +248,64 @@ struct PeerPtrs {
     const float* flag[kMaxPeers];
 };
 
+// In-kernel rank synchronisation (ExchangeSync.epoch != nullptr).  The flag buffer of every rank is peer-mapped; words
+// [kSyncArrive + r] and [kSyncDone + r] of MY buffer are written by rank r only.  Epoch e = *epoch + 1 of this step:
+//   arrive: block 0 stores e into word kSyncArrive + me of every rank's buffer (system-scope release after a system fence: this
+//           rank's gradient and non-finite flag are complete -- they were written by earlier kernels of the same stream), and every
+//           block waits until its own words kSyncArrive + r hold >= e for all r before it touches a peer's gradient;
+//   done:   after all blocks have stored their share of the new fp16 values into every rank's table (system fence per thread),
+//           the block that finishes last stores e into word kSyncDone + me of every rank and publishes *epoch = e;
+// k_exchange_finish (the next launch of the stream) waits for the R done-words before it clears the local gradient, and so
+// orders the next forward pass behind every peer's stores.  Replaces two symmetric-memory barrier launches and a memset.
+// Waits are bounded (__trap after ~4 s): a lost rank is a launch failure, not a hung GPU.
+constexpr uint32_t kSyncArrive = 8, kSyncDone = 16;
+struct ExchangeSync {
+    uint32_t* epoch;    // local device word: last completed epoch
+    uint32_t* ticket;   // local device word, zero between launches
+    uint32_t me;
+};
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_words_ge(const uint32_t* words, uint32_t R, uint32_t e) {  // threads r < R poll word r; then barrier
+    if (threadIdx.x < R) {
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys_u32(words + threadIdx.x) - e) < 0) {
+            if (clock64() - t0 > 8000000000ll) __trap();
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kOptBlock)
 k_adam_step_p2p(const PeerPtrs peers, const uint32_t R, const uint64_t lo, const uint64_t n, float* __restrict__ master,
                 float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, AdamHyper h, const float* __restrict__ grad_scale,
-                float* __restrict__ found_inf_out, const float* __restrict__ step_count, const float* __restrict__ lr_scale) {
+                float* __restrict__ found_inf_out, const float* __restrict__ step_count, const float* __restrict__ lr_scale,
+                const ExchangeSync sync) {
+    uint32_t epoch = 0;
+    if (sync.epoch) {
+        epoch = *sync.epoch + 1u;
+        if (blockIdx.x == 0 && threadIdx.x < R) {
+            __threadfence_system();
+            st_release_sys_u32(reinterpret_cast<uint32_t*>(const_cast<float*>(peers.flag[threadIdx.x])) + kSyncArrive + sync.me, epoch);
+        }
+        wait_words_ge(reinterpret_cast<const uint32_t*>(peers.flag[sync.me]) + kSyncArrive, R, epoch);
+    }
     bool skip = false;
-    for (uint32_t r = 0; r < R; r++) skip |= (*peers.flag[r] != 0.0f);
+    for (uint32_t r = 0; r < R; r++) skip |= (*reinterpret_cast<const volatile float*>(peers.flag[r]) != 0.0f);
     if (blockIdx.x == 0 && threadIdx.x == 0) *found_inf_out = skip ? 1.0f : 0.0f;
-    if (skip) return;  // GradScaler: nothing is updated; the gradients are cleared by the caller after the closing barrier
+    // GradScaler: when any rank saw a non-finite gradient nothing is updated (the gradients are cleared after the closing sync)
     if (lr_scale) h.lr *= (double)*lr_scale;
     const AdamStepConsts c = adam_step_consts(h, grad_scale, step_count);
     const float inv_R = 1.0f / (float)R;
 
-    for (uint64_t base = (uint64_t)blockIdx.x * kOptChunk; base < n; base += (uint64_t)gridDim.x * kOptChunk) {
+    for (uint64_t base = (uint64_t)blockIdx.x * kOptChunk; base < n && !skip; base += (uint64_t)gridDim.x * kOptChunk) {
         const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;  // n is a multiple of 8: no ragged tail
         if (i >= n) continue;
         float g[kOptPerThread], p[kOptPerThread], m[kOptPerThread], v[kOptPerThread];
@@ -301,6 +346,36 @@ k_adam_step_p2p(const PeerPtrs peers, const uint32_t R, const uint64_t lo, const
         for (int r = 0; r < kMaxPeers; r++)
             if (r < (int)R) *reinterpret_cast<uint4*>(peers.shadow[r] + lo + i) = o.u;
     }
+    if (sync.epoch) {
+        __shared__ bool s_last;
+        __syncthreads();  // every store of the block happens-before thread 0's fence (fences are cumulative): ONE system fence per
+        if (threadIdx.x == 0) {  // block, not one per thread (a per-thread membar.sys made the kernel 25 us slower than the barriers it replaces)
+            __threadfence_system();
+            s_last = atomicAdd(sync.ticket, 1u) == gridDim.x - 1u;
+        }
+        __syncthreads();
+        if (s_last) {
+            if (threadIdx.x < R) {
+                __threadfence_system();
+                st_release_sys_u32(reinterpret_cast<uint32_t*>(const_cast<float*>(peers.flag[threadIdx.x])) + kSyncDone + sync.me, epoch);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                *sync.ticket = 0u;
+                *sync.epoch = epoch;
+            }
+        }
+    }
+}
+
+// Closing half of the in-kernel synchronisation: wait until every rank has finished storing into MY table (done-words >= the epoch
+// the exchange kernel just published), then clear the local gradient for the next step.
+__global__ void __launch_bounds__(kOptBlock)
+k_exchange_finish(const uint32_t* __restrict__ my_flag_words, const uint32_t R, const uint32_t* __restrict__ epoch,
+                  uint4* __restrict__ grad, const uint64_t n_vec) {
+    wait_words_ge(my_flag_words + kSyncDone, R, *epoch);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (uint64_t)gridDim.x * blockDim.x)
+        grad[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // GradScaler.update() (torch amp_update_scale_cuda_kernel) + the bookkeeping around it, one thread: adjust the scale,
@@ -395,10 +470,11 @@ int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, flo
     return LNRF_OK;
 }
 
-int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* const* shadow_peers_host, const float* const* flag_peers_host,
+static int adam_step_sharded_impl(const void* const* grad_peers_host, void* const* shadow_peers_host, const float* const* flag_peers_host,
                            uint32_t world, uint64_t lo, uint64_t n, float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
                            double lr, double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
-                           float* found_inf_out, const float* step_count, const float* lr_scale, lnrf_stream_t stream) {
+                           float* found_inf_out, const float* step_count, const float* lr_scale, uint32_t rank, uint32_t* sync_epoch,
+                           uint32_t* sync_ticket, lnrf_stream_t stream) {
     LNRF_REQUIRE(world >= 1 && world <= (uint32_t)kMaxPeers, "adam_step_sharded: 1..%d ranks, got %u", kMaxPeers, world);
     LNRF_REQUIRE(grad_peers_host && shadow_peers_host && flag_peers_host && master_shard && exp_avg_shard && exp_avg_sq_shard &&
                      found_inf_out && step_count,
@@ -414,9 +490,42 @@ int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* const* shad
     }
     AdamHyper h{lr, beta1, beta2, eps, weight_decay};
     const uint64_t chunks = (n + kOptChunk - 1) / kOptChunk, cap = (uint64_t)kNumSMs * 8;
+    ExchangeSync sy{sync_epoch, sync_ticket, rank};
     k_adam_step_p2p<<<(uint32_t)(chunks < cap ? chunks : cap), kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        pp, world, lo, n, master_shard, exp_avg_shard, exp_avg_sq_shard, h, grad_scale, found_inf_out, step_count, lr_scale);
+        pp, world, lo, n, master_shard, exp_avg_shard, exp_avg_sq_shard, h, grad_scale, found_inf_out, step_count, lr_scale, sy);
     LNRF_LAUNCH_CHECK("adam_step_sharded");
+    return LNRF_OK;
+}
+
+int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* const* shadow_peers_host, const float* const* flag_peers_host,
+                           uint32_t world, uint64_t lo, uint64_t n, float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
+                           double lr, double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
+                           float* found_inf_out, const float* step_count, const float* lr_scale, lnrf_stream_t stream) {
+    return adam_step_sharded_impl(grad_peers_host, shadow_peers_host, flag_peers_host, world, lo, n, master_shard, exp_avg_shard,
+                                  exp_avg_sq_shard, lr, beta1, beta2, eps, weight_decay, grad_scale, found_inf_out, step_count, lr_scale, 0u,
+                                  nullptr, nullptr, stream);
+}
+
+int lnrf_adam_step_sharded_sync(const void* const* grad_peers_host, void* const* shadow_peers_host, const float* const* flag_peers_host,
+                                uint32_t world, uint32_t rank, uint64_t lo, uint64_t n, float* master_shard, float* exp_avg_shard,
+                                float* exp_avg_sq_shard, double lr, double beta1, double beta2, double eps, double weight_decay,
+                                const float* grad_scale, float* found_inf_out, const float* step_count, const float* lr_scale,
+                                uint32_t* sync_state, lnrf_stream_t stream) {
+    LNRF_REQUIRE(sync_state && rank < world, "adam_step_sharded_sync: null sync state / rank %u outside the world of %u", rank, world);
+    return adam_step_sharded_impl(grad_peers_host, shadow_peers_host, flag_peers_host, world, lo, n, master_shard, exp_avg_shard,
+                                  exp_avg_sq_shard, lr, beta1, beta2, eps, weight_decay, grad_scale, found_inf_out, step_count, lr_scale, rank,
+                                  sync_state, sync_state + 1, stream);
+}
+
+int lnrf_exchange_finish(const float* my_flags, uint32_t world, const uint32_t* sync_state, void* grad_f16, uint64_t n,
+                         lnrf_stream_t stream) {
+    LNRF_REQUIRE(my_flags && sync_state && grad_f16 && world >= 1 && world <= (uint32_t)kMaxPeers, "exchange_finish: bad arguments");
+    LNRF_REQUIRE(n % 8 == 0 && (reinterpret_cast<uintptr_t>(grad_f16) & 15) == 0, "exchange_finish: the gradient must be 16-byte vectors");
+    const uint64_t n_vec = n / 8;
+    const uint64_t want = (n_vec + kOptBlock - 1) / kOptBlock, cap = (uint64_t)kNumSMs * 8;
+    k_exchange_finish<<<(uint32_t)(want < cap ? (want ? want : 1) : cap), kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t*>(my_flags), world, sync_state, reinterpret_cast<uint4*>(grad_f16), n_vec);
+    LNRF_LAUNCH_CHECK("exchange_finish");
     return LNRF_OK;
 }
 

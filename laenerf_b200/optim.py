@@ -124,9 +124,34 @@ class AmpAdam:
             raise RuntimeError(f"symmetric memory rendezvous returned {ptrs}")
         mk = lambda v: (C.c_void_p * self.world)(*v)
         self._peer_arrays = (mk(ptrs["grad"]), mk(ptrs["shadow"]), mk(ptrs["flag"]))
+        # LNRF_INKERNEL_SYNC=1: rank synchronisation inside the exchange kernels instead of symmetric-memory barrier launches
+        self.inkernel_sync = os.environ.get("LNRF_INKERNEL_SYNC", "0") == "1" and self.world <= 8
+        self._sync_state = torch.zeros(2, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         hdls["grad"].barrier(channel=0)
         return hdls
+
+    # ---- optional timing of the exchange pieces (diagnostics; never inside graph capture) --------------------------
+    def _mark(self, name):
+        if os.environ.get("LNRF_TIME_EXCHANGE", "0") != "1" or torch.cuda.is_current_stream_capturing():
+            return
+        if not hasattr(self, "_marks"):
+            self._marks = []
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._marks.append((name, e))
+
+    def exchange_timing(self):
+        """Mean microseconds between consecutive marks of _step_sharded over the eager steps run so far (LNRF_TIME_EXCHANGE=1)."""
+        marks = getattr(self, "_marks", [])
+        torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (n0, e0), (n1, e1) in zip(marks, marks[1:]):
+            if n1 == "start":
+                continue
+            acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) * 1e3
+            cnt[n1] = cnt.get(n1, 0) + 1
+        return {k: acc[k] / cnt[k] for k in acc}
 
     # ---- GradScaler surface -------------------------------------------------------------------------------------
     def scale(self, loss):
@@ -182,17 +207,43 @@ class AmpAdam:
         if self.p2p is not None:
             # own gradient checked locally, flag published beside it; barrier; ONE kernel averages the R gradients of the slice
             # over NVLink, updates, and writes the new fp16 slice into every rank's table; barrier; clear the local gradient
+            mark = self._mark  # LNRF_TIME_EXCHANGE=1: CUDA events between the pieces (eager steps only), see exchange_timing()
+            mark("start")
+            if self.inkernel_sync:
+                # the ranks meet INSIDE the kernels (signal + poll on the peer-mapped flag words, csrc/optim.cu): no barrier launches,
+                # and the closing wait clears the gradient -- 3 launches instead of 6
+                self.flag_buf[:1].zero_()  # word 0 only: the other words carry the epochs of the synchronisation
+                N.check(lib.lnrf_grad_nonfinite_check(C.cast(self._one(None, None, self.grad_flat, None, self.P_pad), C.c_void_p), 1,
+                                                      N.ptr(self.flag_buf), st))
+                mark("inf check")
+                g, sh, fl = self._peer_arrays
+                N.check(lib.lnrf_adam_step_sharded_sync(C.cast(g, C.c_void_p), C.cast(sh, C.c_void_p), C.cast(fl, C.c_void_p), self.world,
+                                                        self.rank, self.lo, self.Sz, N.ptr(self.master_shard),
+                                                        N.ptr(self.state[0]["exp_avg"]), N.ptr(self.state[0]["exp_avg_sq"]), *hyper,
+                                                        N.ptr(self._scale), N.ptr(self.found_inf), N.ptr(self.step_count),
+                                                        N.ptr(self.lr_scale), N.ptr(self._sync_state), st))
+                mark("exchange + Adam kernel (arrive sync inside)")
+                N.check(lib.lnrf_exchange_finish(N.ptr(self.flag_buf), self.world, N.ptr(self._sync_state), N.ptr(self.grad_flat), self.P_pad, st))
+                mark("done sync + gradient clear")
+                N.check(lib.lnrf_amp_update(N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf), N.ptr(self.step_count),
+                                            self.growth_factor, self.backoff_factor, self.growth_interval, st))
+                return
             self.flag_buf.zero_()
             N.check(lib.lnrf_grad_nonfinite_check(C.cast(self._one(None, None, self.grad_flat, None, self.P_pad), C.c_void_p), 1,
                                                   N.ptr(self.flag_buf), st))
+            mark("inf check")
             self.p2p["grad"].barrier(channel=0)
+            mark("barrier A")
             g, sh, fl = self._peer_arrays
             N.check(lib.lnrf_adam_step_sharded(C.cast(g, C.c_void_p), C.cast(sh, C.c_void_p), C.cast(fl, C.c_void_p), self.world, self.lo,
                                                self.Sz, N.ptr(self.master_shard), N.ptr(self.state[0]["exp_avg"]),
                                                N.ptr(self.state[0]["exp_avg_sq"]), *hyper, N.ptr(self._scale), N.ptr(self.found_inf),
                                                N.ptr(self.step_count), N.ptr(self.lr_scale), st))
+            mark("exchange + Adam kernel")
             self.p2p["grad"].barrier(channel=1)
+            mark("barrier B")
             self.grad_flat.zero_()
+            mark("gradient clear")
         else:
             nccl = dist.get_backend(self.group) == "nccl"
             if nccl:  # mean inside the collective (pre-scaled sum: no fp16 overflow from adding `world` loss-scaled gradients)
