@@ -201,3 +201,16 @@ def test_paired_table_access_equals_unpaired(ours_backend):
         assert np.array_equal(f0, f1), half
         assert np.abs(b0).max() > 0
         assert np.allclose(b0, b1, rtol=2e-2, atol=2e-3) if half else np.allclose(b0, b1, rtol=1e-4, atol=1e-5), half
+
+
+def test_sph_from_ray_matches_oracle():
+    """raymarching.sph_from_ray (raymarching.cu:162-209; no LAENeRF config calls it, the binding exists) against the C oracle:
+    atan2f / sqrtf on the device are not bit-identical to libm, measured 2.1e-7 on the lego-shape rays."""
+    import torch
+    from oracle import pyoracle
+    from laenerf_b200 import raymarching
+    sc, ro, rd, rng = scene_rays("lego", 3000, 51)
+    want = pyoracle.sph_from_ray(ro, rd, 4.0)
+    got = raymarching.sph_from_ray(torch.from_numpy(ro).cuda(), torch.from_numpy(rd).cuda(), 4.0).cpu().numpy()
+    assert got.shape == want.shape == (3000, 2) and np.isfinite(got).all()
+    assert float(np.abs(got - want).max()) <= 2e-6
