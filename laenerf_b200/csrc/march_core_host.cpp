@@ -212,6 +212,70 @@ void mch_set_fast_forward(int on) { g_fast_forward = on; }
 static uint32_t g_max_emit = 0;
 void mch_set_max_emit(uint32_t m) { g_max_emit = m; }   // 0: max_steps (training); else the per-call sample budget (inference rounds)
 
+// march_jump against a linear search: over `windows` closed-form windows starting at t, every lane v and the probe targets
+// tt = s_v + f * dt for a sweep of f (0 .. 40 steps, including exact member values and half-way points).  Returns mismatches.
+uint64_t mch_check_jump(float t, uint32_t max_steps, uint32_t C, uint32_t H, int G, uint32_t windows) {
+    const MarchParams p = make_march_params(1.0f, 0.0f, max_steps, C, H);
+    uint64_t bad = 0;
+    for (uint32_t w = 0; w < windows; w++) {
+        float s[33], nxt = 0.f;
+        WindowInfo wi;
+        for (int l = 0; l < G; l++) s[l] = (G == 32) ? march_window<32>(p, t, l, &nxt, &wi) : march_window<8>(p, t, l, &nxt, &wi);
+        if (wi.closed) {
+            for (int v = 0; v < G; v++) {
+                for (int k = 0; k <= 80; k++) {
+                    float tt = k % 2 == 0 ? (v + k / 2 < G ? s[v + k / 2] : s[G - 1] + p.dt0 * (float)(v + k / 2 - G + 1))
+                                          : s[v] + p.dt0 * (0.5f * (float)k + 0.01f * (float)(k % 7));
+                    if (tt < s[v]) tt = s[v];
+                    int want = G;
+                    for (int l = v + 1; l < G; l++)
+                        if (s[l] >= tt) { want = l; break; }
+                    if (march_jump(wi, v, tt, G) != want) bad++;
+                }
+                if (march_jump(wi, v, INFINITY, G) != G) bad++;
+                if (march_jump(wi, v, s[v] * 4.0f, G) != G) bad++;  // a later binade
+            }
+        }
+        t = nxt;
+    }
+    return bad;
+}
+
+// march_fast_forward against the definition: the returned t must be the k-th sequential sum for some k >= 0, every skipped member
+// must lie strictly below pend, and either the returned member is the first one >= pend or it is the last member of its binade /
+// the function declined (returned t).  Returns the number of violations over a sweep of skip distances from t.
+uint64_t mch_check_fast_forward(float t, uint32_t max_steps, uint32_t C, uint32_t H, int G) {
+    const MarchParams p = make_march_params(16.0f, 0.0f, max_steps, C, H);
+    uint64_t bad = 0;
+    for (int d = 0; d <= 400; d += 3) {
+        const float pend = t + p.dt0 * ((float)d + 0.37f);
+        const float r = march_fast_forward(p, t, pend, G);
+        if (r == t) continue;  // declined: always valid
+        float s = t;
+        int k = 0;
+        bool found = false;
+        for (; k < 100000; k++) {
+            if (s == r) { found = true; break; }
+            if (s >= pend) break;  // walked past the target without meeting the returned value
+            s = s + p.dt0;
+        }
+        if (!found) { bad++; continue; }
+        // s == r is member k; all members before it were < pend by the loop; r itself is >= pend unless the binade ended
+        if (r < pend) {
+            const float next = r + p.dt0;
+            union { float f; uint32_t u; } a, b;
+            a.f = r; b.f = next;
+            if ((a.u >> 23) == (b.u >> 23)) {
+                // still inside the binade: then the function must have stopped because the closed form caps at the last member whose
+                // successor leaves the binade lattice; accept only if fewer than one window remains to the boundary
+                union { float f; uint32_t u; } e; e.u = ((a.u >> 23) + 1u) << 23;
+                if ((e.f - r) > p.dt0 * (float)(G + 1)) bad++;
+            }
+        }
+    }
+    return bad;
+}
+
 // Emulated group march of N rays (G > 0: serial resolve, G < 0: jump-table resolve with |G| lanes); counts[n] and, concatenated in ray order, the visited t values (ts, capacity cap).
 // Returns the total number of samples.
 uint64_t mch_group_march(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,

@@ -125,3 +125,28 @@ def test_fast_forward_over_pending_skips_changes_nothing_but_the_window_count(ho
         assert total == int(want[4][0]) and np.array_equal(counts.astype(np.int32), want[3][:, 2])
     assert np.array_equal(results[0][2], results[1][2])
     assert windows[1] * (2 if G < 32 else 1) < windows[0], windows  # a 32-member window already spans most of a 37-member voxel
+
+
+@pytest.mark.parametrize("G", [8, 32])
+@pytest.mark.parametrize("max_steps,Cc", [(1024, 1), (1024, 5), (333, 2), (64, 1)])
+def test_march_jump_equals_linear_search(host, G, max_steps, Cc):
+    """march_jump (integer arithmetic on mantissa fields) against "first later member with s >= tt" by linear search, for every
+    lane of closed-form windows and targets on members, between members, beyond the window, in a later binade and at infinity."""
+    host.mch_check_jump.restype = C.c_uint64
+    host.mch_check_jump.argtypes = [C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32]
+    rng = np.random.default_rng(G + max_steps)
+    starts = np.concatenate([rng.uniform(0.05, 40.0, 100), [0.2, 0.5, 1.0, 2.0, 3.99, 4.0, 7.99999, 15.9]]).astype(np.float32)
+    for t0 in starts:
+        assert host.mch_check_jump(float(t0), max_steps, Cc, 128, G, 12) == 0, f"t0={t0!r}"
+
+
+@pytest.mark.parametrize("G", [4, 8, 32])
+def test_march_fast_forward_lands_on_the_sequence(host, G):
+    """march_fast_forward returns a member of the sequential t-sequence, never skips a member >= the pending target, and stops
+    at the target or at the end of the binade."""
+    host.mch_check_fast_forward.restype = C.c_uint64
+    host.mch_check_fast_forward.argtypes = [C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    rng = np.random.default_rng(G)
+    starts = np.concatenate([rng.uniform(0.05, 50.0, 150), [0.2, 1.0, 1.99, 3.9, 4.0, 7.9, 15.99, 31.5]]).astype(np.float32)
+    for t0 in starts:
+        assert host.mch_check_fast_forward(float(t0), 1024, 5, 128, G) == 0, f"t0={t0!r}"
