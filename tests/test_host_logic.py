@@ -89,3 +89,23 @@ def test_scene_generator_shapes():
     from laenerf_b200.scene import packbits_np
     from oracle import pyoracle
     assert np.array_equal(packbits_np(sc.density_grid, 10.0), pyoracle.packbits(sc.density_grid, 10.0))
+
+
+def test_style_encoder_module_topology_without_a_gpu():
+    """Row a-13 host logic: the LAENeRF mirror sizes its two nets like tcnn does (inputs padded to 16, 3 matmuls for
+    num_layers = 3) and refuses what is out of scope instead of silently training without it."""
+    from types import SimpleNamespace
+    from laenerf_b200.style_encoder import LAENeRF
+    with pytest.raises(RuntimeError):
+        LAENeRF(SimpleNamespace(bound=2, num_palette_bases=8, style_weight=1.0), device="cpu")
+    with pytest.raises(RuntimeError):
+        LAENeRF(SimpleNamespace(bound=2, num_palette_bases=17, style_weight=0.0), device="cpu")
+    m = LAENeRF(SimpleNamespace(bound=2, num_palette_bases=8, style_weight=0.0), dir_encoding="sphere_harmonics", device="cpu")
+    assert m.in_dim == 32 and m.in_dim_dir == 9 and m.offset_in_dim == 48
+    assert (m.offset_net.input_dim, m.offset_net.num_layers, m.offset_net.output_dim) == (48, 2, 3)
+    assert (m.weight_net.input_dim, m.weight_net.num_layers, m.weight_net.output_dim) == (32, 2, 8)
+    assert m.encoder.embeddings.shape[0] == 6328848  # bound 2 table (SURVEY.md section 8: cfg3/5)
+    groups = m.get_params(1e-3)
+    assert [g["lr"] for g in groups] == [1e-3, 1e-3, 1e-3, 2e-3] and groups[3]["params"] is m.color_palette
+    assert m.get_params_but_dont_learn_palette(1e-3)[3]["lr"] == 0
+    assert m.color_palette.shape == (8, 3) and m.color_palette.requires_grad
