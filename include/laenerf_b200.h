@@ -58,6 +58,10 @@ LNRF_API int lnrf_version(void);
 LNRF_API int lnrf_compiled_arch(void);
 /* Number of kernels this library has launched from this process (all threads); used by bench.py gpu_launches. */
 LNRF_API uint64_t lnrf_launch_count(void);
+/* sizeof(lnrf_render_desc) / sizeof(lnrf_opt_tensor) in this build, so that an FFI mirror of the two descriptor structs
+ * (ctypes.Structure, cgo, ...) can be checked before the first call. */
+LNRF_API size_t lnrf_sizeof_render_desc(void);
+LNRF_API size_t lnrf_sizeof_opt_tensor(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * raymarching utilities -- replaces raymarching/src/raymarching.cu:148-156, 201-209, 229-232, 257-260, 292-300

@@ -29,6 +29,8 @@ SIGNATURES = {
     "lnrf_version": (i32, []),
     "lnrf_compiled_arch": (i32, []),
     "lnrf_launch_count": (u64, []),
+    "lnrf_sizeof_render_desc": (sz, []),
+    "lnrf_sizeof_opt_tensor": (sz, []),
     "lnrf_near_far_from_aabb": (i32, [vp, vp, vp, u32, f32, vp, vp, vp]),
     "lnrf_sph_from_ray": (i32, [vp, vp, f32, u32, vp, vp]),
     "lnrf_morton3D": (i32, [vp, u32, vp, vp]),
@@ -126,6 +128,9 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
+        if l.lnrf_sizeof_render_desc() != C.sizeof(RenderDesc) or l.lnrf_sizeof_opt_tensor() != C.sizeof(OptTensor):
+            raise RuntimeError("laenerf_b200: the ctypes mirrors of lnrf_render_desc / lnrf_opt_tensor do not match "
+                               f"{SO_PATH} (stale build?) -- rebuild with `make -C laenerf_b200/csrc`")
         _lib = l
     return _lib
 

@@ -26,4 +26,7 @@ const char* lnrf_last_error(void) { return lnrf::t_error; }
 int lnrf_version(void) { return 100; }  // 0.1.0
 int lnrf_compiled_arch(void) { return 100; }  // sm_100a
 uint64_t lnrf_launch_count(void) { return lnrf::g_launch_count.load(std::memory_order_relaxed); }
+// struct sizes of this build: a binding checks its own mirror of the two descriptor structs against these before the first call
+size_t lnrf_sizeof_render_desc(void) { return sizeof(lnrf_render_desc); }
+size_t lnrf_sizeof_opt_tensor(void) { return sizeof(lnrf_opt_tensor); }
 }

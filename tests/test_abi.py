@@ -83,3 +83,13 @@ def test_missing_library_fails_loudly(native, monkeypatch):
     monkeypatch.setattr(native, "SO_PATH", "/nonexistent/liblaenerf_b200.so")
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         native.lib()
+
+
+def test_descriptor_struct_mirrors_match_the_library():
+    """The ctypes mirrors of lnrf_render_desc / lnrf_opt_tensor have the size the library was built with (the loader refuses
+    a mismatch; this pins it in the CPU tier)."""
+    import ctypes as C
+    from laenerf_b200 import _native as N
+    lib = N.lib()
+    assert lib.lnrf_sizeof_render_desc() == C.sizeof(N.RenderDesc)
+    assert lib.lnrf_sizeof_opt_tensor() == C.sizeof(N.OptTensor)
