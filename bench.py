@@ -1,20 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the ray-marched NeRF step (BASELINE.json: train rays/s & render Msamples/s on a
-lego-shape 800x800 synthetic scene, % of roofline).
+lego-shape 800x800 synthetic scene at 1/2/4/8 B200, % of roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); training shards RAYS (4096 per GPU, weak scaling) with one
-all-reduce of the hash-grid + MLP gradients per step.  A "step" is one full training step of configs[1]:
+exchange of the hash-grid + MLP gradients per step.  A "step" is one full training step of configs[1]:
 near/far -> march_rays_train -> hash-grid encode -> sigma MLP -> SH -> colour MLP -> composite -> MSE -> backward of
 all of it -> Adam, under fp16 autocast exactly as `-O` runs it.  One JSON line is printed by rank 0.
 
+Besides the headline (`value`, `e2e`, `roofline`, `cpu_baseline`) the line carries
+  render          one 800x800 view on the reference's round schedule (bit-identical sample positions), the fast schedule beside it
+  configs         BASELINE.json configs 3-5: flower-shape training (ray-sharded at N > 1), bonsai-shape bound-16 test view
+                  (tile-sharded), edit stage (view-sharded distillation renders + data-parallel style-network steps)
+  gpu_reference   the reference's OWN stack on the same GPU in the same process: its Python callers (nerf/renderer.py run_cuda,
+                  network_ff.py / network.py, staged untouched under oracle/_ref/py) on its own extensions (oracle/_ref/*.so) --
+                  the `--ff` stack, the default `-O` stack (nn.Linear MLPs) and the host-loop render -- with `vs_gpu_reference`
+  roofline_large  march / encode / composite at 65 536 rays (~4 M samples), the regime where an HBM roofline is meaningful
+
 `--impl reference` times the CPU arm: the PyTorch-CPU restatement of the reference's non-cuda_ray renderer
-(oracle/cpu_renderer.py, BASELINE.json configs[0]) on the host cores, same metric and unit.
+(oracle/cpu_renderer.py, BASELINE.json configs[0]) on the host cores, same metric and unit, exactly K timed steps.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -22,6 +32,7 @@ import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -31,7 +42,7 @@ N_RAYS = 4096
 _OUT = sys.stdout
 WORKLOAD = "lego-shape 800x800 hash-grid NeRF training step (16 levels, 2^19 table, 4096 rays/GPU, cuda_ray, fp16 autocast, Adam)"
 
-# algorithmic bytes / FLOPs per unit (restated in DESIGN.md section 7)
+# algorithmic bytes / FLOPs per unit (restated in DESIGN.md section 8)
 ALGO = {
     "lnrf_march_rays_train": dict(bound="hbm", per_ray=48, per_sample=32),
     "lnrf_grid_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
@@ -47,7 +58,7 @@ ALGO = {
     "lnrf_ffmlp_backward": dict(bound="tensor", flops_per_sample_padded=73728 / 2),
     "lnrf_sh_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=12 + 64),
     "lnrf_near_far_from_aabb": dict(bound="hbm", per_ray=32, per_sample=0),
-    # fused rows f-1 / f-4 (one C-ABI call each; nerf_backward = colour-net + sigma-net launches and two finalize launches)
+    # fused rows f-1 / f-4 (one C-ABI call each)
     "lnrf_nerf_forward": dict(bound="tensor", flops_per_sample_padded=36864),
     "lnrf_nerf_backward": dict(bound="tensor", flops_per_sample_padded=73728),
     "lnrf_adam_step": dict(bound="hbm", per_param=30),            # g16 R+W 4, p/m/v R+W 24, p16 W 2
@@ -79,6 +90,7 @@ class ClockSampler:
             threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
         if self.proc is None:
@@ -114,6 +126,9 @@ class TimedLib:
         self.events = {n: [] for n in names}
         self.enabled = False
 
+    def reset(self):
+        self.events = {n: [] for n in self._names}
+
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
         if name not in self._names:
@@ -140,28 +155,590 @@ class TimedLib:
         return out
 
 
+def base_config(world):
+    """The static part of `config` (identical in both arms)."""
+    return {"workload": WORKLOAD, "rays_per_gpu": N_RAYS,
+            "l2": "no explicit flush: one step touches ~245 MB (fp32 table + grads + Adam moments + fp16 copies) > 126 MB L2",
+            "parallelism": (f"ray-sharded dp{world}: the fp16 hash-grid + MLP gradients are averaged over NVLink peer memory, Adam runs on a "
+                            f"1/{world} slice per rank, the new fp16 values are stored into every rank's table (ZeRO-1 style, one kernel)")
+            if world > 1 else "single GPU"}
+
+
 def run_reference(args, rank, world):
-    """CPU arm: oracle/cpu_renderer.py (PyTorch-CPU port of NeRFRenderer.run + nn.Linear NeRFNetwork, freq encodings)."""
+    """CPU arm: oracle/cpu_renderer.py (PyTorch-CPU port of NeRFRenderer.run + nn.Linear NeRFNetwork, freq encodings), all host
+    cores, EXACTLY --steps timed steps after --warmup untimed ones, each step a bounded sample of the 4096-ray batch."""
     if rank != 0:
         return
     import torch
     from cases import scene_rays
     from oracle import cpu_renderer
-    n = min(N_RAYS, int(os.environ.get("LNRF_CPU_RAYS", "2048")))
+    steps, warm = args.steps, args.warmup
+    # ~0.15 ms per ray-step on 16 cores: keep the whole run near 30 s whatever K is
+    n = int(os.environ.get("LNRF_CPU_RAYS", str(max(256, min(2048, int(200_000 / max(1, steps + warm)) // 128 * 128)))))
     sc, ro, rd, rng = scene_rays("lego", n, 0)
     gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(0))
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     sec, threads, used = cpu_renderer.time_train_steps(torch.from_numpy(ro), torch.from_numpy(rd), gt, steps=steps, warmup=warm,
                                                        num_steps=512, bound=sc.bound, min_near=sc.min_near)
     value = used / sec
-    sample = f"{used} rays x 512 uniform samples/ray per step (hits of a {n}-ray draw), {steps} timed + {warm} warm-up steps, fp32"
-    line = {"impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "arm": "reference non-cuda_ray renderer (nerf/renderer.py run + nerf/network.py, "
-                                            "frequency encodings) restated for CPU in oracle/cpu_renderer.py; bounded sample"},
+    sample = (f"{used} rays x 512 uniform samples/ray per step (the rays of a {n}-ray draw that hit the box; non-cuda_ray renderer "
+              f"nerf/renderer.py:128-256 + nerf/network.py with frequency encodings restated in oracle/cpu_renderer.py), {steps} timed + {warm} warm-up "
+              f"steps, fp32, ONE host whatever --gpus is")
+    cfg = base_config(1)
+    cfg["arm"] = "cpu port of the reference's non-cuda_ray path; bounded sample of the workload (see cpu_baseline.sample)"
+    line = {"impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": 1, "requested_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), file=_OUT, flush=True)
+
+
+# =====================================================================================================================
+class Ctx:
+    """Process-wide handles shared by the measurement functions."""
+
+    def __init__(self, args, torch, dist, rank, world, local, timed):
+        self.args, self.torch, self.dist, self.rank, self.world, self.local, self.timed = args, torch, dist, rank, world, local, timed
+        self.dev = torch.device("cuda", local)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_loop(self, fn, n):
+        """n calls of fn(i) bracketed by barrier + synchronize, CUDA events, max over ranks -> total ms."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def make_model(ctx, name, n_poses=8):
+    from laenerf_b200.nerf import NeRFNetwork
+    from laenerf_b200.scene import make_scene
+    torch = ctx.torch
+    sc = make_scene(name, seed=0, n_poses=n_poses)
+    torch.manual_seed(0)
+    model = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_thresh=sc.density_thresh).to(ctx.dev)
+    model.set_density_grid(torch.from_numpy(sc.density_grid).to(ctx.dev), thresh=10.0)
+    return sc, model
+
+
+def make_batches(ctx, sc, n_batches=8, seed=1000):
+    import numpy as np
+    from laenerf_b200.scene import get_rays_np
+    torch = ctx.torch
+    rng = np.random.default_rng(seed + ctx.rank)
+    host = []
+    for b in range(n_batches):
+        ro, rd, _ = get_rays_np(sc.poses[b % len(sc.poses)], sc.intrinsics, sc.H, sc.W, N=N_RAYS, rng=rng)
+        gt = rng.random((N_RAYS, 3), dtype=np.float32)
+        host.append(tuple(torch.from_numpy(x).pin_memory() for x in (ro, rd, gt)))
+    return host, [tuple(x.to(ctx.dev) for x in hb) for hb in host]
+
+
+def size_sample_buffer(model, step, dev_batches):
+    """The reference sizes the sample buffer from a running mean of the last <= 16 counters (renderer.py:643-647) and silently drops
+    the rays that overflow it.  A timed pass must not drop work it is credited for: every batch is marched once, the buffer is
+    sized for the largest one plus 3 % for the march noise, and mean_count stays fixed afterwards."""
+    counts = []
+    model.mean_count = 0
+    for b in dev_batches:
+        model.local_step = 0
+        step(*b)  # mean_count <= 0: exact size from the counter (one host sync per step, as in the reference's first epoch)
+        counts.append(int(model.step_counter[0, 0].item()))
+    model.mean_count = int(max(counts) * 1.03) + 128
+    model.local_step = 0
+    return counts
+
+
+def train_config(ctx, name, headline):
+    """Training step of one scene: eager pass with per-kernel events, graph pass (`value`), end-to-end pass; headline adds the
+    occupancy-update variant."""
+    from laenerf_b200 import _native
+    from laenerf_b200.nerf import GraphedTrainStep, TrainStep
+    torch, args, world, timed = ctx.torch, ctx.args, ctx.world, ctx.timed
+    sc, model = make_model(ctx, name)
+    step = TrainStep(model, world_size=world)
+    host_batches, dev_batches = make_batches(ctx, sc)
+    nb = len(dev_batches)
+    for i in range(max(args.warmup - nb, 0)):
+        step(*dev_batches[i % nb])
+    counts = size_sample_buffer(model, step, dev_batches)
+    for i in range(3):
+        step(*dev_batches[i % nb])
+    ctx.barrier()
+    steps = args.steps if headline else max(10, args.steps // 2)
+
+    # ---- pass 1 (eager, Python-issued launches): per-kernel CUDA events live on the launching stream ------------------
+    points = []
+    timed.reset()
+    timed.enabled = True
+    l0 = _native.launch_count()
+    model.local_step = 0
+    eager_ms = ctx.timed_loop(lambda i: points.append(step(*dev_batches[i % nb])[1]["num_points"]), steps)
+    timed.enabled = False
+    eager_launches = _native.launch_count() - l0
+    rows = int(points[0])
+    seen = model.step_counter[: min(16, steps), 0].tolist()
+    actual = int(sum(seen) / len(seen))
+    dropped_samples = int(sum(max(0, c - rows) for c in seen))
+    kern = timed.summary()
+
+    # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
+    lookahead = os.environ.get("LNRF_LOOKAHEAD", "0") == "1"
+    gstep, graph_note = None, "cuda graph (one capture per sample-buffer size)" + ("; look-ahead march on a second stream" if lookahead else "")
+    if os.environ.get("LNRF_NO_GRAPH", "0") != "1":
+        try:
+            gstep = GraphedTrainStep(step, N_RAYS, lookahead=lookahead)
+            gstep.capture(*dev_batches[0])
+            for i in range(3):
+                gstep(*dev_batches[i % nb])
+        except Exception as e:  # never silently: the JSON line says which path was timed
+            gstep, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"[:300]
+            torch.cuda.synchronize()
+    run = gstep if gstep is not None else (lambda *b: step(*b))
+    clocks = ClockSampler(ctx.local).start() if ctx.rank == 0 else None
+    ms = ctx.timed_loop(lambda i: run(*dev_batches[i % nb]), steps)
+    clk = clocks.stop() if clocks else None
+    graph_seen = model.step_counter[: min(16, steps), 0].tolist()
+    graph_rows = int(gstep.out["num_points"]) if gstep is not None else rows
+    dropped_samples += int(sum(max(0, c - graph_rows) for c in graph_seen))
+    in_sync = None
+    if world > 1 and step.fused_optimizer:  # every rank must hold the same fp16 table after the sharded optimizer steps
+        chk = model.encoder._shadow_f16.float().abs().sum().double().reshape(1)
+        lo_, hi_ = chk.clone(), chk.clone()
+        ctx.dist.all_reduce(lo_, op=ctx.dist.ReduceOp.MIN)
+        ctx.dist.all_reduce(hi_, op=ctx.dist.ReduceOp.MAX)
+        in_sync = bool(lo_.item() == hi_.item())
+    value = world * N_RAYS * steps / (ms * 1e-3)
+    res = dict(scene=name, image=[sc.H, sc.W], bound=sc.bound, cascades=model.cascade, ms_per_step=ms / steps, value=value, unit="rays/s",
+               steps=steps, samples_per_step=actual, samples_per_ray=actual / N_RAYS, sample_rows_eager=rows, sample_rows_graph=graph_rows,
+               samples_per_batch_at_sizing=counts, dropped_samples=dropped_samples, dropped_rays=0 if dropped_samples == 0 else None,
+               train_msamples_per_s=world * actual * steps / (ms * 1e-3) / 1e6, occupancy=sc.occupancy_fraction(),
+               eager_ms_per_step=eager_ms / steps, step_mode=graph_note, replicas_in_sync=in_sync, clocks=clk)
+    if world > 1 and step.fused_optimizer:
+        opt = step.optimizer
+        res["exchange"] = ("one fused kernel over NVLink peer memory (torch symmetric memory): mean of the ranks' fp16 gradients + Adam on a 1/N "
+                           "slice + store of the new fp16 values into every rank's table" if opt.p2p is not None else
+                           "NCCL reduce-scatter + Adam on a 1/N slice + NCCL all-gather (symmetric memory unavailable: " +
+                           str(getattr(opt, "p2p_error", "disabled")) + ")")
+        res["exchange_sync"] = (None if opt.p2p is None else "inside the kernels (signal + poll on peer-mapped flag words)" if opt.inkernel_sync
+                                else "two symmetric-memory barrier launches around the kernel")
+        if os.environ.get("LNRF_TIME_EXCHANGE", "1") == "1":
+            res["exchange_timing_us"] = opt.exchange_timing()
+
+    # ---- per-kernel roofline (events recorded live inside the eager timed region) -------------------------------------
+    peaks = measured_peaks()
+    n_params = sum(p.numel() for p in model.parameters())
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
+    table = {}
+    for kname, k in kern.items():
+        a = ALGO[kname]
+        calls_per_step = k["calls"] / steps
+        if a["bound"] == "hbm":
+            byts = (a.get("per_ray", 0) * N_RAYS + a.get("per_sample", 0) * actual + a.get("per_sample_padded", 0) * rows +
+                    a.get("per_param", 0) * (n_params // world))  # sharded optimizer: each rank updates 1/world of the table
+            ach = byts / (k["mean_ms"] * 1e-3) / 1e9
+            table[kname] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], mean_ms=k["mean_ms"],
+                                calls_per_step=calls_per_step, algorithmic_bytes=byts, traffic=traffic.get(kname))
+        else:
+            fl = a["flops_per_sample_padded"] * rows
+            ach = fl / (k["mean_ms"] * 1e-3) / 1e12
+            table[kname] = dict(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s", frac=ach / peaks["tensor"],
+                                mean_ms=k["mean_ms"], calls_per_step=calls_per_step, algorithmic_flops=fl, traffic=traffic.get(kname))
+    dominant = max(table, key=lambda n: kern[n]["total_ms"]) if table else None
+    roofline = None
+    if dominant:
+        d = table[dominant]
+        roofline = dict(bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=d["traffic"],
+                        kernel=dominant, mean_ms=d["mean_ms"], peak_source=peaks["source"] + (" (sustained)" if d["bound"] == "tensor" else ""),
+                        share_of_step=kern[dominant]["total_ms"] / sum(k["total_ms"] for k in kern.values()),
+                        timing="CUDA events around each C-ABI launch during the eager pass of the same step (graph replays cannot be bracketed)")
+    res.update(roofline=roofline, kernels=table, gpu_launches=int(eager_launches))
+
+    if headline:
+        # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ------------------------------------
+        def e2e_iter(i):
+            hb = host_batches[i % nb]
+            if gstep is not None:
+                loss, _ = gstep(*hb)  # static device buffers are filled straight from pinned memory (non_blocking copies)
+            else:
+                loss, _ = step(*(x.to(ctx.dev, non_blocking=True) for x in hb))
+            float(loss.item())
+
+        e2e_ms = ctx.timed_loop(e2e_iter, steps)
+        res["e2e"] = {"value": world * N_RAYS * steps / (e2e_ms * 1e-3), "unit": "rays/s",
+                      "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_batches[0]), "d2h_bytes_per_step": 4}
+
+        # ---- with the occupancy maintenance the reference pays every 16 steps (nerf/utils.py:1465-1467, renderer.py:556-649) ---------
+        # The synthetic scene IS its procedural occupancy grid: letting a random-init network rewrite it would change the workload
+        # (every cell becomes occupied).  So the update runs for real -- point generation, encoder, sigma net, scatter, EMA, mean,
+        # packbits -- and the grid / bitfield are restored from a copy right after (8.6 MB of device copies, inside the timed region).
+        try:
+            keep = (model.density_grid.clone(), model.density_bitfield.clone(), model.mean_count)
+
+            def occ_update(full):
+                model.iter_density = 0 if full else 16
+                with torch.autocast("cuda", dtype=torch.float16):
+                    model.update_extra_state()
+                model.density_grid.copy_(keep[0]); model.density_bitfield.copy_(keep[1])
+                model.mean_count, model.local_step = keep[2], 0
+
+            occ_ms = {}
+            for full in (True, False):
+                occ_update(full)
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                ev0.record()
+                for _ in range(3):
+                    occ_update(full)
+                ev1.record()
+                torch.cuda.synchronize()
+                occ_ms["full" if full else "partial"] = ev0.elapsed_time(ev1) / 3
+
+            def with_occ(i):
+                if i % 16 == 0:
+                    occ_update(False)
+                run(*dev_batches[i % nb])
+
+            k16 = max(16, steps // 16 * 16)
+            oms = ctx.timed_loop(with_occ, k16)
+            res["value_with_occupancy_update"] = {
+                "value": world * N_RAYS * k16 / (oms * 1e-3), "unit": "rays/s", "ms_per_step": oms / k16, "steps": k16, "update_every": 16,
+                "update_ms": occ_ms, "note": "steady-state (partial) update_extra_state every 16 steps inside the timed region; the grid is restored "
+                                             "after each update so the workload stays the procedural scene (full updates run only in the first 256 steps)"}
+        except Exception as e:
+            res["value_with_occupancy_update"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    res["_model"], res["_sc"], res["_step"], res["_batches"] = model, sc, step, (host_batches, dev_batches)
+    return res
+
+
+def count_real_samples(ctx, model, ro_d, rd_d):
+    """Occupied-cell samples of these rays (the slots of a round include the zero padding the API mandates): counted once, outside
+    the timed region, by the one-shot marcher without a sample budget."""
+    from laenerf_b200 import raymarching as _rm
+    torch = ctx.torch
+    real = 0
+    with torch.no_grad():
+        for c0 in range(0, ro_d.shape[0], 65536):
+            o_, d_ = ro_d[c0:c0 + 65536].contiguous(), rd_d[c0:c0 + 65536].contiguous()
+            ne_, fa_ = _rm.near_far_from_aabb(o_, d_, model.aabb_infer, model.min_near)
+            cnt_ = torch.zeros(2, dtype=torch.int32, device=ctx.dev)
+            # force_all_rays with a 128-row token buffer would allocate N x 1024 rows: march with mean_count = 128 instead (counters are exact)
+            _rm.march_rays_train(o_, d_, model.bound, model.density_bitfield, model.cascade, model.grid_size, ne_, fa_, cnt_, 128, False, -1, False, 0, 1024)
+            real += int(cnt_[0].item())
+    return real
+
+
+def render_config(ctx, model, sc, pose_index=0, frames=3):
+    """One full view, tile-sharded over ranks (no collective but the final gather), on both round schedules.  `value` is the
+    reference schedule: bit-identical sample positions to nerf/renderer.py:335-387 (tests/test_gpu_refstack.py, test_gpu_fused.py)."""
+    import numpy as np
+    from laenerf_b200.parallel import gather_tiles, tile_shard_indices
+    from laenerf_b200.scene import get_rays_np
+    torch, world, rank = ctx.torch, ctx.world, ctx.rank
+    ro, rd, _ = get_rays_np(sc.poses[pose_index], sc.intrinsics, sc.H, sc.W)
+    # N > 1: 32 x 32 pixel tiles dealt round-robin over the ranks (contiguous row ranges leave the object to the middle ranks)
+    mine = tile_shard_indices(sc.H, sc.W, rank, world).numpy() if world > 1 else np.arange(sc.H * sc.W)
+    ro_d, rd_d = torch.from_numpy(ro[mine]).to(ctx.dev), torch.from_numpy(rd[mine]).to(ctx.dev)
+    model.eval()
+    real = ctx.sum_over_ranks(count_real_samples(ctx, model, ro_d, rd_d))
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for schedule in ("reference", "fast"):
+        model.render_schedule = schedule
+        marks, slots = [], 0
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            for _ in range(2):  # warm-up frames, final gather included (the first collective of a shape pays NCCL's lazy set-up)
+                gather_tiles(model.render(ro_d, rd_d, perturb=False, bg_color=1)["image"], sc.H, sc.W, rank, world)
+            ctx.barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(frames):
+                a, b, c = ev(), ev(), ev()
+                a.record()
+                o = model.render(ro_d, rd_d, perturb=False, bg_color=1)
+                b.record()
+                img = gather_tiles(o["image"], sc.H, sc.W, rank, world)
+                c.record()
+                marks.append((a, b, c))
+                slots += o["num_points"]
+            e1.record()
+            ctx.barrier()
+        rms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        loop_ms = ctx.max_over_ranks(sum(a.elapsed_time(b) for a, b, _ in marks) / frames)
+        gather_ms = ctx.max_over_ranks(sum(b.elapsed_time(c) for _, b, c in marks) / frames)
+        slots_all = ctx.sum_over_ranks(slots)
+        out[schedule] = dict(value=real * frames / (rms * 1e-3) / 1e6, unit="Msamples/s", ms_per_frame=rms / frames, render_loop_ms=loop_ms,
+                             gather_ms=gather_ms, rounds=o.get("rounds"), sample_slots_per_frame=slots_all / frames,
+                             slots_msamples_per_s=slots_all / (rms * 1e-3) / 1e6, rays_per_s=ro.shape[0] * frames / (rms * 1e-3))
+    model.render_schedule = "reference"
+    model.train()
+    res = dict(out["reference"])
+    res.update(scene=sc.name, image_shape=list(img.shape), rays_per_frame=int(ro.shape[0]), samples_per_frame=real, schedule="reference",
+               note=("value counts REAL samples (occupied-cell samples of the frame's rays; slots include the zero padding of every round) on the "
+                     "reference's n_step rule: same rounds, bit-identical sample positions; `fast_schedule` = up to 32 samples per ray per round "
+                     "after the first, NOT bit-identical (sample positions move by an ulp where a round boundary moves), reported for context"),
+               fast_schedule=out["fast"],
+               sharding=("32x32-pixel tiles dealt round-robin over the ranks; all_gather + index_select by the known index lists"
+                         if world > 1 else "single GPU, row-major rays"))
+    return res
+
+
+def edit_config(ctx, flower):
+    """BASELINE.json configs[4]: the recolor/style stage on the flower shape.  (1) EditDataset construction: one full-image
+    run_cuda_distill per training view against the edit grid, VIEWS sharded over ranks (editing/edit_dataset.py:74-234);
+    (2) style-network training: StyleTrainStep on the masked points of a view, data parallel over views (nerf/utils.py:953-1055)."""
+    import numpy as np
+    from laenerf_b200.parallel import shard_range
+    from laenerf_b200.scene import get_rays_np
+    from laenerf_b200.style_encoder import LAENeRF, StyleTrainStep
+    torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
+    sc, model = flower["_sc"], flower["_model"]
+    model.eval()
+    model.render_schedule = "reference"
+    n_views = max(8, world)
+    lo, hi = shard_range(n_views, rank, world)
+    views = []
+    for v in range(lo, hi):
+        ro, rd, _ = get_rays_np(sc.poses[v % len(sc.poses)], sc.intrinsics, sc.H, sc.W)
+        views.append((torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)))
+    # edit grid: the occupied cells of two quarters of the Morton range of each cascade (same layout as the density bitfield)
+    edit = model.density_bitfield.clone()
+    edit[edit.numel() // 4: edit.numel() // 2] = 0
+    edit[3 * edit.numel() // 4:] = 0
+    outs = []
+
+    def distill_all(_):
+        outs.clear()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            for ro, rd in views:
+                outs.append(model.run_cuda_distill(ro, rd, edit, perturb=False))
+
+    distill_all(0)
+    ms = ctx.timed_loop(distill_all, 2) / 2
+    o, (ro, rd) = outs[0], views[0]
+    mask = o["weights_edit"] > 0.05
+    x_term, d = o["x_term"][mask].contiguous(), rd[mask].contiguous()
+    masked = int(x_term.shape[0])
+    # the reference's fp16 regularisers overflow beyond ~75k points (sum of (1 - max w) in half, style_encoder.py:185-189): one
+    # iteration trains on a view's worth of at most 49 152 masked points
+    x_term, d = x_term[:49152].contiguous(), d[:49152].contiguous()
+    K = int(x_term.shape[0])
+    params = SimpleNamespace(bound=sc.bound, num_palette_bases=8, style_weight=0.0, weight_loss_uniform=1e-6, weight_loss_non_uniform=1e-6,
+                             offset_loss=1e-6, palette_loss_valid=1e-3, palette_loss_distinct=1e-3)
+    res = dict(scene="flower", image=[sc.H, sc.W], views=n_views, views_per_rank=hi - lo, distill_ms_per_view_set=ms,
+               distill_views_per_s=n_views / (ms * 1e-3), distill_rays_per_s=n_views * sc.H * sc.W / (ms * 1e-3),
+               masked_points_of_view=masked, points_per_style_step=K)
+    model.train()
+    if K < 128:
+        res["style"] = {"error": "edit grid hit by fewer than 128 pixels"}
+        return res
+    target = torch.rand(K, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+    timings = {}
+    for fused in (True, False):
+        torch.manual_seed(1)
+        style = LAENeRF(params, dir_encoding="sphere_harmonics").to(dev)
+        st = StyleTrainStep(style, params, fused_optimizer=fused, world_size=world, rank=rank)
+        losses = []
+        for _ in range(5):
+            st(x_term, d, target)
+        sms = ctx.timed_loop(lambda i: losses.append(st(x_term, d, target)[0]), 20) / 20
+        l = [float(x) for x in losses]
+        timings["fused_adam" if fused else "torch_adam"] = dict(ms_per_step=sms, points_per_s=world * K / (sms * 1e-3), loss_first=l[0], loss_last=l[-1])
+        del style, st
+    res["style"] = dict(timings["fused_adam"], torch_adam=timings["torch_adam"],
+                        note="StyleTrainStep: hash grid fwd/bwd (fp32 table, as the reference runs it without autocast), SH-3, two FFMLP nets on tcgen05, "
+                             "palette mix, MSE + regularisers, GradScaler + Adam; `torch_adam` = the same step with torch.optim.Adam + torch GradScaler; "
+                             "N > 1: one view per rank per step, gradients averaged over ranks")
+    return res
+
+
+def roofline_large(ctx, model, sc):
+    """march / encode / composite at 65 536 rays (~4 M samples): the regime where the >= 60 %-of-HBM target is meaningful
+    (the 4096-ray launches move 6-130 MB and are latency-bound)."""
+    import numpy as np
+    from laenerf_b200 import raymarching
+    from laenerf_b200.scene import get_rays_np
+    torch, dev = ctx.torch, ctx.dev
+    HBM = measured_peaks()["hbm"]
+    N = 65536
+
+    def timed(fn, n=8, warm=2):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ro, rd, _ = get_rays_np(sc.poses[0], sc.intrinsics, sc.H, sc.W, N=N, rng=np.random.default_rng(0))
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    nears, fars = raymarching.near_far_from_aabb(ro, rd, model.aabb_train, model.min_near)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    raymarching.march_rays_train(ro, rd, model.bound, model.density_bitfield, model.cascade, model.grid_size, nears, fars, counter, 128, True, -1, False, 0, 1024)
+    M_real = int(counter[0].item())
+    mean_count = int(M_real * 1.02)
+
+    def march():
+        counter.zero_()
+        return raymarching.march_rays_train(ro, rd, model.bound, model.density_bitfield, model.cascade, model.grid_size, nears, fars, counter,
+                                            mean_count, True, 128, False, 0, 1024)
+
+    clocks = ClockSampler(ctx.local).start()
+    xyzs, dirs, deltas, rays = march()
+    M = int(xyzs.shape[0])
+    out = {"rays": N, "samples": M_real, "rows": M, "hbm_peak_gbs": HBM, "kernels": {}}
+
+    def rec(name, ms, byts):
+        out["kernels"][name] = dict(ms=ms, algorithmic_bytes=byts, achieved_gbs=byts / ms / 1e6, frac=byts / ms / 1e6 / HBM)
+
+    rec("march_rays_train", timed(march), 48 * N + 32 * M_real)
+    enc = model.encoder
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        rec("grid_encode_forward", timed(lambda: enc(xyzs, bound=model.bound)), 588 * M)
+    g = torch.randn(M, 32, device=dev).half() * 1e-3
+    enc._grad_f16.zero_() if enc._grad_f16 is not None else None
+    with torch.autocast("cuda", dtype=torch.float16):
+        f2 = enc(xyzs, bound=model.bound)
+
+    def enc_bwd():
+        enc.embeddings.grad = None
+        f2.backward(g, retain_graph=True)
+
+    rec("grid_encode_backward", timed(enc_bwd), 588 * M)
+    if enc._grad_f16 is not None:
+        enc._grad_f16.zero_()
+    sig = torch.rand(M, device=dev) * 20
+    rgb = torch.rand(M, 3, device=dev)
+    rec("composite_rays_train_forward", timed(lambda: raymarching.composite_rays_train(sig, rgb, deltas, rays, 1e-4)), 32 * N + 24 * M_real)
+    gt = torch.rand(N, 3, device=dev)
+    sg, rg = sig.clone().requires_grad_(True), rgb.clone().requires_grad_(True)
+    loss, _, _, _ = raymarching.composite_loss_train(sg, rg, deltas, rays, gt, 1, nears, fars, 1e-4)
+
+    def comp_bwd():
+        sg.grad = rg.grad = None
+        loss.backward(retain_graph=True)
+
+    rec("composite_loss_train_forward", timed(lambda: raymarching.composite_loss_train(sig, rgb, deltas, rays, gt, 1, nears, fars, 1e-4)), 64 * N + 24 * M_real)
+    rec("composite_loss_train_backward", timed(comp_bwd), 60 * N + 40 * M_real)
+    out["clocks"] = clocks.stop()
+    return out
+
+
+def gpu_reference(ctx, lego, render):
+    """The reference's OWN stack on this GPU, in this process (the >= 10x target needs driver-side evidence):
+    nerf/renderer.py + nerf/network_ff.py (`--ff`) / nerf/network.py (default `-O`: nn.Linear MLPs on cuBLAS) of the reference, untouched,
+    on the reference's wrapper packages and compiled extensions (oracle/_ref), driven like Trainer.train_step + the `-O` optimizer recipe
+    (nerf/utils.py:535-642, 1474-1484; main_nerf.py:223).  Same scene, same 4096-ray batches, same sample-buffer size, CUDA events."""
+    import ref_stack
+    torch, args, dev = ctx.torch, ctx.args, ctx.dev
+    if not ref_stack.available("reference"):
+        return {"unavailable": "oracle/_ref (reference extensions + staged python) not built: python oracle/build_ref.py"}
+    sc, ours = lego["_sc"], lego["_model"]
+    _, dev_batches = lego["_batches"]
+    nb = len(dev_batches)
+    steps = max(5, min(args.steps, 20))
+    out = {"what": "reference Python callers + reference CUDA extensions (sm_100a build of the untouched sources), eager as its trainer issues them",
+           "steps": steps}
+    clocks = ClockSampler(ctx.local).start()
+    for variant in ("ff", "default"):
+        try:
+            m = ref_stack.make_model("reference", variant, device=dev, bound=sc.bound, density_scale=1, min_near=sc.min_near, density_thresh=10.0)
+            with torch.no_grad():
+                m.density_grid.copy_(ours.density_grid)
+                m.density_bitfield.copy_(ours.density_bitfield)
+            m.mean_count, m.local_step = ours.mean_count, 0
+            m.train()
+            opt = torch.optim.Adam(m.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+            scaler = torch.amp.GradScaler("cuda")
+            pts = []
+
+            def one(i):
+                ro, rd, gt = dev_batches[i % nb]
+                opt.zero_grad()
+                with torch.autocast("cuda", dtype=torch.float16):
+                    o = m.render(ro[None], rd[None], staged=False, bg_color=1, perturb=True, force_all_rays=False, dt_gamma=0, max_steps=1024)
+                    loss = torch.nn.functional.mse_loss(o["image"], gt[None], reduction="none").mean(-1).mean()
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+                m.local_step = 0
+
+            for i in range(3):
+                one(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                one(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            rec = dict(ms_per_step=ms, rays_per_s=N_RAYS / (ms * 1e-3), sample_rows=int(ours.mean_count),
+                       stack=("--ff: nerf/network_ff.py (FFMLP extension, CUTLASS split-K wgrad)" if variant == "ff" else
+                              "default -O: nerf/network.py (nn.Linear on cuBLAS) + raymarching / gridencoder / shencoder extensions"))
+            if variant == "ff":  # the occupancy update and the host-loop render of the same 800 x 800 view, on this stack
+                m.iter_density = 16
+                keep = (m.density_grid.clone(), m.density_bitfield.clone())
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                    m.update_extra_state()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    m.iter_density = 16
+                    m.update_extra_state()
+                    torch.cuda.synchronize()
+                rec["occupancy_partial_update_ms"] = (time.perf_counter() - t0) * 1e3
+                with torch.no_grad():
+                    m.density_grid.copy_(keep[0]); m.density_bitfield.copy_(keep[1])
+                if render is not None:
+                    from laenerf_b200.scene import get_rays_np
+                    ro, rd, _ = get_rays_np(sc.poses[0], sc.intrinsics, sc.H, sc.W)
+                    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+                    m.eval()
+                    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                        m.render(ro[None], rd[None], staged=False, bg_color=1, perturb=False, dt_gamma=0, max_steps=1024, T_thresh=1e-4, scale_depth=True)
+                        torch.cuda.synchronize()
+                        e0.record()
+                        for _ in range(2):
+                            m.render(ro[None], rd[None], staged=False, bg_color=1, perturb=False, dt_gamma=0, max_steps=1024, T_thresh=1e-4, scale_depth=True)
+                        e1.record()
+                        torch.cuda.synchronize()
+                    rms = e0.elapsed_time(e1) / 2
+                    out["render"] = dict(ms_per_frame=rms, value=render["samples_per_frame"] / (rms * 1e-3) / 1e6, unit="Msamples/s",
+                                         note="NeRFRenderer.run_cuda inference loop (renderer.py:335-387, one host sync per round) on the same view")
+            out[variant] = rec
+            del m, opt
+        except Exception as e:
+            out[variant] = {"error": f"{type(e).__name__}: {e}"[:400]}
+    out["clocks"] = clocks.stop()
+    return out
 
 
 def main():
@@ -172,6 +749,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-render", action="store_true", help="skip the full-image render measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gpu-ref", action="store_true", help="skip the gpu_reference leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5")
+    ap.add_argument("--no-large", action="store_true", help="skip the large-batch kernel roofline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -183,282 +763,102 @@ def main():
     _OUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # whatever NCCL logs (its version banner included) stays off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from laenerf_b200 import _native
-    from laenerf_b200.nerf import GraphedTrainStep, NeRFNetwork, TrainStep
-    from laenerf_b200.parallel import gather_tiles, init_distributed, tile_shard_indices
-    from laenerf_b200.scene import get_rays_np, make_scene
+    from laenerf_b200.parallel import init_distributed
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    if world > 1:
+        os.environ.setdefault("LNRF_TIME_EXCHANGE", "1")
     rank, world, local = init_distributed()
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    torch.cuda.set_device(torch.device("cuda", local))
     timed = TimedLib(_native.lib(), list(ALGO), torch)
     _native._lib = timed
+    ctx = Ctx(args, torch, dist, rank, world, local, timed)
 
-    # ---- synthetic lego-shape scene, random-init weights (seed = rank for the ray draws) -------------------------
-    sc = make_scene("lego", seed=0, n_poses=8)
-    torch.manual_seed(0)
-    model = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_thresh=sc.density_thresh).to(dev)
-    model.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
-    step = TrainStep(model, world_size=world)
-    rng = np.random.default_rng(1000 + rank)
-    n_batches = 8
-    host_batches = []
-    for b in range(n_batches):
-        ro, rd, _ = get_rays_np(sc.poses[b % len(sc.poses)], sc.intrinsics, sc.H, sc.W, N=N_RAYS, rng=rng)
-        gt = rng.random((N_RAYS, 3), dtype=np.float32)
-        host_batches.append(tuple(torch.from_numpy(x).pin_memory() for x in (ro, rd, gt)))
-    dev_batches = [tuple(x.to(dev) for x in hb) for hb in host_batches]
-
-    # ---- warm-up: the first step sizes the sample buffer from the counters like the reference (renderer.py:643-647) ----
-    for i in range(args.warmup):
-        step(*dev_batches[i % n_batches])
-        if i == 0:
-            model.update_mean_count()
-    model.update_mean_count()
-    barrier()
-
-    def timed_loop(fn, n):
-        """n calls of fn(i) bracketed by barrier + synchronize, CUDA events, max over ranks -> total ms."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for i in range(n):
-            fn(i)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- pass 1 (eager, Python-issued launches): per-kernel CUDA events live on the launching stream ------------------
-    points = []
-    timed.enabled = True
-    eager_l0 = _native.launch_count()
-    eager_ms = timed_loop(lambda i: points.append(step(*dev_batches[i % n_batches])[1]["num_points"]), args.steps)
-    timed.enabled = False
-    eager_launches = _native.launch_count() - eager_l0
-    actual = int(model.step_counter[: min(16, args.steps), 0].float().mean().item())
-    model.update_mean_count()
-
-    # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
-    # look-ahead (march of batch k+1 beside the exchange + Adam of batch k) paid while the exchange was an NCCL all-reduce (N = 2:
-    # 0.623 -> 0.590 ms); with the fused peer-memory kernel it measures within +-1 % of the plain graph at N = 2 / 4 / 8
-    # (profiles/r1k_bench_n*.json, r1l_bench_n8.json: 0.484 / 0.468 / 0.474 vs 0.480 / 0.462 / 0.479 ms), and on one GPU the march only
-    # competes with Adam for the same SMs -- so it is off unless asked for
-    lookahead = os.environ.get("LNRF_LOOKAHEAD", "0") == "1"
-    gstep, graph_note = None, ("cuda graph (one capture per sample-buffer size)" +
-                               ("; look-ahead: the parameter-independent near/far + march of batch k runs on a second stream beside "
-                                "the network/backward/Adam of batch k-1 -- every step still marches one batch and trains on one" if lookahead else ""))
-    if os.environ.get("LNRF_NO_GRAPH", "0") != "1":
+    def guarded(fn, *a):
+        """Secondary records never take the headline down: an exception becomes {"error": ...} on every rank alike."""
         try:
-            gstep = GraphedTrainStep(step, N_RAYS, lookahead=lookahead)
-            gstep.capture(*dev_batches[0])
-            for i in range(3):
-                gstep(*dev_batches[i % n_batches])
-        except Exception as e:  # never silently: the JSON line says which path was timed
-            gstep, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {e})"[:300]
-            torch.cuda.synchronize()
-    run = gstep if gstep is not None else (lambda *b: step(*b))
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    launches0 = _native.launch_count()
-    ms = timed_loop(lambda i: run(*dev_batches[i % n_batches]), args.steps)
-    launches = _native.launch_count() - launches0
-    if gstep is not None:  # replays do not pass through the C ABI: count the launches the captured step contains
-        launches = eager_launches  # same step, same number of steps, counted when it was issued through the C ABI
-    clk = clocks.stop() if rank == 0 else None
-    in_sync = None
-    if world > 1 and step.fused_optimizer:  # every rank must hold the same fp16 table after the sharded optimizer steps
-        chk = model.encoder._shadow_f16.float().abs().sum().double().reshape(1)
-        lo_, hi_ = chk.clone(), chk.clone()
-        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
-        in_sync = bool(lo_.item() == hi_.item())
-    seq_ms = None
-    if gstep is not None and lookahead:  # the same graph without the cross-step overlap, for reference
-        try:
-            model.update_mean_count()
-            g2 = GraphedTrainStep(step, N_RAYS, lookahead=False)
-            g2.capture(*dev_batches[0])
-            for i in range(3):
-                g2(*dev_batches[i % n_batches])
-            seq_ms = timed_loop(lambda i: g2(*dev_batches[i % n_batches]), args.steps) / args.steps
-            del g2
+            return fn(*a)
         except Exception as e:
-            seq_ms = f"failed: {type(e).__name__}: {e}"[:200]
-    ms_per_step = ms / args.steps
-    value = world * N_RAYS * args.steps / (ms * 1e-3)
+            torch.cuda.synchronize()
+            return {"error": f"{type(e).__name__}: {e}"[:400]}
 
-    # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ----------------------------------------
-    h2d = sum(x.numel() * x.element_size() for x in host_batches[0])
+    # ---- headline: configs[1], lego-shape training step ----------------------------------------------------------------
+    lego = train_config(ctx, "lego", headline=True)
+    render = None if args.no_render else guarded(render_config, ctx, lego["_model"], lego["_sc"])
 
-    def e2e_iter(i):
-        hb = host_batches[i % n_batches]
-        if gstep is not None:
-            loss, _ = gstep(*hb)  # static device buffers are filled straight from pinned memory (non_blocking copies)
-        else:
-            loss, _ = step(*(x.to(dev, non_blocking=True) for x in hb))
-        float(loss.item())
+    # ---- BASELINE configs 3-5 ----------------------------------------------------------------------------------------------
+    configs = {}
+    if not args.no_configs:
+        flower = guarded(train_config, ctx, "flower", False)
+        configs["flower_train"] = {k: v for k, v in flower.items() if not k.startswith("_") and k != "kernels"}
+        if "_model" in flower:
+            configs["flower_train"]["kernels_ms"] = {k: round(v["mean_ms"], 5) for k, v in flower["kernels"].items()}
+            configs["edit_stage"] = guarded(edit_config, ctx, flower)
 
-    e2e_ms = timed_loop(e2e_iter, args.steps)
-    e2e_value = world * N_RAYS * args.steps / (e2e_ms * 1e-3)
-
-    # ---- per-kernel roofline (events recorded live inside the timed region above) -----------------------------------
-    peaks = measured_peaks()
-    n_params = sum(p.numel() for p in model.parameters())
-    m_pad = int(statistics.mean(points))
-    kern = timed.summary()
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
-    table = {}
-    for name, k in kern.items():
-        a = ALGO[name]
-        calls_per_step = k["calls"] / args.steps
-        if a["bound"] == "hbm":
-            byts = (a.get("per_ray", 0) * N_RAYS + a.get("per_sample", 0) * actual + a.get("per_sample_padded", 0) * m_pad +
-                    a.get("per_param", 0) * (n_params // world))  # sharded optimizer: each rank updates 1/world of the table
-            ach = byts / (k["mean_ms"] * 1e-3) / 1e9
-            table[name] = dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"], mean_ms=k["mean_ms"],
-                               calls_per_step=calls_per_step, algorithmic_bytes=byts, traffic=traffic.get(name))
-        else:
-            fl = a["flops_per_sample_padded"] * m_pad
-            ach = fl / (k["mean_ms"] * 1e-3) / 1e12
-            table[name] = dict(bound="tensor", achieved=ach, peak=peaks["tensor"], unit="TFLOP/s", frac=ach / peaks["tensor"],
-                               mean_ms=k["mean_ms"], calls_per_step=calls_per_step, algorithmic_flops=fl, traffic=traffic.get(name))
-    dominant = max(table, key=lambda n: kern[n]["total_ms"]) if table else None
-    roofline = None
-    if dominant:
-        d = table[dominant]
-        roofline = dict(bound=d["bound"], achieved=d["achieved"], peak=d["peak"], unit=d["unit"], frac=d["frac"], traffic=d["traffic"],
-                        kernel=dominant, mean_ms=d["mean_ms"], peak_source=peaks["source"] + (" (sustained)" if d["bound"] == "tensor" else ""),
-                        share_of_step=kern[dominant]["total_ms"] / sum(k["total_ms"] for k in kern.values()),
-                        timing="CUDA events around each C-ABI launch during the eager pass of the same step (graph replays cannot be bracketed)")
-
-    # ---- render: one full 800x800 view, tile-sharded over ranks (no collective but the final gather) -------------------
-    # (at N = 1 the rays are in plain row-major order, as the reference renders them)
-    render = None
-    if not args.no_render:
-        ro, rd, _ = get_rays_np(sc.poses[0], sc.intrinsics, sc.H, sc.W)
-        # N > 1: 32 x 32 pixel tiles dealt round-robin over the ranks (contiguous row ranges leave the object to the middle ranks)
-        mine = tile_shard_indices(sc.H, sc.W, rank, world).numpy() if world > 1 else np.arange(sc.H * sc.W)
-        ro_d, rd_d = torch.from_numpy(ro[mine]).to(dev), torch.from_numpy(rd[mine]).to(dev)
-        model.eval()
-        model.render_schedule = os.environ.get("LNRF_RENDER_SCHEDULE", "fast")  # "reference": run_cuda's n_step rule, bit for bit
-        # real samples of this rank's rays (the slots of a round include the zero padding the API mandates, and the fast schedule
-        # pads more): counted once, outside the timed region, by the one-shot marcher on the same rays without a sample budget
-        from laenerf_b200 import raymarching as _rm
-        real = 0
-        with torch.no_grad():
-            for c0 in range(0, ro_d.shape[0], 65536):
-                o_, d_ = ro_d[c0:c0 + 65536].contiguous(), rd_d[c0:c0 + 65536].contiguous()
-                ne_, fa_ = _rm.near_far_from_aabb(o_, d_, model.aabb_infer, model.min_near)
-                cnt_ = torch.zeros(2, dtype=torch.int32, device=dev)
-                _rm.march_rays_train(o_, d_, model.bound, model.density_bitfield, model.cascade, model.grid_size, ne_, fa_, cnt_, -1, False,
-                                     128, True, 0, 1024)
-                real += int(cnt_[0].item())
-        frames, samples = 0, 0
-        ev = lambda: torch.cuda.Event(enable_timing=True)
-        e0, e1 = ev(), ev()
-        marks = []
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            for _ in range(2):  # warm-up frames, final gather included (the first collective of a shape pays NCCL's lazy set-up)
-                gather_tiles(model.render(ro_d, rd_d, perturb=False, bg_color=1)["image"], sc.H, sc.W, rank, world)
-            barrier()
-            e0.record()
-            for _ in range(3):
-                a, b, c = ev(), ev(), ev()
-                a.record()
-                out = model.render(ro_d, rd_d, perturb=False, bg_color=1)
-                b.record()
-                img = gather_tiles(out["image"], sc.H, sc.W, rank, world)
-                c.record()
-                marks.append((a, b, c))
-                samples += out["num_points"]
-                frames += 1
-            e1.record()
-            barrier()
-        loop_ms = sum(a.elapsed_time(b) for a, b, _ in marks) / frames
-        gather_ms = sum(b.elapsed_time(c) for _, b, c in marks) / frames
-        tt = torch.tensor([e0.elapsed_time(e1), float(samples), loop_ms, gather_ms, float(real)], device=dev, dtype=torch.float64)
-        if world > 1:
-            tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            tt = torch.stack([tmax[0], tsum[1], tmax[2], tmax[3], tsum[4]])
-        rms, rs, real_all = float(tt[0].item()), float(tt[1].item()), float(tt[4].item())
-        render = dict(value=real_all * frames / (rms * 1e-3) / 1e6, unit="Msamples/s", ms_per_frame=rms / frames, rays_per_frame=int(ro.shape[0]),
-                      samples_per_frame=real_all, sample_slots_per_frame=rs / frames, slots_msamples_per_s=rs / (rms * 1e-3) / 1e6,
-                      note="value counts REAL samples (occupied-cell samples of the frame's rays); slots include the zero padding of every round",
-                      rays_per_s=ro.shape[0] * frames / (rms * 1e-3), image_shape=list(img.shape),
-                      rounds=out.get("rounds"), schedule=model.render_schedule, render_loop_ms=float(tt[2].item()), gather_ms=float(tt[3].item()),
-                      sharding=("32x32-pixel tiles dealt round-robin over the ranks; all_gather + scatter by the known index lists"
-                                if world > 1 else "single GPU, row-major rays"))
-        model.train()
+        def bonsai_render():
+            sc_b, model_b = make_model(ctx, "bonsai")
+            return render_config(ctx, model_b, sc_b, frames=2)
+        configs["bonsai_render"] = guarded(bonsai_render)
 
     if rank != 0:
         _finish(world)
         return
+
+    large = None if (args.no_large or world > 1) else guarded(roofline_large, ctx, lego["_model"], lego["_sc"])
+    gref = None if (args.no_gpu_ref or world > 1) else guarded(gpu_reference, ctx, lego, render if render and "error" not in render else None)
+    vs_gref = None
+    if gref and "error" not in gref and "unavailable" not in gref:
+        vs_gref = {}
+        for k in ("ff", "default"):
+            if isinstance(gref.get(k), dict) and "ms_per_step" in gref[k]:
+                vs_gref[k] = gref[k]["ms_per_step"] / lego["ms_per_step"]
+        if isinstance(gref.get("render"), dict) and render and "ms_per_frame" in render:
+            vs_gref["render"] = gref["render"]["ms_per_frame"] / render["ms_per_frame"]
+        vs_gref["target"] = ">= 10x the reference's own extensions on one B200 (BASELINE.json north_star)"
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
         from oracle import cpu_renderer
         n = int(os.environ.get("LNRF_CPU_RAYS", "1024"))
-        hb = host_batches[0]
+        hb = lego["_batches"][0][0]
+        sc = lego["_sc"]
         sec, threads, used = cpu_renderer.time_train_steps(hb[0][:n].clone(), hb[1][:n].clone(), hb[2][:n].clone(), steps=2, warmup=1,
                                                            num_steps=512, bound=sc.bound, min_near=sc.min_near)
         cpu = dict(value=used / sec, unit="rays/s", cores=threads, kind="port",
                    sample=f"{used} rays x 512 uniform samples/ray per step (non-cuda_ray renderer restated in oracle/cpu_renderer.py), 2 timed + 1 warm-up steps")
 
+    cfg = base_config(world)
+    for k in ("samples_per_step", "samples_per_ray", "sample_rows_eager", "sample_rows_graph", "dropped_rays", "dropped_samples", "step_mode",
+              "replicas_in_sync", "exchange", "exchange_sync", "exchange_timing_us"):
+        if k in lego:
+            cfg[k] = lego[k]
+    cfg["scene_occupancy"] = lego["occupancy"]
+    cfg["occupancy_update"] = "excluded from `value` (fixed procedural grid); included in `value_with_occupancy_update`"
+    if vs_gref:
+        cfg["vs_gpu_reference"] = {k: (round(v, 2) if isinstance(v, float) else v) for k, v in vs_gref.items()}
+    if render and "value" in render:
+        cfg["render_msamples_per_s"] = round(render["value"], 1)
     line = {
-        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "samples_per_step_padded": m_pad, "samples_per_step": actual,
-                   "samples_per_ray": actual / N_RAYS, "scene_occupancy": sc.occupancy_fraction(),
-                   "l2": "no explicit flush: one step touches ~245 MB (fp32 table + grads + Adam moments + fp16 copies) > 126 MB L2",
-                   "occupancy_update": "excluded (row f-2 of SURVEY.md section 8: fixed procedural occupancy grid)",
-                   "parallelism": (f"ray-sharded dp{world}: reduce-scatter of the fp16 hash-grid gradient, Adam on a 1/{world} table slice per "
-                                   f"rank, all-gather of the fp16 table (ZeRO-1 style)") if world > 1 else "single GPU"},
-        "clocks": clk,
-        "step_mode": graph_note,
-        "graph_sequential_ms_per_step": seq_ms,
-        "replicas_in_sync": in_sync,
-        "exchange_sync": (None if world == 1 or not step.fused_optimizer or step.optimizer.p2p is None else
-                          ("inside the kernels (signal + poll on peer-mapped flag words)" if step.optimizer.inkernel_sync else
-                           "two symmetric-memory barrier launches around the kernel")),
-        "exchange_timing_us": (step.optimizer.exchange_timing() if world > 1 and step.fused_optimizer and os.environ.get("LNRF_TIME_EXCHANGE") == "1"
-                               else None),
-        "exchange": (None if world == 1 or not step.fused_optimizer else
-                     ("one fused kernel over NVLink peer memory (torch symmetric memory): average of the ranks' fp16 gradients + Adam on "
-                      "a 1/N slice + store of the new fp16 values into every rank's table" if step.optimizer.p2p is not None else
-                      "NCCL reduce-scatter + Adam on a 1/N slice + NCCL all-gather (symmetric memory unavailable: " +
-                      str(getattr(step.optimizer, "p2p_error", "disabled")) + ")")),
-        "eager": {"ms_per_step": eager_ms / args.steps, "value": world * N_RAYS * args.steps / (eager_ms * 1e-3), "unit": "rays/s",
-                  "note": "same step issued launch by launch from Python (the drop-in modules without graph capture)"},
-        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "kernels": table,
-        "render": render,
+        "metric": "train_rays_per_s", "value": lego["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": lego["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": cfg, "clocks": lego["clocks"], "e2e": lego.get("e2e"), "gpu_launches": lego["gpu_launches"], "roofline": lego["roofline"],
         "cpu_baseline": cpu,
-        "train_msamples_per_s": world * actual * args.steps / (ms * 1e-3) / 1e6,
+        "eager": {"ms_per_step": lego["eager_ms_per_step"], "value": world * N_RAYS / (lego["eager_ms_per_step"] * 1e-3), "unit": "rays/s",
+                  "note": "same step issued launch by launch from Python (the drop-in modules without graph capture)"},
+        "value_with_occupancy_update": lego.get("value_with_occupancy_update"),
+        "train_msamples_per_s": lego["train_msamples_per_s"],
+        "kernels": lego["kernels"], "render": render, "configs": configs, "roofline_large": large,
+        "gpu_reference": gref, "vs_gpu_reference": vs_gref,
     }
     print(json.dumps(line), file=_OUT, flush=True)
     _finish(world)

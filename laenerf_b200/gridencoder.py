@@ -16,6 +16,7 @@ from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _native as N
+from ._shadow import shadow_f16
 
 _gridtype_to_id = {"hash": 0, "tiled": 1}
 _interp_to_id = {"linear": 0, "smoothstep": 1}
@@ -170,7 +171,7 @@ class GridEncoder(nn.Module):
         inputs = inputs.view(-1, self.input_dim)
         outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
                               inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id,
-                              self._shadow_f16, self._grad_f16, float(bound) if in_kernel else 0.0)
+                              shadow_f16(self, self.embeddings), self._grad_f16, float(bound) if in_kernel else 0.0)
         return outputs.view(prefix_shape + [self.output_dim])
 
     @torch.autocast(device_type="cuda", enabled=False)

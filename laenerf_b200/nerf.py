@@ -17,6 +17,7 @@ from torch.amp import custom_bwd, custom_fwd
 
 from . import _native as N
 from . import raymarching
+from ._shadow import half_of, shadow_f16
 from .ffmlp import FFMLP
 from .gridencoder import GridEncoder
 from .shencoder import SHEncoder
@@ -136,8 +137,18 @@ class NeRFNetwork(nn.Module):
         # sample-buffer memory on ~5x fewer rounds (same per-sample arithmetic; see _render_rounds_device)
         self.render_schedule = "reference"
         self.render_samples_per_round = 32  # "fast" only: cap on the samples a ray takes per round after the first
+        self._amp_adam = None  # weak reference to the AmpAdam that owns the fp16 shadows, if any
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
                           self.in_dim_color == 32 and self.encoder_dir.degree == 4)
+
+    def train(self, mode: bool = True):
+        # ray-sharded AmpAdam keeps the fp32 masters as per-rank slices: bring the modules' fp32 parameters up to date (from the
+        # local fp16 shadow, no collective) before anything evaluates or serialises them
+        opt = getattr(self, "_amp_adam", None)
+        opt = opt() if opt is not None else None
+        if opt is not None and not mode:
+            opt.refresh_params()
+        return super().train(mode)
 
     def _use_fused(self, x):
         return (self.fused and self._fused_ok and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and x.shape[0] % 128 == 0 and
@@ -150,7 +161,7 @@ class NeRFNetwork(nn.Module):
             train = torch.is_grad_enabled() and (enc.requires_grad or self.sigma_net.weights.requires_grad)
             sn, cn = self.sigma_net, self.color_net
             return fused_network(enc, d, sn.weights, cn.weights, sn.num_layers, cn.num_layers, self.density_scale, train,
-                                 getattr(sn, "_shadow_f16", None), getattr(cn, "_shadow_f16", None),
+                                 shadow_f16(sn, sn.weights), shadow_f16(cn, cn.weights),
                                  getattr(sn, "_grad_f16", None), getattr(cn, "_grad_f16", None))
         sigmas, rgbs = self(x, d)
         return self.density_scale * sigmas, rgbs
@@ -188,8 +199,7 @@ class NeRFNetwork(nn.Module):
         if self.fused and self._fused_ok and xyzs.is_cuda and torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.float16:
             from .gridencoder import _offsets_host
             enc, sn = self.encoder, self.sigma_net
-            emb = enc._shadow_f16 if enc._shadow_f16 is not None else enc.embeddings.detach().half()
-            ws = sn._shadow_f16 if getattr(sn, "_shadow_f16", None) is not None else sn.weights.detach().half()
+            emb, ws = half_of(enc, enc.embeddings), half_of(sn, sn.weights)
             Mp = (M + 127) // 128 * 128
             if Mp != M:
                 xyzs = torch.cat([xyzs, torch.zeros(Mp - M, 3, dtype=xyzs.dtype, device=xyzs.device)], 0)
@@ -326,9 +336,7 @@ class NeRFNetwork(nn.Module):
         rows = (8 * n_rays if fast else n_rays) + 128
         distill = edit_bitfield is not None
         enc, sn, cn = self.encoder, self.sigma_net, self.color_net
-        emb = enc._shadow_f16 if enc._shadow_f16 is not None else enc.embeddings.detach().half()
-        ws = sn._shadow_f16 if getattr(sn, "_shadow_f16", None) is not None else sn.weights.detach().half()
-        wc = cn._shadow_f16 if getattr(cn, "_shadow_f16", None) is not None else cn.weights.detach().half()
+        emb, ws, wc = half_of(enc, enc.embeddings), half_of(sn, sn.weights), half_of(cn, cn.weights)
         t = dict(
             ctl=torch.zeros(16, dtype=torch.int32, device=dev),
             alive0=torch.empty(n_rays, dtype=torch.int32, device=dev), alive1=torch.empty(n_rays, dtype=torch.int32, device=dev),
@@ -499,23 +507,28 @@ class NeRFNetwork(nn.Module):
 
     # ---- renderer.py:394-480 (edit-grid distillation render used to build LAENeRF's EditDataset) --------------
     @torch.no_grad()
-    def run_cuda_distill(self, rays_o, rays_d, edit_bitfield, dt_gamma=0, bg_color=None, perturb=False, max_steps=1024,
-                         T_thresh=1e-4, **kwargs):
+    def run_cuda_distill(self, rays_o, rays_d, edit_bitfield, dt_gamma=0, bg_color=None, perturb=False, force_all_rays=False,
+                         max_steps=1024, T_thresh=1e-4, perturb_depth=False, grow_grid=False, **kwargs):
+        """Same result dict as the reference (renderer.py:466-480): the UN-blended composite `image`, `depth`, `depth_edit`,
+        `x_term = rays_o + depth * rays_d`, `weights_edit`, `weights`, `min_near` (+ `weights_sum` / `weights_edit_sum` aliases)."""
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.contiguous().view(-1, 3)
         rays_d = rays_d.contiguous().view(-1, 3)
         n_rays = rays_o.shape[0]
         device = rays_o.device
-        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_infer, self.min_near)
-        if bg_color is None:
-            bg_color = 1
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
+        dens_bitfield = edit_bitfield if grow_grid else self.density_bitfield  # renderer.py:410-413
+
+        def finish(weights_sum, weights_edit_sum, depth, depth_edit, image):
+            if perturb_depth:  # renderer.py:463-464
+                depth = depth + (torch.rand(depth.shape, device=device) - 0.5) * (depth.max() - depth.min()) / max_steps
+            return {"depth": depth.view(*prefix), "depth_edit": depth_edit, "image": image.view(*prefix, 3),
+                    "x_term": rays_o + depth[..., None] * rays_d, "weights_edit": weights_edit_sum, "weights": weights_sum,
+                    "min_near": nears.min(), "weights_sum": weights_sum, "weights_edit_sum": weights_edit_sum}
+
         if self.device_loop and self._device_loop_ok(rays_o):
-            t = self._render_rounds_device(rays_o, rays_d, nears, fars, self.density_bitfield, edit_bitfield, dt_gamma, perturb, max_steps,
-                                           T_thresh)
-            weights_sum, weights_edit_sum, depth, depth_edit = t["weights_sum"], t["wes"], t["depth"], t["de"]
-            image = t["image"] + (1 - weights_sum).unsqueeze(-1) * bg_color
-            return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum,
-                    "weights_edit_sum": weights_edit_sum, "depth_edit": depth_edit, "x_term": rays_o + depth_edit.unsqueeze(-1) * rays_d}
+            t = self._render_rounds_device(rays_o, rays_d, nears, fars, dens_bitfield, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh)
+            return finish(t["weights_sum"], t["wes"], t["depth"], t["de"], t["image"])
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
         weights_sum, weights_edit_sum, depth, depth_edit, image = z(n_rays), z(n_rays), z(n_rays), z(n_rays), z(n_rays, 3)
         n_alive = n_rays
@@ -527,7 +540,7 @@ class NeRFNetwork(nn.Module):
         while step < max_steps and n_alive > 0:
             n_step = max(min(n_rays // n_alive, 8), 1)
             xyzs, dirs, deltas, edit_occ = raymarching.march_rays_distill(
-                n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, edit_bitfield, self.cascade,
+                n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, dens_bitfield, edit_bitfield, self.cascade,
                 self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
             sigmas, rgbs = self.forward_scaled(xyzs, dirs)
             raymarching.composite_rays_distill(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum,
@@ -536,9 +549,7 @@ class NeRFNetwork(nn.Module):
             rays_alive, spare = spare, rays_alive
             n_alive = int(count.item())
             step += n_step
-        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
-        return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum,
-                "weights_edit_sum": weights_edit_sum, "depth_edit": depth_edit, "x_term": rays_o + depth_edit.unsqueeze(-1) * rays_d}
+        return finish(weights_sum, weights_edit_sum, depth, depth_edit, image)
 
     def render(self, rays_o, rays_d, **kwargs):
         return self.run_cuda(rays_o, rays_d, **kwargs)

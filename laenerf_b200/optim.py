@@ -1,86 +1,121 @@
 """Adam + GradScaler for the NeRF step in two launches (row f-4 of SURVEY.md section 8: "Optimizer + AMP glue on the
-12.2 M-param table").
+12.2 M-param table"), for the NeRF network and for the edit stage's style network (row a-13).
 
 The reference trains with `torch.optim.Adam(lr 1e-2, betas (0.9, 0.99), eps 1e-15)` under `torch.cuda.amp.GradScaler`
 (main_nerf.py:223, nerf/utils.py:1474-1484) and casts the whole hash table to fp16 on every forward
 (gridencoder/grid.py:43-44).  Per step that is ~610 MB of HBM traffic in six or more launches around the 49 MB table.
-`AmpAdam` keeps
+`AmpAdam` keeps, for every *persistent* parameter tensor,
 
-  * a persistent fp16 shadow of every parameter tensor (what the kernels read under autocast), rewritten by the update,
-  * a persistent fp16 gradient buffer per tensor that the backward kernels accumulate into (cleared by the update),
+  * a persistent fp16 shadow (what the kernels read under fp16 autocast), rewritten by the update,
+  * a persistent gradient buffer the backward kernels accumulate into (cleared by the update),
 
 and runs `lnrf_grad_nonfinite_check` + `lnrf_adam_step` + `lnrf_amp_update` (csrc/optim.cu): GradScaler's inf check,
 unscale, skip-on-inf, scale growth/backoff and torch's Adam arithmetic, with no host synchronisation, so the whole
-training step stays capturable in a CUDA graph.  `state_dict()` uses torch.optim.Adam's layout so checkpoints
-interchange with the reference's optimizer.
+training step stays capturable in a CUDA graph.  Tensors whose gradient arrives through autograd (`p.grad`, e.g. the
+two small FFMLPs and the palette of the style network) ride in the same launches.
+
+Checkpoints: `state_dict()` has torch.optim.Adam's layout with the reference's parameter groups (`model.get_params()`:
+encoder / sigma_net / encoder_dir (empty) / color_net, network_ff.py:139-153), so `torch.optim.Adam.load_state_dict`
+accepts it and vice versa; the GradScaler state is separate (`scaler_state_dict()`), as in the reference's
+`state['scaler']` (nerf/utils.py:1793).
 
 Ray-sharded training (world_size > 1): the exchange step and the optimizer are fused ZeRO-1 style.
 Instead of all-reduce(24.5 MB) followed by the full 367 MB Adam pass on every rank, the hash-table gradient is
 REDUCE-SCATTERED (mean over ranks, fp16), every rank runs Adam on its 1/N slice of the table only (fp32 master, moments and
 the slice of the fp16 shadow), and the updated fp16 shadow slices are ALL-GATHERED -- the same NVLink bytes as the
-all-reduce, but the HBM-bound optimizer pass shrinks N-fold, which more than pays for the exchange.  The two small MLP
-gradient vectors share one flat buffer and one all-reduce; the skip-on-inf decision is agreed with a one-float MAX.
+all-reduce, but the HBM-bound optimizer pass shrinks N-fold, which more than pays for the exchange.  In that mode the fp32
+masters exist only as per-rank slices: the modules' fp32 parameters are refreshed from the (complete, local) fp16 shadow
+whenever somebody reads them through `state_dict()` or switches the model to eval (`refresh_params()`, not a collective),
+and `gather_master()` (a collective) restores the exact fp32 values for checkpoints.
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 
 from . import _native as N
+from ._shadow import mark_current
+
+
+class _Owner:
+    """One parameter tensor of the step.  persistent = fp16 shadow + persistent gradient buffer on `module`."""
+    __slots__ = ("module", "param", "lr_mult", "persistent", "group")
+
+    def __init__(self, module, param, lr_mult=1.0, persistent=True, group=0):
+        self.module, self.param, self.lr_mult, self.persistent, self.group = module, param, float(lr_mult), bool(persistent), int(group)
 
 
 class AmpAdam:
     def __init__(self, model, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, fp16=True, init_scale=2.0 ** 16,
-                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, world_size=1, rank=0, group=None):
+                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, world_size=1, rank=0, group=None, owners=None,
+                 n_groups=None):
+        """`owners`: None = the NeRF network (table, sigma-net, colour-net; torch.optim order of NeRFNetwork.get_params), or a list
+        of (module, parameter, lr_multiplier, persistent, param_group_index).  fp16 = train under fp16 autocast with a GradScaler
+        (persistent tensors get fp16 shadows and fp16 gradient buffers); fp16 = False keeps everything fp32 without a scaler."""
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         self.fp16 = bool(fp16)
         self.growth_factor, self.backoff_factor, self.growth_interval = float(growth_factor), float(backoff_factor), int(growth_interval)
         self.world, self.rank, self.group = int(world_size), int(rank), group
         self.sharded = self.world > 1 and self.fp16
-        # (owner module, parameter) in torch.optim order of NeRFNetwork.get_params (network_ff.py:139-153)
-        self.owners = [(model.encoder, model.encoder.embeddings), (model.sigma_net, model.sigma_net.weights),
-                       (model.color_net, model.color_net.weights)]
-        dev = model.encoder.embeddings.device
+        if owners is None:
+            # (owner module, parameter) in torch.optim order of NeRFNetwork.get_params (network_ff.py:139-153): groups 0, 1, (2 empty), 3
+            self.owners = [_Owner(model.encoder, model.encoder.embeddings, group=0), _Owner(model.sigma_net, model.sigma_net.weights, group=1),
+                           _Owner(model.color_net, model.color_net.weights, group=3)]
+            self.n_groups = 4
+        else:
+            self.owners = [o if isinstance(o, _Owner) else _Owner(*o) for o in owners]
+            self.n_groups = int(n_groups) if n_groups is not None else 1 + max(o.group for o in self.owners)
+        if not self.fp16:
+            for o in self.owners:
+                o.persistent = False
+        dev = self.owners[0].param.device
         if dev.type != "cuda":
             raise RuntimeError("AmpAdam: the model must live on a CUDA device (there is no CPU path)")
         self.state = []
         if self.sharded:
+            if any(not o.persistent for o in self.owners):
+                raise RuntimeError("AmpAdam: ray-sharded mode needs persistent (fp16 shadow) tensors only")
             self._init_sharded(dev)
         else:
-            for owner, p in self.owners:
-                st = {"exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)}
-                if self.fp16:
-                    owner._shadow_f16 = p.data.half()
-                    owner._grad_f16 = torch.zeros_like(owner._shadow_f16)
-                else:
-                    owner._shadow_f16 = owner._grad_f16 = None
-                self.state.append(st)
+            for o in self.owners:
+                p = o.param
+                self.state.append({"exp_avg": torch.zeros_like(p.data), "exp_avg_sq": torch.zeros_like(p.data)})
+                if o.persistent:
+                    o.module._shadow_f16 = p.data.half()
+                    o.module._grad_f16 = torch.zeros_like(o.module._shadow_f16)
+                    o.module._shadow_resync = None
+                    mark_current(o.module, p)
         self.step_count = torch.ones(1, dtype=torch.float32, device=dev)       # 1-based number of the NEXT update
         self.found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scale = torch.full((1,), float(init_scale), dtype=torch.float32, device=dev) if self.fp16 else None
         self._growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev) if self.fp16 else None
         self.lr_scale = torch.ones(1, dtype=torch.float32, device=dev)  # schedule factor (LambdaLR), read on the device
+        self._stale_params = False
+        if model is not None:
+            model._amp_adam = weakref.ref(self)
+            if self.sharded and hasattr(model, "register_state_dict_pre_hook"):
+                # the fp32 parameters of the modules are NOT updated by the sharded step: refresh them before anybody serialises them
+                self._sd_hook = model.register_state_dict_pre_hook(lambda m, prefix, keep_vars: self.refresh_params())
 
+    # ---- ray-sharded layout -------------------------------------------------------------------------------------------
     def _init_sharded(self, dev):
         """One flat parameter vector [table | sigma-net weights | colour-net weights | pad] whose [lo, hi) slice this rank owns:
         the fp32 master and the Adam moments exist for that slice only; the fp16 shadow and the fp16 gradient exist in full on
         every rank and the modules' `_shadow_f16` / `_grad_f16` are views of them.  With torch symmetric memory the two flat
         fp16 vectors are peer-mapped and the whole exchange is one kernel (lnrf_adam_step_sharded); otherwise NCCL
         reduce-scatter / all-gather move the same bytes."""
-        sizes = [p.numel() for _, p in self.owners]
+        sizes = [o.param.numel() for o in self.owners]
         T = sum(sizes)
         unit = self.world * 8  # every slice a multiple of 8 elements: 16-byte fp16 vectors
         self.P, self.P_pad = T, (T + unit - 1) // unit * unit
         self.Sz = self.P_pad // self.world
         self.lo, self.hi = self.rank * self.Sz, (self.rank + 1) * self.Sz
-        flat32 = torch.zeros(self.P_pad, dtype=torch.float32, device=dev)
-        off = 0
-        for (_, p), n in zip(self.owners, sizes):
-            flat32[off:off + n] = p.data.reshape(-1)
-            off += n
+        self._sizes = sizes
+        flat32 = self._flat_from_params(dev)
         self.p2p = None
         if os.environ.get("LNRF_P2P", "1") == "1":
             try:
@@ -96,14 +131,23 @@ class AmpAdam:
         self.master_shard = flat32[self.lo:self.hi].clone()
         del flat32
         off = 0
-        for (owner, p), n in zip(self.owners, sizes):
-            owner._shadow_f16 = self.shadow_flat[off:off + n].view_as(p)
-            owner._grad_f16 = self.grad_flat[off:off + n].view_as(p)
+        for o, n in zip(self.owners, sizes):
+            o.module._shadow_f16 = self.shadow_flat[off:off + n].view_as(o.param)
+            o.module._grad_f16 = self.grad_flat[off:off + n].view_as(o.param)
+            o.module._shadow_resync = self._resync_from_params  # an outside write to ANY fp32 parameter re-derives shadow + master slice
+            mark_current(o.module, o.param)
             off += n
         # ONE state entry in sharded mode: the moments of this rank's slice of the flat vector
         self.state.append({"exp_avg": torch.zeros(self.Sz, dtype=torch.float32, device=dev),
                            "exp_avg_sq": torch.zeros(self.Sz, dtype=torch.float32, device=dev)})
-        self._sizes = sizes
+
+    def _flat_from_params(self, dev):
+        flat = torch.zeros(self.P_pad, dtype=torch.float32, device=dev)
+        off = 0
+        for o, n in zip(self.owners, self._sizes):
+            flat[off:off + n] = o.param.data.reshape(-1)
+            off += n
+        return flat
 
     def _init_symmetric(self, dev):
         """Peer-mapped gradient / shadow / flag buffers (torch.distributed._symmetric_memory): returns the handles and the
@@ -163,32 +207,37 @@ class AmpAdam:
     def grads(self):
         """The gradient tensors the next step() will consume (the all-reduce of ray-sharded training acts on these)."""
         out = []
-        for owner, p in self.owners:
-            g = owner._grad_f16 if self.fp16 else p.grad
+        for o in self.owners:
+            g = o.module._grad_f16 if o.persistent else o.param.grad
             if g is not None:
                 out.append(g)
         return out
 
     def zero_grad(self, set_to_none=True):
-        if not self.fp16:
-            for _, p in self.owners:
-                p.grad = None  # fp32 mode: autograd allocates; the update kernel has consumed them
+        for o in self.owners:
+            if not o.persistent:
+                o.param.grad = None  # autograd allocates; the update kernel has consumed them
 
-    def _descriptors(self):
-        arr = (N.OptTensor * len(self.owners))()
+    def _descriptors(self, owners, states):
+        arr = (N.OptTensor * len(owners))()
         keep = []
-        for i, ((owner, p), st) in enumerate(zip(self.owners, self.state)):
-            g = owner._grad_f16 if self.fp16 else p.grad
+        for i, (o, st) in enumerate(zip(owners, states)):
+            p = o.param
+            g = o.module._grad_f16 if o.persistent else p.grad
             if g is None:
                 raise RuntimeError("AmpAdam.step(): a parameter has no gradient (call backward first)")
-            if self.fp16 and p.grad is not None:
-                raise RuntimeError("AmpAdam.step(): a parameter received an autograd .grad -- the fp16 mode needs the fused network "
-                                   "path (NeRFNetwork.fused = True under fp16 autocast) so that gradients land in its fp16 buffers")
+            if o.persistent and p.grad is not None:
+                raise RuntimeError("AmpAdam.step(): a persistent parameter received an autograd .grad -- under fp16 autocast the kernels "
+                                   "accumulate into its fp16 buffer (NeRFNetwork.fused = True / GridEncoder with a shadow); a module path that "
+                                   "bypasses them was used")
+            g = g.contiguous()
             keep.append(g)
             arr[i].params, arr[i].exp_avg, arr[i].exp_avg_sq = p.data.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             arr[i].grad = g.data_ptr()
-            arr[i].params_f16 = owner._shadow_f16.data_ptr() if self.fp16 else None
+            arr[i].params_f16 = o.module._shadow_f16.data_ptr() if o.persistent else None
             arr[i].n = p.numel()
+            if g.dtype not in (torch.float16, torch.float32):
+                raise RuntimeError(f"AmpAdam.step(): unsupported gradient dtype {g.dtype}")
             arr[i].grad_dtype = N.F16 if g.dtype == torch.float16 else N.F32
         return arr, keep
 
@@ -204,6 +253,7 @@ class AmpAdam:
         import torch.distributed as dist
         lib, st = N.lib(), N.stream()
         hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay)
+        self._stale_params = True
         if self.p2p is not None:
             # own gradient checked locally, flag published beside it; barrier; ONE kernel averages the R gradients of the slice
             # over NVLink, updates, and writes the new fp16 slice into every rank's table; barrier; clear the local gradient
@@ -262,22 +312,40 @@ class AmpAdam:
         N.check(lib.lnrf_amp_update(N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf), N.ptr(self.step_count),
                                     self.growth_factor, self.backoff_factor, self.growth_interval, st))
 
+    def _allreduce_autograd_grads(self):
+        """world_size > 1 without fp16 sharding (e.g. the fp32 style network): plain mean all-reduce of every gradient."""
+        import torch.distributed as dist
+        for g in self.grads():
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            g.div_(self.world)
+
     @torch.no_grad()
     def step(self):
         if self.sharded:
             return self._step_sharded()
+        if self.world > 1:
+            self._allreduce_autograd_grads()
         lib = N.lib()
-        arr, keep = self._descriptors()
-        n = len(self.owners)
         st = N.stream()
+        arr, keep = self._descriptors(self.owners, self.state)
+        n = len(self.owners)
         if self.fp16:
             N.check(lib.lnrf_grad_nonfinite_check(C.cast(arr, C.c_void_p), n, N.ptr(self.found_inf), st))
-        N.check(lib.lnrf_adam_step(C.cast(arr, C.c_void_p), n, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                   N.ptr(self._scale), N.ptr(self.found_inf), N.ptr(self.step_count), N.ptr(self.lr_scale), st))
+        # one launch per distinct learning rate (the style network trains its palette at 2 x lr, style_encoder.py:247-255)
+        for mult in sorted({o.lr_mult for o in self.owners}):
+            idx = [i for i, o in enumerate(self.owners) if o.lr_mult == mult]
+            if len(idx) == n:
+                sub = arr
+            else:
+                sub, _k = self._descriptors([self.owners[i] for i in idx], [self.state[i] for i in idx])
+                keep += _k
+            N.check(lib.lnrf_adam_step(C.cast(sub, C.c_void_p), len(idx), self.lr * mult, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                       N.ptr(self._scale), N.ptr(self.found_inf), N.ptr(self.step_count), N.ptr(self.lr_scale), st))
         N.check(lib.lnrf_amp_update(N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf), N.ptr(self.step_count),
                                     self.growth_factor, self.backoff_factor, self.growth_interval, st))
         del keep
 
+    # ---- sharded mode: where the fp32 parameters live ----------------------------------------------------------------
     def _gather_flat(self, shard):
         import torch.distributed as dist
         full = torch.empty(self.P_pad, dtype=shard.dtype, device=shard.device)
@@ -286,72 +354,134 @@ class AmpAdam:
 
     def _split_flat(self, full):
         out, off = [], 0
-        for (_, p), n in zip(self.owners, self._sizes):
-            out.append(full[off:off + n].view_as(p))
+        for o, n in zip(self.owners, self._sizes):
+            out.append(full[off:off + n].view_as(o.param))
             off += n
         return out
+
+    def _write_params(self, tensors):
+        for o, t in zip(self.owners, tensors):
+            o.param.data.copy_(t)
+            mark_current(o.module, o.param)  # our own write: the shadow is (still) the truth
+        self._stale_params = False
+
+    @torch.no_grad()
+    def refresh_params(self):
+        """Sharded mode, NOT a collective: bring the modules' fp32 parameters up to date from this rank's complete fp16 shadow
+        (the values every kernel reads; fp16-rounded).  Runs automatically before `model.state_dict()` and on `model.eval()`.
+        For the exact fp32 masters use gather_master()."""
+        if not self.sharded or not self._stale_params:
+            return
+        self._resync_if_params_changed()
+        self._write_params([o.module._shadow_f16 for o in self.owners])
 
     @torch.no_grad()
     def gather_master(self):
         """Sharded mode (collective): bring the fp32 masters of every slice back into the modules' parameters (checkpoints)."""
         if not self.sharded:
             return
-        for (_, p), t in zip(self.owners, self._split_flat(self._gather_flat(self.master_shard))):
-            p.data.copy_(t)
+        self._resync_if_params_changed()
+        self._write_params(self._split_flat(self._gather_flat(self.master_shard)))
 
+    def _resync_if_params_changed(self):
+        if any(o.param._version != getattr(o.module, "_shadow_version", None) for o in self.owners if o.persistent):
+            self.sync_shadows()
+
+    @torch.no_grad()
+    def _resync_from_params(self):
+        """Sharded mode: the fp32 parameters were written from outside (load_state_dict, manual edit): they are the truth now."""
+        for o in self.owners:
+            o.module._shadow_f16.copy_(o.param.data)
+            mark_current(o.module, o.param)
+        self.master_shard.copy_(self._flat_from_params(self.master_shard.device)[self.lo:self.hi])
+        self._stale_params = False
+
+    @torch.no_grad()
     def sync_shadows(self):
-        """Re-derive the fp16 shadows (and, sharded, this rank's master slice) after the fp32 parameters were changed from
-        outside (load_state_dict, manual edits)."""
-        if not self.fp16:
-            return
-        for owner, p in self.owners:
-            owner._shadow_f16.copy_(p.data)
+        """Re-derive the fp16 shadows (and, sharded, this rank's master slice) from the fp32 parameters.  Happens by itself when a
+        parameter was written through torch (see _shadow.py); call it after writing through raw pointers."""
         if self.sharded:
-            flat = torch.zeros(self.P_pad, dtype=torch.float32, device=self.master_shard.device)
-            off = 0
-            for (_, p), n in zip(self.owners, self._sizes):
-                flat[off:off + n] = p.data.reshape(-1)
-                off += n
-            self.master_shard.copy_(flat[self.lo:self.hi])
+            return self._resync_from_params()
+        for o in self.owners:
+            if o.persistent:
+                o.module._shadow_f16.copy_(o.param.data)
+                mark_current(o.module, o.param)
 
     def detach(self):
         """Give the modules back to the plain torch path (drops the shadows and persistent gradient buffers)."""
-        for owner, _ in self.owners:
-            owner._shadow_f16 = owner._grad_f16 = None
+        if self.sharded:
+            self.refresh_params()
+        for o in self.owners:
+            if o.persistent:
+                o.module._shadow_f16 = o.module._grad_f16 = None
+                o.module._shadow_resync = None
+        if self.model is not None and getattr(self.model, "_amp_adam", None) is not None and self.model._amp_adam() is self:
+            self.model._amp_adam = None
+        hook = getattr(self, "_sd_hook", None)
+        if hook is not None:
+            hook.remove()
+            self._sd_hook = None
 
     # ---- torch.optim.Adam-compatible checkpoint layout ------------------------------------------------------------
     def state_dict(self):
+        """torch.optim.Adam's layout with the reference's parameter groups.  Sharded mode: a collective (every rank calls it)."""
         step = float(self.step_count.item()) - 1.0
-        state = {i: {"step": torch.tensor(step), "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]} for i, st in enumerate(self.state)}
-        if self.sharded:  # collective: every rank must call it; the moments are gathered back into the per-parameter layout
+        if self.sharded:  # the moments are gathered back into the per-parameter layout
             ea = self._split_flat(self._gather_flat(self.state[0]["exp_avg"]))
             es = self._split_flat(self._gather_flat(self.state[0]["exp_avg_sq"]))
-            state = {i: {"step": torch.tensor(step), "exp_avg": ea[i], "exp_avg_sq": es[i]} for i in range(len(self.owners))}
-        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
-                 "maximize": False, "params": list(range(len(self.owners)))}
-        scaler = {"scale": self.get_scale(), "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
-                  "growth_interval": self.growth_interval, "_growth_tracker": int(self._growth_tracker.item()) if self.fp16 else 0}
-        return {"state": state, "param_groups": [group], "scaler": scaler}
+        else:
+            ea = [st["exp_avg"] for st in self.state]
+            es = [st["exp_avg_sq"] for st in self.state]
+        state = {i: {"step": torch.tensor(step), "exp_avg": ea[i], "exp_avg_sq": es[i]} for i in range(len(self.owners))}
+        groups = []
+        for gi in range(self.n_groups):
+            idx = [i for i, o in enumerate(self.owners) if o.group == gi]
+            mult = self.owners[idx[0]].lr_mult if idx else 1.0
+            groups.append({"lr": self.lr * mult, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                           "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                           "decoupled_weight_decay": False, "params": idx})
+        return {"state": state, "param_groups": groups}
+
+    def scaler_state_dict(self):
+        """torch.amp.GradScaler.state_dict() layout (the reference stores it beside the optimizer's, nerf/utils.py:1793)."""
+        if not self.fp16:
+            return {}
+        return {"scale": self.get_scale(), "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": int(self._growth_tracker.item())}
+
+    def load_scaler_state_dict(self, sd):
+        if self.fp16 and sd:
+            self._scale.fill_(float(sd["scale"]))
+            self._growth_tracker.fill_(int(sd["_growth_tracker"]))
+            self.growth_factor, self.backoff_factor = float(sd["growth_factor"]), float(sd["backoff_factor"])
+            self.growth_interval = int(sd["growth_interval"])
 
     def load_state_dict(self, sd):
-        if self.sharded:
-            for k in ("exp_avg", "exp_avg_sq"):
-                flat = torch.zeros(self.P_pad, dtype=torch.float32, device=self.master_shard.device)
-                off = 0
-                for i, n in enumerate(self._sizes):
-                    flat[off:off + n] = sd["state"][i][k].reshape(-1)
-                    off += n
-                self.state[0][k].copy_(flat[self.lo:self.hi])
-        else:
-            for i, st in enumerate(self.state):
-                src = sd["state"][i]
-                st["exp_avg"].copy_(src["exp_avg"])
-                st["exp_avg_sq"].copy_(src["exp_avg_sq"])
-        steps = [float(sd["state"][i]["step"]) for i in range(len(self.owners))]
-        self.step_count.fill_(steps[0] + 1.0)
-        g = sd["param_groups"][0]
-        self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(map(float, g["betas"])), float(g["eps"]), float(g["weight_decay"])
-        if self.fp16 and "scaler" in sd:
-            self._scale.fill_(float(sd["scaler"]["scale"]))
-            self._growth_tracker.fill_(int(sd["scaler"]["_growth_tracker"]))
-        self.sync_shadows()
+        """Accepts this class's state_dict() and torch.optim.Adam's (full per-parameter tensors in both).  The fp32 parameters
+        themselves are not part of an optimizer checkpoint: if the caller loaded the MODEL beforehand, the shadows (and the sharded
+        master slice) follow that write by themselves (_shadow.py); nothing is derived from parameters that were not touched."""
+        n = len(self.owners)
+        if len(sd["state"]) not in (0, n):
+            raise RuntimeError(f"AmpAdam.load_state_dict: {len(sd['state'])} state entries for {n} parameter tensors")
+        if len(sd["state"]) == n:
+            if self.sharded:
+                for k in ("exp_avg", "exp_avg_sq"):
+                    flat = torch.zeros(self.P_pad, dtype=torch.float32, device=self.master_shard.device)
+                    off = 0
+                    for i, cnt in enumerate(self._sizes):
+                        flat[off:off + cnt] = sd["state"][i][k].reshape(-1)
+                        off += cnt
+                    self.state[0][k].copy_(flat[self.lo:self.hi])
+            else:
+                for i, st in enumerate(self.state):
+                    src = sd["state"][i]
+                    st["exp_avg"].copy_(src["exp_avg"])
+                    st["exp_avg_sq"].copy_(src["exp_avg_sq"])
+            self.step_count.fill_(float(sd["state"][0]["step"]) + 1.0)
+        g = next((g for g in sd["param_groups"] if g["params"]), sd["param_groups"][0])
+        first = self.owners[g["params"][0]].lr_mult if g["params"] else 1.0
+        self.lr = float(g["lr"]) / first
+        self.betas, self.eps, self.weight_decay = tuple(map(float, g["betas"])), float(g["eps"]), float(g["weight_decay"])
+        if "scaler" in sd:  # round-1 checkpoints nested the scaler state here
+            self.load_scaler_state_dict(sd["scaler"])
+        self._resync_if_params_changed()

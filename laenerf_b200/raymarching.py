@@ -10,6 +10,8 @@ through the API, all on purpose:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
@@ -23,12 +25,15 @@ __all__ = [
 ]
 
 _scratch = {}  # (device index, stream, kind) -> zero-initialised int64 scratch the kernels keep zeroed
+_DEBUG_LAYOUT = os.environ.get("LNRF_DEBUG_LAYOUT", "0") == "1"  # composite_loss_train: verify the canonical `rays` layout (one sync)
 
 
 def _get_scratch(kind: str, nbytes: int, device) -> torch.Tensor:
     key = (device.index, N.stream(), kind)
     t = _scratch.get(key)
     if t is None or t.numel() * 8 < nbytes:
+        if len(_scratch) >= _MAX_SCRATCH:  # oldest first (dicts keep insertion order)
+            del _scratch[next(iter(_scratch))]
         t = torch.zeros(max(1024, (nbytes + 7) // 8 * 2), dtype=torch.int64, device=device)
         _scratch[key] = t
     return t
@@ -36,6 +41,68 @@ def _get_scratch(kind: str, nbytes: int, device) -> torch.Tensor:
 
 def _cuda(t):
     return t if t.is_cuda else t.cuda()
+
+
+_MAX_SCRATCH = 32  # cache entries (streams x kinds); warm-up side streams and re-captures must not grow it without bound
+
+
+def _scratch_reset(device) -> None:
+    """After a failed launch the look-back status words may be left non-zero and every later launch would read stale flags:
+    drop the cached scratch of the device so the next call starts from fresh zeros."""
+    for k in [k for k in _scratch if k[0] == device.index]:
+        del _scratch[k]
+
+
+def _check(status: int, device) -> None:
+    if status != 0:
+        _scratch_reset(device)
+        N.check(status)
+
+
+def _in(t, dtype, name):
+    """Read-only kernel input: the reference raises through CHECK_CUDA / CHECK_CONTIGUOUS and dispatches on the dtype
+    (raymarching.cu: AT_DISPATCH_FLOATING_TYPES_AND_HALF); here the tensor must be on the GPU and is brought to the one dtype the
+    kernels are built for (fp32 values / int32 indices / uint8 bitfields) -- never reinterpreted."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        if dtype is torch.float32 and t.dtype in (torch.float16, torch.bfloat16, torch.float64):
+            t = t.float()
+        elif dtype is torch.uint8 and t.dtype is torch.bool:
+            t = t.view(torch.uint8)
+        else:
+            raise RuntimeError(f"{name} must be {dtype}, but got {t.dtype}")
+    return t.contiguous()
+
+
+def _inout(t, dtype, name):
+    """Tensor the kernel updates in place: it must already be what the kernel writes (a converted copy would lose the result)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, but got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    return t
+
+
+class _on:
+    """Launch on the device the tensors live on (the reference has no device guard; kernels would launch on the current device)."""
+
+    def __init__(self, t):
+        self.guard = None if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *a):
+        if self.guard is not None:
+            self.guard.__exit__(*a)
 
 
 class _near_far_from_aabb(Function):
@@ -119,7 +186,8 @@ class _march_rays_train(Function):
                 perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
         rays_o = _cuda(rays_o).contiguous().view(-1, 3)
         rays_d = _cuda(rays_d).contiguous().view(-1, 3)
-        density_bitfield = _cuda(density_bitfield).contiguous()
+        density_bitfield = _in(_cuda(density_bitfield), torch.uint8, "density_bitfield")
+        nears, fars = _in(nears, torch.float32, "nears"), _in(fars, torch.float32, "fars")
         dev = rays_o.device
         n = rays_o.shape[0]
         M = n * max_steps
@@ -133,14 +201,16 @@ class _march_rays_train(Function):
         rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        step_counter = _inout(step_counter, torch.int32, "step_counter")
         noises = torch.rand(n, dtype=rays_o.dtype, device=dev) if perturb else torch.zeros(n, dtype=rays_o.dtype, device=dev)
         lib = N.lib()
         nbytes = lib.lnrf_march_rays_train_scratch_bytes(n)
         scratch = _get_scratch("march", nbytes, dev)
-        N.check(lib.lnrf_march_rays_train(N.ptr(rays_o), N.ptr(rays_d), N.ptr(density_bitfield), float(bound), float(dt_gamma),
-                                          int(max_steps), n, int(C), int(H), M, N.ptr(nears), N.ptr(fars), N.ptr(xyzs),
-                                          N.ptr(dirs), N.ptr(deltas), N.ptr(rays), N.ptr(step_counter), N.ptr(noises),
-                                          N.ptr(scratch), scratch.numel() * 8, N.stream()))
+        with _on(rays_o):
+            _check(lib.lnrf_march_rays_train(N.ptr(rays_o), N.ptr(rays_d), N.ptr(density_bitfield), float(bound), float(dt_gamma),
+                                             int(max_steps), n, int(C), int(H), M, N.ptr(nears), N.ptr(fars), N.ptr(xyzs),
+                                             N.ptr(dirs), N.ptr(deltas), N.ptr(rays), N.ptr(step_counter), N.ptr(noises),
+                                             N.ptr(scratch), scratch.numel() * 8, N.stream()), dev)
         if force_all_rays or mean_count <= 0:  # raymarching.py:222-231 (first epochs only)
             m = int(step_counter[0].item())
             if align > 0:
@@ -156,7 +226,8 @@ class _composite_rays_train(Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, sigmas, rgbs, deltas, rays, T_thresh=1e-4):
-        sigmas, rgbs, deltas = sigmas.contiguous(), rgbs.contiguous(), deltas.contiguous()
+        sigmas, rgbs, deltas = _in(sigmas, torch.float32, "sigmas"), _in(rgbs, torch.float32, "rgbs"), _in(deltas, torch.float32, "deltas")
+        rays = _in(rays, torch.int32, "rays")
         M, n = sigmas.shape[0], rays.shape[0]
         weights_sum = torch.empty(n, dtype=sigmas.dtype, device=sigmas.device)
         depth = torch.empty(n, dtype=sigmas.dtype, device=sigmas.device)
@@ -171,7 +242,7 @@ class _composite_rays_train(Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, grad_weights_sum, grad_depth, grad_image):  # grad_depth is dropped (raymarching.py:275)
-        grad_weights_sum, grad_image = grad_weights_sum.contiguous(), grad_image.contiguous()
+        grad_weights_sum, grad_image = _in(grad_weights_sum, torch.float32, "grad_weights_sum"), _in(grad_image, torch.float32, "grad_image")
         sigmas, rgbs, deltas, rays, weights_sum, depth, image = ctx.saved_tensors
         M, n, T_thresh = ctx.dims
         grad_sigmas = torch.zeros_like(sigmas)
@@ -194,9 +265,17 @@ class _composite_loss_train(Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears, fars, T_thresh=1e-4):
-        sigmas, rgbs, deltas = sigmas.contiguous(), rgbs.contiguous(), deltas.contiguous()
+        sigmas, rgbs, deltas = _in(sigmas, torch.float32, "sigmas"), _in(rgbs, torch.float32, "rgbs"), _in(deltas, torch.float32, "deltas")
+        rays = _in(rays, torch.int32, "rays")
         M, n = sigmas.shape[0], rays.shape[0]
         dev = sigmas.device
+        if _DEBUG_LAYOUT and n > 1:
+            # the backward's zero-fill assumes march_rays_train's canonical layout: rows in ray-id order, offsets = exclusive prefix
+            # sum of the counts (a `rays` tensor in the reference's atomic-arrival order must go through composite_rays_train)
+            kept = rays[:, 1].long() + rays[:, 2].long() <= M
+            off_ok = rays[1:, 1] == rays[:-1, 1] + rays[:-1, 2]
+            if not (bool((rays[:, 0] == torch.arange(n, device=dev, dtype=torch.int32)).all()) and bool(off_ok[kept[1:] & kept[:-1]].all())):
+                raise RuntimeError("composite_loss_train: `rays` is not in march_rays_train's canonical (ray-id ordered, prefix-sum) layout")
         gt_rgb = _cuda(gt_rgb).contiguous().view(n, 3)
         if torch.is_tensor(bg_color) and bg_color.numel() == 3 * n:
             bg, bg_scalar = _cuda(bg_color).contiguous().view(n, 3), 0.0
@@ -248,6 +327,10 @@ def _march_infer(distill, n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, b
                  near, far, align, perturb, dt_gamma, max_steps):
     rays_o = _cuda(rays_o).contiguous().view(-1, 3)
     rays_d = _cuda(rays_d).contiguous().view(-1, 3)
+    rays_alive, rays_t = _in(rays_alive, torch.int32, "rays_alive"), _in(rays_t, torch.float32, "rays_t")
+    near, far = _in(near, torch.float32, "near"), _in(far, torch.float32, "far")
+    density_bitfield = _in(density_bitfield, torch.uint8, "density_bitfield")
+    edit_bitfield = _in(edit_bitfield, torch.uint8, "edit_bitfield")
     dev = rays_o.device
     M = n_alive * n_step
     if align > 0:
@@ -298,9 +381,13 @@ class _composite_rays(Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
-        sigmas, rgbs = sigmas.contiguous(), rgbs.contiguous()
-        N.check(N.lib().lnrf_composite_rays(n_alive, n_step, float(T_thresh), N.ptr(rays_alive), N.ptr(rays_t), N.ptr(sigmas),
-                                            N.ptr(rgbs), N.ptr(deltas), N.ptr(weights_sum), N.ptr(depth), N.ptr(image), N.stream()))
+        sigmas, rgbs, deltas = _in(sigmas, torch.float32, "sigmas"), _in(rgbs, torch.float32, "rgbs"), _in(deltas, torch.float32, "deltas")
+        rays_alive, rays_t = _inout(rays_alive, torch.int32, "rays_alive"), _inout(rays_t, torch.float32, "rays_t")
+        weights_sum, depth, image = (_inout(weights_sum, torch.float32, "weights_sum"), _inout(depth, torch.float32, "depth"),
+                                     _inout(image, torch.float32, "image"))
+        with _on(sigmas):
+            N.check(N.lib().lnrf_composite_rays(n_alive, n_step, float(T_thresh), N.ptr(rays_alive), N.ptr(rays_t), N.ptr(sigmas),
+                                                N.ptr(rgbs), N.ptr(deltas), N.ptr(weights_sum), N.ptr(depth), N.ptr(image), N.stream()))
         return tuple()
 
 
@@ -312,11 +399,17 @@ class _composite_rays_distill(Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, weights_edit_sum, depth, depth_edit,
                 image, int_edit, T_thresh=1e-2):
-        sigmas, rgbs = sigmas.contiguous(), rgbs.contiguous()
-        N.check(N.lib().lnrf_composite_rays_distill(n_alive, n_step, float(T_thresh), N.ptr(rays_alive), N.ptr(rays_t),
-                                                    N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(weights_sum),
-                                                    N.ptr(weights_edit_sum), N.ptr(depth), N.ptr(depth_edit), N.ptr(int_edit),
-                                                    N.ptr(image), N.stream()))
+        sigmas, rgbs, deltas = _in(sigmas, torch.float32, "sigmas"), _in(rgbs, torch.float32, "rgbs"), _in(deltas, torch.float32, "deltas")
+        rays_alive, rays_t = _inout(rays_alive, torch.int32, "rays_alive"), _inout(rays_t, torch.float32, "rays_t")
+        weights_sum, depth, image = (_inout(weights_sum, torch.float32, "weights_sum"), _inout(depth, torch.float32, "depth"),
+                                     _inout(image, torch.float32, "image"))
+        weights_edit_sum, depth_edit = _inout(weights_edit_sum, torch.float32, "weights_edit_sum"), _inout(depth_edit, torch.float32, "depth_edit")
+        int_edit = _in(int_edit, torch.uint8, "int_edit")
+        with _on(sigmas):
+            N.check(N.lib().lnrf_composite_rays_distill(n_alive, n_step, float(T_thresh), N.ptr(rays_alive), N.ptr(rays_t),
+                                                        N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(weights_sum),
+                                                        N.ptr(weights_edit_sum), N.ptr(depth), N.ptr(depth_edit), N.ptr(int_edit),
+                                                        N.ptr(image), N.stream()))
         return tuple()
 
 
@@ -333,6 +426,6 @@ def compact_alive(rays_alive: torch.Tensor, n_alive: int, out: torch.Tensor | No
         count = torch.empty(1, dtype=torch.int32, device=dev)
     lib = N.lib()
     scratch = _get_scratch("compact", lib.lnrf_compact_alive_scratch_bytes(n_alive), dev)
-    N.check(lib.lnrf_compact_alive(N.ptr(rays_alive), n_alive, N.ptr(out), N.ptr(count), N.ptr(scratch), scratch.numel() * 8,
-                                   N.stream()))
+    _check(lib.lnrf_compact_alive(N.ptr(rays_alive), n_alive, N.ptr(out), N.ptr(count), N.ptr(scratch), scratch.numel() * 8,
+                                  N.stream()), dev)
     return out, count

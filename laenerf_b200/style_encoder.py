@@ -140,12 +140,29 @@ class LAENeRF(nn.Module):
 class StyleTrainStep:
     """One iteration of the loop in `Trainer.train_LAENeRF_step` (nerf/utils.py:983-1034) without the image-space style / TV
     terms: forward_train on one view's masked points, MSE against the recoloured target + the weight / offset / palette
-    regularisers, GradScaler backward, Adam(lr 1e-3; palette 2e-3) -- the reference's "naive Adam" (:969-971)."""
+    regularisers, GradScaler backward, Adam(lr 1e-3; palette 2e-3) -- the reference's "naive Adam" (:969-971).
 
-    def __init__(self, style_encoder: LAENeRF, params=None, lr: float = 1e-3):
+    fused_optimizer (default): `laenerf_b200.optim.AmpAdam` over the style network's own 12.2 M-entry table, the two MLPs and the
+    palette -- inf check + unscale + Adam for all four tensors in 2 + 2 launches instead of torch's GradScaler + Adam passes
+    (the reference's precision is kept: no autocast around the encoder, fp32 table and fp32 gradients, as nerf/utils.py:983 runs it).
+    world_size > 1 = data parallel over VIEWS: every rank trains on the masked points of its own view, gradients
+    are averaged across ranks inside optimizer.step()."""
+
+    def __init__(self, style_encoder: LAENeRF, params=None, lr: float = 1e-3, fused_optimizer: bool = True, world_size: int = 1, rank: int = 0):
         self.model, self.params = style_encoder, params
-        self.optimizer = torch.optim.Adam(style_encoder.get_params(lr))
-        self.scaler = torch.amp.GradScaler("cuda")
+        self.world = int(world_size)
+        self.fused_optimizer = bool(fused_optimizer)
+        if self.fused_optimizer:
+            from .optim import AmpAdam
+            m = style_encoder
+            owners = [(m.encoder, m.encoder.embeddings, 1.0, False, 0), (m.weight_net, m.weight_net.weights, 1.0, False, 1),
+                      (m.offset_net, m.offset_net.weights, 1.0, False, 2), (m, m.color_palette, 2.0, False, 3)]  # get_params(): palette at 2 lr
+            self.optimizer = AmpAdam(None, lr=lr, betas=(0.9, 0.999), eps=1e-8, fp16=True, world_size=1, rank=rank, owners=owners, n_groups=4)
+            self.optimizer.world = self.world  # fp32 tensors only: plain mean all-reduce of the gradients, replicated update
+            self.scaler = None
+        else:
+            self.optimizer = torch.optim.Adam(style_encoder.get_params(lr))
+            self.scaler = torch.amp.GradScaler("cuda")
         self.loss_fct = nn.MSELoss()
         self.style_step = 0
 
@@ -159,7 +176,14 @@ class StyleTrainStep:
         loss = loss + m.weights_loss(pred_weight, p).half()
         loss = loss + m.offset_loss(pred_offset, p).half()
         loss = loss + m.palet_loss(p).half()
-        self.scaler.scale(loss).backward()
-        self.scaler.step(self.optimizer)
-        self.scaler.update()
+        if self.fused_optimizer:
+            self.optimizer.scale(loss).backward()
+            self.optimizer.step()
+        else:
+            self.scaler.scale(loss).backward()
+            if self.world > 1:
+                from .parallel import allreduce_gradients
+                allreduce_gradients([q for g in self.optimizer.param_groups for q in g["params"]], self.world)
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
         return loss.detach(), pred_colors.detach()

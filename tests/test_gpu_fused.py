@@ -220,6 +220,70 @@ def test_train_step_fused_optimizer_tracks_torch_path(dev):
     assert float(sd["state"][0]["step"]) == 6 and sd["state"][0]["exp_avg"].shape == a.encoder.embeddings.shape
 
 
+def test_amp_adam_checkpoints_interchange_with_torch_adam(dev):
+    """state_dict() has torch.optim.Adam's layout with the reference's four parameter groups (network_ff.py:139-153: encoder,
+    sigma_net, an EMPTY encoder_dir group, color_net): torch's optimizer built from model.get_params() loads it, and AmpAdam
+    loads torch's; the GradScaler state is separate, in torch.amp.GradScaler's layout."""
+    from laenerf_b200.nerf import TrainStep
+    a = _model(dev, True, 51)
+    sa = TrainStep(a)
+    _, ro, rd, _ = scene_rays("lego", 1024, 3)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    gt = torch.rand(1024, 3, device=dev)
+    for _ in range(3):
+        sa(ro, rd, gt)
+    sd = sa.optimizer.state_dict()
+    assert [g["params"] for g in sd["param_groups"]] == [[0], [1], [], [2]] and "scaler" not in sd
+    topt = torch.optim.Adam(a.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    topt.load_state_dict(sd)                                   # AmpAdam -> torch
+    st = topt.state[a.encoder.embeddings]
+    assert float(st["step"]) == 3 and torch.equal(st["exp_avg"], sa.optimizer.state[0]["exp_avg"])
+    scaler = torch.amp.GradScaler("cuda")
+    scaler.load_state_dict(sa.optimizer.scaler_state_dict())   # scaler state in GradScaler's own layout
+    assert scaler.get_scale() == sa.optimizer.get_scale()
+    b = _model(dev, True, 51)
+    sb = TrainStep(b)
+    sb.optimizer.load_state_dict(topt.state_dict())            # torch -> AmpAdam
+    sb.optimizer.load_scaler_state_dict(scaler.state_dict())
+    assert float(sb.optimizer.step_count) == 4.0
+    for x, y in zip(sb.optimizer.state, sa.optimizer.state):
+        assert torch.equal(x["exp_avg"], y["exp_avg"]) and torch.equal(x["exp_avg_sq"], y["exp_avg_sq"])
+
+
+def test_fp16_shadows_follow_outside_writes_to_the_fp32_parameters(dev):
+    """the kernels read AmpAdam's fp16 shadows; load_state_dict / reset_parameters / an EMA copy_to() write the fp32
+    parameters behind its back.  torch bumps `_version` on those writes, the shadow is re-derived before its next use
+    (laenerf_b200/_shadow.py) -- the reference re-casts on every forward (grid.py:43-44)."""
+    from laenerf_b200.nerf import TrainStep
+    a, donor = _model(dev, True, 61), _model(dev, True, 62)
+    with torch.no_grad():
+        donor.sigma_net.weights.mul_(0.5)
+    sa = TrainStep(a)
+    x = torch.rand(1280, 3, device=dev) * 1.6 - 0.8
+    d = torch.nn.functional.normalize(torch.randn(1280, 3, device=dev), dim=-1)
+    a.eval()
+
+    def out():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            return [t.clone() for t in a.forward_scaled(x, d)]
+
+    before = out()
+    donor.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        want = [t.clone() for t in donor.forward_scaled(x, d)]
+    assert not torch.equal(before[0], want[0])
+    a.load_state_dict(donor.state_dict())          # after AmpAdam construction
+    after = out()
+    assert torch.equal(after[0], want[0]) and torch.equal(after[1], want[1])
+    assert torch.equal(a.encoder._shadow_f16, a.encoder.embeddings.detach().half())
+    # and the optimizer keeps training from the loaded state (its own raw-pointer writes do not trigger a re-derivation)
+    _, ro, rd, _ = scene_rays("lego", 1024, 5)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    sa(ro, rd, torch.rand(1024, 3, device=dev))
+    assert torch.equal(a.encoder._shadow_f16, a.encoder.embeddings.detach().half())
+    assert not torch.equal(a.sigma_net.weights.detach(), donor.sigma_net.weights.detach())
+
+
 def test_graphed_train_step_with_fused_optimizer(dev):
     from laenerf_b200.nerf import GraphedTrainStep, TrainStep
     m = _model(dev, True, 21)

@@ -109,3 +109,23 @@ def test_style_encoder_module_topology_without_a_gpu():
     assert [g["lr"] for g in groups] == [1e-3, 1e-3, 1e-3, 2e-3] and groups[3]["params"] is m.color_palette
     assert m.get_params_but_dont_learn_palette(1e-3)[3]["lr"] == 0
     assert m.color_palette.shape == (8, 3) and m.color_palette.requires_grad
+
+
+def test_reference_callers_construct_on_the_dropin_packages():
+    """The reference's own nerf/network_ff.py + nerf/renderer.py (staged untouched by oracle/build_ref.py) import and construct with
+    dropin/ in front of the path: `import raymarching`, `from gridencoder import GridEncoder`, `from ffmlp import FFMLP`, `from
+    shencoder import SHEncoder` resolve to laenerf_b200 (the GPU tier then RUNS them: tests/test_gpu_refstack.py)."""
+    import sys
+    import pytest
+    import ref_stack
+    if not ref_stack.available("dropin"):
+        pytest.skip("oracle/_ref/py not staged (python oracle/build_ref.py py)")
+    before = {k: sys.modules.get(k) for k in ("raymarching", "gridencoder", "ffmlp", "shencoder", "nerf", "encoding")}
+    m = ref_stack.make_model("dropin", "ff", bound=2, density_scale=1, min_near=0.2, density_thresh=10)
+    assert type(m).__module__ == "nerf.network_ff" and type(m).__mro__[1].__module__ == "nerf.renderer"
+    for sub in (m.encoder, m.sigma_net, m.color_net, m.encoder_dir):
+        assert type(sub).__module__.startswith("laenerf_b200."), type(sub)
+    assert m.cascade == 2 and m.density_bitfield.numel() == 2 * 128 ** 3 // 8
+    assert [tuple(p.shape) for p in m.parameters()] == [(6328848, 2), (7168,), (11264,)]
+    # the flavour's modules do not leak into (or replace anything in) the process-wide module table
+    assert before == {k: sys.modules.get(k) for k in before}
