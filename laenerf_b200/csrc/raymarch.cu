@@ -778,8 +778,17 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
 //   ctl[8] survivors of the running compaction (internal)    ctl[9] sample slots marched so far
 //   ctl[10] row budget of the rounds after the first (n_rays: the reference schedule; more: see lnrf_render_desc.sample_rows)
 //   ctl[11] most samples a ray takes per round after the first (8: the reference schedule)
+//   ctl[12] schedule-dependence flag: set when the frame's result COULD depend on where the round boundaries fall (see below)
 enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, kCtlMaxSteps = 5, kCtlFinished = 6, kCtlRounds = 7,
-       kCtlBudget = 10, kCtlStepCap = 11 };
+       kCtlBudget = 10, kCtlStepCap = 11, kCtlInexact = 12 };
+// Why a schedule other than the reference's n_step rule can be bit-identical to it.  Between rounds a ray's t travels through
+// rays_t, which composite_rays rebuilds as rays_t + sum of deltas[.][1] (raymarching.cu:1006), each delta being fl(t_after -
+// t_prev) from the marcher (:789).  When t_after / t_prev <= 2 that difference is exact (Sterbenz) and fl(t_prev + delta) is
+// t_after itself, so the rebuilt rays_t equals the marcher's own t wherever the round ends: boundaries leave no trace.  Only an
+// inexact delta (a skip longer than t itself: cameras inside the volume, min_near << gap) injects a rounding error whose position
+// depends on the schedule.  The marcher checks fl(t_prev + delta) == t_after for every sample it emits and raises ctl[12]
+// otherwise; so does a frame that runs into the max_steps cap with rays still alive.  No flag = every schedule gives the
+// reference's bits (measured: the lego-shape view, 91 vs 16 rounds, image / depth / weights identical).
 
 __device__ __forceinline__ void ctl_set_round(int* ctl, uint32_t n_alive) {
     const uint32_t n_rays = (uint32_t)ctl[kCtlRays];
@@ -831,14 +840,18 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
             t = f_fma(f_clamp(f_mul(t_in, p.dt_gamma), p.dt_min, p.dt_max), noise, t_in);  // raymarching.cu:746
         }
         const size_t row0 = (size_t)g * n_step;
+        bool inexact = false;
         const uint32_t cnt = march_group<G, true>(
             grp, p, r, grid, t, far, n_step, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
                 const size_t row = row0 + rank;
                 xyzs[row * 3] = q.x; xyzs[row * 3 + 1] = q.y; xyzs[row * 3 + 2] = q.z;
                 dirs[row * 3] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz;
-                reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, f_add(f_add(s, dt), -prev_after));
+                const float t_after = f_add(s, dt), d1 = f_add(t_after, -prev_after);
+                reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, d1);
+                inexact |= f_add(prev_after, d1) != t_after;
                 if (DISTILL) edit_occ[row] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
             });
+        if (ctl && inexact) const_cast<int*>(ctl)[kCtlInexact] = 1;  // benign race: every writer stores the same value
         if (g >= n_groups) continue;
         // zero-fill the slots this ray did not use, and whole padding groups (torch.zeros in raymarching.py:334-336)
         const size_t zlo = row0 + (active ? cnt : 0u);
@@ -999,7 +1012,9 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
                 ctl[kCtlSteps] += ctl[kCtlStep];
                 ctl[kCtlRounds] += 1;
                 ctl[kCtlRounds + 2] += ctl[kCtlRows];  // sample slots marched so far (what the host loop sums up)
-                ctl_set_round(ctl, (uint32_t)((volatile int*)ctl)[kCtlRounds + 1]);
+                const uint32_t survivors = (uint32_t)((volatile int*)ctl)[kCtlRounds + 1];
+                if (survivors > 0u && (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps]) ctl[kCtlInexact] = 1;  // the cap cut rays off
+                ctl_set_round(ctl, survivors);
             }
         }
     }
@@ -1028,6 +1043,7 @@ k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_
         ctl[kCtlRounds + 2] = 0;
         ctl[kCtlBudget] = (int)row_budget;
         ctl[kCtlStepCap] = (int)step_cap;
+        ctl[kCtlInexact] = 0;
         ctl_set_round(ctl, n_rays);
     }
 }

@@ -133,9 +133,12 @@ class NeRFNetwork(nn.Module):
         # they are built for (fp16 autocast, hidden 64, 16+15+1 colour inputs, sample count a multiple of 128)
         self.fused = True
         self.device_loop = True  # row f-3: inference rounds driven from the device (falls back to the host loop when not fused)
-        # round schedule of the device loop: "reference" reproduces run_cuda's n_step rule bit for bit; "fast" spends 8x the
-        # sample-buffer memory on ~5x fewer rounds (same per-sample arithmetic; see _render_rounds_device)
-        self.render_schedule = "reference"
+        # round schedule of the device loop.  "reference": run_cuda's n_step rule.  "fast": 8x the sample-buffer memory for ~5x fewer
+        # rounds, same per-sample arithmetic.  "auto" (default): "fast" whenever the marcher PROVES the frame's bits do not depend on
+        # the round boundaries (every emitted delta exactly representable -- csrc/raymarch.cu, kCtlInexact), otherwise the frame is
+        # rendered again on the reference schedule and later frames of this model go there directly: always the reference's bits
+        self.render_schedule = "auto"
+        self._auto_fast_ok = True
         self.render_samples_per_round = 32  # "fast" only: cap on the samples a ray takes per round after the first
         self._amp_adam = None  # weak reference to the AmpAdam that owns the fp16 shadows, if any
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
@@ -320,6 +323,25 @@ class NeRFNetwork(nn.Module):
     # ---- row f-3: the inference loop of run_cuda / run_cuda_distill driven from the device -----------------------------
     def _render_rounds_device(self, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
                               rounds_per_call: int = 8):
+        """The device loop on self.render_schedule; "auto" = fast where provably bit-identical to the reference schedule."""
+        sched = self.render_schedule
+        if sched != "auto":
+            return self._render_rounds_on(sched, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
+                                          rounds_per_call)
+        if self._auto_fast_ok and not perturb:
+            t = self._render_rounds_on("fast", rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
+                                       rounds_per_call)
+            if not t["schedule_dependent"]:
+                t["schedule"] = "fast (proven bit-identical to the reference schedule for this frame)"
+                return t
+            self._auto_fast_ok = False  # this scene produces inexact deltas (cameras inside the volume): do not try again
+        t = self._render_rounds_on("reference", rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
+                                   rounds_per_call)
+        t["schedule"] = "reference"
+        return t
+
+    def _render_rounds_on(self, schedule, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
+                          rounds_per_call: int = 8):
         """renderer.py:335-387 (and :425-470 with an edit grid) without a host synchronisation per round: the kernels read
         n_alive / n_step from a control block in device memory that the compaction kernel updates (csrc/render.cu); the
         host queues `rounds_per_call` rounds at a time and only then looks at the `finished` flag.  Same kernels, same
@@ -332,7 +354,7 @@ class NeRFNetwork(nn.Module):
         # host loop.  "fast": buffers of 8 n_rays + 128 rows; the first round (n_step = 1) weeds out the rays that miss, every later
         # round takes up to render_samples_per_round samples per ray -- several times fewer rounds, each of which costs ~90 us of
         # latency whatever its size
-        fast = self.render_schedule == "fast"
+        fast = schedule == "fast"
         rows = (8 * n_rays if fast else n_rays) + 128
         distill = edit_bitfield is not None
         enc, sn, cn = self.encoder, self.sigma_net, self.color_net
@@ -387,6 +409,8 @@ class NeRFNetwork(nn.Module):
             if ctl[6]:
                 break
         t["rounds"], t["steps"], t["slots"] = ctl[7], ctl[2], ctl[9]
+        t["schedule_dependent"] = bool(ctl[12])
+        t["schedule"] = schedule
         return t
 
     def _device_loop_ok(self, rays_o):
@@ -466,6 +490,7 @@ class NeRFNetwork(nn.Module):
             depth = depth.view(*prefix)
             results["num_points"] = t["slots"]
             results["rounds"] = t["rounds"]
+            results["schedule"] = t["schedule"]
         else:
             weights_sum = torch.zeros(n_rays, dtype=torch.float32, device=device)
             depth = torch.zeros(n_rays, dtype=torch.float32, device=device)

@@ -316,7 +316,8 @@ def test_nerf_backward_matches_oracle_composition(dev, oracle_backend, M, ns, nc
     dh = torch.empty(M, 16, dtype=torch.half, device=dev)
     nbytes = lib.lnrf_nerf_wgrad_scratch_bytes(ns, nc)
     scratch = torch.empty(nbytes // 4, device=dev)
-    N.check(lib.lnrf_nerf_backward(N.ptr(t(gsig, torch.float32)), N.ptr(t(grgb, torch.float32)), N.ptr(rgb), N.ptr(h0), N.ptr(enc_d), N.ptr(cin),
+    gsig_d, grgb_d = t(gsig, torch.float32), t(grgb, torch.float32)  # named: a temporary would be freed (and its block reused) before the launch
+    N.check(lib.lnrf_nerf_backward(N.ptr(gsig_d), N.ptr(grgb_d), N.ptr(rgb), N.ptr(h0), N.ptr(enc_d), N.ptr(cin),
                                    N.ptr(ws_d), N.ptr(wc_d), N.ptr(fb), M, ns, nc, ds, N.ptr(genc), N.ptr(gws), N.ptr(gwc), 0, N.ptr(dh),
                                    N.ptr(scratch), nbytes, None))
     torch.cuda.synchronize()

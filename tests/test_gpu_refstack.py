@@ -127,7 +127,7 @@ def test_full_view_image_parity_reference_vs_dropin_vs_product(dev, stacks, trai
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
             imgs[name] = m.run_cuda(ro, rd, dt_gamma=0, bg_color=1, perturb=False, max_steps=1024, T_thresh=1e-4, scale_depth=True)
     ours.eval()
-    ours.fused, ours.device_loop, ours.render_schedule = True, True, "reference"
+    ours.fused, ours.device_loop, ours.render_schedule = True, True, "auto"
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         imgs["P"] = ours.render(ro, rd, perturb=False, bg_color=1, T_thresh=1e-4)
     psnr = {k: _psnr(v["image"], gt) for k, v in imgs.items()}
@@ -192,7 +192,7 @@ def test_update_extra_state_against_the_reference_renderer(dev, stacks, trained,
     assert torch.equal(gr < 0, gp < 0)
     # same query points (same RNG stream); the densities differ by the fp16-accumulate (reference) vs fp32-accumulate MLP arithmetic
     rel = (gr - gp).abs() / gr.abs().clamp(min=1e-3)
-    assert float(rel.mean()) < 5e-3, float(rel.mean())
+    assert float(rel.mean()) < (2e-2 if partial else 5e-3), float(rel.mean())
     frac_off = float((rel > 0.1).float().mean())
     assert frac_off < (0.12 if partial else 1e-3), frac_off  # partial updates: duplicate draws make torch's own scatter order-dependent
     assert abs(R.mean_density - P.mean_density) <= 2e-2 * abs(R.mean_density) + 1e-6
