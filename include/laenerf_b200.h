@@ -351,6 +351,24 @@ LNRF_API int lnrf_nerf_backward(const float* grad_sigmas, const float* grad_rgbs
                                 void* dh_scratch_f16, void* wgrad_scratch, size_t wgrad_scratch_bytes,
                                 lnrf_stream_t stream);
 
+/* Round 2: the same pair WITHOUT saved hidden activations.  The forward keeps only h = sigma_net(enc) [M,16] fp16 (32 B/sample
+ * instead of 704); the backward RECOMPUTES every hidden activation from enc and h on the tensor cores inside one warp-specialised
+ * kernel (csrc/nerfbwd.cu: TMA producer warp, MMA warp, two epilogue warpgroups) -- DRAM traffic of the two calls drops from
+ * ~366 MB to ~60 MB per 228 k-sample step.  Same values as lnrf_nerf_forward / lnrf_nerf_backward (identical MMAs and rounding points).
+ * M_dev (optional, may be NULL): device-side count of live samples (the training marcher's counter[0], the render control block);
+ * rows at or beyond ceil(*M_dev / 128) * 128 are padding and are skipped.  h_f16 may be NULL (inference).
+ * lnrf_nerf_backward_recompute_supported: 2 <= num_layers_sigma <= num_layers_color and the shared-memory / TMEM budget (LAENeRF's
+ * 2 / 3 layers fit); otherwise use lnrf_nerf_forward(train) + lnrf_nerf_backward. */
+LNRF_API int lnrf_nerf_forward_lean(const void* enc_f16, const float* dirs, const void* w_sigma_f16, const void* w_color_f16, uint32_t M,
+                                    const int32_t* M_dev, uint32_t num_layers_sigma, uint32_t num_layers_color, float density_scale,
+                                    void* h_f16, float* sigmas, float* rgbs, lnrf_stream_t stream);
+LNRF_API int lnrf_nerf_backward_recompute_supported(uint32_t num_layers_sigma, uint32_t num_layers_color);
+LNRF_API int lnrf_nerf_backward_recompute(const float* grad_sigmas, const float* grad_rgbs, const float* rgbs, const void* h_f16,
+                                          const void* enc_f16, const float* dirs, const void* w_sigma_f16, const void* w_color_f16,
+                                          uint32_t M, const int32_t* M_dev, uint32_t num_layers_sigma, uint32_t num_layers_color,
+                                          float density_scale, void* grad_enc_f16, void* grad_w_sigma_f16, void* grad_w_color_f16,
+                                          int accumulate_wgrad, void* wgrad_scratch, size_t wgrad_scratch_bytes, lnrf_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * occupancy-grid maintenance (row f-2) -- NeRFRenderer.update_extra_state, nerf/renderer.py:556-649
  * --------------------------------------------------------------------------------------------------------- */

@@ -76,6 +76,9 @@ SIGNATURES = {
     "lnrf_nerf_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "lnrf_nerf_wgrad_scratch_bytes": (sz, [u32, u32]),
     "lnrf_nerf_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, f32, vp, vp, vp, i32, vp, vp, sz, vp]),
+    "lnrf_nerf_forward_lean": (i32, [vp, vp, vp, vp, u32, vp, u32, u32, f32, vp, vp, vp, vp]),
+    "lnrf_nerf_backward_recompute_supported": (i32, [u32, u32]),
+    "lnrf_nerf_backward_recompute": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, vp, u32, u32, f32, vp, vp, vp, i32, vp, sz, vp]),
     "lnrf_grad_nonfinite_check": (i32, [vp, u32, vp, vp]),
     "lnrf_adam_step": (i32, [vp, u32, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp]),
     "lnrf_adam_step_sharded": (i32, [vp, vp, vp, u32, u64, u64, vp, vp, vp, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp]),

@@ -18,6 +18,7 @@
 //   Accumulation is fp32 everywhere (the reference accumulates in fp16); activations are rounded to fp16 exactly
 //   where the reference stores them (forward_buffer, backward chain, outputs).
 #include "mlp_core.cuh"
+#include <string.h>
 
 namespace lnrf {
 
@@ -742,8 +743,11 @@ static int ffmlp_fwd_launch(const char* who, const void* inputs, const void* wei
 
 namespace lnrf {
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library links only cudart)
-int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, const char* who) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (the library links only cudart).
+// `cols` x `rows` fp16 row-major with `row_bytes` between rows; box = box_cols x box_rows; SWIZZLE_128B; out-of-bounds elements of a
+// box read as zero (a 64-column box over a 32-column tensor lands as full 128-byte rows whose upper half is zero).
+int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t row_bytes, uint32_t box_cols,
+                       uint32_t box_rows, const char* who) {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -761,9 +765,10 @@ int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, cons
         enc = reinterpret_cast<encode_fn>(fn);
         s_encode.store(enc, std::memory_order_release);
     }
-    const cuuint64_t gdim[2] = {64, rows};
-    const cuuint64_t gstride[1] = {128};       // bytes between rows
-    const cuuint32_t box[2] = {64, kRows};     // one 128-row x 128-byte tile
+    memset(map, 0, sizeof(*map));
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {row_bytes};   // bytes between rows
+    const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -773,6 +778,11 @@ int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, cons
         return LNRF_ERR_CUDA;
     }
     return LNRF_OK;
+}
+
+// [rows, 64] fp16 row-major global tensor, box = one 128-row x 128-byte tile
+int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, const char* who) {
+    return make_tensor_map_2d(map, base, 64, rows, 128, 64, kRows, who);
 }
 
 int mlp_shape(const char* who, uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t num_layers, MlpShape* sh) {

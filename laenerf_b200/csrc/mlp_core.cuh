@@ -282,6 +282,9 @@ __device__ __forceinline__ void umma_chain_k(uint32_t nk, uint32_t d_tmem, uint6
 // ---- TMA (bulk tensor copies): one elected thread moves a whole 128-row x 128-byte SWIZZLE_128B tile ----
 // [rows, 64] fp16 row-major global tensor, box = one tile; defined in ffmlp.cu
 int make_tile_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, const char* who);
+// generic 2-D fp16 map, SWIZZLE_128B, zero fill outside the tensor; defined in ffmlp.cu
+int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t row_bytes, uint32_t box_cols,
+                       uint32_t box_rows, const char* who);
 
 __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, uint32_t smem_tile, int32_t col, int32_t row) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),

@@ -45,10 +45,11 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
            const __half* __restrict__ w_color, const uint32_t M, const uint32_t ns, const uint32_t nc, const float density_scale,
            const __grid_constant__ CUtensorMap tm_fwd_buf, __half* __restrict__ color_in, __half* __restrict__ h0_out,
            float* __restrict__ sigmas, float* __restrict__ rgbs, uint32_t ntiles, const int* __restrict__ M_dev,
-           const uint32_t sigma_only) {
+           const uint32_t sigma_only, __half* __restrict__ h_all_out) {
     extern __shared__ uint8_t smem_raw[];
-    if (M_dev) {  // device-driven inference round (row f-3): the sample count lives in the render control block
-        ntiles = (uint32_t)*M_dev / kRows;
+    if (M_dev) {  // device-side sample count: the render control block (row f-3) or the training marcher's counter; capacity = ntiles
+        const uint32_t live = div_up((uint32_t)max(*M_dev, 0), kRows);
+        ntiles = live < ntiles || ntiles == 0u ? live : ntiles;
         if (ntiles == 0u) return;
     }
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
@@ -180,6 +181,12 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
                 fence_proxy_async();
                 group_barrier(g);
                 __stcs(sigmas + r0 + row, density_scale * expf(__half2float(h0)));
+                if (h_all_out) {  // lean training forward: the 16 outputs of the sigma net are all the backward needs besides enc (nerfbwd.cu)
+                    uint32_t ph[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) ph[i] = pack_h2(h[2 * i], h[2 * i + 1]);
+                    st_global_32B(h_all_out + (r0 + row) * 16, ph);
+                }
                 if (TRAIN) {
                     h0_out[r0 + row] = h0;
                     __half* dst = color_in + (r0 + row) * kColIn;
@@ -240,7 +247,7 @@ int nerf_forward_dev_launch(const void* enc_f16, const float* dirs, const void* 
     const uint32_t want = div_up(div_up(M_cap, kRows), kGroups);
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     k_nerf_fwd<false><<<grid, 128 * kGroups, smem, st>>>((const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M_cap,
-                                                         ns, nc, density_scale, tm, nullptr, nullptr, sigmas, rgbs, 0u, M_dev, 0u);
+                                                         ns, nc, density_scale, tm, nullptr, nullptr, sigmas, rgbs, div_up(M_cap, kRows), M_dev, 0u, nullptr);
     LNRF_LAUNCH_CHECK("render_rounds(network)");
     return LNRF_OK;
 }
@@ -282,8 +289,34 @@ int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigm
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     kern<<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale,
-        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles, nullptr, 0u);
+        tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles, nullptr, 0u, nullptr);
     LNRF_LAUNCH_CHECK("nerf_forward");
+    return LNRF_OK;
+}
+
+int lnrf_nerf_forward_lean(const void* enc_f16, const float* dirs, const void* w_sigma_f16, const void* w_color_f16, uint32_t M,
+                           const int32_t* M_dev, uint32_t num_layers_sigma, uint32_t num_layers_color, float density_scale, void* h_f16,
+                           float* sigmas, float* rgbs, lnrf_stream_t stream) {
+    const uint32_t ns = num_layers_sigma, nc = num_layers_color;
+    LNRF_REQUIRE(M % 128 == 0, "nerf_forward_lean: the sample count must be 128 * m, but got %u", M);
+    LNRF_REQUIRE(ns >= 2 && nc >= 2 && ns <= kMaxLayers && nc <= kMaxLayers, "nerf_forward_lean: num_layers outside [2, %u]", kMaxLayers);
+    if (M == 0) return LNRF_OK;
+    LNRF_REQUIRE(enc_f16 && dirs && w_sigma_f16 && w_color_f16 && sigmas && rgbs, "nerf_forward_lean: null pointer");
+    LNRF_REQUIRE(((reinterpret_cast<uintptr_t>(enc_f16) | reinterpret_cast<uintptr_t>(w_sigma_f16) | reinterpret_cast<uintptr_t>(w_color_f16)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(h_f16) & 31) == 0,
+                 "nerf_forward_lean: tensors must be 16-byte (h: 32-byte) aligned");
+    const size_t smem = nerf_fwd_smem(ns, nc);
+    LNRF_REQUIRE(smem <= 227 * 1024, "nerf_forward_lean: networks need %zu B of shared memory (> 227 KiB)", smem);
+    if (int e = ensure_nerf_fwd_smem(false, smem, "nerf_forward_lean")) return e;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    const uint32_t ntiles = M / kRows;
+    const uint32_t want = div_up(ntiles, kGroups);
+    const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
+    k_nerf_fwd<false><<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale, tm, nullptr, nullptr,
+        sigmas, rgbs, ntiles, M_dev, 0u, (__half*)h_f16);
+    LNRF_LAUNCH_CHECK("nerf_forward_lean");
     return LNRF_OK;
 }
 
@@ -303,7 +336,7 @@ int lnrf_nerf_density(const void* enc_f16, const void* w_sigma_f16, uint32_t M, 
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     k_nerf_fwd<false><<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)enc_f16, nullptr, (const __half*)w_sigma_f16, nullptr, M, ns, 0u, density_scale, tm, nullptr, nullptr, sigmas, nullptr,
-        ntiles, nullptr, 1u);
+        ntiles, nullptr, 1u, nullptr);
     LNRF_LAUNCH_CHECK("nerf_density");
     return LNRF_OK;
 }

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -40,57 +41,90 @@ class _trunc_exp(Function):  # activation.py:5-17
 trunc_exp = _trunc_exp.apply
 
 
+def _recompute_ok(ns, nc) -> bool:
+    """Round-2 pair (lean forward + recompute backward, csrc/nerfbwd.cu); LNRF_MLP_RECOMPUTE=0 selects the round-1 save/reload pair."""
+    return os.environ.get("LNRF_MLP_RECOMPUTE", "1") != "0" and bool(N.lib().lnrf_nerf_backward_recompute_supported(int(ns), int(nc)))
+
+
 class _fused_network(Function):
     """NeRFNetwork.forward after the hash-grid encoder (network_ff.py:57-79 + `density_scale * sigma`, renderer.py:299)
-    as ONE kernel (lnrf_nerf_forward) and its backward as two (lnrf_nerf_backward): row f-1 of SURVEY.md section 8.
+    as ONE kernel and its backward as one more (+ the weight-gradient reduction): row f-1 of SURVEY.md section 8.
     Inputs/outputs and every fp16 rounding point are those of the module-by-module path below; the ~25 elementwise /
-    cat / cast launches between the MLP kernels are gone."""
+    cat / cast launches between the MLP kernels are gone.  Training keeps only h = sigma_net(enc) [M,16] fp16 for the backward,
+    which recomputes the hidden activations on the tensor cores (lnrf_nerf_forward_lean / lnrf_nerf_backward_recompute).
+    m_dev: optional device int32 holding the number of live samples (the marcher's counter): padding rows are skipped."""
 
     @staticmethod
-    def forward(ctx, enc, dirs, w_sigma, w_color, ns, nc, density_scale, train, w_sigma_f16, w_color_f16, gw_sigma_f16, gw_color_f16):
+    def forward(ctx, enc, dirs, w_sigma, w_color, ns, nc, density_scale, train, w_sigma_f16, w_color_f16, gw_sigma_f16, gw_color_f16,
+                m_dev=None):
         M = enc.shape[0]
         enc = enc.contiguous()
         dirs = dirs.contiguous().float()
         ws = w_sigma_f16 if w_sigma_f16 is not None else w_sigma.detach().half()
         wc = w_color_f16 if w_color_f16 is not None else w_color.detach().half()
         dev = enc.device
-        sigmas = torch.empty(M, dtype=torch.float32, device=dev)
-        rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
-        fb = cin = h0 = None
-        if train:
-            fb = torch.empty(ns + nc, M, 64, dtype=torch.half, device=dev)
-            cin = torch.empty(M, 32, dtype=torch.half, device=dev)
-            h0 = torch.empty(M, dtype=torch.half, device=dev)
-        N.check(N.lib().lnrf_nerf_forward(N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, ns, nc, float(density_scale), int(train),
+        lean = _recompute_ok(ns, nc)
+        if m_dev is not None and not lean:
+            m_dev = None
+        # with a device-side count the rows past it are never written: they must still read as zeros downstream (compositing
+        # indexes live samples only; the padding rows of sigmas / rgbs are what torch.zeros would have left)
+        alloc = torch.zeros if m_dev is not None else torch.empty
+        sigmas = alloc(M, dtype=torch.float32, device=dev)
+        rgbs = alloc(M, 3, dtype=torch.float32, device=dev)
+        lib = N.lib()
+        if lean:
+            h = torch.empty(M, 16, dtype=torch.half, device=dev) if train else None
+            N.check(lib.lnrf_nerf_forward_lean(N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, N.ptr(m_dev), ns, nc, float(density_scale),
+                                               N.ptr(h), N.ptr(sigmas), N.ptr(rgbs), N.stream()))
+            if train:
+                ctx.save_for_backward(enc, dirs, ws, wc, h, rgbs, m_dev)
+        else:
+            fb = cin = h0 = None
+            if train:
+                fb = torch.empty(ns + nc, M, 64, dtype=torch.half, device=dev)
+                cin = torch.empty(M, 32, dtype=torch.half, device=dev)
+                h0 = torch.empty(M, dtype=torch.half, device=dev)
+            N.check(lib.lnrf_nerf_forward(N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, ns, nc, float(density_scale), int(train),
                                           N.ptr(fb), N.ptr(cin), N.ptr(h0), N.ptr(sigmas), N.ptr(rgbs), N.stream()))
+            if train:
+                ctx.save_for_backward(enc, ws, wc, fb, cin, h0, rgbs)
         if train:
-            ctx.save_for_backward(enc, ws, wc, fb, cin, h0, rgbs)
+            ctx.lean = lean
             ctx.cfg = (ns, nc, float(density_scale))
             ctx.gw = (gw_sigma_f16, gw_color_f16)
         return sigmas, rgbs
 
     @staticmethod
     def backward(ctx, grad_sigmas, grad_rgbs):
-        enc, ws, wc, fb, cin, h0, rgbs = ctx.saved_tensors
         ns, nc, density_scale = ctx.cfg
+        lib = N.lib()
+        if ctx.lean:
+            enc, dirs, ws, wc, h, rgbs, m_dev = ctx.saved_tensors
+        else:
+            enc, ws, wc, fb, cin, h0, rgbs = ctx.saved_tensors
+            m_dev = None
         M = enc.shape[0]
         dev = enc.device
         grad_sigmas = torch.zeros(M, dtype=torch.float32, device=dev) if grad_sigmas is None else grad_sigmas.contiguous().float()
         grad_rgbs = torch.zeros(M, 3, dtype=torch.float32, device=dev) if grad_rgbs is None else grad_rgbs.contiguous().float()
-        grad_enc = torch.empty_like(enc)
+        grad_enc = (torch.zeros_like if m_dev is not None else torch.empty_like)(enc)
         persistent = ctx.gw[0] is not None
         gws = ctx.gw[0] if persistent else torch.empty_like(ws)
         gwc = ctx.gw[1] if persistent else torch.empty_like(wc)
-        dh = torch.empty(M, 16, dtype=torch.half, device=dev)
-        lib = N.lib()
         nbytes = lib.lnrf_nerf_wgrad_scratch_bytes(ns, nc)
         scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
-        N.check(lib.lnrf_nerf_backward(N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(rgbs), N.ptr(h0), N.ptr(enc), N.ptr(cin), N.ptr(ws),
-                                       N.ptr(wc), N.ptr(fb), M, ns, nc, density_scale, N.ptr(grad_enc), N.ptr(gws), N.ptr(gwc),
-                                       int(persistent), N.ptr(dh), N.ptr(scratch), nbytes, N.stream()))
+        if ctx.lean:
+            N.check(lib.lnrf_nerf_backward_recompute(N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(rgbs), N.ptr(h), N.ptr(enc), N.ptr(dirs),
+                                                     N.ptr(ws), N.ptr(wc), M, N.ptr(m_dev), ns, nc, density_scale, N.ptr(grad_enc), N.ptr(gws),
+                                                     N.ptr(gwc), int(persistent), N.ptr(scratch), nbytes, N.stream()))
+        else:
+            dh = torch.empty(M, 16, dtype=torch.half, device=dev)
+            N.check(lib.lnrf_nerf_backward(N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(rgbs), N.ptr(h0), N.ptr(enc), N.ptr(cin), N.ptr(ws),
+                                           N.ptr(wc), N.ptr(fb), M, ns, nc, density_scale, N.ptr(grad_enc), N.ptr(gws), N.ptr(gwc),
+                                           int(persistent), N.ptr(dh), N.ptr(scratch), nbytes, N.stream()))
         if persistent:  # AmpAdam reads (and clears) the persistent fp16 buffers; autograd sees no weight gradient
             gws = gwc = None
-        return grad_enc, None, gws, gwc, None, None, None, None, None, None, None, None
+        return grad_enc, None, gws, gwc, None, None, None, None, None, None, None, None, None
 
 
 fused_network = _fused_network.apply

@@ -286,8 +286,9 @@ def _h(a):
     return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
 
 
-@pytest.mark.parametrize("M,ns,nc", [(8192, 2, 3), (1152, 3, 2)])
-def test_nerf_backward_matches_oracle_composition(dev, oracle_backend, M, ns, nc):
+@pytest.mark.parametrize("M,ns,nc,variant", [(8192, 2, 3, "saved"), (1152, 3, 2, "saved"), (8192, 2, 3, "recompute"), (1280, 2, 2, "recompute"),
+                                             (640, 3, 3, "recompute"), (128 * 301, 2, 3, "recompute")])
+def test_nerf_backward_matches_oracle_composition(dev, oracle_backend, M, ns, nc, variant):
     """lnrf_nerf_backward (colour-net backward with the glue fused + sigma-net backward + weight-gradient reduction) against the
     CPU oracle composed the way autograd composes network_ff.py:51-79: sigmoid', FFMLP backward, cat split, trunc_exp backward
     (activation.py:13-16), FFMLP backward."""
@@ -305,21 +306,30 @@ def test_nerf_backward_matches_oracle_composition(dev, oracle_backend, M, ns, nc
     t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
     enc_d, dirs_d, ws_d, wc_d = t(enc, torch.half), t(dirs, torch.float32), t(ws, torch.half), t(wc, torch.half)
     sig, rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
-    fb = torch.empty(ns + nc, M, 64, dtype=torch.half, device=dev)
-    cin = torch.empty(M, 32, dtype=torch.half, device=dev)
-    h0 = torch.empty(M, dtype=torch.half, device=dev)
     lib = N.lib()
-    N.check(lib.lnrf_nerf_forward(N.ptr(enc_d), N.ptr(dirs_d), N.ptr(ws_d), N.ptr(wc_d), M, ns, nc, ds, 1, N.ptr(fb), N.ptr(cin), N.ptr(h0),
-                                  N.ptr(sig), N.ptr(rgb), None))
     genc = torch.full((M, 32), float("nan"), dtype=torch.half, device=dev)
     gws, gwc = torch.full_like(ws_d, float("nan")), torch.full_like(wc_d, float("nan"))
-    dh = torch.empty(M, 16, dtype=torch.half, device=dev)
     nbytes = lib.lnrf_nerf_wgrad_scratch_bytes(ns, nc)
-    scratch = torch.empty(nbytes // 4, device=dev)
+    scratch = torch.full((nbytes // 4,), float("nan"), device=dev)
     gsig_d, grgb_d = t(gsig, torch.float32), t(grgb, torch.float32)  # named: a temporary would be freed (and its block reused) before the launch
-    N.check(lib.lnrf_nerf_backward(N.ptr(gsig_d), N.ptr(grgb_d), N.ptr(rgb), N.ptr(h0), N.ptr(enc_d), N.ptr(cin),
-                                   N.ptr(ws_d), N.ptr(wc_d), N.ptr(fb), M, ns, nc, ds, N.ptr(genc), N.ptr(gws), N.ptr(gwc), 0, N.ptr(dh),
-                                   N.ptr(scratch), nbytes, None))
+    dh = None
+    if variant == "saved":   # round-1 pair: hidden activations saved by the forward, read back by two backward launches
+        fb = torch.empty(ns + nc, M, 64, dtype=torch.half, device=dev)
+        cin = torch.empty(M, 32, dtype=torch.half, device=dev)
+        h0 = torch.empty(M, dtype=torch.half, device=dev)
+        N.check(lib.lnrf_nerf_forward(N.ptr(enc_d), N.ptr(dirs_d), N.ptr(ws_d), N.ptr(wc_d), M, ns, nc, ds, 1, N.ptr(fb), N.ptr(cin), N.ptr(h0),
+                                      N.ptr(sig), N.ptr(rgb), None))
+        dh = torch.empty(M, 16, dtype=torch.half, device=dev)
+        N.check(lib.lnrf_nerf_backward(N.ptr(gsig_d), N.ptr(grgb_d), N.ptr(rgb), N.ptr(h0), N.ptr(enc_d), N.ptr(cin), N.ptr(ws_d), N.ptr(wc_d),
+                                       N.ptr(fb), M, ns, nc, ds, N.ptr(genc), N.ptr(gws), N.ptr(gwc), 0, N.ptr(dh), N.ptr(scratch), nbytes, None))
+    else:                    # round-2 pair: only h is kept; the backward recomputes the hidden activations (csrc/nerfbwd.cu)
+        assert lib.lnrf_nerf_backward_recompute_supported(ns, nc) == 1
+        hbuf = torch.full((M, 16), float("nan"), dtype=torch.half, device=dev)
+        N.check(lib.lnrf_nerf_forward_lean(N.ptr(enc_d), N.ptr(dirs_d), N.ptr(ws_d), N.ptr(wc_d), M, None, ns, nc, ds, N.ptr(hbuf), N.ptr(sig),
+                                           N.ptr(rgb), None))
+        N.check(lib.lnrf_nerf_backward_recompute(N.ptr(gsig_d), N.ptr(grgb_d), N.ptr(rgb), N.ptr(hbuf), N.ptr(enc_d), N.ptr(dirs_d), N.ptr(ws_d),
+                                                 N.ptr(wc_d), M, None, ns, nc, ds, N.ptr(genc), N.ptr(gws), N.ptr(gwc), 0, N.ptr(scratch), nbytes,
+                                                 None))
     torch.cuda.synchronize()
     # ---- oracle composition ----
     ob = oracle_backend
@@ -342,7 +352,76 @@ def test_nerf_backward_matches_oracle_composition(dev, oracle_backend, M, ns, nc
         a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
         return np.abs(a - b).max() / np.abs(b).max()
 
-    assert relmax(dh.float().cpu().numpy(), dh_o) <= 3e-3
-    assert relmax(genc.float().cpu().numpy(), gi_s) <= 5e-3, relmax(genc.float().cpu().numpy(), gi_s)
+    if dh is not None:
+        assert relmax(dh.float().cpu().numpy(), dh_o) <= 3e-3
+    else:
+        assert np.allclose(hbuf.float().cpu().numpy(), h, rtol=2e-3, atol=2e-3)   # the one tensor the lean forward keeps
+    assert bool(torch.isfinite(genc).all()) and bool(torch.isfinite(gws).all()) and bool(torch.isfinite(gwc).all())
+    # dL/denc row by row: a hidden unit whose pre-activation is within an fp32 summation-order ulp of zero has its ReLU mask flipped
+    # between the tensor-core sum and the oracle's sequential sum, which changes that ROW by a few per cent of the largest element;
+    # measured: < 1e-4 of the rows at M = 8192.  Everything else agrees to fp16 rounding.
+    ge, go = genc.float().cpu().numpy().astype(np.float64), np.asarray(gi_s, np.float64)
+    row_err = np.abs(ge - go).max(axis=1) / np.abs(go).max()
+    assert float((row_err > 5e-3).mean()) <= 1e-3, float((row_err > 5e-3).mean())
+    assert float(np.median(row_err)) <= 1e-3 and float(row_err.max()) <= 0.2
     assert relmax(gwc.float().cpu().numpy(), gwc_o) <= 3e-3, relmax(gwc.float().cpu().numpy(), gwc_o)
     assert relmax(gws.float().cpu().numpy(), gws_o) <= 3e-3, relmax(gws.float().cpu().numpy(), gws_o)
+
+
+def test_recompute_pair_equals_saved_pair_and_honours_the_device_side_count(dev):
+    """Round-2 kernels against the round-1 kernels on the same inputs: same MMAs and rounding points, so dL/denc is bit-identical and
+    the weight gradients differ only by the order of the fp32 partial sums; with a device-side sample count the rows past it are
+    skipped (outputs untouched, gradients as if those rows carried zero gradient)."""
+    N = _N()
+    lib = N.lib()
+    M, ns, nc, ds = 128 * 77, 2, 3, 1.0
+    g = torch.Generator(device=dev).manual_seed(3)
+    enc = (torch.randn(M, 32, device=dev, generator=g) * 0.5).half()
+    dirs = torch.nn.functional.normalize(torch.randn(M, 3, device=dev, generator=g), dim=-1)
+    ws = ((torch.rand(64 * (32 + 64 * (ns - 1) + 16), device=dev, generator=g) - 0.5) * 0.5).half()
+    wc = ((torch.rand(64 * (32 + 64 * (nc - 1) + 16), device=dev, generator=g) - 0.5) * 0.5).half()
+    gsig = torch.randn(M, device=dev, generator=g) * 1e-2
+    grgb = torch.randn(M, 3, device=dev, generator=g) * 1e-1
+    nbytes = lib.lnrf_nerf_wgrad_scratch_bytes(ns, nc)
+    scratch = torch.empty(nbytes // 4, device=dev)
+
+    def saved():
+        sig, rgb = torch.empty(M, device=dev), torch.empty(M, 3, device=dev)
+        fb, cin, h0 = (torch.empty(ns + nc, M, 64, dtype=torch.half, device=dev), torch.empty(M, 32, dtype=torch.half, device=dev),
+                       torch.empty(M, dtype=torch.half, device=dev))
+        N.check(lib.lnrf_nerf_forward(N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, ns, nc, ds, 1, N.ptr(fb), N.ptr(cin), N.ptr(h0), N.ptr(sig),
+                                      N.ptr(rgb), None))
+        genc, gws, gwc, dh = torch.empty_like(enc), torch.empty_like(ws), torch.empty_like(wc), torch.empty(M, 16, dtype=torch.half, device=dev)
+        N.check(lib.lnrf_nerf_backward(N.ptr(gsig), N.ptr(grgb), N.ptr(rgb), N.ptr(h0), N.ptr(enc), N.ptr(cin), N.ptr(ws), N.ptr(wc), N.ptr(fb), M, ns, nc,
+                                       ds, N.ptr(genc), N.ptr(gws), N.ptr(gwc), 0, N.ptr(dh), N.ptr(scratch), nbytes, None))
+        torch.cuda.synchronize()
+        return sig, rgb, genc, gws, gwc
+
+    def lean(m_dev=None, gs=gsig, gr=grgb):
+        sig, rgb = torch.full((M,), -7.0, device=dev), torch.full((M, 3), -7.0, device=dev)
+        h = torch.empty(M, 16, dtype=torch.half, device=dev)
+        N.check(lib.lnrf_nerf_forward_lean(N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, N.ptr(m_dev), ns, nc, ds, N.ptr(h), N.ptr(sig), N.ptr(rgb),
+                                           None))
+        genc, gws, gwc = torch.full_like(enc, -7.0), torch.empty_like(ws), torch.empty_like(wc)
+        N.check(lib.lnrf_nerf_backward_recompute(N.ptr(gs), N.ptr(gr), N.ptr(rgb), N.ptr(h), N.ptr(enc), N.ptr(dirs), N.ptr(ws), N.ptr(wc), M, N.ptr(m_dev),
+                                                 ns, nc, ds, N.ptr(genc), N.ptr(gws), N.ptr(gwc), 0, N.ptr(scratch), nbytes, None))
+        torch.cuda.synchronize()
+        return sig, rgb, genc, gws, gwc
+
+    a, b = saved(), lean()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for x, y in ((a[3], b[3]), (a[4], b[4])):
+        assert float((x.float() - y.float()).abs().max()) <= 2e-3 * float(x.float().abs().max())
+    # device-side count: 5000 live samples -> 40 tiles of 128 rows are processed, the other 37 are left alone
+    live = 5000
+    m_dev = torch.tensor([live, 0], dtype=torch.int32, device=dev)
+    rows = (live + 127) // 128 * 128
+    gs2, gr2 = gsig.clone(), grgb.clone()
+    gs2[live:] = 0
+    gr2[live:] = 0     # what composite_rays_train's backward leaves for rows no ray owns
+    c = lean(m_dev, gs2, gr2)
+    assert torch.equal(c[0][:rows], b[0][:rows]) and bool((c[0][rows:] == -7.0).all()) and bool((c[2][rows:] == -7.0).all())
+    d = lean(None, gs2, gr2)
+    assert torch.equal(c[2][:rows], d[2][:rows])
+    for x, y in ((c[3], d[3]), (c[4], d[4])):
+        assert float((x.float() - y.float()).abs().max()) <= 2e-3 * float(y.float().abs().max()) + 1e-6
