@@ -61,6 +61,10 @@ ALGO = {
     # fused rows f-1 / f-4 (one C-ABI call each)
     "lnrf_nerf_forward": dict(bound="tensor", flops_per_sample_padded=36864),
     "lnrf_nerf_backward": dict(bound="tensor", flops_per_sample_padded=73728),
+    # round 2: lean forward (keeps only h) + recompute backward (csrc/nerfbwd.cu); the algorithmic FLOPs stay the contract's figures
+    # (the recomputed forward layers are overhead, not credited)
+    "lnrf_nerf_forward_lean": dict(bound="tensor", flops_per_sample_padded=36864),
+    "lnrf_nerf_backward_recompute": dict(bound="tensor", flops_per_sample_padded=73728),
     "lnrf_adam_step": dict(bound="hbm", per_param=30),            # g16 R+W 4, p/m/v R+W 24, p16 W 2
     "lnrf_grad_nonfinite_check": dict(bound="hbm", per_param=2),
 }

@@ -266,9 +266,9 @@ LNRF_API int lnrf_grid_encode_forward_world(const float* inputs_world, float bou
                                             uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
                                             uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream);
 LNRF_API int lnrf_grid_encode_backward_world(const void* grad, const float* inputs_world, float bound,
-                                             const int32_t* offsets_host, void* grad_embeddings, uint32_t B, uint32_t L,
-                                             float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t interp,
-                                             lnrf_dtype emb_dtype, lnrf_stream_t stream);
+                                             const int32_t* offsets_host, void* grad_embeddings, uint32_t B,
+                                             const int32_t* B_dev, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                             int align_corners, uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * device-driven inference rounds (row f-3) -- the loop of NeRFRenderer.run_cuda / run_cuda_distill

@@ -62,7 +62,7 @@ SIGNATURES = {
     "lnrf_sh_encode_forward": (i32, [vp, vp, u32, u32, vp, i32, vp]),
     "lnrf_sh_encode_backward": (i32, [vp, u32, u32, vp, vp, vp]),
     "lnrf_grid_encode_forward_world": (i32, [vp, f32, vp, vp, vp, u32, vp, u32, f32, u32, u32, i32, u32, i32, vp]),
-    "lnrf_grid_encode_backward_world": (i32, [vp, vp, f32, vp, vp, u32, u32, f32, u32, u32, i32, u32, i32, vp]),
+    "lnrf_grid_encode_backward_world": (i32, [vp, vp, f32, vp, vp, u32, vp, u32, f32, u32, u32, i32, u32, i32, vp]),
     "lnrf_render_scratch_bytes": (sz, [u32]),
     "lnrf_render_begin": (i32, [vp, vp]),
     "lnrf_render_rounds": (i32, [vp, u32, u32, vp]),

@@ -193,8 +193,11 @@ k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* 
     __shared__ Level s_lv[kMaxLevels];
     __shared__ float s_in[kTile * 3];
     T2* s_out = reinterpret_cast<T2*>(s_raw);
-    if (B_dev) {  // device-driven inference round (row f-3): the sample count lives in the render control block
-        B = (uint32_t)*B_dev;
+    if (B_dev) {  // device-side sample count (render control block, row f-3; the training marcher's counter): whole 128-row tiles up
+                  // to the capacity B -- the rows between the count and the tile end are the marcher's zero padding, encoded like any
+                  // other point (the network kernels work on the same 128-row tiles)
+        const uint32_t live = div_up((uint32_t)max(*B_dev, 0), (uint32_t)kTile) * (uint32_t)kTile;
+        B = live < B ? live : B;
         ntiles = div_up(B, (uint32_t)kTile);
     }
     // torch evaluates `t / python_scalar` as t * (1 / scalar) with the reciprocal rounded to fp32 (div_true_kernel_cuda), and that
@@ -283,12 +286,16 @@ __global__ void __launch_bounds__(kGridThreads)
 k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __restrict__ inputs,
                 typename Vec2<T>::type* __restrict__ grad_emb, const uint32_t B, const uint32_t L, const float S,
                 const uint32_t H, const uint32_t gridtype, const bool align_corners, const GridOffsets off,
-                const uint32_t ntiles, const float in_bound) {
+                uint32_t ntiles, const float in_bound, const int* __restrict__ B_dev) {
     using T2 = typename Vec2<T>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ Level s_lv[kMaxLevels];
     __shared__ float s_in[kTile * 3];
     T2* s_g = reinterpret_cast<T2*>(s_raw);
+    if (B_dev) {  // rows at or beyond the device-side count carry no gradient (and may be unwritten memory): skipped by whole tiles
+        const uint32_t live = div_up((uint32_t)max(*B_dev, 0), (uint32_t)kTile);
+        ntiles = live < ntiles ? live : ntiles;
+    }
     // torch evaluates `t / python_scalar` as t * (1 / scalar) with the reciprocal rounded to fp32 (div_true_kernel_cuda), and that
     // is what the reference's grid.py:147 runs; the same two roundings here
     const float in_inv = in_bound > 0.0f ? __fdiv_rn(1.0f, __fmul_rn(2.0f, in_bound)) : 0.0f;
@@ -655,13 +662,13 @@ static int grid_forward_t(const float* inputs, const T* emb, const GridOffsets& 
 template <typename T>
 static int grid_backward_t(const T* grad, const float* inputs, const GridOffsets& off, T* grad_emb, uint32_t B, uint32_t D, uint32_t C,
                            uint32_t L, float S, uint32_t H, const T* dy_dx, T* grad_inputs, uint32_t gridtype, bool ac, uint32_t interp,
-                           int layout, cudaStream_t st, float in_bound = 0.0f) {
+                           int layout, cudaStream_t st, float in_bound = 0.0f, const int* B_dev = nullptr) {
     using T2 = typename Vec2<T>::type;
     const bool smooth = interp == 1;
     const bool hot = D == 3 && C == 2 && layout == LNRF_GRID_BLC && (reinterpret_cast<uintptr_t>(grad_emb) % sizeof(T2)) == 0 &&
                      (reinterpret_cast<uintptr_t>(grad) % sizeof(T2)) == 0;
-    if (in_bound > 0.0f && (!hot || dy_dx)) {
-        set_error("grid_encode_backward: in_bound needs the D=3, C=2, [B, L*C] kernel without input gradients");
+    if ((in_bound > 0.0f || B_dev) && (!hot || dy_dx)) {
+        set_error("grid_encode_backward: in_bound / device-side B need the D=3, C=2, [B, L*C] kernel without input gradients");
         return LNRF_ERR_UNSUPPORTED;
     }
     if (hot) {
@@ -671,7 +678,7 @@ static int grid_backward_t(const T* grad, const float* inputs, const GridOffsets
         auto kern = smooth ? (pair_mode() & 2 ? k_grid_bwd_tile<T, true, true> : k_grid_bwd_tile<T, true, false>)
                            : (pair_mode() & 2 ? k_grid_bwd_tile<T, false, true> : k_grid_bwd_tile<T, false, false>);
         kern<<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb), B, L, S, H, gridtype,
-                                               ac, off, ntiles, in_bound);
+                                               ac, off, ntiles, in_bound, B_dev);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);
 #define CALL_(DD, CC) launch_bwd_generic<T, DD, CC>(smooth, g, st, grad, inputs, grad_emb, B, L, S, H, gridtype, ac, off, layout)
@@ -736,18 +743,18 @@ int lnrf_grid_encode_forward_world(const float* inputs_world, float bound, const
 }
 
 int lnrf_grid_encode_backward_world(const void* grad, const float* inputs_world, float bound, const int32_t* offsets_host,
-                                    void* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-                                    int align_corners, uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream) {
+                                    void* grad_embeddings, uint32_t B, const int32_t* B_dev, uint32_t L, float S, uint32_t H,
+                                    uint32_t gridtype, int align_corners, uint32_t interp, lnrf_dtype emb_dtype, lnrf_stream_t stream) {
     GridOffsets off;
     if (int e = check_grid_args("grid_encode_backward_world", offsets_host, 3, 2, L, gridtype, interp, &off)) return e;
     if (B == 0) return LNRF_OK;
     LNRF_REQUIRE(grad && inputs_world && grad_embeddings && bound > 0.0f, "grid_encode_backward_world: null pointer / bound <= 0");
     if (emb_dtype == LNRF_F16)
         return grid_backward_t<__half>((const __half*)grad, inputs_world, off, (__half*)grad_embeddings, B, 3, 2, L, S, H, nullptr, nullptr,
-                                       gridtype, align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound);
+                                       gridtype, align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound, B_dev);
     if (emb_dtype == LNRF_F32)
         return grid_backward_t<float>((const float*)grad, inputs_world, off, (float*)grad_embeddings, B, 3, 2, L, S, H, nullptr, nullptr,
-                                      gridtype, align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound);
+                                      gridtype, align_corners != 0, interp, (int)LNRF_GRID_BLC, S_(stream), bound, B_dev);
     set_error("grid_encode_backward_world: unsupported embedding dtype %d", (int)emb_dtype);
     return LNRF_ERR_UNSUPPORTED;
 }

@@ -53,7 +53,9 @@ class _grid_encode(Function):
     @staticmethod
     @custom_fwd(device_type="cuda")
     def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
-                align_corners=False, interpolation=0, shadow_f16=None, grad_f16=None, world_bound=0.0):
+                align_corners=False, interpolation=0, shadow_f16=None, grad_f16=None, world_bound=0.0, b_dev=None):
+        # b_dev: optional device int32 with the number of live rows (world_bound > 0 only): whole 128-row tiles past it are neither
+        # encoded nor differentiated -- their output rows stay unwritten, which is fine for a consumer that honours the same count
         # world_bound > 0: `inputs` are world coordinates and the kernel applies GridEncoder.forward's (x + bound) / (2 * bound)
         # itself (hot shape only: D = 3, C = 2, no input gradients) -- two elementwise passes over [B, 3] less per call
         inputs = inputs.contiguous().float()
@@ -73,15 +75,17 @@ class _grid_encode(Function):
         off_h = _offsets_host(offsets)
         outputs = torch.empty(B, L * C, device=inputs.device, dtype=embeddings.dtype)
         dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=embeddings.dtype) if calc_grad_inputs else None
+        if b_dev is not None and not world_bound > 0:
+            raise RuntimeError("GridEncoder: a device-side row count needs the world-coordinate kernel (D = 3, C = 2, no input gradients)")
         if world_bound > 0:
             N.check(N.lib().lnrf_grid_encode_forward_world(N.ptr(inputs), float(world_bound), N.ptr(embeddings), N.ptr(off_h), N.ptr(outputs),
-                                                           B, None, L, S, H, int(gridtype), int(bool(align_corners)), int(interpolation),
+                                                           B, N.ptr(b_dev), L, S, H, int(gridtype), int(bool(align_corners)), int(interpolation),
                                                            _dt(embeddings), N.stream()))
         else:
             N.check(N.lib().lnrf_grid_encode_forward(N.ptr(inputs), N.ptr(embeddings), N.ptr(off_h), N.ptr(outputs), B, D, C, L, S, H,
                                                      N.ptr(dy_dx), int(gridtype), int(bool(align_corners)), int(interpolation),
                                                      _dt(embeddings), N.GRID_BLC, N.stream()))
-        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
+        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx, b_dev)
         ctx.dims = [B, D, C, L, S, H, gridtype, interpolation]
         ctx.world_bound = float(world_bound)
         ctx.align_corners = align_corners
@@ -90,7 +94,7 @@ class _grid_encode(Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, grad):
-        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        inputs, embeddings, offsets, dy_dx, b_dev = ctx.saved_tensors
         B, D, C, L, S, H, gridtype, interpolation = ctx.dims
         grad = grad.contiguous().to(embeddings.dtype)
         # with AmpAdam the gradient accumulates straight into its persistent fp16 buffer (cleared by the optimizer kernel)
@@ -98,8 +102,8 @@ class _grid_encode(Function):
         grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if dy_dx is not None else None
         if ctx.world_bound > 0:
             N.check(N.lib().lnrf_grid_encode_backward_world(N.ptr(grad), N.ptr(inputs), ctx.world_bound, N.ptr(_offsets_host(offsets)),
-                                                            N.ptr(grad_embeddings), B, L, S, H, int(gridtype), int(bool(ctx.align_corners)),
-                                                            int(interpolation), _dt(embeddings), N.stream()))
+                                                            N.ptr(grad_embeddings), B, N.ptr(b_dev), L, S, H, int(gridtype),
+                                                            int(bool(ctx.align_corners)), int(interpolation), _dt(embeddings), N.stream()))
         else:
             N.check(N.lib().lnrf_grid_encode_backward(N.ptr(grad), N.ptr(inputs), N.ptr(embeddings), N.ptr(_offsets_host(offsets)),
                                                       N.ptr(grad_embeddings), B, D, C, L, S, H, N.ptr(dy_dx), N.ptr(grad_inputs),
@@ -109,7 +113,7 @@ class _grid_encode(Function):
             grad_inputs = grad_inputs.to(inputs.dtype)
         if ctx.grad_f16 is not None:
             grad_embeddings = None
-        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None, None, None
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None, None, None, None
 
 
 grid_encode = _grid_encode.apply
@@ -161,17 +165,19 @@ class GridEncoder(nn.Module):
                 f"per_level_scale={self.per_level_scale:.4f} params={tuple(self.embeddings.shape)} gridtype={self.gridtype} "
                 f"align_corners={self.align_corners} interpolation={self.interpolation}")
 
-    def forward(self, inputs, bound=1):
+    def forward(self, inputs, bound=1, b_dev=None):
         # hot shape on the GPU: the kernel maps to [0, 1] itself (same IEEE add + divide as the line below)
         in_kernel = (inputs.is_cuda and self.input_dim == 3 and self.level_dim == 2 and not inputs.requires_grad and
                      inputs.dtype == torch.float32 and bound > 0)
+        if not in_kernel:
+            b_dev = None
         if not in_kernel:
             inputs = (inputs + bound) / (2 * bound)  # map to [0, 1]
         prefix_shape = list(inputs.shape[:-1])
         inputs = inputs.view(-1, self.input_dim)
         outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
                               inputs.requires_grad, self.gridtype_id, self.align_corners, self.interp_id,
-                              shadow_f16(self, self.embeddings), self._grad_f16, float(bound) if in_kernel else 0.0)
+                              shadow_f16(self, self.embeddings), self._grad_f16, float(bound) if in_kernel else 0.0, b_dev)
         return outputs.view(prefix_shape + [self.output_dim])
 
     @torch.autocast(device_type="cuda", enabled=False)

@@ -66,11 +66,10 @@ class _fused_network(Function):
         lean = _recompute_ok(ns, nc)
         if m_dev is not None and not lean:
             m_dev = None
-        # with a device-side count the rows past it are never written: they must still read as zeros downstream (compositing
-        # indexes live samples only; the padding rows of sigmas / rgbs are what torch.zeros would have left)
-        alloc = torch.zeros if m_dev is not None else torch.empty
-        sigmas = alloc(M, dtype=torch.float32, device=dev)
-        rgbs = alloc(M, 3, dtype=torch.float32, device=dev)
+        # with a device-side count the tiles past it are never written; the compositor only indexes live samples, the backward
+        # kernels honour the same count
+        sigmas = torch.empty(M, dtype=torch.float32, device=dev)
+        rgbs = torch.empty(M, 3, dtype=torch.float32, device=dev)
         lib = N.lib()
         if lean:
             h = torch.empty(M, 16, dtype=torch.half, device=dev) if train else None
@@ -107,7 +106,7 @@ class _fused_network(Function):
         dev = enc.device
         grad_sigmas = torch.zeros(M, dtype=torch.float32, device=dev) if grad_sigmas is None else grad_sigmas.contiguous().float()
         grad_rgbs = torch.zeros(M, 3, dtype=torch.float32, device=dev) if grad_rgbs is None else grad_rgbs.contiguous().float()
-        grad_enc = (torch.zeros_like if m_dev is not None else torch.empty_like)(enc)
+        grad_enc = torch.empty_like(enc)
         persistent = ctx.gw[0] is not None
         gws = ctx.gw[0] if persistent else torch.empty_like(ws)
         gwc = ctx.gw[1] if persistent else torch.empty_like(wc)
@@ -191,15 +190,21 @@ class NeRFNetwork(nn.Module):
         return (self.fused and self._fused_ok and x.is_cuda and x.dim() == 2 and x.shape[0] > 0 and x.shape[0] % 128 == 0 and
                 torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.float16)
 
-    def forward_scaled(self, x, d):
-        """(density_scale * sigma, rgb): what run_cuda feeds the compositor (renderer.py:298-299, 363-364)."""
+    def forward_scaled(self, x, d, m_dev=None):
+        """(density_scale * sigma, rgb): what run_cuda feeds the compositor (renderer.py:298-299, 363-364).
+        m_dev: optional device int32 with the number of LIVE samples among the rows of x (the training marcher's counter): the
+        sample buffer is sized for the largest batch, the rows past the count are zero padding that the reference pushes through
+        encoder and MLPs like real samples; with the count the fused kernels skip those 128-row tiles
+        (their sigma / rgb rows stay unwritten -- no ray refers to them -- and they receive no gradient)."""
         if self._use_fused(x):
-            enc = self.encoder(x, bound=self.bound)
-            train = torch.is_grad_enabled() and (enc.requires_grad or self.sigma_net.weights.requires_grad)
             sn, cn = self.sigma_net, self.color_net
+            if m_dev is not None and not (_recompute_ok(sn.num_layers, cn.num_layers) and os.environ.get("LNRF_DEVICE_COUNT", "1") != "0"):
+                m_dev = None
+            enc = self.encoder(x, bound=self.bound, b_dev=m_dev)
+            train = torch.is_grad_enabled() and (enc.requires_grad or self.sigma_net.weights.requires_grad)
             return fused_network(enc, d, sn.weights, cn.weights, sn.num_layers, cn.num_layers, self.density_scale, train,
                                  shadow_f16(sn, sn.weights), shadow_f16(cn, cn.weights),
-                                 getattr(sn, "_grad_f16", None), getattr(cn, "_grad_f16", None))
+                                 getattr(sn, "_grad_f16", None), getattr(cn, "_grad_f16", None), m_dev)
         sigmas, rgbs = self(x, d)
         return self.density_scale * sigmas, rgbs
 
@@ -462,7 +467,7 @@ class NeRFNetwork(nn.Module):
         xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
                                                                 self.grid_size, nears, fars, counter, self.mean_count, perturb,
                                                                 128, force_all_rays, dt_gamma, max_steps)
-        return dict(xyzs=xyzs, dirs=dirs, deltas=deltas, rays=rays, nears=nears, fars=fars)
+        return dict(xyzs=xyzs, dirs=dirs, deltas=deltas, rays=rays, nears=nears, fars=fars, counter=counter)
 
     def march_train(self, rays_o, rays_d, perturb=True, force_all_rays=False, dt_gamma=0, max_steps=1024, edit_grid=None):
         rays_o = rays_o.contiguous().view(-1, 3)
@@ -474,7 +479,7 @@ class NeRFNetwork(nn.Module):
     def shade_train(self, marched, bg_color=1, T_thresh=1e-4, prefix=None, scale_depth=True):
         xyzs, dirs, deltas, rays, nears, fars = (marched[k] for k in ("xyzs", "dirs", "deltas", "rays", "nears", "fars"))
         prefix = (rays.shape[0],) if prefix is None else prefix
-        sigmas, rgbs = self.forward_scaled(xyzs, dirs)
+        sigmas, rgbs = self.forward_scaled(xyzs, dirs, marched.get("counter"))
         weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
         image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
         if scale_depth:
@@ -488,7 +493,7 @@ class NeRFNetwork(nn.Module):
         Returns (loss, results) with the same `results` dict as shade_train."""
         xyzs, dirs, deltas, rays, nears, fars = (marched[k] for k in ("xyzs", "dirs", "deltas", "rays", "nears", "fars"))
         prefix = (rays.shape[0],) if prefix is None else prefix
-        sigmas, rgbs = self.forward_scaled(xyzs, dirs)
+        sigmas, rgbs = self.forward_scaled(xyzs, dirs, marched.get("counter"))
         loss, weights_sum, depth, image = raymarching.composite_loss_train(
             sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears if scale_depth else None, fars if scale_depth else None, T_thresh)
         return loss, {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum, "nears": nears,

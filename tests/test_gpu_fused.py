@@ -331,6 +331,7 @@ def test_device_driven_render_equals_host_loop(dev):
     _, ro, rd, _ = scene_rays("lego", 6000, 23)
     ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
     m.eval()
+    m.render_schedule = "reference"   # the host loop IS the reference's n_step rule: same rounds, same slot counts
     outs = []
     for loop in (True, False):
         m.device_loop = loop
@@ -353,6 +354,7 @@ def test_device_driven_render_equals_host_loop(dev):
         assert torch.allclose(a[k], b[k], rtol=0, atol=0, equal_nan=True), k
     assert float(a["weights_edit_sum"].sum()) > 0
     m.device_loop = True
+    m.render_schedule = "auto"
 
 
 def test_grid_encoder_world_coordinates_equal_prenormalised_inputs(dev):
