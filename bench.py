@@ -471,8 +471,9 @@ def render_config(ctx, model, sc, pose_index=0, frames=3):
     real = ctx.sum_over_ranks(count_real_samples(ctx, model, ro_d, rd_d))
     out = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    for schedule in ("reference", "fast"):
+    for schedule in ("auto", "reference", "fast"):
         model.render_schedule = schedule
+        model._auto_fast_ok = True
         marks, slots = [], 0
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
             for _ in range(2):  # warm-up frames, final gather included (the first collective of a shape pays NCCL's lazy set-up)
@@ -496,16 +497,20 @@ def render_config(ctx, model, sc, pose_index=0, frames=3):
         gather_ms = ctx.max_over_ranks(sum(b.elapsed_time(c) for _, b, c in marks) / frames)
         slots_all = ctx.sum_over_ranks(slots)
         out[schedule] = dict(value=real * frames / (rms * 1e-3) / 1e6, unit="Msamples/s", ms_per_frame=rms / frames, render_loop_ms=loop_ms,
-                             gather_ms=gather_ms, rounds=o.get("rounds"), sample_slots_per_frame=slots_all / frames,
+                             gather_ms=gather_ms, rounds=o.get("rounds"), resolved_schedule=o.get("schedule"), sample_slots_per_frame=slots_all / frames,
                              slots_msamples_per_s=slots_all / (rms * 1e-3) / 1e6, rays_per_s=ro.shape[0] * frames / (rms * 1e-3))
-    model.render_schedule = "reference"
+    model.render_schedule = "auto"
+    model._auto_fast_ok = True
     model.train()
-    res = dict(out["reference"])
-    res.update(scene=sc.name, image_shape=list(img.shape), rays_per_frame=int(ro.shape[0]), samples_per_frame=real, schedule="reference",
-               note=("value counts REAL samples (occupied-cell samples of the frame's rays; slots include the zero padding of every round) on the "
-                     "reference's n_step rule: same rounds, bit-identical sample positions; `fast_schedule` = up to 32 samples per ray per round "
-                     "after the first, NOT bit-identical (sample positions move by an ulp where a round boundary moves), reported for context"),
-               fast_schedule=out["fast"],
+    res = dict(out["auto"])
+    res.update(scene=sc.name, image_shape=list(img.shape), rays_per_frame=int(ro.shape[0]), samples_per_frame=real, schedule="auto",
+               note=("value counts REAL samples (occupied-cell samples of the frame's rays; slots include the zero padding of every round).  "
+                     "schedule 'auto': up to 32 samples per ray per round after the first WHEN the marcher proves the frame's bits cannot depend "
+                     "on the round boundaries (every emitted delta exactly representable, checked per sample on the device), else the frame is "
+                     "rendered on the reference's n_step rule -- either way image / depth / weights are bit-identical to the reference schedule "
+                     "(tests/test_gpu_fused.py); `reference_schedule` and `fast_schedule` are the two fixed schedules for context (fast alone is "
+                     "NOT bit-identical on scenes with cameras inside the volume)"),
+               reference_schedule=out["reference"], fast_schedule=out["fast"],
                sharding=("32x32-pixel tiles dealt round-robin over the ranks; all_gather + index_select by the known index lists"
                          if world > 1 else "single GPU, row-major rays"))
     return res
@@ -522,7 +527,7 @@ def edit_config(ctx, flower):
     torch, world, rank, dev = ctx.torch, ctx.world, ctx.rank, ctx.dev
     sc, model = flower["_sc"], flower["_model"]
     model.eval()
-    model.render_schedule = "reference"
+    model.render_schedule = "auto"
     n_views = max(8, world)
     lo, hi = shard_range(n_views, rank, world)
     views = []

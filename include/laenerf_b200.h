@@ -449,6 +449,15 @@ LNRF_API int lnrf_exchange_finish(const float* my_flags, uint32_t world, const u
 /* GradScaler.update() (growth / backoff of the loss scale from found_inf) fused with the step bookkeeping:
  * step_count += 1 unless the step was skipped, found_inf re-armed to 0.  scale / growth_tracker may be NULL
  * (no loss scaling). */
+/* Round 2: the three calls above (non-finite check, Adam, GradScaler.update) as ONE launch.  Every block checks the gradient chunks
+ * it is about to update, the blocks meet at a grid-wide barrier (the grid is capped at what is resident at once), read the combined
+ * flag and run the update; the block that finishes last applies the scale growth / backoff, advances step_count when the step was
+ * not skipped and re-arms found_inf.  grad_scale may be NULL (no GradScaler: nothing is unscaled, the check still guards the step).
+ * sync_words: 3 zero-initialised device uint32 owned by the caller (left zero / advanced consistently by every call). */
+LNRF_API int lnrf_adam_amp_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double lr, double beta1, double beta2,
+                                double eps, double weight_decay, float* grad_scale, int32_t* growth_tracker, float* found_inf,
+                                float* step_count, const float* lr_scale, float growth_factor, float backoff_factor,
+                                int32_t growth_interval, uint32_t* sync_words, lnrf_stream_t stream);
 LNRF_API int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, float* step_count,
                              float growth_factor, float backoff_factor, int32_t growth_interval, lnrf_stream_t stream);
 

@@ -47,10 +47,19 @@ struct NerfBwdArgs {
     float* wgrad_sigma;         // [grid][n_params_sigma] per-CTA partial sums
     float* wgrad_color;         // [grid][n_params_color]
     const int* M_dev;           // optional device-side sample count (rows beyond it are padding: skipped)
+    long long* dbg;             // optional [nsteps][2] cycle sums (block 0, set 0): waiting for the MMA batch / epilogue work (diagnostics)
     uint32_t M, ns, nc, ntiles;
     float density_scale;
 };
 
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking: has the phase with this parity completed?
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0u;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -91,7 +100,8 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
     uint64_t* ready = bars + kBG;        // [kBG] the epilogue wrote the next operand (128 arrivals)
     uint64_t* xfull = bars + 2 * kBG;    // [kBG] enc tile landed (TMA complete_tx)
     uint64_t* dyfree = bars + 3 * kBG;   // [kBG] the DY tile may be overwritten by the enc rows (tcgen05.commit)
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4 * kBG);
+    uint64_t* wdone = bars + 4 * kBG;    // [kBG] the weight-gradient MMAs of a backward step are complete: its operand tiles may be overwritten
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 5 * kBG);
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t stride = gridDim.x * kBG;
     const uint32_t nsteps = 2u * (nc + ns) + 2u;
@@ -112,6 +122,7 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
             mbar_init(ready + g, 128);
             mbar_init(xfull + g, 1);
             mbar_init(dyfree + g, 1);
+            mbar_init(wdone + g, 1);
         }
         fence_mbar_init();
     }
@@ -143,63 +154,77 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        uint32_t ph_ready[kBG], ph_x[kBG];
-        for (uint32_t g = 0; g < kBG; g++) ph_ready[g] = ph_x[g] = 0u;
-        for (uint32_t it = 0;; it++) {
-            bool valid[kBG];
-            bool any = false;
-            for (uint32_t g = 0; g < kBG; g++) { valid[g] = blockIdx.x * kBG + g + it * stride < ntiles; any |= valid[g]; }
-            if (!any) break;
-            for (uint32_t s = 0; s < nsteps; s++) {
-                for (uint32_t g = 0; g < kBG; g++) {
-                    if (!valid[g]) continue;
-                    mbar_wait_hot(ready + g, ph_ready[g]);
-                    ph_ready[g] ^= 1u;
-                    if (s == sB) { mbar_wait_hot(xfull + g, ph_x[g]); ph_x[g] ^= 1u; }
-                    tc_fence_after();
-                    const uint32_t set = smem_u32(sSets + g * set_bytes);
-                    const uint32_t tCIN = set + nc * kTileBytes, tDY = tCIN + kTileBytes;
-                    const uint32_t work = tbase + 64u * g;
-                    const uint32_t accf = (it > 0u || g > 0u) ? 1u : 0u;   // group 0 always owns the CTA's first tile
-                    // which net, which of its phases
-                    const bool sig = s >= sB;
-                    const uint32_t n = sig ? ns : nc, ls = sig ? s - sB : s;        // layers, step inside the net's part
-                    const uint32_t sW = smem_u32(sig ? sWs : sWc), wcol = sig ? wcol_s : wcol_c;
-                    // tile of hidden layer k of this net: colour C(k) = tile k; sigma H(k) = tile nc-1-k; inputs / output-gradient tiles
-                    auto hid = [&](uint32_t k) { return set + (sig ? (nc - 1u - k) : k) * kTileBytes; };
-                    const uint32_t tIN = sig ? tDY : tCIN;      // X (enc rows) | cin
-                    const uint32_t tGout = sig ? tCIN : tDY;    // dh | dY
-                    if (elect_one()) {
-                        if (ls < n) {                 // forward hidden layer k = ls
-                            const uint32_t k = ls;
-                            const uint64_t da = desc_sw128(k ? hid(k - 1u) : tIN, 16), db = desc_sw128(sW + k * kWBytes, 16);
-                            const uint32_t idesc = make_idesc(128, 64, false, false);
-                            if (k == 0u) umma_chain<2>(work, da, db, 2, 2, idesc, false);
-                            else umma_chain<4>(work, da, db, 2, 2, idesc, false);
-                        } else if (ls < 2u * n) {     // backward through matmul m = n .. 1
-                            const uint32_t m = 2u * n - ls;
-                            const uint32_t tG = m == n ? tGout : hid(m);
-                            const uint64_t wa = desc_sw128(hid(m - 1u), kTileBytes), wb = desc_sw128(tG, kTileBytes);
-                            const uint64_t da = desc_sw128(tG, 16), db = desc_sw128(sW + m * kWBytes, kTileBytes);
-                            const uint32_t didesc = make_idesc(128, 64, false, true);
-                            if (m == n) {
-                                umma_chain<8>(wcol + wacc_col(n, m), wa, wb, 128, 128, make_idesc(128, 16, true, true), accf != 0u);
-                                umma_chain<1>(work, da, db, 2, 128, didesc, false);     // K = 16 output channels
-                            } else {
-                                umma_chain<8>(wcol + wacc_col(n, m), wa, wb, 128, 128, make_idesc(128, 64, true, true), accf != 0u);
-                                umma_chain<4>(work, da, db, 2, 128, didesc, false);     // K = 64
-                            }
-                        } else {                      // input layer: dX = G(0) W(0) (N = 32), dW(0) += G(0)^T X
-                            const uint64_t wa = desc_sw128(hid(0), kTileBytes), wb = desc_sw128(tIN, kTileBytes);
-                            const uint64_t da = desc_sw128(hid(0), 16), db = desc_sw128(sW, kTileBytes);
-                            umma_chain<8>(wcol + wacc_col(n, 0), wa, wb, 128, 128, make_idesc(128, 32, true, true), accf != 0u);
-                            umma_chain<4>(work, da, db, 2, 128, make_idesc(128, 32, false, true), false);
-                        }
-                        umma_commit(full + g);
-                        if (s == nc) umma_commit(dyfree + g);   // dY consumed (dgrad + wgrad of the colour output layer)
-                    }
-                    __syncwarp();
+        // Each tile set advances through its own chain; the warp serves whichever set has its next operand ready (test_wait, no
+        // fixed order), so a slow epilogue of one set never holds the other set's MMAs back.  A backward step issues the dgrad first
+        // and commits it alone (`full`): the epilogue starts reading TMEM while the 8 weight-gradient MMAs of the step still run;
+        // their completion is a second commit (`wdone`) that the epilogue waits for before it overwrites the tiles they read.
+        uint32_t ph_ready[kBG], ph_x[kBG], step[kBG], iter[kBG];
+        bool live[kBG];
+        uint32_t n_live = 0, started = 0u;   // bit per weight-gradient accumulator: has it received its first (non-accumulating) MMA?
+        for (uint32_t g = 0; g < kBG; g++) {
+            ph_ready[g] = ph_x[g] = step[g] = iter[g] = 0u;
+            live[g] = blockIdx.x * kBG + g < ntiles;
+            n_live += live[g] ? 1u : 0u;
+        }
+        uint32_t g = 0;
+        while (n_live > 0u) {
+            g = (g + 1u) % kBG;
+            if (!live[g]) continue;
+            const uint32_t s = step[g];
+            if (!mbar_test(ready + g, ph_ready[g])) continue;
+            if (s == sB && !mbar_test(xfull + g, ph_x[g])) continue;
+            ph_ready[g] ^= 1u;
+            if (s == sB) ph_x[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t set = smem_u32(sSets + g * set_bytes);
+            const uint32_t tCIN = set + nc * kTileBytes, tDY = tCIN + kTileBytes;
+            const uint32_t work = tbase + 64u * g;
+            // which net, which of its phases
+            const bool sig = s >= sB;
+            const uint32_t n = sig ? ns : nc, ls = sig ? s - sB : s;        // layers, step inside the net's part
+            const uint32_t sW = smem_u32(sig ? sWs : sWc), wcol = sig ? wcol_s : wcol_c;
+            // tile of hidden layer k of this net: colour C(k) = tile k; sigma H(k) = tile nc-1-k; inputs / output-gradient tiles
+            auto hid = [&](uint32_t k) { return set + (sig ? (nc - 1u - k) : k) * kTileBytes; };
+            const uint32_t tIN = sig ? tDY : tCIN;      // X (enc rows) | cin
+            const uint32_t tGout = sig ? tCIN : tDY;    // dh | dY
+            uint32_t accbit = 0u;
+            if (ls >= n) accbit = 1u << ((sig ? 8u : 0u) + (2u * n - ls));   // accumulator of matmul m = 2n - ls (0 for the input layer)
+            const bool accf = (started & accbit) != 0u;
+            started |= accbit;
+            if (elect_one()) {
+                if (ls < n) {                 // forward hidden layer k = ls
+                    const uint32_t k = ls;
+                    const uint64_t da = desc_sw128(k ? hid(k - 1u) : tIN, 16), db = desc_sw128(sW + k * kWBytes, 16);
+                    const uint32_t idesc = make_idesc(128, 64, false, false);
+                    if (k == 0u) umma_chain<2>(work, da, db, 2, 2, idesc, false);
+                    else umma_chain<4>(work, da, db, 2, 2, idesc, false);
+                    umma_commit(full + g);
+                } else if (ls < 2u * n) {     // backward through matmul m = n .. 1
+                    const uint32_t m = 2u * n - ls;
+                    const uint32_t tG = m == n ? tGout : hid(m);
+                    const uint64_t wa = desc_sw128(hid(m - 1u), kTileBytes), wb = desc_sw128(tG, kTileBytes);
+                    const uint64_t da = desc_sw128(tG, 16), db = desc_sw128(sW + m * kWBytes, kTileBytes);
+                    const uint32_t didesc = make_idesc(128, 64, false, true);
+                    if (m == n) umma_chain<1>(work, da, db, 2, 128, didesc, false);     // K = 16 output channels
+                    else umma_chain<4>(work, da, db, 2, 128, didesc, false);           // K = 64
+                    umma_commit(full + g);
+                    umma_chain<8>(wcol + wacc_col(n, m), wa, wb, 128, 128, make_idesc(128, m == n ? 16u : 64u, true, true), accf);
+                    umma_commit(wdone + g);
+                    if (s == nc) umma_commit(dyfree + g);   // dY consumed (dgrad + wgrad of the colour output layer)
+                } else {                      // input layer: dX = G(0) W(0) (N = 32), dW(0) += G(0)^T X
+                    const uint64_t wa = desc_sw128(hid(0), kTileBytes), wb = desc_sw128(tIN, kTileBytes);
+                    const uint64_t da = desc_sw128(hid(0), 16), db = desc_sw128(sW, kTileBytes);
+                    umma_chain<4>(work, da, db, 2, 128, make_idesc(128, 32, false, true), false);
+                    umma_commit(full + g);
+                    umma_chain<8>(wcol + wacc_col(n, 0), wa, wb, 128, 128, make_idesc(128, 32, true, true), accf);
+                    umma_commit(wdone + g);
                 }
+            }
+            __syncwarp();
+            if (++step[g] == nsteps) {
+                step[g] = 0u;
+                iter[g]++;
+                if (blockIdx.x * kBG + g + iter[g] * stride >= ntiles) { live[g] = false; n_live--; }
             }
         }
     } else if (warp >= 4) {
@@ -209,7 +234,7 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
         uint8_t* tCIN = set + nc * kTileBytes;
         uint8_t* tDY = tCIN + kTileBytes;
         const uint32_t taddr = tbase + 64u * g + ((uint32_t)((warp & 3u) * 32u) << 16);
-        uint32_t ph_full = 0;
+        uint32_t ph_full = 0, ph_w = 0;
         const uint32_t first = blockIdx.x * kBG + g;
 
         // per-row inputs of a tile: h (16 halves), direction, dL/drgb, rgb, dL/dsigma
@@ -278,9 +303,11 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
 #pragma unroll
                     for (uint32_t q = 0; q < 8; q++) hrow[q] = *reinterpret_cast<const uint4*>(Hp + sw128(row, q));
                 }
+                const long long c0 = a.dbg ? clock64() : 0;
                 mbar_wait_hot(full + g, ph_full);
                 ph_full ^= 1u;
                 tc_fence_after();
+                const long long c1 = a.dbg ? clock64() : 0;
                 if (ls < n) {
                     // forward hidden layer: ReLU, fp16, into the layer's tile
                     uint8_t* T = hid(ls);
@@ -305,17 +332,21 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
                     tmem_ld32_nowait(taddr + 32, r + 32);
                     tmem_wait_ld();
                     const __half2 zero2 = __float2half2_rn(0.0f);
+                    uint32_t o[32];
 #pragma unroll
                     for (uint32_t q = 0; q < 8; q++) {
                         const uint32_t hw[4] = {hrow[q].x, hrow[q].y, hrow[q].z, hrow[q].w};
-                        uint32_t o[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint32_t pk = pack_h2(__uint_as_float(r[q * 8 + 2 * j]), __uint_as_float(r[q * 8 + 2 * j + 1]));
-                            o[j] = pk & __hgt2_mask(*reinterpret_cast<const __half2*>(&hw[j]), zero2);
+                            o[q * 4 + j] = pk & __hgt2_mask(*reinterpret_cast<const __half2*>(&hw[j]), zero2);
                         }
-                        *reinterpret_cast<uint4*>(Hp + sw128(row, q)) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
+                    mbar_wait_hot(wdone + g, ph_w);   // the step's weight-gradient MMAs have read H(m-1): it may become G(m-1)
+                    ph_w ^= 1u;
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; q++)
+                        *reinterpret_cast<uint4*>(Hp + sw128(row, q)) = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
                     publish();
                 } else if (!sig) {
                     // colour input layer done: dh = [dL/dsigma * density_scale * exp(clamp(h0, -15, 15)) | dL/dgeo_feat] into the CIN tile
@@ -327,6 +358,8 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
                     uint32_t pk[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) pk[i] = pack_h2(o[2 * i], o[2 * i + 1]);
+                    mbar_wait_hot(wdone + g, ph_w);   // dW(0) += G(0)^T cin has read the CIN tile
+                    ph_w ^= 1u;
                     *reinterpret_cast<uint4*>(tCIN + sw128(row, 0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4*>(tCIN + sw128(row, 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     publish();
@@ -342,12 +375,18 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
                         for (int i = 0; i < 8; i++) pk[i] = pack_h2(v[2 * i], v[2 * i + 1]);
                         st_global_32B(gi + q * 16, pk);
                     }
+                    mbar_wait_hot(wdone + g, ph_w);   // every MMA of this tile is complete: all of its tiles are free
+                    ph_w ^= 1u;
                     if (next < ntiles) {
                         build_inputs();
                         publish();
                     } else {
                         tc_fence_before();
                     }
+                }
+                if (a.dbg && blockIdx.x == 0 && g == 0 && row == 0) {
+                    a.dbg[2 * s] += c1 - c0;
+                    a.dbg[2 * s + 1] += clock64() - c1;
                 }
             }
         }
@@ -399,7 +438,11 @@ static size_t nerf_bwd_smem(uint32_t ns, uint32_t nc) { return 1024 + (ns + nc) 
 
 using namespace lnrf;
 
+static long long* g_nerf_bwd_dbg = nullptr;  // diagnostics only (scripts/diag_bwd_steps.py): device buffer of per-step cycle sums
+
 extern "C" {
+
+LNRF_API void lnrf_debug_set_nerf_bwd_counters(long long* device_buffer) { g_nerf_bwd_dbg = device_buffer; }
 
 int lnrf_nerf_backward_recompute_supported(uint32_t num_layers_sigma, uint32_t num_layers_color) {
     const uint32_t ns = num_layers_sigma, nc = num_layers_color;
@@ -449,6 +492,7 @@ int lnrf_nerf_backward_recompute(const float* grad_sigmas, const float* grad_rgb
         a.w_sigma = (const __half*)w_sigma_f16; a.w_color = (const __half*)w_color_f16; a.grad_enc = (__half*)grad_enc_f16;
         a.wgrad_sigma = (float*)wgrad_scratch; a.wgrad_color = (float*)((uint8_t*)wgrad_scratch + need_s);
         a.M_dev = M_dev; a.M = M; a.ns = ns; a.nc = nc; a.ntiles = ntiles; a.density_scale = density_scale;
+        a.dbg = g_nerf_bwd_dbg;
         k_nerf_bwd<<<grid, kBwdThreads, smem, st>>>(tm, a);
         LNRF_LAUNCH_CHECK("nerf_backward_recompute");
     } else {

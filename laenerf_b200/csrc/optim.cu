@@ -230,6 +230,171 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// One launch for the whole optimizer step (round 2): non-finite check + Adam + GradScaler update
+// ---------------------------------------------------------------------------------------------------------------------
+// The three launches of the step above (k_grad_nonfinite, k_adam_step, k_amp_update) cost a 24.5 MB pass of their own for the
+// check plus two launch gaps (10.6 + 3.7 us of kernels and the gaps between them in the 0.41 ms step).  Here every block first
+// scans the gradient chunks it is about to update (phase 1), the blocks meet at a grid-wide barrier (the grid is capped at what is
+// resident at once, so a spin barrier on a device counter cannot deadlock), read the combined flag, and run the update (phase 2) on
+// the same chunks -- still in L2 from phase 1; the block that finishes last applies GradScaler.update() and re-arms the flag.
+// `sync` = three zero-initialised device words owned by the optimizer: [0] arrivals, [1] barrier generation, [2] finished blocks.
+struct AmpUpdateArgs {
+    float* scale;
+    int* growth_tracker;
+    float* found_inf;
+    float* step_count;
+    float growth_factor, backoff_factor;
+    int growth_interval;
+};
+__device__ __forceinline__ void amp_update_body(const AmpUpdateArgs& u) {
+    if (*u.found_inf != 0.0f) {
+        if (u.scale) *u.scale = *u.scale * u.backoff_factor;
+        if (u.growth_tracker) *u.growth_tracker = 0;
+    } else {
+        if (u.scale && u.growth_tracker) {
+            const int successful = *u.growth_tracker + 1;
+            if (successful == u.growth_interval) {
+                const float grown = *u.scale * u.growth_factor;
+                if (isfinite(grown)) *u.scale = grown;
+                *u.growth_tracker = 0;
+            } else {
+                *u.growth_tracker = successful;
+            }
+        }
+        *u.step_count += 1.0f;
+    }
+    *u.found_inf = 0.0f;
+}
+
+__global__ void __launch_bounds__(kOptBlock)
+k_adam_amp_fused(const OptBatch b, AdamHyper h, const float* __restrict__ lr_scale, const AmpUpdateArgs u, unsigned int* __restrict__ sync) {
+    const int k = find_tensor(b, blockIdx.x);
+    const OptTensor& t = b.t[k];
+    const uint32_t nblocks = (k + 1 < (int)b.count ? b.t[k + 1].first_block : gridDim.x) - t.first_block;
+    __shared__ unsigned int s_gen;
+    if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned int*>(sync + 1);
+    if (lr_scale) h.lr *= (double)*lr_scale;
+    const AdamStepConsts c = adam_step_consts(h, u.scale, u.step_count);   // reads scale / step_count before anybody may update them
+
+    // ---- phase 1: non-finite check over this block's own chunks (fp16 gradients) ----
+    bool bad = false;
+    for (uint64_t base = (uint64_t)(blockIdx.x - t.first_block) * kOptChunk; base < t.n; base += (uint64_t)nblocks * kOptChunk) {
+        const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;
+        if (i + kOptPerThread <= t.n) {
+            if (t.g_is_f16) {
+                const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i);
+                bad |= !(finite_h2(w.x) && finite_h2(w.y) && finite_h2(w.z) && finite_h2(w.w));
+            } else {
+                const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i);
+                const float4 d = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i + 4);
+                bad |= !(isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w) && isfinite(d.x) && isfinite(d.y) &&
+                         isfinite(d.z) && isfinite(d.w));
+            }
+        } else {
+            for (uint64_t j = i; j < t.n; j++) {
+                const float g = t.g_is_f16 ? __half2float(reinterpret_cast<const __half*>(t.g)[j]) : reinterpret_cast<const float*>(t.g)[j];
+                bad |= !isfinite(g);
+            }
+        }
+    }
+    const bool block_bad = __syncthreads_or(bad) != 0;
+    // ---- grid barrier ----
+    if (threadIdx.x == 0) {
+        if (block_bad) *reinterpret_cast<volatile float*>(u.found_inf) = 1.0f;
+        __threadfence();
+        const unsigned int arrived = atomicAdd(sync, 1u);
+        if (arrived == gridDim.x - 1u) {
+            sync[0] = 0u;
+            __threadfence();
+            atomicAdd(sync + 1, 1u);
+        } else {
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned int*>(sync + 1) == s_gen) {
+                __nanosleep(32);
+                if (clock64() - t0 > 8000000000ll) __trap();   // a barrier that cannot complete is a launch failure, not a hung GPU
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    const bool skip = *reinterpret_cast<volatile float*>(u.found_inf) != 0.0f;
+
+    // ---- phase 2: the update of k_adam_step on the same chunks ----
+    for (uint64_t base = (uint64_t)(blockIdx.x - t.first_block) * kOptChunk; base < t.n; base += (uint64_t)nblocks * kOptChunk) {
+        const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;
+        if (i >= t.n) continue;
+        if (i + kOptPerThread > t.n) {  // ragged tail of the tensor: scalar path
+            for (uint64_t j = i; j < t.n; j++) {
+                float g;
+                if (t.g_is_f16) {
+                    g = __half2float(reinterpret_cast<const __half*>(t.g)[j]);
+                    reinterpret_cast<__half*>(t.g)[j] = __float2half_rn(0.f);
+                } else {
+                    g = reinterpret_cast<const float*>(t.g)[j];
+                    reinterpret_cast<float*>(t.g)[j] = 0.f;
+                }
+                if (skip) continue;
+                float p = t.p[j], m = t.m[j], v = t.v[j];
+                adam_update(p, m, v, adam_unscale(g, c), h, c);
+                t.p[j] = p; t.m[j] = m; t.v[j] = v;
+                if (t.p16) t.p16[j] = __float2half_rn(p);
+            }
+            continue;
+        }
+        float g[kOptPerThread], p[kOptPerThread], m[kOptPerThread], v[kOptPerThread];
+        uint4 gw = make_uint4(0u, 0u, 0u, 0u);
+        if (t.g_is_f16) {
+            gw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(t.g) + i);
+        } else {
+            const float4* gp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(t.g) + i);
+            *reinterpret_cast<float4*>(g) = *gp;
+            *reinterpret_cast<float4*>(g + 4) = *(gp + 1);
+        }
+        *reinterpret_cast<float4*>(p) = ld_state<true>(t.p + i);
+        *reinterpret_cast<float4*>(p + 4) = ld_state<true>(t.p + i + 4);
+        *reinterpret_cast<float4*>(m) = ld_state<true>(t.m + i);
+        *reinterpret_cast<float4*>(m + 4) = ld_state<true>(t.m + i + 4);
+        *reinterpret_cast<float4*>(v) = ld_state<true>(t.v + i);
+        *reinterpret_cast<float4*>(v + 4) = ld_state<true>(t.v + i + 4);
+        if (t.g_is_f16) {
+            union { uint4 u; __half2 h2[4]; } w;
+            w.u = gw;
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float2 f = __half22float2(w.h2[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(t.g) + i) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            float* gp = reinterpret_cast<float*>(t.g) + i;
+            *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(gp + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (skip) continue;
+#pragma unroll
+        for (int j = 0; j < (int)kOptPerThread; j++) adam_update(p[j], m[j], v[j], adam_unscale(g[j], c), h, c);
+        st_state<true>(t.p + i, *reinterpret_cast<const float4*>(p));
+        st_state<true>(t.p + i + 4, *reinterpret_cast<const float4*>(p + 4));
+        st_state<true>(t.m + i, *reinterpret_cast<const float4*>(m));
+        st_state<true>(t.m + i + 4, *reinterpret_cast<const float4*>(m + 4));
+        st_state<true>(t.v + i, *reinterpret_cast<const float4*>(v));
+        st_state<true>(t.v + i + 4, *reinterpret_cast<const float4*>(v + 4));
+        if (t.p16) {
+            union { uint4 u; __half2 h2[4]; } w;
+#pragma unroll
+            for (int j = 0; j < 4; j++) w.h2[j] = __floats2half2_rn(p[2 * j], p[2 * j + 1]);
+            *reinterpret_cast<uint4*>(t.p16 + i) = w.u;
+        }
+    }
+    // ---- the block that finishes last applies GradScaler.update() (every block has consumed scale / step_count / found_inf) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(sync + 2, 1u) == gridDim.x - 1u) {
+            sync[2] = 0u;
+            amp_update_body(u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Ray-sharded training: gradient exchange + Adam + parameter broadcast as ONE kernel over NVLink peer memory
 // ---------------------------------------------------------------------------------------------------------------------
 // Every rank holds its full local fp16 gradient and the full fp16 shadow table in symmetric (peer-mapped) memory.  Rank r
@@ -405,7 +570,8 @@ __global__ void k_amp_update(float* scale, int* growth_tracker, float* found_inf
     *found_inf = 0.0f;
 }
 
-static int make_batch(const char* who, const lnrf_opt_tensor* tensors, uint32_t count, OptBatch* b, uint32_t* grid, bool need_state) {
+static int make_batch(const char* who, const lnrf_opt_tensor* tensors, uint32_t count, OptBatch* b, uint32_t* grid, bool need_state,
+                      uint32_t max_blocks = 0) {
     LNRF_REQUIRE(tensors && count >= 1 && count <= (uint32_t)kMaxOptTensors, "%s: 1..%d tensors per call, got %u", who, kMaxOptTensors, count);
     uint32_t blocks = 0;
     b->count = count;
@@ -424,8 +590,17 @@ static int make_batch(const char* who, const lnrf_opt_tensor* tensors, uint32_t 
         // enough blocks to fill the machine (8 resident blocks per SM), never more than the tensor has chunks
         const uint64_t chunks = (s.n + kOptChunk - 1) / kOptChunk;
         const char* ec = getenv("LNRF_ADAM_BLOCKS_PER_SM");  // A/B switch
-        const uint64_t cap = (uint64_t)kNumSMs * (uint64_t)(ec && atoi(ec) > 0 ? atoi(ec) : 8);
+        uint64_t cap = (uint64_t)kNumSMs * (uint64_t)(ec && atoi(ec) > 0 ? atoi(ec) : 8);
+        if (max_blocks) {  // co-resident grids (k_adam_amp_fused): the tensors share max_blocks in proportion to their sizes
+            uint64_t total = 0;
+            for (uint32_t j = 0; j < count; j++) total += tensors[j].n;
+            cap = 1ull + (uint64_t)(max_blocks > count ? max_blocks - count : 0u) * s.n / (total ? total : 1);   // sum of caps <= max_blocks
+        }
         blocks += (uint32_t)(chunks < cap ? chunks : cap);
+    }
+    if (max_blocks && blocks > max_blocks) {
+        set_error("%s: %u blocks needed but only %u can be resident at once", who, blocks, max_blocks);
+        return LNRF_ERR_UNSUPPORTED;
     }
     *grid = blocks;
     return LNRF_OK;
@@ -461,6 +636,33 @@ int lnrf_adam_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double l
     else
         k_adam_step<false><<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
     LNRF_LAUNCH_CHECK("adam_step");
+    return LNRF_OK;
+}
+
+int lnrf_adam_amp_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, float* grad_scale, int32_t* growth_tracker, float* found_inf, float* step_count,
+                       const float* lr_scale, float growth_factor, float backoff_factor, int32_t growth_interval, uint32_t* sync_words,
+                       lnrf_stream_t stream) {
+    LNRF_REQUIRE(found_inf && step_count && sync_words, "adam_amp_step: null found_inf / step_count / sync_words");
+    static std::atomic<int> s_per_sm{0};
+    int per_sm = s_per_sm.load(std::memory_order_relaxed);
+    if (per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_adam_amp_fused, (int)kOptBlock, 0);
+        if (e != cudaSuccess) return cuda_fail(e, "adam_amp_step");
+        LNRF_REQUIRE(per_sm >= 1, "adam_amp_step: the kernel does not fit an SM");
+        s_per_sm.store(per_sm, std::memory_order_relaxed);
+    }
+    int dev = 0, sms = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    OptBatch b;
+    uint32_t grid;
+    // every block must be resident at once (grid-wide spin barrier): at most occupancy x SMs blocks, a count tensor-count larger
+    // than the SM count keeps one block per small tensor
+    if (int e = make_batch("adam_amp_step", tensors_host, count, &b, &grid, true, (uint32_t)(per_sm * sms))) return e;
+    AdamHyper h{lr, beta1, beta2, eps, weight_decay};
+    AmpUpdateArgs u{grad_scale, growth_tracker, found_inf, step_count, growth_factor, backoff_factor, growth_interval};
+    k_adam_amp_fused<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, lr_scale, u, sync_words);
+    LNRF_LAUNCH_CHECK("adam_amp_step");
     return LNRF_OK;
 }
 

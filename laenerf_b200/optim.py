@@ -94,6 +94,8 @@ class AmpAdam:
         self._scale = torch.full((1,), float(init_scale), dtype=torch.float32, device=dev) if self.fp16 else None
         self._growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev) if self.fp16 else None
         self.lr_scale = torch.ones(1, dtype=torch.float32, device=dev)  # schedule factor (LambdaLR), read on the device
+        self._sync_words = torch.zeros(4, dtype=torch.int32, device=dev)  # grid barrier / last-block ticket of lnrf_adam_amp_step
+        self.one_launch = os.environ.get("LNRF_ADAM_ONE_LAUNCH", "1") != "0"
         self._stale_params = False
         if model is not None:
             model._amp_adam = weakref.ref(self)
@@ -329,6 +331,14 @@ class AmpAdam:
         st = N.stream()
         arr, keep = self._descriptors(self.owners, self.state)
         n = len(self.owners)
+        if self.fp16 and self.one_launch and len({o.lr_mult for o in self.owners}) == 1:
+            # non-finite check + Adam + GradScaler.update() in ONE launch (csrc/optim.cu k_adam_amp_fused)
+            N.check(lib.lnrf_adam_amp_step(C.cast(arr, C.c_void_p), n, self.lr * self.owners[0].lr_mult, self.betas[0], self.betas[1], self.eps,
+                                           self.weight_decay, N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf),
+                                           N.ptr(self.step_count), N.ptr(self.lr_scale), self.growth_factor, self.backoff_factor,
+                                           self.growth_interval, N.ptr(self._sync_words), st))
+            del keep
+            return
         if self.fp16:
             N.check(lib.lnrf_grad_nonfinite_check(C.cast(arr, C.c_void_p), n, N.ptr(self.found_inf), st))
         # one launch per distinct learning rate (the style network trains its palette at 2 x lr, style_encoder.py:247-255)

@@ -192,6 +192,58 @@ def test_adam_step_skips_on_inf_like_gradscaler(dev):
     assert float(sc.item()) == 1024.0 and int(tracker.item()) == 0 and float(step.item()) == 2.0 and not torch.equal(p, p_before)
 
 
+def test_one_launch_optimizer_step_equals_the_three_launch_sequence(dev):
+    """lnrf_adam_amp_step (non-finite check + Adam + GradScaler.update in one launch, grid barrier inside) against
+    lnrf_grad_nonfinite_check + lnrf_adam_step + lnrf_amp_update on the same data, including a skipped (inf) step and a scale growth:
+    bit-identical parameters, moments, shadows, scale, tracker, step count."""
+    from laenerf_b200 import _native as N
+    lib = N.lib()
+    sizes = [6119864 * 2, 7168, 11264]   # the lego-shape table and the two MLPs
+    g = torch.Generator(device=dev).manual_seed(21)
+
+    def fresh():
+        st = []
+        g2 = torch.Generator(device=dev).manual_seed(22)
+        for n in sizes:
+            p = torch.randn(n, device=dev, generator=g2) * 1e-2
+            st.append(dict(p=p, m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev), p16=p.half(), g=torch.zeros(n, dtype=torch.half, device=dev)))
+        return dict(t=st, step=torch.ones(1, device=dev), found=torch.zeros(1, device=dev), scale=torch.full((1,), 8192.0, device=dev),
+                    tracker=torch.full((1,), 1, dtype=torch.int32, device=dev), sync=torch.zeros(4, dtype=torch.int32, device=dev))
+
+    def desc(S):
+        arr = (N.OptTensor * len(sizes))()
+        for i, t in enumerate(S["t"]):
+            arr[i].params, arr[i].exp_avg, arr[i].exp_avg_sq, arr[i].grad = t["p"].data_ptr(), t["m"].data_ptr(), t["v"].data_ptr(), t["g"].data_ptr()
+            arr[i].params_f16, arr[i].n, arr[i].grad_dtype = t["p16"].data_ptr(), sizes[i], N.F16
+        return arr
+
+    A, B = fresh(), fresh()
+    hyper = (1e-2, 0.9, 0.99, 1e-15, 0.0)
+    for it in range(4):
+        grads = [(torch.randn(n, device=dev, generator=g) * 4.0).half() for n in sizes]
+        if it == 1:
+            grads[0][123457] = float("nan")   # this step must be skipped
+        for S in (A, B):
+            for t, gr in zip(S["t"], grads):
+                t["g"].copy_(gr)
+        arr = desc(A)
+        N.check(lib.lnrf_grad_nonfinite_check(C.cast(arr, C.c_void_p), 3, N.ptr(A["found"]), None))
+        N.check(lib.lnrf_adam_step(C.cast(arr, C.c_void_p), 3, *hyper, N.ptr(A["scale"]), N.ptr(A["found"]), N.ptr(A["step"]), None, None))
+        N.check(lib.lnrf_amp_update(N.ptr(A["scale"]), N.ptr(A["tracker"]), N.ptr(A["found"]), N.ptr(A["step"]), 2.0, 0.5, 3, None))
+        arr = desc(B)
+        N.check(lib.lnrf_adam_amp_step(C.cast(arr, C.c_void_p), 3, *hyper, N.ptr(B["scale"]), N.ptr(B["tracker"]), N.ptr(B["found"]), N.ptr(B["step"]),
+                                       None, 2.0, 0.5, 3, N.ptr(B["sync"]), None))
+        torch.cuda.synchronize()
+        for ta, tb in zip(A["t"], B["t"]):
+            for k in ("p", "m", "v", "p16", "g"):
+                assert torch.equal(ta[k], tb[k]), (it, k)
+            assert not tb["g"].any()
+        for k in ("step", "found", "scale", "tracker"):
+            assert torch.equal(A[k], B[k]), (it, k, A[k], B[k])
+        assert B["sync"][0].item() == 0 and B["sync"][2].item() == 0 and B["sync"][1].item() == it + 1
+    assert float(B["step"]) == 4.0 and float(B["scale"]) == 8192.0 * 0.5 * 2.0   # one skip (backoff), then growth after 3 clean steps
+
+
 def test_train_step_fused_optimizer_tracks_torch_path(dev):
     """Whole training steps: AmpAdam + fused network against torch Adam/GradScaler + module path from the same init.
     Hash-grid atomics make both paths run-to-run nondeterministic in the last fp16 bits, so the check is statistical:
