@@ -458,6 +458,11 @@ LNRF_API int lnrf_adam_amp_step(const lnrf_opt_tensor* tensors_host, uint32_t co
                                 double eps, double weight_decay, float* grad_scale, int32_t* growth_tracker, float* found_inf,
                                 float* step_count, const float* lr_scale, float growth_factor, float backoff_factor,
                                 int32_t growth_interval, uint32_t* sync_words, lnrf_stream_t stream);
+/* Closing launch of the barrier-bracketed sharded step: clears the local fp16 gradient (n elements, a multiple of 8) and applies
+ * GradScaler.update() (as lnrf_amp_update) in the same launch. */
+LNRF_API int lnrf_exchange_tail(void* grad_f16, uint64_t n, float* scale, int32_t* growth_tracker, float* found_inf,
+                                float* step_count, float growth_factor, float backoff_factor, int32_t growth_interval,
+                                lnrf_stream_t stream);
 LNRF_API int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, float* step_count,
                              float growth_factor, float backoff_factor, int32_t growth_interval, lnrf_stream_t stream);
 

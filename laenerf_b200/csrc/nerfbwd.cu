@@ -81,7 +81,13 @@ __device__ __forceinline__ uint32_t wacc_col(uint32_t n, uint32_t m) {
     return 16u + 64u * (n - 1u - m);
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 1)
+// Measured and dropped (scripts/diag_overlap.py): capping the kernel at 128 registers (launch bound 512) so that a CTA of the
+// hash-grid backward fits beside it on every SM.  Launched together on two streams the pair took 164 us against 100 + 97 us one after
+// the other -- the encoder kernel only gets 8 warps per SM while this one is resident -- and the spills cost this kernel 10 us.
+#ifndef LNRF_BWD_LB
+#define LNRF_BWD_LB kBwdThreads
+#endif
+__global__ void __launch_bounds__(LNRF_BWD_LB, 1)
 k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
@@ -154,77 +160,67 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        // Each tile set advances through its own chain; the warp serves whichever set has its next operand ready (test_wait, no
-        // fixed order), so a slow epilogue of one set never holds the other set's MMAs back.  A backward step issues the dgrad first
-        // and commits it alone (`full`): the epilogue starts reading TMEM while the 8 weight-gradient MMAs of the step still run;
-        // their completion is a second commit (`wdone`) that the epilogue waits for before it overwrites the tiles they read.
-        uint32_t ph_ready[kBG], ph_x[kBG], step[kBG], iter[kBG];
-        bool live[kBG];
-        uint32_t n_live = 0, started = 0u;   // bit per weight-gradient accumulator: has it received its first (non-accumulating) MMA?
-        for (uint32_t g = 0; g < kBG; g++) {
-            ph_ready[g] = ph_x[g] = step[g] = iter[g] = 0u;
-            live[g] = blockIdx.x * kBG + g < ntiles;
-            n_live += live[g] ? 1u : 0u;
-        }
-        uint32_t g = 0;
-        while (n_live > 0u) {
-            g = (g + 1u) % kBG;
-            if (!live[g]) continue;
-            const uint32_t s = step[g];
-            if (!mbar_test(ready + g, ph_ready[g])) continue;
-            if (s == sB && !mbar_test(xfull + g, ph_x[g])) continue;
-            ph_ready[g] ^= 1u;
-            if (s == sB) ph_x[g] ^= 1u;
-            tc_fence_after();
-            const uint32_t set = smem_u32(sSets + g * set_bytes);
-            const uint32_t tCIN = set + nc * kTileBytes, tDY = tCIN + kTileBytes;
-            const uint32_t work = tbase + 64u * g;
-            // which net, which of its phases
-            const bool sig = s >= sB;
-            const uint32_t n = sig ? ns : nc, ls = sig ? s - sB : s;        // layers, step inside the net's part
-            const uint32_t sW = smem_u32(sig ? sWs : sWc), wcol = sig ? wcol_s : wcol_c;
-            // tile of hidden layer k of this net: colour C(k) = tile k; sigma H(k) = tile nc-1-k; inputs / output-gradient tiles
-            auto hid = [&](uint32_t k) { return set + (sig ? (nc - 1u - k) : k) * kTileBytes; };
-            const uint32_t tIN = sig ? tDY : tCIN;      // X (enc rows) | cin
-            const uint32_t tGout = sig ? tCIN : tDY;    // dh | dY
-            uint32_t accbit = 0u;
-            if (ls >= n) accbit = 1u << ((sig ? 8u : 0u) + (2u * n - ls));   // accumulator of matmul m = 2n - ls (0 for the input layer)
-            const bool accf = (started & accbit) != 0u;
-            started |= accbit;
-            if (elect_one()) {
-                if (ls < n) {                 // forward hidden layer k = ls
-                    const uint32_t k = ls;
-                    const uint64_t da = desc_sw128(k ? hid(k - 1u) : tIN, 16), db = desc_sw128(sW + k * kWBytes, 16);
-                    const uint32_t idesc = make_idesc(128, 64, false, false);
-                    if (k == 0u) umma_chain<2>(work, da, db, 2, 2, idesc, false);
-                    else umma_chain<4>(work, da, db, 2, 2, idesc, false);
-                    umma_commit(full + g);
-                } else if (ls < 2u * n) {     // backward through matmul m = n .. 1
-                    const uint32_t m = 2u * n - ls;
-                    const uint32_t tG = m == n ? tGout : hid(m);
-                    const uint64_t wa = desc_sw128(hid(m - 1u), kTileBytes), wb = desc_sw128(tG, kTileBytes);
-                    const uint64_t da = desc_sw128(tG, 16), db = desc_sw128(sW + m * kWBytes, kTileBytes);
-                    const uint32_t didesc = make_idesc(128, 64, false, true);
-                    if (m == n) umma_chain<1>(work, da, db, 2, 128, didesc, false);     // K = 16 output channels
-                    else umma_chain<4>(work, da, db, 2, 128, didesc, false);           // K = 64
-                    umma_commit(full + g);
-                    umma_chain<8>(wcol + wacc_col(n, m), wa, wb, 128, 128, make_idesc(128, m == n ? 16u : 64u, true, true), accf);
-                    umma_commit(wdone + g);
-                    if (s == nc) umma_commit(dyfree + g);   // dY consumed (dgrad + wgrad of the colour output layer)
-                } else {                      // input layer: dX = G(0) W(0) (N = 32), dW(0) += G(0)^T X
-                    const uint64_t wa = desc_sw128(hid(0), kTileBytes), wb = desc_sw128(tIN, kTileBytes);
-                    const uint64_t da = desc_sw128(hid(0), 16), db = desc_sw128(sW, kTileBytes);
-                    umma_chain<4>(work, da, db, 2, 128, make_idesc(128, 32, false, true), false);
-                    umma_commit(full + g);
-                    umma_chain<8>(wcol + wacc_col(n, 0), wa, wb, 128, 128, make_idesc(128, 32, true, true), accf);
-                    umma_commit(wdone + g);
+        // Fixed interleaved order (set 0, set 1, set 0, ...): the mbarrier waits suspend in hardware and wake ~60 cycles after the
+        // arrival, where a polling loop that serves "whichever set is ready" measured 20 % slower (poll + bookkeeping in local memory).
+        // A backward step issues the dgrad first and commits it alone (`full`): the epilogue starts reading TMEM while the 8
+        // weight-gradient MMAs of the step still run; their completion is a second commit (`wdone`) that the epilogue waits for
+        // before it overwrites the tiles they read.
+        uint32_t ph_ready = 0u, ph_x = 0u;   // both sets run the same step sequence: one parity each serves both
+        for (uint32_t it = 0;; it++) {
+            const bool v0 = blockIdx.x * kBG + it * stride < ntiles, v1 = blockIdx.x * kBG + 1u + it * stride < ntiles;
+            if (!v0 && !v1) break;
+            for (uint32_t s = 0; s < nsteps; s++) {
+                // which net, which of its phases
+                const bool sig = s >= sB;
+                const uint32_t n = sig ? ns : nc, ls = sig ? s - sB : s;        // layers, step inside the net's part
+                const uint32_t sW = smem_u32(sig ? sWs : sWc), wcol = sig ? wcol_s : wcol_c;
+#pragma unroll
+                for (uint32_t g = 0; g < kBG; g++) {
+                    if (!(g == 0u ? v0 : v1)) continue;
+                    mbar_wait_hot(ready + g, ph_ready);
+                    if (s == sB) mbar_wait_hot(xfull + g, ph_x);
+                    tc_fence_after();
+                    const uint32_t set = smem_u32(sSets + g * set_bytes);
+                    const uint32_t tCIN = set + nc * kTileBytes, tDY = tCIN + kTileBytes;
+                    const uint32_t work = tbase + 64u * g;
+                    const bool accf = it > 0u || g > 0u;   // set 0 always owns the CTA's first tile
+                    // tile of hidden layer k of this net: colour C(k) = tile k; sigma H(k) = tile nc-1-k; inputs / output-gradient tiles
+                    auto hid = [&](uint32_t k) { return set + (sig ? (nc - 1u - k) : k) * kTileBytes; };
+                    const uint32_t tIN = sig ? tDY : tCIN;      // X (enc rows) | cin
+                    const uint32_t tGout = sig ? tCIN : tDY;    // dh | dY
+                    if (elect_one()) {
+                        if (ls < n) {                 // forward hidden layer k = ls
+                            const uint32_t k = ls;
+                            const uint64_t da = desc_sw128(k ? hid(k - 1u) : tIN, 16), db = desc_sw128(sW + k * kWBytes, 16);
+                            const uint32_t idesc = make_idesc(128, 64, false, false);
+                            if (k == 0u) umma_chain<2>(work, da, db, 2, 2, idesc, false);
+                            else umma_chain<4>(work, da, db, 2, 2, idesc, false);
+                            umma_commit(full + g);
+                        } else if (ls < 2u * n) {     // backward through matmul m = n .. 1
+                            const uint32_t m = 2u * n - ls;
+                            const uint32_t tG = m == n ? tGout : hid(m);
+                            const uint64_t wa = desc_sw128(hid(m - 1u), kTileBytes), wb = desc_sw128(tG, kTileBytes);
+                            const uint64_t da = desc_sw128(tG, 16), db = desc_sw128(sW + m * kWBytes, kTileBytes);
+                            const uint32_t didesc = make_idesc(128, 64, false, true);
+                            if (m == n) umma_chain<1>(work, da, db, 2, 128, didesc, false);     // K = 16 output channels
+                            else umma_chain<4>(work, da, db, 2, 128, didesc, false);           // K = 64
+                            umma_commit(full + g);
+                            umma_chain<8>(wcol + wacc_col(n, m), wa, wb, 128, 128, make_idesc(128, m == n ? 16u : 64u, true, true), accf);
+                            umma_commit(wdone + g);
+                            if (s == nc) umma_commit(dyfree + g);   // dY consumed (dgrad + wgrad of the colour output layer)
+                        } else {                      // input layer: dX = G(0) W(0) (N = 32), dW(0) += G(0)^T X
+                            const uint64_t wa = desc_sw128(hid(0), kTileBytes), wb = desc_sw128(tIN, kTileBytes);
+                            const uint64_t da = desc_sw128(hid(0), 16), db = desc_sw128(sW, kTileBytes);
+                            umma_chain<4>(work, da, db, 2, 128, make_idesc(128, 32, false, true), false);
+                            umma_commit(full + g);
+                            umma_chain<8>(wcol + wacc_col(n, 0), wa, wb, 128, 128, make_idesc(128, 32, true, true), accf);
+                            umma_commit(wdone + g);
+                        }
+                    }
+                    __syncwarp();
                 }
-            }
-            __syncwarp();
-            if (++step[g] == nsteps) {
-                step[g] = 0u;
-                iter[g]++;
-                if (blockIdx.x * kBG + g + iter[g] * stride >= ntiles) { live[g] = false; n_live--; }
+                ph_ready ^= 1u;
+                if (s == sB) ph_x ^= 1u;
             }
         }
     } else if (warp >= 4) {

@@ -546,6 +546,15 @@ k_exchange_finish(const uint32_t* __restrict__ my_flag_words, const uint32_t R, 
         grad[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Closing launch of the barrier-bracketed sharded step: clear the local gradient (the peers have finished reading it: barrier B) and,
+// in one thread, GradScaler.update() -- instead of a memset launch followed by k_amp_update.
+__global__ void __launch_bounds__(kOptBlock)
+k_clear_and_amp_update(uint4* __restrict__ grad, const uint64_t n_vec, const AmpUpdateArgs u) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (uint64_t)gridDim.x * blockDim.x)
+        grad[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) amp_update_body(u);
+}
+
 // GradScaler.update() (torch amp_update_scale_cuda_kernel) + the bookkeeping around it, one thread: adjust the scale,
 // advance the step number when the step was not skipped, and re-arm found_inf for the next step.
 __global__ void k_amp_update(float* scale, int* growth_tracker, float* found_inf, float* step_count, float growth_factor,
@@ -652,6 +661,10 @@ int lnrf_adam_amp_step(const lnrf_opt_tensor* tensors_host, uint32_t count, doub
         LNRF_REQUIRE(per_sm >= 1, "adam_amp_step: the kernel does not fit an SM");
         s_per_sm.store(per_sm, std::memory_order_relaxed);
     }
+    if (const char* ec = getenv("LNRF_ADAM_BLOCKS_PER_SM")) {  // fewer resident blocks leave registers for a kernel on another stream
+        const int want = atoi(ec);                               // (the look-ahead march of the next batch, nerf.py GraphedTrainStep)
+        if (want > 0 && want < per_sm) per_sm = want;
+    }
     int dev = 0, sms = kNumSMs;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     OptBatch b;
@@ -720,6 +733,19 @@ int lnrf_adam_step_sharded_sync(const void* const* grad_peers_host, void* const*
     return adam_step_sharded_impl(grad_peers_host, shadow_peers_host, flag_peers_host, world, lo, n, master_shard, exp_avg_shard,
                                   exp_avg_sq_shard, lr, beta1, beta2, eps, weight_decay, grad_scale, found_inf_out, step_count, lr_scale, rank,
                                   sync_state, sync_state + 1, stream);
+}
+
+int lnrf_exchange_tail(void* grad_f16, uint64_t n, float* scale, int32_t* growth_tracker, float* found_inf, float* step_count,
+                       float growth_factor, float backoff_factor, int32_t growth_interval, lnrf_stream_t stream) {
+    LNRF_REQUIRE(grad_f16 && found_inf && step_count, "exchange_tail: null pointer");
+    LNRF_REQUIRE(n % 8 == 0 && (reinterpret_cast<uintptr_t>(grad_f16) & 15) == 0, "exchange_tail: the gradient must be 16-byte vectors");
+    const uint64_t n_vec = n / 8;
+    const uint64_t want = (n_vec + kOptBlock - 1) / kOptBlock, cap = (uint64_t)kNumSMs * 8;
+    AmpUpdateArgs u{scale, growth_tracker, found_inf, step_count, growth_factor, backoff_factor, growth_interval};
+    k_clear_and_amp_update<<<(uint32_t)(want < cap ? (want ? want : 1) : cap), kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<uint4*>(grad_f16), n_vec, u);
+    LNRF_LAUNCH_CHECK("exchange_tail");
+    return LNRF_OK;
 }
 
 int lnrf_exchange_finish(const float* my_flags, uint32_t world, const uint32_t* sync_state, void* grad_f16, uint64_t n,

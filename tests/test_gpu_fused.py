@@ -241,7 +241,8 @@ def test_one_launch_optimizer_step_equals_the_three_launch_sequence(dev):
         for k in ("step", "found", "scale", "tracker"):
             assert torch.equal(A[k], B[k]), (it, k, A[k], B[k])
         assert B["sync"][0].item() == 0 and B["sync"][2].item() == 0 and B["sync"][1].item() == it + 1
-    assert float(B["step"]) == 4.0 and float(B["scale"]) == 8192.0 * 0.5 * 2.0   # one skip (backoff), then growth after 3 clean steps
+    # steps 0, 2, 3 ran, step 1 was skipped: scale backed off once (8192 -> 4096), two clean steps since (growth needs three)
+    assert float(B["step"]) == 4.0 and float(B["scale"]) == 4096.0 and int(B["tracker"]) == 2
 
 
 def test_train_step_fused_optimizer_tracks_torch_path(dev):
