@@ -20,7 +20,7 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=6)
 ap.add_argument("--render-rays", type=int, default=0, help="also profile one render of this many rays")
 ap.add_argument("--render-shard", type=int, default=0, help="render rank 0's share of a frame tile-sharded over this many ranks")
-ap.add_argument("--render-schedule", default="fast", choices=["fast", "reference"])
+ap.add_argument("--render-schedule", default="fast", choices=["fast", "reference", "auto"])
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
