@@ -851,7 +851,14 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
                 inexact |= f_add(prev_after, d1) != t_after;
                 if (DISTILL) edit_occ[row] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
             });
-        if (ctl && inexact) const_cast<int*>(ctl)[kCtlInexact] = 1;  // benign race: every writer stores the same value
+        // Round 0 is exempt: it takes ONE sample per ray on every schedule (ctl_set_round), so the boundary after a ray's first sample
+        // -- typically the one long skip from `near` to the first occupied cell, where t can more than double -- sits in the same
+        // place whatever happens afterwards.
+        if (ctl && inexact && ctl[kCtlRounds] > 0) {
+            int* c = const_cast<int*>(ctl);
+            c[kCtlInexact] = 1;                  // benign race: every writer stores the same value
+            if (grp.gl == 0) atomicAdd(c + 13, 1);  // how many rays raised it (diagnostics)
+        }
         if (g >= n_groups) continue;
         // zero-fill the slots this ray did not use, and whole padding groups (torch.zeros in raymarching.py:334-336)
         const size_t zlo = row0 + (active ? cnt : 0u);
@@ -1044,6 +1051,7 @@ k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_
         ctl[kCtlBudget] = (int)row_budget;
         ctl[kCtlStepCap] = (int)step_cap;
         ctl[kCtlInexact] = 0;
+        ctl[13] = 0;
         ctl_set_round(ctl, n_rays);
     }
 }

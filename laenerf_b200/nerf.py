@@ -449,6 +449,7 @@ class NeRFNetwork(nn.Module):
                 break
         t["rounds"], t["steps"], t["slots"] = ctl[7], ctl[2], ctl[9]
         t["schedule_dependent"] = bool(ctl[12])
+        t["inexact_rays"] = int(ctl[13])
         t["schedule"] = schedule
         return t
 
