@@ -172,7 +172,7 @@ class NeRFNetwork(nn.Module):
         # rendered again on the reference schedule and later frames of this model go there directly: always the reference's bits
         self.render_schedule = "auto"
         self._auto_fast_ok = True
-        self.render_samples_per_round = 32  # "fast" only: cap on the samples a ray takes per round after the first
+        self.render_samples_per_round = 64  # "fast" only: cap on the samples a ray takes per round after the first
         self._amp_adam = None  # weak reference to the AmpAdam that owns the fp16 shadows, if any
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
                           self.in_dim_color == 32 and self.encoder_dir.degree == 4)
@@ -394,7 +394,10 @@ class NeRFNetwork(nn.Module):
         # round takes up to render_samples_per_round samples per ray -- several times fewer rounds, each of which costs ~90 us of
         # latency whatever its size
         fast = schedule == "fast"
-        rows = (8 * n_rays if fast else n_rays) + 128
+        # "fast": a round's row budget is 8 n_rays, or -- for the small ray sets a rank renders when a frame is tile-sharded over many
+        # GPUs -- up to 4 M rows: every round costs ~100 us of latency whatever its size (march of the longest gap + four dependent
+        # launches), so a small ray set should finish in as few rounds as possible (up to 64 samples per ray per round)
+        rows = (max(8 * n_rays, min(64 * n_rays, 1 << 22)) if fast else n_rays) + 128
         distill = edit_bitfield is not None
         enc, sn, cn = self.encoder, self.sigma_net, self.color_net
         emb, ws, wc = half_of(enc, enc.embeddings), half_of(sn, sn.weights), half_of(cn, cn.weights)
