@@ -275,9 +275,10 @@ LNRF_API int lnrf_grid_encode_backward_world(const void* grad, const float* inpu
  * (nerf/renderer.py:335-387, 425-470) without a device->host synchronisation per round.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct {
-    int32_t* ctl;                 /* device int32[16] control block: [0] n_alive [1] n_step [2] steps marched [3] rows of the
+    int32_t* ctl;                 /* device int32[32] control block: [0] n_alive [1] n_step [2] steps marched [3] rows of the
                                      round (n_alive*n_step padded past 128) [4] n_rays [5] max_steps [6] finished [7] rounds
-                                     [9] sample slots marched so far */
+                                     [9] sample slots marched so far [12] the result may depend on the round schedule (see
+                                     ray_flags) [13] rays that raised [12] [14] the max_steps cap cut rays off; [16..22] internal (copies of the four fields below) */
     uint32_t n_rays, max_steps;
     /* rays and marching (raymarching.march_rays arguments) */
     const float *rays_o, *rays_d, *nears, *fars;       /* [n_rays,3] x2, [n_rays] x2 */
@@ -314,6 +315,16 @@ typedef struct {
      * positions can differ in the last ulp where a round boundary moves (composite_rays re-sums t from deltas). */
     uint32_t sample_rows;
     uint32_t samples_per_round;   /* cap on n_step after the first round when sample_rows is in force (0: 8; at most 64) */
+    /* Making a non-reference schedule exact (all optional, NULL / 0 = off).  ray_steps [n_rays] int32: += the samples a ray completed
+     * in each round (cleared by lnrf_render_begin): its total is the sample index at which the ray dies, whatever the schedule.
+     * ray_flags [n_rays] uint8: set to 1 for a ray that emitted a delta that is not exactly representable after round 0 -- the
+     * only rays whose result depends on where the round boundaries fall (cleared by lnrf_render_begin).  nstep_seq [nstep_len]
+     * int32 (device): a prescribed n_step per round instead of either rule above -- with the reference's sequence (which follows
+     * from the histogram of ray_steps) a subset of rays is rendered exactly as the reference's full-frame loop renders it. */
+    int32_t* ray_steps;
+    uint8_t* ray_flags;
+    const int32_t* nstep_seq;
+    uint32_t nstep_len;
 } lnrf_render_desc;
 LNRF_API size_t lnrf_render_scratch_bytes(uint32_t n_rays);
 /* rays_alive[0] = 0..n_rays-1, rays_t = nears, accumulators = 0, control block = first round. */

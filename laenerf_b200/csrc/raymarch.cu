@@ -779,8 +779,19 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
 //   ctl[10] row budget of the rounds after the first (n_rays: the reference schedule; more: see lnrf_render_desc.sample_rows)
 //   ctl[11] most samples a ray takes per round after the first (8: the reference schedule)
 //   ctl[12] schedule-dependence flag: set when the frame's result COULD depend on where the round boundaries fall (see below)
+//   ctl[16] length of a prescribed n_step sequence (0: none)   ctl[17,18] its device address   ctl[19,20] address of the per-ray
+//   completed-step counters   ctl[21,22] address of the per-ray schedule-dependence flags (see lnrf_render_desc)
 enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, kCtlMaxSteps = 5, kCtlFinished = 6, kCtlRounds = 7,
-       kCtlBudget = 10, kCtlStepCap = 11, kCtlInexact = 12 };
+       kCtlBudget = 10, kCtlStepCap = 11, kCtlInexact = 12, kCtlSeqLen = 16, kCtlSeqPtr = 17, kCtlStepsPtr = 19, kCtlFlagsPtr = 21 };
+template <typename T>
+__device__ __forceinline__ T* ctl_ptr(const int* ctl, int slot) {
+    return reinterpret_cast<T*>(((unsigned long long)(unsigned int)ctl[slot + 1] << 32) | (unsigned long long)(unsigned int)ctl[slot]);
+}
+__device__ __forceinline__ void ctl_set_ptr(int* ctl, int slot, const void* p) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    ctl[slot] = (int)(unsigned int)(a & 0xffffffffull);
+    ctl[slot + 1] = (int)(unsigned int)(a >> 32);
+}
 // Why a schedule other than the reference's n_step rule can be bit-identical to it.  Between rounds a ray's t travels through
 // rays_t, which composite_rays rebuilds as rays_t + sum of deltas[.][1] (raymarching.cu:1006), each delta being fl(t_after -
 // t_prev) from the marcher (:789).  When t_after / t_prev <= 2 that difference is exact (Sterbenz) and fl(t_prev + delta) is
@@ -792,11 +803,16 @@ enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, k
 
 __device__ __forceinline__ void ctl_set_round(int* ctl, uint32_t n_alive) {
     const uint32_t n_rays = (uint32_t)ctl[kCtlRays];
-    const bool fin = n_alive == 0u || (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps];
+    bool fin = n_alive == 0u || (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps];
     const uint32_t budget = ctl[kCtlRounds] > 0 ? (uint32_t)ctl[kCtlBudget] : n_rays;
     uint32_t n_step = n_alive ? budget / n_alive : 1u;
     const uint32_t step_cap = ctl[kCtlRounds] > 0 ? (uint32_t)ctl[kCtlStepCap] : 8u;
     n_step = n_step > step_cap ? step_cap : (n_step < 1u ? 1u : n_step);
+    if (ctl[kCtlSeqLen] > 0) {  // prescribed schedule: round r takes seq[r] samples per ray, whatever n_alive is
+        const uint32_t r = (uint32_t)ctl[kCtlRounds];
+        if (r >= (uint32_t)ctl[kCtlSeqLen]) fin = true;
+        else n_step = (uint32_t)ctl_ptr<const int>(ctl, kCtlSeqPtr)[r];
+    }
     uint32_t rows = n_alive * n_step;
     rows += 128u - rows % 128u;
     ctl[kCtlAlive] = fin ? 0 : (int)n_alive;
@@ -831,8 +847,9 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
         const bool active = g < n_alive;
         Ray r = Ray{};
         float t = 0.f, far = 0.f;
+        int index = 0;
         if (active) {
-            const int index = __ldg(rays_alive + g);
+            index = __ldg(rays_alive + g);
             r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
             far = fars[index];
             const float t_in = rays_t[index];
@@ -857,7 +874,11 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
         if (ctl && inexact && ctl[kCtlRounds] > 0) {
             int* c = const_cast<int*>(ctl);
             c[kCtlInexact] = 1;                  // benign race: every writer stores the same value
-            if (grp.gl == 0) atomicAdd(c + 13, 1);  // how many rays raised it (diagnostics)
+            if (grp.gl == 0) {
+                atomicAdd(c + 13, 1);            // how many rays raised it
+                uint8_t* flags = ctl_ptr<uint8_t>(ctl, kCtlFlagsPtr);
+                if (flags) flags[index] = 1;
+            }
         }
         if (g >= n_groups) continue;
         // zero-fill the slots this ray did not use, and whole padding groups (torch.zeros in raymarching.py:334-336)
@@ -878,7 +899,7 @@ __device__ __forceinline__ void composite_infer_ray(const uint32_t n, const uint
                   float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                   const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ weights_edit_sum,
                   float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
-                  float* __restrict__ image);
+                  float* __restrict__ image, int* __restrict__ ray_steps = nullptr);
 
 template <bool DISTILL>
 __global__ void __launch_bounds__(256)
@@ -888,10 +909,11 @@ k_composite_infer(const uint32_t n_alive, const uint32_t n_step, const float T_t
                   float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
                   float* __restrict__ image, const int* __restrict__ ctl) {
     uint32_t na = n_alive, ns = n_step;
-    if (ctl) { na = (uint32_t)ctl[kCtlAlive]; ns = (uint32_t)ctl[kCtlStep]; }
+    int* ray_steps = nullptr;
+    if (ctl) { na = (uint32_t)ctl[kCtlAlive]; ns = (uint32_t)ctl[kCtlStep]; ray_steps = ctl_ptr<int>(ctl, kCtlStepsPtr); }
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < na; n += gridDim.x * blockDim.x)
         composite_infer_ray<DISTILL>(n, ns, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, weights_edit_sum, depth,
-                                     depth_edit, edit_occ, image);
+                                     depth_edit, edit_occ, image, ray_steps);
 }
 
 template <bool DISTILL>
@@ -899,7 +921,7 @@ __device__ __forceinline__ void composite_infer_ray(const uint32_t n, const uint
                   float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                   const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ weights_edit_sum,
                   float* __restrict__ depth, float* __restrict__ depth_edit, const uint8_t* __restrict__ edit_occ,
-                  float* __restrict__ image) {
+                  float* __restrict__ image, int* __restrict__ ray_steps) {
     const int index = rays_alive[n];
     const float* ps = sigmas + (size_t)n * n_step;
     const float* pc = rgbs + (size_t)n * n_step * 3;
@@ -931,6 +953,7 @@ __device__ __forceinline__ void composite_infer_ray(const uint32_t n, const uint
         step++;
     }
     if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+    if (ray_steps) ray_steps[index] += (int)step;  // completed samples: the total is where the ray dies, on any schedule
     if (DISTILL) { weights_edit_sum[index] = weight_edit_sum; depth_edit[index] = d_edit; }
     weights_sum[index] = weight_sum;
     depth[index] = d;
@@ -1020,7 +1043,10 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
                 ctl[kCtlRounds] += 1;
                 ctl[kCtlRounds + 2] += ctl[kCtlRows];  // sample slots marched so far (what the host loop sums up)
                 const uint32_t survivors = (uint32_t)((volatile int*)ctl)[kCtlRounds + 1];
-                if (survivors > 0u && (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps]) ctl[kCtlInexact] = 1;  // the cap cut rays off
+                if (survivors > 0u && (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps]) {  // the cap cut rays off
+                    ctl[kCtlInexact] = 1;
+                    ctl[14] = 1;
+                }
                 ctl_set_round(ctl, survivors);
             }
         }
@@ -1033,10 +1059,13 @@ k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_
                int* __restrict__ rays_alive,
                float* __restrict__ rays_t, const float* __restrict__ nears, float* __restrict__ weights_sum,
                float* __restrict__ depth, float* __restrict__ image, float* __restrict__ weights_edit_sum,
-               float* __restrict__ depth_edit) {
+               float* __restrict__ depth_edit, int* __restrict__ ray_steps, uint8_t* __restrict__ ray_flags,
+               const int* __restrict__ nstep_seq, const uint32_t nstep_len) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x) {
         rays_alive[i] = (int)i;
         rays_t[i] = nears[i];
+        if (ray_steps) ray_steps[i] = 0;
+        if (ray_flags) ray_flags[i] = 0;
         weights_sum[i] = 0.f; depth[i] = 0.f;
         image[(size_t)i * 3] = 0.f; image[(size_t)i * 3 + 1] = 0.f; image[(size_t)i * 3 + 2] = 0.f;
         if (weights_edit_sum) { weights_edit_sum[i] = 0.f; depth_edit[i] = 0.f; }
@@ -1052,6 +1081,11 @@ k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_
         ctl[kCtlStepCap] = (int)step_cap;
         ctl[kCtlInexact] = 0;
         ctl[13] = 0;
+        ctl[14] = 0;
+        ctl[kCtlSeqLen] = nstep_seq ? (int)nstep_len : 0;
+        ctl_set_ptr(ctl, kCtlSeqPtr, nstep_seq);
+        ctl_set_ptr(ctl, kCtlStepsPtr, ray_steps);
+        ctl_set_ptr(ctl, kCtlFlagsPtr, ray_flags);
         ctl_set_round(ctl, n_rays);
     }
 }
@@ -1060,13 +1094,14 @@ k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_
 // ---- host launchers of the device-driven rounds (declared in render_core.cuh) ----
 int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, uint32_t row_budget, uint32_t step_cap, int32_t* rays_alive, float* rays_t,
                         const float* nears,
-                        float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, cudaStream_t st) {
+                        float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, int32_t* ray_steps,
+                        uint8_t* ray_flags, const int32_t* nstep_seq, uint32_t nstep_len, cudaStream_t st) {
     LNRF_REQUIRE(ctl && (n_rays == 0 || (rays_alive && rays_t && nears && weights_sum && depth && image)), "render_begin: null pointer");
     const uint32_t blocks = n_rays ? (div_up(n_rays, 256u) < (uint32_t)kNumSMs * 8u ? div_up(n_rays, 256u) : (uint32_t)kNumSMs * 8u) : 1u;
     LNRF_REQUIRE(row_budget >= n_rays, "render_begin: the row budget (%u) must cover one sample per ray (%u)", row_budget, n_rays);
     LNRF_REQUIRE(step_cap >= 1 && step_cap <= 64, "render_begin: samples per ray per round must be in [1, 64], got %u", step_cap);
     k_render_begin<<<blocks, 256, 0, st>>>(ctl, n_rays, max_steps, row_budget, step_cap, rays_alive, rays_t, nears, weights_sum, depth, image, weights_edit_sum,
-                                           depth_edit);
+                                           depth_edit, ray_steps, ray_flags, nstep_seq, nstep_len);
     LNRF_LAUNCH_CHECK("render_begin");
     return LNRF_OK;
 }

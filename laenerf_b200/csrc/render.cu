@@ -23,7 +23,8 @@ size_t lnrf_render_scratch_bytes(uint32_t n_rays) { return lnrf_compact_alive_sc
 int lnrf_render_begin(const lnrf_render_desc* d, lnrf_stream_t stream) {
     LNRF_REQUIRE(d && d->ctl, "render_begin: null descriptor / control block");
     return render_begin_launch(d->ctl, d->n_rays, d->max_steps, sample_row_budget(d), d->sample_rows > d->n_rays + 128u && d->samples_per_round ? d->samples_per_round : 8u, d->rays_alive[0], d->rays_t, d->nears, d->weights_sum, d->depth, d->image,
-                               d->weights_edit_sum, d->depth_edit, reinterpret_cast<cudaStream_t>(stream));
+                               d->weights_edit_sum, d->depth_edit, d->ray_steps, d->ray_flags, d->nstep_seq, d->nstep_len,
+                               reinterpret_cast<cudaStream_t>(stream));
 }
 
 int lnrf_render_rounds(const lnrf_render_desc* d, uint32_t first_round, uint32_t n_rounds, lnrf_stream_t stream) {

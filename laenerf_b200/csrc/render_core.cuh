@@ -5,11 +5,12 @@
 
 namespace lnrf {
 
-constexpr int kRenderCtlInts = 16;
+constexpr int kRenderCtlInts = 32;
 
 int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, uint32_t row_budget, uint32_t step_cap, int32_t* rays_alive, float* rays_t,
                         const float* nears,
-                        float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, cudaStream_t st);
+                        float* weights_sum, float* depth, float* image, float* weights_edit_sum, float* depth_edit, int32_t* ray_steps,
+                        uint8_t* ray_flags, const int32_t* nstep_seq, uint32_t nstep_len, cudaStream_t st);
 // one march over the rays of the current round (grids sized by the ray capacity; geometry read from ctl)
 int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
                            const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,

@@ -362,25 +362,91 @@ class NeRFNetwork(nn.Module):
     # ---- row f-3: the inference loop of run_cuda / run_cuda_distill driven from the device -----------------------------
     def _render_rounds_device(self, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
                               rounds_per_call: int = 8):
-        """The device loop on self.render_schedule; "auto" = fast where provably bit-identical to the reference schedule."""
+        """The device loop on self.render_schedule.  "auto" renders on the fast schedule and makes the result the reference
+        schedule's, bit for bit:
+
+          * no ray emitted an inexact delta after round 0 (csrc/raymarch.cu, kCtlInexact): the round boundaries leave no trace -- done;
+          * some rays did (cameras inside the volume): only THEIR results depend on where the boundaries fall.  Every other ray dies at
+            the same sample on any schedule, and the fast pass recorded that sample index for all rays (`ray_steps`), so the reference's
+            n_step sequence -- a function of how many rays are alive after each round -- follows from the histogram of those indices
+            (`_reference_sequence`).  The flagged rays alone are rendered again with that sequence prescribed (`nstep_seq`), i.e. exactly
+            as the reference's full-frame loop would render them, and take their places in the outputs.  Their own death indices may
+            move in that pass; the sequence is recomputed and the pass repeated until it reproduces itself (a fixed point IS the
+            reference's run: by induction over the rounds both make the same n_step decisions) -- in practice at once;
+          * the max_steps cap cut rays off, or no fixed point after three passes: the frame is rendered on the reference schedule."""
         sched = self.render_schedule
+        args = (rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh, rounds_per_call)
         if sched != "auto":
-            return self._render_rounds_on(sched, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
-                                          rounds_per_call)
+            return self._render_rounds_on(sched, *args)
         if self._auto_fast_ok and not perturb:
-            t = self._render_rounds_on("fast", rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
-                                       rounds_per_call)
+            t = self._render_rounds_on("fast", *args, track=True)
             if not t["schedule_dependent"]:
                 t["schedule"] = "fast (proven bit-identical to the reference schedule for this frame)"
                 return t
-            self._auto_fast_ok = False  # this scene produces inexact deltas (cameras inside the volume): do not try again
-        t = self._render_rounds_on("reference", rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
-                                   rounds_per_call)
+            fixed = self._fix_schedule_dependent_rays(t, *args) if (t["inexact_rays"] > 0 and not t["cap_cut"]) else None
+            if fixed is not None:
+                return fixed
+            self._auto_fast_ok = False  # the cap cut rays off / no fixed point: this scene goes to the reference schedule directly
+        t = self._render_rounds_on("reference", *args)
         t["schedule"] = "reference"
         return t
 
+    @staticmethod
+    def _reference_sequence(hist, n_rays, max_steps):
+        """n_step of every round of the reference loop (renderer.py:353-379) from the histogram of the rays' death sample indices:
+        a ray that completes k samples in total is alive at the start of a round iff the rounds before it handed out <= k samples."""
+        alive_from = np.concatenate([np.cumsum(hist[::-1])[::-1], [0]])  # alive_from[b] = rays with k >= b
+        seq, b = [], 0
+        while b < max_steps:
+            alive = int(alive_from[min(b, len(alive_from) - 1)])
+            if alive <= 0:
+                break
+            n = max(min(n_rays // alive, 8), 1)
+            seq.append(n)
+            b += n
+        return seq
+
+    def _fix_schedule_dependent_rays(self, t, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
+                                     rounds_per_call):
+        n_rays = rays_o.shape[0]
+        dev = rays_o.device
+        cap = int(max_steps) + 72
+        idx = t["ray_flags"].nonzero().flatten()
+        if idx.numel() == 0:
+            return None
+        steps = t["ray_steps"].long().clamp_(max=cap)
+        hist = torch.bincount(steps, minlength=cap + 1).cpu().numpy().astype(np.int64)
+        sub_steps = steps[idx]
+        sub = [x[idx].contiguous() for x in (rays_o, rays_d, nears, fars)]
+        for _ in range(3):
+            seq = self._reference_sequence(hist, n_rays, max_steps)
+            if not seq:
+                return None
+            seq_dev = torch.tensor(seq, dtype=torch.int32, device=dev)
+            t2 = self._render_rounds_on("prescribed", *sub, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh, rounds_per_call,
+                                        track=True, seq=seq_dev)
+            new_steps = t2["ray_steps"].long().clamp_(max=cap)
+            hist = hist - torch.bincount(sub_steps, minlength=cap + 1).cpu().numpy() + torch.bincount(new_steps, minlength=cap + 1).cpu().numpy()
+            sub_steps = new_steps
+            seq2 = self._reference_sequence(hist, n_rays, max_steps)
+            # the flagged rays only see the rounds up to the death of the last of them
+            last, b, need = int(new_steps.max().item()), 0, 0
+            for need, n in enumerate(seq2, 1):
+                b += n
+                if b > last:
+                    break
+            if seq2[:need] == seq[:need]:
+                for k in ("weights_sum", "depth", "image", "wes", "de"):
+                    if t.get(k) is not None:
+                        t[k][idx] = t2[k]
+                t["schedule"] = (f"fast + {idx.numel()} schedule-dependent rays re-rendered on the reference's n_step sequence "
+                                 f"({len(seq)} rounds, from the histogram of the rays' death samples): bit-identical to the reference schedule")
+                t["rounds_fixup"], t["slots"] = t2["rounds"], t["slots"] + t2["slots"]
+                return t
+        return None
+
     def _render_rounds_on(self, schedule, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
-                          rounds_per_call: int = 8):
+                          rounds_per_call: int = 8, track: bool = False, seq=None):
         """renderer.py:335-387 (and :425-470 with an edit grid) without a host synchronisation per round: the kernels read
         n_alive / n_step from a control block in device memory that the compaction kernel updates (csrc/render.cu); the
         host queues `rounds_per_call` rounds at a time and only then looks at the `finished` flag.  Same kernels, same
@@ -398,11 +464,15 @@ class NeRFNetwork(nn.Module):
         # GPUs -- up to 4 M rows: every round costs ~100 us of latency whatever its size (march of the longest gap + four dependent
         # launches), so a small ray set should finish in as few rounds as possible (up to 64 samples per ray per round)
         rows = (max(8 * n_rays, min(64 * n_rays, 1 << 22)) if fast else n_rays) + 128
+        if schedule == "prescribed":  # n_step per round from `seq` (at most 8): a subset of a frame on the full frame's schedule
+            rows = 8 * n_rays + 128
         distill = edit_bitfield is not None
         enc, sn, cn = self.encoder, self.sigma_net, self.color_net
         emb, ws, wc = half_of(enc, enc.embeddings), half_of(sn, sn.weights), half_of(cn, cn.weights)
         t = dict(
-            ctl=torch.zeros(16, dtype=torch.int32, device=dev),
+            ctl=torch.zeros(32, dtype=torch.int32, device=dev),
+            ray_steps=torch.empty(n_rays, dtype=torch.int32, device=dev) if track else None,
+            ray_flags=torch.empty(n_rays, dtype=torch.uint8, device=dev) if track else None,
             alive0=torch.empty(n_rays, dtype=torch.int32, device=dev), alive1=torch.empty(n_rays, dtype=torch.int32, device=dev),
             rays_t=torch.empty(n_rays, **f32), xyzs=torch.empty(rows, 3, **f32), dirs=torch.empty(rows, 3, **f32),
             deltas=torch.empty(rows, 2, **f32), enc=torch.empty(rows, 32, dtype=torch.half, device=dev),
@@ -437,11 +507,15 @@ class NeRFNetwork(nn.Module):
         d.weights_sum, d.depth, d.image = t["weights_sum"].data_ptr(), t["depth"].data_ptr(), t["image"].data_ptr()
         d.weights_edit_sum, d.depth_edit = N.ptr(t["wes"]), N.ptr(t["de"])
         d.scratch, d.scratch_bytes = t["scratch"].data_ptr(), nbytes
-        d.sample_rows = rows if fast else 0
-        d.samples_per_round = int(self.render_samples_per_round) if fast else 0
+        d.sample_rows = rows if (fast or seq is not None) else 0
+        d.samples_per_round = int(self.render_samples_per_round) if fast else (8 if seq is not None else 0)
+        d.ray_steps, d.ray_flags = N.ptr(t["ray_steps"]), N.ptr(t["ray_flags"])
+        d.nstep_seq, d.nstep_len = (seq.data_ptr(), int(seq.numel())) if seq is not None else (None, 0)
         st = N.stream()
         N.check(lib.lnrf_render_begin(C.byref(d), st))
         launched = 0
+        if seq is not None:
+            rounds_per_call = 32  # a prescribed schedule is run for a few thousand rays: tiny rounds, fewer host look-ups
         max_rounds = int(max_steps)  # n_step >= 1: the reference loop cannot run more rounds than this
         while launched < max_rounds:
             k = min(rounds_per_call, max_rounds - launched)
@@ -453,6 +527,7 @@ class NeRFNetwork(nn.Module):
         t["rounds"], t["steps"], t["slots"] = ctl[7], ctl[2], ctl[9]
         t["schedule_dependent"] = bool(ctl[12])
         t["inexact_rays"] = int(ctl[13])
+        t["cap_cut"] = bool(ctl[14])
         t["schedule"] = schedule
         return t
 

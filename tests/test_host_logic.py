@@ -129,3 +129,31 @@ def test_reference_callers_construct_on_the_dropin_packages():
     assert [tuple(p.shape) for p in m.parameters()] == [(6328848, 2), (7168,), (11264,)]
     # the flavour's modules do not leak into (or replace anything in) the process-wide module table
     assert before == {k: sys.modules.get(k) for k in before}
+
+
+def test_reference_round_sequence_from_death_histogram():
+    """NeRFNetwork._reference_sequence reconstructs the n_step of every round of the reference's inference loop
+    (renderer.py:353-379: n_step = clamp(N // n_alive, 1, 8), a ray dies in the round that offers it more samples than it has left)
+    from the histogram of the rays' death sample indices -- checked against a literal emulation of that loop."""
+    import numpy as np
+    from laenerf_b200.nerf import NeRFNetwork
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        N = int(rng.integers(50, 5000))
+        max_steps = int(rng.choice([64, 256, 1024]))
+        k = rng.integers(0, 300, size=N)
+        k[rng.random(N) < 0.6] = 0
+        hist = np.bincount(np.minimum(k, max_steps + 72), minlength=max_steps + 73)
+        seq = NeRFNetwork._reference_sequence(hist, N, max_steps)
+        alive, done, step, want = np.ones(N, bool), np.zeros(N, int), 0, []
+        while step < max_steps:
+            na = int(alive.sum())
+            if na <= 0:
+                break
+            n = max(min(N // na, 8), 1)
+            want.append(n)
+            take = np.where(alive, np.minimum(n, k - done), 0)
+            alive &= ~(alive & (take < n))
+            done += take
+            step += n
+        assert seq == want, (trial, seq[:12], want[:12])
