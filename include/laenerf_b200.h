@@ -141,6 +141,16 @@ LNRF_API int lnrf_composite_loss_train_backward(const float* grad_loss, const fl
                                                 const float* image, const float* image_raw, uint32_t M, uint32_t N,
                                                 float T_thresh, float* grad_sigmas, float* grad_rgbs,
                                                 lnrf_stream_t stream);
+/* Both of the above in ONE launch: dL_total/dloss is known before the forward runs (the AMP loss scale, a device
+ * scalar), so the warp that composited a ray writes the ray's sample gradients right away, its samples still in L1.
+ * Outputs of the forward AND of the backward, bit-identical to the two calls made one after the other. */
+LNRF_API int lnrf_composite_loss_train_forward_backward(const float* grad_loss, const float* sigmas, const float* rgbs,
+                                                        const float* deltas, const int32_t* rays, const float* gt_rgb,
+                                                        const float* bg_rgb, float bg_scalar, const float* nears,
+                                                        const float* fars, uint32_t M, uint32_t N, float T_thresh,
+                                                        float* weights_sum, float* depth, float* image, float* image_raw,
+                                                        float* loss, float* grad_sigmas, float* grad_rgbs, void* scratch,
+                                                        size_t scratch_bytes, lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * inference / distillation march + compositing -- replaces raymarching.cu:929-945, 1145-1159
@@ -476,6 +486,14 @@ LNRF_API int lnrf_exchange_tail(void* grad_f16, uint64_t n, float* scale, int32_
                                 lnrf_stream_t stream);
 LNRF_API int lnrf_amp_update(float* scale, int32_t* growth_tracker, float* found_inf, float* step_count,
                              float growth_factor, float backoff_factor, int32_t growth_interval, lnrf_stream_t stream);
+/* lnrf_grad_nonfinite_check and lnrf_amp_update in ONE launch that runs AHEAD of lnrf_adam_step: the last block out freezes what
+ * this step's optimizer kernel must see into snapshot[0..2] = {found_inf, the scale the gradients carry, step_count before the
+ * increment} and then performs GradScaler.update().  Pass &snapshot[1], &snapshot[0], &snapshot[2] to lnrf_adam_step as
+ * grad_scale, found_inf, step_count.  snapshot: 8 floats on the device, zero before first use ([4] is a ticket the kernel re-arms). */
+LNRF_API int lnrf_grad_nonfinite_check_amp_update(const lnrf_opt_tensor* tensors_host, uint32_t count, float* grad_scale,
+                                                  int32_t* growth_tracker, float* found_inf, float* step_count,
+                                                  float growth_factor, float backoff_factor, int32_t growth_interval,
+                                                  float* snapshot, lnrf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "lnrf_composite_loss_scratch_bytes": (sz, [u32]),
     "lnrf_composite_loss_train_forward": (i32, [vp, vp, vp, vp, vp, vp, f32, vp, vp, u32, u32, f32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "lnrf_composite_loss_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, u32, u32, f32, vp, vp, vp]),
+    "lnrf_composite_loss_train_forward_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, u32, u32, f32, vp, vp, vp, vp, vp, vp, vp,
+                                                         vp, sz, vp]),
     "lnrf_march_rays": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
     "lnrf_march_rays_distill": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
     "lnrf_composite_rays": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -87,6 +89,7 @@ SIGNATURES = {
     "lnrf_adam_amp_step": (i32, [vp, u32, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp]),
     "lnrf_exchange_tail": (i32, [vp, u64, vp, vp, vp, vp, f32, f32, i32, vp]),
     "lnrf_amp_update": (i32, [vp, vp, vp, vp, f32, f32, i32, vp]),
+    "lnrf_grad_nonfinite_check_amp_update": (i32, [vp, u32, vp, vp, vp, vp, f32, f32, i32, vp, vp]),
 }
 
 class RenderDesc(C.Structure):

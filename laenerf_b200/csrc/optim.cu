@@ -48,8 +48,8 @@ __device__ __forceinline__ int find_tensor(const OptBatch& b, uint32_t block) {
     return k;
 }
 
-// found_inf[0] = 1.0f when any gradient element is inf/nan (never cleared here: torch's GradScaler convention)
-__global__ void __launch_bounds__(kOptBlock) k_grad_nonfinite(const OptBatch b, float* __restrict__ found_inf) {
+// does this block's share of the gradients hold an inf / nan?  (per thread; combine with __syncthreads_or)
+__device__ __forceinline__ bool grad_block_nonfinite(const OptBatch& b) {
     const int k = find_tensor(b, blockIdx.x);
     const OptTensor& t = b.t[k];
     const uint32_t nblocks = (k + 1 < (int)b.count ? b.t[k + 1].first_block : gridDim.x) - t.first_block;
@@ -88,6 +88,12 @@ __global__ void __launch_bounds__(kOptBlock) k_grad_nonfinite(const OptBatch b, 
             }
         }
     }
+    return bad;
+}
+
+// found_inf[0] = 1.0f when any gradient element is inf/nan (never cleared here: torch's GradScaler convention)
+__global__ void __launch_bounds__(kOptBlock) k_grad_nonfinite(const OptBatch b, float* __restrict__ found_inf) {
+    const bool bad = grad_block_nonfinite(b);
     if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.0f;
 }
 
@@ -261,8 +267,8 @@ struct AmpUpdateArgs {
     float growth_factor, backoff_factor;
     int growth_interval;
 };
-__device__ __forceinline__ void amp_update_body(const AmpUpdateArgs& u) {
-    if (*u.found_inf != 0.0f) {
+__device__ __forceinline__ void amp_update_body(const AmpUpdateArgs& u, const float* found_now = nullptr) {
+    if ((found_now ? *found_now : *u.found_inf) != 0.0f) {
         if (u.scale) *u.scale = *u.scale * u.backoff_factor;
         if (u.growth_tracker) *u.growth_tracker = 0;
     } else {
@@ -279,6 +285,30 @@ __device__ __forceinline__ void amp_update_body(const AmpUpdateArgs& u) {
         *u.step_count += 1.0f;
     }
     *u.found_inf = 0.0f;
+}
+
+// Non-finite check AND GradScaler.update() in one launch, ahead of Adam: the last block out (ticket) freezes what the optimizer
+// kernel of THIS step must see -- snap[0] = found_inf, snap[1] = the scale the gradients carry, snap[2] = the step count before the
+// increment -- and then updates scale / growth tracker / step count / found_inf for the next step.  lnrf_adam_step reads the
+// snapshot instead of the live words, so the separate one-thread k_amp_update launch behind it disappears.  snap[4] is the ticket
+// (zero before first use, re-armed here).
+__global__ void __launch_bounds__(kOptBlock)
+k_grad_nonfinite_amp(const OptBatch b, const AmpUpdateArgs u, float* __restrict__ snap) {
+    const bool bad = grad_block_nonfinite(b);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *u.found_inf = 1.0f;
+    if (threadIdx.x == 0) {
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(snap + 4);
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            const float found = __ldcg(u.found_inf);
+            snap[0] = found;
+            snap[1] = u.scale ? *u.scale : 1.0f;
+            snap[2] = *u.step_count;
+            amp_update_body(u, &found);
+            *ticket = 0u;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kOptBlock)
@@ -691,6 +721,19 @@ int lnrf_adam_amp_step(const lnrf_opt_tensor* tensors_host, uint32_t count, doub
     AmpUpdateArgs u{grad_scale, growth_tracker, found_inf, step_count, growth_factor, backoff_factor, growth_interval};
     k_adam_amp_fused<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, lr_scale, u, sync_words);
     LNRF_LAUNCH_CHECK("adam_amp_step");
+    return LNRF_OK;
+}
+
+int lnrf_grad_nonfinite_check_amp_update(const lnrf_opt_tensor* tensors_host, uint32_t count, float* grad_scale, int32_t* growth_tracker,
+                                         float* found_inf, float* step_count, float growth_factor, float backoff_factor,
+                                         int32_t growth_interval, float* snapshot, lnrf_stream_t stream) {
+    LNRF_REQUIRE(found_inf && step_count && snapshot, "grad_nonfinite_check_amp_update: null found_inf / step_count / snapshot");
+    OptBatch b;
+    uint32_t grid;
+    if (int e = make_batch("grad_nonfinite_check_amp_update", tensors_host, count, &b, &grid, false)) return e;
+    AmpUpdateArgs u{grad_scale, growth_tracker, found_inf, step_count, growth_factor, backoff_factor, growth_interval};
+    k_grad_nonfinite_amp<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, u, snapshot);
+    LNRF_LAUNCH_CHECK("grad_nonfinite_check_amp_update");
     return LNRF_OK;
 }
 

@@ -502,6 +502,8 @@ struct RaySums {
     float r, g, b, ws, d;
 };
 
+// KEEP: plain loads (the fused forward+backward kernel reads the samples again right away) instead of streaming ones
+template <bool KEEP = false>
 __device__ __forceinline__ RaySums composite_ray_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                                                      const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps,
                                                      uint32_t M, float T_thresh, int lane) {
@@ -516,10 +518,14 @@ __device__ __forceinline__ RaySums composite_ray_fwd(const float* __restrict__ s
             const bool act = k < num_steps;
             float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dd = 0.f;
             if (act) {
-                const float2 dl = __ldcs(pl + k);
-                alpha = 1.0f - __expf(-__ldcs(ps + k) * dl.x);
+                const float2 dl = KEEP ? __ldg(pl + k) : __ldcs(pl + k);
+                alpha = 1.0f - __expf(-(KEEP ? __ldg(ps + k) : __ldcs(ps + k)) * dl.x);
                 dd = dl.y;
-                cr = __ldcs(pc + (size_t)k * 3); cg = __ldcs(pc + (size_t)k * 3 + 1); cb = __ldcs(pc + (size_t)k * 3 + 2);
+                if (KEEP) {
+                    cr = __ldg(pc + (size_t)k * 3); cg = __ldg(pc + (size_t)k * 3 + 1); cb = __ldg(pc + (size_t)k * 3 + 2);
+                } else {
+                    cr = __ldcs(pc + (size_t)k * 3); cg = __ldcs(pc + (size_t)k * 3 + 1); cb = __ldcs(pc + (size_t)k * 3 + 2);
+                }
             }
             float P = 1.0f - alpha;  // inclusive product scan of (1 - alpha)
             float S = dd;            // inclusive sum scan of the depth deltas
@@ -585,43 +591,46 @@ struct LossArgs {
     const float* grad_loss;  // backward only: dL_total/dloss on the device (the AMP loss scale)
 };
 
-__global__ void __launch_bounds__(256)
-k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
-                     const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
-                     float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+// per-ray part of the loss forward: blended image, depth, squared error (returned in every lane; lane 0 stores)
+template <bool KEEP>
+__device__ __forceinline__ float composite_loss_ray_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                        const float* __restrict__ deltas, uint32_t index, uint32_t offset,
+                                                        uint32_t num_steps, uint32_t M, float T_thresh, const LossArgs& la,
+                                                        float* __restrict__ weights_sum, float* __restrict__ depth,
+                                                        float* __restrict__ image, int lane, RaySums& a, float v[3]) {
+    a = composite_ray_fwd<KEEP>(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane);
+    const size_t i3 = (size_t)index * 3;
+    const float raw[3] = {a.r, a.g, a.b};
+    const float omw = __fadd_rn(1.0f, -a.ws);
+    float e = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float bgc = la.bg ? __ldg(la.bg + i3 + c) : la.bg_scalar;
+        v[c] = __fadd_rn(raw[c], __fmul_rn(omw, bgc));  // image + (1 - weights_sum) * bg_color
+        const float df = __fadd_rn(v[c], -__ldg(la.gt + i3 + c));
+        e = __fadd_rn(e, __fmul_rn(df, df));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            la.image_raw[i3 + c] = raw[c];
+            image[i3 + c] = v[c];
+        }
+        weights_sum[index] = a.ws;
+        float dpt = a.d;
+        if (la.nears) {  // clamp(depth - nears, min=0) / (fars - nears)
+            const float nr = __ldg(la.nears + index);
+            dpt = __fdiv_rn(fmaxf(__fadd_rn(dpt, -nr), 0.0f), __fadd_rn(__ldg(la.fars + index), -nr));
+        }
+        depth[index] = dpt;
+    }
+    return e;
+}
+
+// deterministic loss reduction: per-block partials, then the last block out adds them in index order
+__device__ __forceinline__ void composite_loss_reduce(float err, const LossArgs& la, uint32_t N, int lane, int warp) {
     __shared__ float s_err[8];
     __shared__ bool s_last;
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float err = 0.f;
-    if (n < N) {
-        const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
-                       num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
-        const RaySums a = composite_ray_fwd(sigmas, rgbs, deltas, offset, num_steps, M, T_thresh, lane);
-        if (lane == 0) {
-            const size_t i3 = (size_t)index * 3;
-            const float raw[3] = {a.r, a.g, a.b};
-            const float omw = __fadd_rn(1.0f, -a.ws);
-            float e = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const float bgc = la.bg ? __ldg(la.bg + i3 + c) : la.bg_scalar;
-                const float v = __fadd_rn(raw[c], __fmul_rn(omw, bgc));  // image + (1 - weights_sum) * bg_color
-                la.image_raw[i3 + c] = raw[c];
-                image[i3 + c] = v;
-                const float df = __fadd_rn(v, -__ldg(la.gt + i3 + c));
-                e = __fadd_rn(e, __fmul_rn(df, df));
-            }
-            err = e;
-            weights_sum[index] = a.ws;
-            float dpt = a.d;
-            if (la.nears) {  // clamp(depth - nears, min=0) / (fars - nears)
-                const float nr = __ldg(la.nears + index);
-                dpt = __fdiv_rn(fmaxf(__fadd_rn(dpt, -nr), 0.0f), __fadd_rn(__ldg(la.fars + index), -nr));
-            }
-            depth[index] = dpt;
-        }
-    }
     if (lane == 0) s_err[warp] = err;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -651,60 +660,52 @@ k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                     const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
+                     float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float err = 0.f;
+    if (n < N) {
+        const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                       num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+        RaySums a;
+        float v[3];
+        err = composite_loss_ray_fwd<false>(sigmas, rgbs, deltas, index, offset, num_steps, M, T_thresh, la, weights_sum, depth, image, lane, a, v);
+    }
+    composite_loss_reduce(err, la, N, lane, warp);
+}
+
 __device__ __forceinline__ void warp_zero_range(float* __restrict__ p, size_t lo, size_t hi, int lane) {
     for (size_t i = lo + lane; i < hi; i += 32) p[i] = 0.f;
 }
 
-// raymarching.cu:601-682
-// LOSS (row f-5): dL/dimage and dL/dweights_sum are not read but formed here from the blended image, the targets and the
-// device-side scalar dL/dloss: g = dloss * 2 (image - gt) / (3 N), gws = -sum_c g_c bg_c; `image` is then the blended image and
-// la.image_raw the composite the C_final - C_acc term needs.
-template <bool ZERO_FILL, bool LOSS>
-__global__ void __launch_bounds__(256)
-k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
-                      const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
-                      const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
-                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs,
-                      const LossArgs la) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
-                   num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
-    const bool fits = offset + num_steps <= M;
-    if (ZERO_FILL) {
-        // canonical layout: rows no fitting ray covers are [first dropped ray's offset, M), or [end of last ray, M)
-        size_t z0 = M;
-        if (num_steps != 0 && !fits && offset <= M) z0 = offset;
-        else if (n == N - 1 && fits) z0 = (size_t)offset + num_steps;
-        if (z0 < M) {
-            warp_zero_range(grad_sigmas, z0, M, lane);
-            warp_zero_range(grad_rgbs, z0 * 3, (size_t)M * 3, lane);
-        }
-        if (n == 0 && offset > 0) {
-            const size_t z1 = offset < M ? offset : M;
-            warp_zero_range(grad_sigmas, 0, z1, lane);
-            warp_zero_range(grad_rgbs, 0, z1 * 3, lane);
-        }
+// the gradient rows no fitting ray covers (canonical layout: [first dropped ray's offset, M), or [end of last ray, M), and rows below
+// the first ray's offset): zero-filled by the warps of the rays next to them
+__device__ __forceinline__ void composite_zero_uncovered(uint32_t n, uint32_t N, uint32_t offset, uint32_t num_steps, bool fits, uint32_t M,
+                                                         float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, int lane) {
+    size_t z0 = M;
+    if (num_steps != 0 && !fits && offset <= M) z0 = offset;
+    else if (n == N - 1 && fits) z0 = (size_t)offset + num_steps;
+    if (z0 < M) {
+        warp_zero_range(grad_sigmas, z0, M, lane);
+        warp_zero_range(grad_rgbs, z0 * 3, (size_t)M * 3, lane);
     }
-    if (num_steps == 0 || !fits) return;
+    if (n == 0 && offset > 0) {
+        const size_t z1 = offset < M ? offset : M;
+        warp_zero_range(grad_sigmas, 0, z1, lane);
+        warp_zero_range(grad_rgbs, 0, z1 * 3, lane);
+    }
+}
 
-    float gws, gr, gg, gb, r_final, g_final, b_final;
-    const size_t i3 = (size_t)index * 3;
-    if (LOSS) {
-        const float gsc = __ldg(la.grad_loss) * (2.0f / (3.0f * (float)N));
-        gr = gsc * (image[i3] - __ldg(la.gt + i3));
-        gg = gsc * (image[i3 + 1] - __ldg(la.gt + i3 + 1));
-        gb = gsc * (image[i3 + 2] - __ldg(la.gt + i3 + 2));
-        gws = la.bg ? -(gr * __ldg(la.bg + i3) + gg * __ldg(la.bg + i3 + 1) + gb * __ldg(la.bg + i3 + 2))
-                    : -(gr + gg + gb) * la.bg_scalar;
-        r_final = la.image_raw[i3]; g_final = la.image_raw[i3 + 1]; b_final = la.image_raw[i3 + 2];
-    } else {
-        gws = grad_weights_sum[index];
-        gr = grad_image[i3]; gg = grad_image[i3 + 1]; gb = grad_image[i3 + 2];
-        r_final = image[i3]; g_final = image[i3 + 1]; b_final = image[i3 + 2];
-    }
-    const float ws_final = weights_sum[index];
+// raymarching.cu:601-682 for one ray (one warp): gradients of its samples from dL/dimage (gr, gg, gb), dL/dweights_sum (gws) and the
+// ray's forward results
+template <bool ZERO_FILL>
+__device__ __forceinline__ void composite_ray_bwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                  const float* __restrict__ deltas, uint32_t offset, uint32_t num_steps, float T_thresh,
+                                                  float gws, float gr, float gg, float gb, float r_final, float g_final, float b_final,
+                                                  float ws_final, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, int lane) {
     const float* ps = sigmas + offset;
     const float* pc = rgbs + (size_t)offset * 3;
     const float2* pl = reinterpret_cast<const float2*>(deltas) + offset;
@@ -762,6 +763,78 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
         warp_zero_range(gs, base, num_steps, lane);
         warp_zero_range(gc, (size_t)base * 3, (size_t)num_steps * 3, lane);
     }
+}
+
+// raymarching.cu:601-682
+// LOSS (row f-5): dL/dimage and dL/dweights_sum are not read but formed here from the blended image, the targets and the
+// device-side scalar dL/dloss: g = dloss * 2 (image - gt) / (3 N), gws = -sum_c g_c bg_c; `image` is then the blended image and
+// la.image_raw the composite the C_final - C_acc term needs.
+template <bool ZERO_FILL, bool LOSS>
+__global__ void __launch_bounds__(256)
+k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
+                      const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
+                      uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs,
+                      const LossArgs la) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                   num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+    const bool fits = offset + num_steps <= M;
+    if (ZERO_FILL) composite_zero_uncovered(n, N, offset, num_steps, fits, M, grad_sigmas, grad_rgbs, lane);
+    if (num_steps == 0 || !fits) return;
+
+    float gws, gr, gg, gb, r_final, g_final, b_final;
+    const size_t i3 = (size_t)index * 3;
+    if (LOSS) {
+        const float gsc = __ldg(la.grad_loss) * (2.0f / (3.0f * (float)N));
+        gr = gsc * (image[i3] - __ldg(la.gt + i3));
+        gg = gsc * (image[i3 + 1] - __ldg(la.gt + i3 + 1));
+        gb = gsc * (image[i3 + 2] - __ldg(la.gt + i3 + 2));
+        gws = la.bg ? -(gr * __ldg(la.bg + i3) + gg * __ldg(la.bg + i3 + 1) + gb * __ldg(la.bg + i3 + 2))
+                    : -(gr + gg + gb) * la.bg_scalar;
+        r_final = la.image_raw[i3]; g_final = la.image_raw[i3 + 1]; b_final = la.image_raw[i3 + 2];
+    } else {
+        gws = grad_weights_sum[index];
+        gr = grad_image[i3]; gg = grad_image[i3 + 1]; gb = grad_image[i3 + 2];
+        r_final = image[i3]; g_final = image[i3 + 1]; b_final = image[i3 + 2];
+    }
+    composite_ray_bwd<ZERO_FILL>(sigmas, rgbs, deltas, offset, num_steps, T_thresh, gws, gr, gg, gb, r_final, g_final, b_final,
+                                 weights_sum[index], grad_sigmas, grad_rgbs, lane);
+}
+
+// Forward AND backward of the tail in one launch: the loss's gradient with respect to itself is a device scalar known before the
+// forward runs (the AMP loss scale), so the warp that composited a ray turns straight around and writes the ray's sample gradients
+// while its samples are still in L1.  Same expressions as k_composite_loss_fwd followed by k_composite_train_bwd<true, true>: the
+// results are bit-identical to the two launches.
+__global__ void __launch_bounds__(256)
+k_composite_loss_fwd_bwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                         const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
+                         float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+                         float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float err = 0.f;
+    if (n < N) {
+        const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
+                       num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
+        RaySums a;
+        float v[3];
+        err = composite_loss_ray_fwd<true>(sigmas, rgbs, deltas, index, offset, num_steps, M, T_thresh, la, weights_sum, depth, image, lane, a, v);
+        const bool fits = offset + num_steps <= M;
+        composite_zero_uncovered(n, N, offset, num_steps, fits, M, grad_sigmas, grad_rgbs, lane);
+        if (num_steps != 0 && fits) {
+            const size_t i3 = (size_t)index * 3;
+            const float gsc = __ldg(la.grad_loss) * (2.0f / (3.0f * (float)N));
+            const float gr = gsc * (v[0] - __ldg(la.gt + i3)), gg = gsc * (v[1] - __ldg(la.gt + i3 + 1)), gb = gsc * (v[2] - __ldg(la.gt + i3 + 2));
+            const float gws = la.bg ? -(gr * __ldg(la.bg + i3) + gg * __ldg(la.bg + i3 + 1) + gb * __ldg(la.bg + i3 + 2))
+                                    : -(gr + gg + gb) * la.bg_scalar;
+            composite_ray_bwd<true>(sigmas, rgbs, deltas, offset, num_steps, T_thresh, gws, gr, gg, gb, a.r, a.g, a.b, a.ws, grad_sigmas,
+                                    grad_rgbs, lane);
+        }
+    }
+    composite_loss_reduce(err, la, N, lane, warp);
 }
 
 // =========================================================================================================
@@ -871,6 +944,7 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
         // Round 0 is exempt: it takes ONE sample per ray on every schedule (ctl_set_round), so the boundary after a ray's first sample
         // -- typically the one long skip from `near` to the first occupied cell, where t can more than double -- sits in the same
         // place whatever happens afterwards.
+        inexact = grp.ballot(inexact) != 0u;     // the lanes of a group hold different samples of the ray: any of them raises it
         if (ctl && inexact && ctl[kCtlRounds] > 0) {
             int* c = const_cast<int*>(ctl);
             c[kCtlInexact] = 1;                  // benign race: every writer stores the same value
@@ -1330,6 +1404,31 @@ int lnrf_composite_loss_train_forward(const float* sigmas, const float* rgbs, co
     la.loss = loss;
     k_composite_loss_fwd<<<div_up(N, 8u), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
     LNRF_LAUNCH_CHECK("composite_loss_train_forward");
+    return LNRF_OK;
+}
+
+int lnrf_composite_loss_train_forward_backward(const float* grad_loss, const float* sigmas, const float* rgbs, const float* deltas,
+                                               const int32_t* rays, const float* gt_rgb, const float* bg_rgb, float bg_scalar,
+                                               const float* nears, const float* fars, uint32_t M, uint32_t N, float T_thresh,
+                                               float* weights_sum, float* depth, float* image, float* image_raw, float* loss,
+                                               float* grad_sigmas, float* grad_rgbs, void* scratch, size_t scratch_bytes,
+                                               lnrf_stream_t stream) {
+    const char* who = "composite_loss_train_forward_backward";
+    LNRF_REQUIRE(N > 0, "%s: the mean over zero rays is undefined", who);
+    LNRF_REQUIRE(grad_loss && rays && gt_rgb && weights_sum && depth && image && image_raw && loss && scratch, "%s: null pointer", who);
+    LNRF_REQUIRE((nears == nullptr) == (fars == nullptr), "%s: nears and fars go together", who);
+    LNRF_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs), "%s: null sample buffer", who);
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "%s: deltas must be 8-byte aligned", who);
+    LNRF_REQUIRE(scratch_bytes >= lnrf_composite_loss_scratch_bytes(N), "%s: scratch too small", who);
+    LossArgs la{};
+    la.gt = gt_rgb; la.bg = bg_rgb; la.bg_scalar = bg_scalar; la.nears = nears; la.fars = fars; la.image_raw = image_raw;
+    la.ticket = reinterpret_cast<unsigned int*>(scratch);
+    la.partial = reinterpret_cast<float*>(scratch) + 4;
+    la.loss = loss;
+    la.grad_loss = grad_loss;
+    k_composite_loss_fwd_bwd<<<div_up(N, 8u), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image,
+                                                                   grad_sigmas, grad_rgbs);
+    LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }
 

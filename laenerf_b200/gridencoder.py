@@ -94,6 +94,8 @@ class _grid_encode(Function):
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, grad):
+        if before_backward is not None:  # GraphedTrainStep(lookahead="bwd"): fork the next batch's march beside this kernel
+            before_backward()
         inputs, embeddings, offsets, dy_dx, b_dev = ctx.saved_tensors
         B, D, C, L, S, H, gridtype, interpolation = ctx.dims
         grad = grad.contiguous().to(embeddings.dtype)
@@ -117,6 +119,7 @@ class _grid_encode(Function):
 
 
 grid_encode = _grid_encode.apply
+before_backward = None
 
 
 class GridEncoder(nn.Module):

@@ -46,6 +46,9 @@ def _recompute_ok(ns, nc) -> bool:
     return os.environ.get("LNRF_MLP_RECOMPUTE", "1") != "0" and bool(N.lib().lnrf_nerf_backward_recompute_supported(int(ns), int(nc)))
 
 
+before_network_backward = None  # experiment hook (GraphedTrainStep, LNRF_LOOKAHEAD_AT=nerf_bwd)
+
+
 class _fused_network(Function):
     """NeRFNetwork.forward after the hash-grid encoder (network_ff.py:57-79 + `density_scale * sigma`, renderer.py:299)
     as ONE kernel and its backward as one more (+ the weight-gradient reduction): row f-1 of SURVEY.md section 8.
@@ -95,6 +98,8 @@ class _fused_network(Function):
 
     @staticmethod
     def backward(ctx, grad_sigmas, grad_rgbs):
+        if before_network_backward is not None:
+            before_network_backward()
         ns, nc, density_scale = ctx.cfg
         lib = N.lib()
         if ctx.lean:
@@ -539,21 +544,31 @@ class NeRFNetwork(nn.Module):
     # (near/far + occupancy-grid march) and everything that depends on the parameters (network, compositing).  run_cuda runs
     # them back to back; GraphedTrainStep(lookahead=True) runs the first half of the NEXT batch beside the second half of
     # the current one.
-    def _march_train_from(self, rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps):
-        counter = self.step_counter[self.local_step % 16]
+    def _march_train_from(self, rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps, into=None):
+        """`into`: a dict of a previous march of the same shape (and its own `counter`) to overwrite -- the second sample buffer of a
+        software-pipelined loop; the step counter history is then the caller's business."""
+        if into is not None:
+            counter = into["counter"]
+        else:
+            counter = self.step_counter[self.local_step % 16]
+            self.local_step += 1
         counter.zero_()
-        self.local_step += 1
+        out = None if into is None else (into["xyzs"], into["dirs"], into["deltas"], into["rays"])
         xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
                                                                 self.grid_size, nears, fars, counter, self.mean_count, perturb,
-                                                                128, force_all_rays, dt_gamma, max_steps)
+                                                                128, force_all_rays, dt_gamma, max_steps, out)
+        if into is not None:
+            into["nears"].copy_(nears)
+            into["fars"].copy_(fars)
+            return into
         return dict(xyzs=xyzs, dirs=dirs, deltas=deltas, rays=rays, nears=nears, fars=fars, counter=counter)
 
-    def march_train(self, rays_o, rays_d, perturb=True, force_all_rays=False, dt_gamma=0, max_steps=1024, edit_grid=None):
+    def march_train(self, rays_o, rays_d, perturb=True, force_all_rays=False, dt_gamma=0, max_steps=1024, edit_grid=None, into=None):
         rays_o = rays_o.contiguous().view(-1, 3)
         rays_d = rays_d.contiguous().view(-1, 3)
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train, self.min_near)
         dens_grid = edit_grid if edit_grid is not None else self.density_bitfield
-        return self._march_train_from(rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps)
+        return self._march_train_from(rays_o, rays_d, nears, fars, dens_grid, perturb, force_all_rays, dt_gamma, max_steps, into)
 
     def shade_train(self, marched, bg_color=1, T_thresh=1e-4, prefix=None, scale_depth=True):
         xyzs, dirs, deltas, rays, nears, fars = (marched[k] for k in ("xyzs", "dirs", "deltas", "rays", "nears", "fars"))
@@ -566,7 +581,7 @@ class NeRFNetwork(nn.Module):
         return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum, "nears": nears,
                 "num_points": xyzs.shape[0]}
 
-    def shade_loss_train(self, marched, gt_rgb, bg_color=1, T_thresh=1e-4, prefix=None, scale_depth=True):
+    def shade_loss_train(self, marched, gt_rgb, bg_color=1, T_thresh=1e-4, prefix=None, scale_depth=True, grad_scale=None):
         """shade_train + the trainer's MSE (nerf/utils.py:592,633) with the whole tail behind the network -- compositing,
         background blend, depth normalisation, loss -- as one launch each way (row f-5, raymarching.composite_loss_train).
         Returns (loss, results) with the same `results` dict as shade_train."""
@@ -574,7 +589,7 @@ class NeRFNetwork(nn.Module):
         prefix = (rays.shape[0],) if prefix is None else prefix
         sigmas, rgbs = self.forward_scaled(xyzs, dirs, marched.get("counter"))
         loss, weights_sum, depth, image = raymarching.composite_loss_train(
-            sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears if scale_depth else None, fars if scale_depth else None, T_thresh)
+            sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears if scale_depth else None, fars if scale_depth else None, T_thresh, grad_scale)
         return loss, {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum, "nears": nears,
                       "num_points": xyzs.shape[0]}
 
@@ -712,6 +727,7 @@ class TrainStep:
         self.fp16 = fp16
         self.world_size = world_size
         self.fused_loss = bool(fused_loss)
+        self.fused_tail = os.environ.get("LNRF_FUSED_TAIL", "1") == "1"  # forward + backward of the compositing tail in one launch
         self.fused_optimizer = bool(fused_optimizer) and fp16 and model.fused and model._fused_ok
         if self.fused_optimizer:
             # row f-4: inf check + unscale + Adam + fp16 shadow rewrite + gradient clear in two launches (optim.py)
@@ -732,10 +748,10 @@ class TrainStep:
     def __call__(self, rays_o, rays_d, gt_rgb, bg_color=1, perturb=True):
         return self.train_on(self.march(rays_o, rays_d, perturb), gt_rgb, bg_color)
 
-    def march(self, rays_o, rays_d, perturb=True):
+    def march(self, rays_o, rays_d, perturb=True, into=None):
         """The parameter-independent half of the step (near/far + occupancy march); see NeRFNetwork.march_train."""
         self.model.train()
-        return self.model.march_train(rays_o, rays_d, perturb=perturb, force_all_rays=False, dt_gamma=0, max_steps=1024)
+        return self.model.march_train(rays_o, rays_d, perturb=perturb, force_all_rays=False, dt_gamma=0, max_steps=1024, into=into)
 
     def train_on(self, marched, gt_rgb, bg_color=1):
         loss, out = self.forward_backward(marched, gt_rgb, bg_color)
@@ -749,9 +765,10 @@ class TrainStep:
         if self.fused_loss and self.fused_optimizer:
             # row f-5: composite + blend + MSE in one launch; the AMP scale enters the backward as a device scalar, so
             # `scale(loss).backward()` costs no launch of its own
+            scale = self.optimizer._scale.view(())
             with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
-                loss, out = self.model.shade_loss_train(marched, gt_rgb, bg_color)
-            torch.autograd.backward(loss, grad_tensors=self.optimizer._scale.view(()))
+                loss, out = self.model.shade_loss_train(marched, gt_rgb, bg_color, grad_scale=scale if self.fused_tail else None)
+            torch.autograd.backward(loss, grad_tensors=scale)
             return loss, out
         with torch.autocast(device_type="cuda", dtype=torch.float16, enabled=self.fp16):
             out = self.model.shade_train(marched, bg_color)
@@ -777,12 +794,15 @@ class GraphedTrainStep:
     steady state is captured once per sample-buffer size and replayed.  Inputs are copied into static device buffers;
     `loss` / `out` are views of graph-owned memory that the next replay overwrites.
 
-    lookahead=True software-pipelines consecutive steps: near/far + the occupancy march depend only on the rays, never
-    on the parameters, and the march is latency-bound (one warp per ray, ~38 % of the warp slots of the GPU for 75 us),
-    so the graph marches the batch handed to call k on a second stream WHILE the gradient all-reduce and Adam of the batch
-    handed to call k-1 run on the first (forking earlier, beside the persistent MLP kernels that need a whole SM's shared
-    memory, measured slower than no overlap).  Every call still consumes one batch and performs one full optimizer step;
-    the returned loss is the previous call's batch (one-step delay, `flush()` trains the last one)."""
+    lookahead=True software-pipelines consecutive steps: near/far + the occupancy march depend only on the rays and the
+    occupancy bitfield, never on the parameters, and the march is latency-bound (a few warps per SM busy walking the grid),
+    while the hash-grid backward is bound by the L2 atomic units with its warps waiting.  So the graph marches the batch handed
+    to call k on a second stream BESIDE the hash-grid backward (and whatever follows) of the batch handed to call k-1.  Two
+    sample-buffer sets and two graphs alternate (train on set p, march into set 1-p): nothing is copied between steps.
+    Forking earlier -- beside the persistent MLP kernels, which need a whole SM's shared memory and registers -- or only
+    beside Adam measured slower than no overlap.  Every call still consumes one batch and performs one full optimizer step;
+    the returned loss is that of the previous call's batch (one-step delay, `flush()` trains the last one).  After an
+    occupancy update call `remarch()`: the batch in flight was marched through the old bitfield."""
 
     def __init__(self, step: TrainStep, n_rays: int, bg_color=1, perturb=True, lookahead: bool = False):
         self.step, self.model = step, step.model
@@ -794,12 +814,46 @@ class GraphedTrainStep:
         self.graph = None
         self.captured_mean_count = 0
         self.loss = self.out = None
-        self.cur = self.gt_cur = None  # lookahead: the marched batch (and its targets) the next replay trains on
+        self.sets = self.graphs = None  # lookahead: the two marched-batch buffer sets (with their targets) and the two graphs
+        self.phase = 0                  # lookahead: the set the next replay trains on
 
     def _load(self, rays_o, rays_d, gt_rgb):
         self.ro.copy_(rays_o, non_blocking=True)
         self.rd.copy_(rays_d, non_blocking=True)
         self.gt.copy_(gt_rgb, non_blocking=True)
+
+    def _capture_pipelined(self, p):
+        """Graph p: train on set p; beside its hash-grid backward, march the loaded batch into set 1-p."""
+        from . import gridencoder as _ge
+        cur, nxt = self.sets[p], self.sets[1 - p]
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            main = torch.cuda.current_stream()
+
+            def fork():  # runs on the autograd thread, right before the encoder backward is queued
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    self.step.march(self.ro, self.rd, self.perturb, into=nxt)
+                    nxt["gt"].copy_(self.gt)
+
+            at = os.environ.get("LNRF_LOOKAHEAD_AT", "enc_bwd")
+            import laenerf_b200.nerf as _me
+            if at == "start":
+                fork()
+            elif at == "nerf_bwd":
+                _me.before_network_backward = fork
+            elif at == "enc_bwd":
+                _ge.before_backward = fork
+            try:
+                loss, out = self.step.forward_backward(cur, cur["gt"], self.bg_color)
+            finally:
+                _ge.before_backward = None
+                _me.before_network_backward = None
+            if at == "adam":
+                fork()
+            self.step.reduce_and_step()
+            main.wait_stream(self._side)
+        return g, loss, out
 
     def capture(self, rays_o, rays_d, gt_rgb, warmup: int = 3):
         m = self.model
@@ -815,27 +869,23 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         m.local_step = 0  # the captured march always counts into step_counter[0]; rotated after each replay
         if self.lookahead:
-            # prime the pipeline: march the capture batch eagerly into persistent buffers
-            self.cur = {k: v.clone() for k, v in self.step.march(self.ro, self.rd, self.perturb).items()}
-            self.gt_cur = self.gt.clone()
+            # prime the pipeline: march the capture batch eagerly into set 0; set 1 is a same-shape twin
+            first = self.step.march(self.ro, self.rd, self.perturb)
             m.local_step = 0
-            self._side = torch.cuda.Stream()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            if self.lookahead:
-                main = torch.cuda.current_stream()
-                # train on the previous batch up to the end of the backward, then fork: the gradient exchange (NVLink) and Adam
-                # (HBM) of this batch on one branch, the march of the batch that was just loaded (latency-bound) on the other
-                self.loss, self.out = self.step.forward_backward(self.cur, self.gt_cur, self.bg_color)
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
-                    nxt = self.step.march(self.ro, self.rd, self.perturb)
-                self.step.reduce_and_step()
-                main.wait_stream(self._side)
-                for k, v in nxt.items():  # hand over: 7 MB of device-to-device copies after the join
-                    self.cur[k].copy_(v)
-                self.gt_cur.copy_(self.gt)
-            else:
+            self.sets = [{k: v.clone() for k, v in first.items()} for _ in range(2)]
+            for s_ in self.sets:
+                s_["gt"] = self.gt.clone()
+            self._side = torch.cuda.Stream(priority=int(os.environ.get("LNRF_LOOKAHEAD_PRIO", "0")))
+            self.graphs, self._results = [], []
+            for p in range(2):
+                g, loss, out = self._capture_pipelined(p)
+                self.graphs.append(g)
+                self._results.append((loss, out))
+            self.graph, self.phase = self.graphs[0], 0
+            # the captures ran no kernels: set 0 still holds the capture batch, marched eagerly above
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
                 self.loss, self.out = self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
         self.captured_mean_count = m.mean_count
         m.local_step = 0
@@ -852,17 +902,34 @@ class GraphedTrainStep:
             if self.lookahead:  # the capture batch is in flight; its loss arrives with the next call
                 return None, None
         self._load(rays_o, rays_d, gt_rgb)
-        self.graph.replay()
         m = self.model
         row = self._replays % 16
-        if row:  # keep the 16-entry counter history the occupancy update averages (renderer.py:643-647)
-            m.step_counter[row].copy_(m.step_counter[0], non_blocking=True)
+        if self.lookahead:
+            p = self.phase
+            self.graphs[p].replay()
+            self.loss, self.out = self._results[p]
+            self.phase = 1 - p
+            # keep the 16-entry counter history the occupancy update averages (renderer.py:643-647)
+            m.step_counter[row].copy_(self.sets[1 - p]["counter"], non_blocking=True)
+        else:
+            self.graph.replay()
+            if row:
+                m.step_counter[row].copy_(m.step_counter[0], non_blocking=True)
         self._replays += 1
         m.local_step = min(16, self._replays)
         return self.loss, self.out
 
+    def remarch(self):
+        """lookahead, after an occupancy update: march the batch in flight again (eagerly) through the new bitfield, as the
+        un-pipelined loop would have."""
+        if self.lookahead and self.sets is not None:
+            keep = self.model.local_step
+            self.step.march(self.ro, self.rd, self.perturb, into=self.sets[self.phase])
+            self.model.local_step = keep
+
     def flush(self):
         """lookahead: train on the batch that is still in flight (eagerly); returns its (loss, out)."""
-        if not self.lookahead or self.cur is None:
+        if not self.lookahead or self.sets is None:
             return None, None
-        return self.step.train_on(self.cur, self.gt_cur, self.bg_color)
+        cur = self.sets[self.phase]
+        return self.step.train_on(cur, cur["gt"], self.bg_color)

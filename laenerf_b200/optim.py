@@ -98,6 +98,8 @@ class AmpAdam:
         # one launch for check + Adam + scale update (grid barrier inside) measured 11 us SLOWER than the three launches on one B200
         # (0.425 vs 0.414 ms/step: the co-resident grid is 3 blocks per SM and the gradient is read twice); kept as an option
         self.one_launch = os.environ.get("LNRF_ADAM_ONE_LAUNCH", "0") == "1"
+        self._snapshot = torch.zeros(8, dtype=torch.float32, device=dev)  # {found_inf, scale, step} of the running step + a ticket
+        self.early_amp_update = os.environ.get("LNRF_EARLY_AMP_UPDATE", "1") == "1"
         self._stale_params = False
         if model is not None:
             model._amp_adam = weakref.ref(self)
@@ -344,7 +346,17 @@ class AmpAdam:
                                            self.growth_interval, N.ptr(self._sync_words), st))
             del keep
             return
-        if self.fp16:
+        scale_p, found_p, count_p = N.ptr(self._scale), N.ptr(self.found_inf), N.ptr(self.step_count)
+        early_update = self.fp16 and self.early_amp_update
+        if early_update:
+            # non-finite check + GradScaler.update() in one launch AHEAD of Adam, which then reads the frozen {found_inf, scale, step}
+            # of this step from the snapshot (csrc/optim.cu k_grad_nonfinite_amp): one launch fewer on the step's critical path
+            N.check(lib.lnrf_grad_nonfinite_check_amp_update(C.cast(arr, C.c_void_p), n, scale_p, N.ptr(self._growth_tracker), found_p, count_p,
+                                                             self.growth_factor, self.backoff_factor, self.growth_interval,
+                                                             N.ptr(self._snapshot), st))
+            base = self._snapshot.data_ptr()
+            found_p, scale_p, count_p = base, base + 4, base + 8
+        elif self.fp16:
             N.check(lib.lnrf_grad_nonfinite_check(C.cast(arr, C.c_void_p), n, N.ptr(self.found_inf), st))
         # one launch per distinct learning rate (the style network trains its palette at 2 x lr, style_encoder.py:247-255)
         for mult in sorted({o.lr_mult for o in self.owners}):
@@ -355,9 +367,10 @@ class AmpAdam:
                 sub, _k = self._descriptors([self.owners[i] for i in idx], [self.state[i] for i in idx])
                 keep += _k
             N.check(lib.lnrf_adam_step(C.cast(sub, C.c_void_p), len(idx), self.lr * mult, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                       N.ptr(self._scale), N.ptr(self.found_inf), N.ptr(self.step_count), N.ptr(self.lr_scale), st))
-        N.check(lib.lnrf_amp_update(N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf), N.ptr(self.step_count),
-                                    self.growth_factor, self.backoff_factor, self.growth_interval, st))
+                                       scale_p, found_p, count_p, N.ptr(self.lr_scale), st))
+        if not early_update:
+            N.check(lib.lnrf_amp_update(N.ptr(self._scale), N.ptr(self._growth_tracker), N.ptr(self.found_inf), N.ptr(self.step_count),
+                                        self.growth_factor, self.backoff_factor, self.growth_interval, st))
         del keep
 
     # ---- sharded mode: where the fp32 parameters live ----------------------------------------------------------------

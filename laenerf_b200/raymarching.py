@@ -183,7 +183,9 @@ class _march_rays_train(Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
-                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, out=None):
+        """raymarching.py:176-240.  `out` (not in the reference): (xyzs, dirs, deltas, rays) to march into instead of new tensors --
+        a software-pipelined training loop alternates between two sample buffers (nerf.GraphedTrainStep)."""
         rays_o = _cuda(rays_o).contiguous().view(-1, 3)
         rays_d = _cuda(rays_d).contiguous().view(-1, 3)
         density_bitfield = _in(_cuda(density_bitfield), torch.uint8, "density_bitfield")
@@ -195,10 +197,17 @@ class _march_rays_train(Function):
             if align > 0:
                 mean_count += align - mean_count % align
             M = mean_count
-        xyzs = torch.empty(M, 3, dtype=rays_o.dtype, device=dev)
-        dirs = torch.empty(M, 3, dtype=rays_o.dtype, device=dev)
-        deltas = torch.empty(M, 2, dtype=rays_o.dtype, device=dev)
-        rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
+        if out is not None:
+            xyzs, dirs, deltas, rays = out
+            for t_, shp, dt_, nm in ((xyzs, (M, 3), rays_o.dtype, "xyzs"), (dirs, (M, 3), rays_o.dtype, "dirs"),
+                                     (deltas, (M, 2), rays_o.dtype, "deltas"), (rays, (n, 3), torch.int32, "rays")):
+                if tuple(t_.shape) != shp or t_.dtype != dt_ or t_.device != dev or not t_.is_contiguous():
+                    raise RuntimeError(f"march_rays_train: out.{nm} must be a contiguous {dt_} tensor of shape {shp} on {dev}")
+        else:
+            xyzs = torch.empty(M, 3, dtype=rays_o.dtype, device=dev)
+            dirs = torch.empty(M, 3, dtype=rays_o.dtype, device=dev)
+            deltas = torch.empty(M, 2, dtype=rays_o.dtype, device=dev)
+            rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
         step_counter = _inout(step_counter, torch.int32, "step_counter")
@@ -260,11 +269,16 @@ class _composite_loss_train(Function):
     """Row f-5 (fused tier, no reference twin): composite_rays_train + background blend + depth normalisation + the trainer's
     MSE loss in ONE launch, and the whole backward of that tail in one more (include/laenerf_b200.h).  What it replaces:
     renderer.py:324-329 and nerf/utils.py:592,633 -- about a dozen elementwise / reduction launches each way.
-    Returns (loss, weights_sum, depth, image); only `loss` is differentiable (w.r.t. sigmas and rgbs)."""
+    Returns (loss, weights_sum, depth, image); only `loss` is differentiable (w.r.t. sigmas and rgbs).
+
+    grad_scale: the device scalar that will come back as dL/dloss (the AMP loss scale the caller hands to autograd.backward).  When
+    given, forward and backward are ONE launch (lnrf_composite_loss_train_forward_backward): the gradients are formed while the
+    ray's samples are still in L1 and the backward only hands them over.  If a different gradient arrives after all, the backward
+    falls back to its own launch -- the results are the same bits either way."""
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears, fars, T_thresh=1e-4):
+    def forward(ctx, sigmas, rgbs, deltas, rays, gt_rgb, bg_color, nears, fars, T_thresh=1e-4, grad_scale=None):
         sigmas, rgbs, deltas = _in(sigmas, torch.float32, "sigmas"), _in(rgbs, torch.float32, "rgbs"), _in(deltas, torch.float32, "deltas")
         rays = _in(rays, torch.int32, "rays")
         M, n = sigmas.shape[0], rays.shape[0]
@@ -293,10 +307,22 @@ class _composite_loss_train(Function):
         lib = N.lib()
         nbytes = lib.lnrf_composite_loss_scratch_bytes(n)
         scratch = _get_scratch("composite_loss", nbytes, dev)
-        N.check(lib.lnrf_composite_loss_train_forward(N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(rays), N.ptr(gt_rgb), N.ptr(bg),
-                                                      bg_scalar, N.ptr(nears), N.ptr(fars), M, n, float(T_thresh), N.ptr(weights_sum),
-                                                      N.ptr(depth), N.ptr(image), N.ptr(image_raw), N.ptr(loss), N.ptr(scratch),
-                                                      nbytes, N.stream()))
+        ctx.ready = None
+        fuse = (grad_scale is not None and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) and
+                grad_scale.is_cuda and grad_scale.dtype == torch.float32 and grad_scale.numel() == 1)
+        if fuse:
+            grad_sigmas = torch.empty_like(sigmas)  # the kernel writes every element (zero_fill contract)
+            grad_rgbs = torch.empty_like(rgbs)
+            N.check(lib.lnrf_composite_loss_train_forward_backward(
+                N.ptr(grad_scale), N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(rays), N.ptr(gt_rgb), N.ptr(bg), bg_scalar, N.ptr(nears),
+                N.ptr(fars), M, n, float(T_thresh), N.ptr(weights_sum), N.ptr(depth), N.ptr(image), N.ptr(image_raw), N.ptr(loss),
+                N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(scratch), nbytes, N.stream()))
+            ctx.ready = (grad_scale.data_ptr(), grad_scale._version, grad_sigmas, grad_rgbs)
+        else:
+            N.check(lib.lnrf_composite_loss_train_forward(N.ptr(sigmas), N.ptr(rgbs), N.ptr(deltas), N.ptr(rays), N.ptr(gt_rgb), N.ptr(bg),
+                                                          bg_scalar, N.ptr(nears), N.ptr(fars), M, n, float(T_thresh), N.ptr(weights_sum),
+                                                          N.ptr(depth), N.ptr(image), N.ptr(image_raw), N.ptr(loss), N.ptr(scratch),
+                                                          nbytes, N.stream()))
         ctx.save_for_backward(sigmas, rgbs, deltas, rays, gt_rgb, bg, weights_sum, image, image_raw)
         ctx.dims = [M, n, T_thresh, bg_scalar]
         ctx.mark_non_differentiable(weights_sum, depth, image)
@@ -307,7 +333,9 @@ class _composite_loss_train(Function):
     @custom_bwd(device_type="cuda")
     def backward(ctx, grad_loss, *_):
         if grad_loss is None:
-            return (None,) * 9
+            return (None,) * 10
+        if ctx.ready is not None and grad_loss.data_ptr() == ctx.ready[0] and grad_loss._version == ctx.ready[1]:
+            return ctx.ready[2], ctx.ready[3], None, None, None, None, None, None, None, None  # formed by the forward's launch
         sigmas, rgbs, deltas, rays, gt_rgb, bg, weights_sum, image, image_raw = ctx.saved_tensors
         M, n, T_thresh, bg_scalar = ctx.dims
         grad_loss = grad_loss.to(device=sigmas.device, dtype=torch.float32).contiguous()
@@ -317,7 +345,7 @@ class _composite_loss_train(Function):
                                                            N.ptr(gt_rgb), N.ptr(bg), bg_scalar, N.ptr(weights_sum), N.ptr(image),
                                                            N.ptr(image_raw), M, n, float(T_thresh), N.ptr(grad_sigmas),
                                                            N.ptr(grad_rgbs), N.stream()))
-        return grad_sigmas, grad_rgbs, None, None, None, None, None, None, None
+        return grad_sigmas, grad_rgbs, None, None, None, None, None, None, None, None
 
 
 composite_loss_train = _composite_loss_train.apply

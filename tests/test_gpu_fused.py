@@ -513,28 +513,50 @@ def test_update_extra_state_matches_torch_restatement(dev, bound):
 
 
 def test_lookahead_graph_trains_the_same_sequence(dev):
-    """GraphedTrainStep(lookahead=True) marches batch k beside the training of batch k-1: same batches, same updates, the
-    loss simply arrives one call later."""
+    """GraphedTrainStep(lookahead=True) marches batch k beside the backward of batch k-1 (two sample-buffer sets, two graphs): same
+    batches, same updates, the loss simply arrives one call later.  Half-way the occupancy bitfield changes (what update_extra_state
+    does every 16 steps): `remarch()` sends the batch in flight through the new bitfield, as the un-pipelined loop would have."""
     from laenerf_b200.nerf import GraphedTrainStep, TrainStep
     batches = []
-    for k in range(6):
+    for k in range(7):
         _, ro, rd, _ = scene_rays("lego", 4096, 50 + k)
         batches.append((torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev),
                         torch.rand(4096, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(k))))
-    runs = []
+    runs, counts = [], []
     for look in (False, True):
         m = _model(dev, True, 61)
         g = GraphedTrainStep(TrainStep(m), 4096, perturb=False, lookahead=look)
         g.capture(*batches[0], warmup=1)
+        losses, pts = [], []
+
+        def change_grid():
+            bf = m.density_bitfield
+            bf[: bf.numel() // 3] = 0
+            g.remarch()
+
         if look:
             # call k trains on batch k-1 (batch 0 was primed by capture); the loss is a view of graph-owned memory that the next
             # replay overwrites, so it is read before the next call
-            losses = [float(g(*b)[0]) for b in batches[1:]] + [float(g.flush()[0])]
+            for k, b in enumerate(batches[1:], 1):
+                losses.append(float(g(*b)[0]))
+                pts.append(int(g.sets[g.phase]["counter"][0]))   # samples of the batch just marched (batch k)
+                if k == 3:
+                    change_grid()   # batch 3 is in flight: marched through the old grid, must be re-marched
+                    pts[-1] = int(g.sets[g.phase]["counter"][0])
+            losses.append(float(g.flush()[0]))
         else:
-            losses = [float(g(*b)[0]) for b in batches]
+            for k, b in enumerate(batches):
+                if k == 3:
+                    change_grid()
+                losses.append(float(g(*b)[0]))
+                if k:
+                    pts.append(int(m.step_counter[0, 0]))
         runs.append(losses)
+        counts.append(pts)
     seq, pipe = runs
-    assert len(seq) == len(pipe) == 6 and all(np.isfinite(seq)) and all(np.isfinite(pipe))
+    assert counts[0] == counts[1], counts   # identical sample counts per batch, also across the grid change
+    assert counts[0][2] < counts[0][1] * 0.95   # ... which really removed samples
+    assert len(seq) == len(pipe) == 7 and all(np.isfinite(seq)) and all(np.isfinite(pipe))
     assert np.allclose(seq, pipe, rtol=2e-2), (seq, pipe)
 
 
@@ -588,6 +610,52 @@ def test_composite_loss_tail_matches_module_tier_and_torch_autograd(dev, bg_kind
     loss_c = raymarching.composite_loss_train(sb.detach(), rb.detach(), mr["deltas"], mr["rays"], gt, bg, None, None, 1e-4)[0]
     loss_d = raymarching.composite_loss_train(sb.detach(), rb.detach(), mr["deltas"], mr["rays"], gt, bg, None, None, 1e-4)[0]
     assert float(loss_c) == float(loss_d) == float(loss_b)
+
+
+@pytest.mark.parametrize("bg_kind,scale_depth,short_buffer", [("scalar", True, False), ("per_ray", False, False), ("scalar", True, True)])
+def test_composite_loss_forward_backward_in_one_launch_is_bit_identical(dev, bg_kind, scale_depth, short_buffer):
+    """lnrf_composite_loss_train_forward_backward (the AMP scale handed to the forward) against the two launches: loss, images,
+    depth and both sample gradients bit for bit -- also with a sample buffer too short for the last rays (dropped rays, zero-filled
+    gradient rows) -- and the fall-back when autograd delivers a different gradient than the forward was promised."""
+    from laenerf_b200 import _native as N
+    from laenerf_b200 import raymarching
+    from laenerf_b200.nerf import NeRFNetwork
+    sc = scene("lego")
+    m = NeRFNetwork(bound=sc.bound, min_near=sc.min_near).to(dev)
+    m.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+    m.train()
+    n = 1500
+    _, ro, rd, _ = scene_rays("lego", n, 23)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    torch.manual_seed(5)
+    mr = m.march_train(ro, rd, perturb=True)
+    if short_buffer:
+        m.mean_count = int(mr["counter"][0]) * 2 // 3
+        torch.manual_seed(5)
+        mr = m.march_train(ro, rd, perturb=True)
+        assert int(mr["counter"][0]) > mr["xyzs"].shape[0]   # rays were dropped
+    M = mr["xyzs"].shape[0]
+    g = torch.Generator(device=dev).manual_seed(3)
+    sig0 = torch.rand(M, device=dev, generator=g) * 40.0
+    rgb0 = torch.rand(M, 3, device=dev, generator=g)
+    gt = torch.rand(n, 3, device=dev, generator=g)
+    bg = torch.rand(n, 3, device=dev, generator=g) if bg_kind == "per_ray" else 1
+    scale = torch.tensor(1024.0, device=dev)
+    nf = (mr["nears"], mr["fars"]) if scale_depth else (None, None)
+    runs = []
+    for promised, delivered in ((None, scale), (scale, scale.view(())), (scale, torch.tensor(512.0, device=dev))):
+        s_, r_ = sig0.clone().requires_grad_(True), rgb0.clone().requires_grad_(True)
+        l0 = N.launch_count()
+        out = raymarching.composite_loss_train(s_, r_, mr["deltas"], mr["rays"], gt, bg, nf[0], nf[1], 1e-4, promised)
+        torch.autograd.backward(out[0], grad_tensors=delivered)
+        runs.append((out, s_.grad, r_.grad, N.launch_count() - l0))
+    (oa, gsa, gra, la), (ob, gsb, grb, lb), (oc, gsc, grc, lc) = runs
+    assert (la, lb, lc) == (2, 1, 2)   # two launches / one / one + the fall-back
+    for x, y in zip(oa, ob):
+        assert torch.equal(x, y) or (torch.equal(x.isnan(), y.isnan()) and torch.equal(x.nan_to_num(), y.nan_to_num()))
+    assert torch.equal(gsa, gsb) and torch.equal(gra, grb) and float(gsa.abs().max()) > 0
+    # the fall-back really used the delivered gradient: exactly half (a power of two) of the other runs'
+    assert torch.equal(gsc * 2, gsa) and torch.equal(grc * 2, gra)
 
 
 def test_train_step_fused_loss_equals_unfused_loss_path(dev):
