@@ -310,8 +310,10 @@ def train_config(ctx, name, headline):
     kern = timed.summary()
 
     # ---- pass 2 (product path): the whole step replayed from one CUDA graph; device-resident inputs ----------------------
-    lookahead = os.environ.get("LNRF_LOOKAHEAD", "0") == "1"
-    gstep, graph_note = None, "cuda graph (one capture per sample-buffer size)" + ("; look-ahead march on a second stream" if lookahead else "")
+    lookahead = os.environ.get("LNRF_LOOKAHEAD", "1") == "1"
+    gstep, graph_note = None, "cuda graph (one capture per sample-buffer size)" + (
+        "; software-pipelined: the occupancy march of batch k runs on a second stream beside the backward of batch k-1 (two sample-buffer "
+        "sets, two graphs; every replay = one batch marched + one full forward/backward/optimizer step, loss one call late)" if lookahead else "")
     if os.environ.get("LNRF_NO_GRAPH", "0") != "1":
         try:
             gstep = GraphedTrainStep(step, N_RAYS, lookahead=lookahead)
@@ -425,6 +427,8 @@ def train_config(ctx, name, headline):
             def with_occ(i):
                 if i % 16 == 0:
                     occ_update(False)
+                    if gstep is not None:
+                        gstep.remarch()  # look-ahead: the batch in flight goes through the updated bitfield again
                 run(*dev_batches[i % nb])
 
             k16 = max(16, steps // 16 * 16)

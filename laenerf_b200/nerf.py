@@ -46,7 +46,7 @@ def _recompute_ok(ns, nc) -> bool:
     return os.environ.get("LNRF_MLP_RECOMPUTE", "1") != "0" and bool(N.lib().lnrf_nerf_backward_recompute_supported(int(ns), int(nc)))
 
 
-before_network_backward = None  # experiment hook (GraphedTrainStep, LNRF_LOOKAHEAD_AT=nerf_bwd)
+before_network_backward = None  # GraphedTrainStep(lookahead=True) forks the next batch's march here
 
 
 class _fused_network(Function):
@@ -797,7 +797,7 @@ class GraphedTrainStep:
     lookahead=True software-pipelines consecutive steps: near/far + the occupancy march depend only on the rays and the
     occupancy bitfield, never on the parameters, and the march is latency-bound (a few warps per SM busy walking the grid),
     while the hash-grid backward is bound by the L2 atomic units with its warps waiting.  So the graph marches the batch handed
-    to call k on a second stream BESIDE the hash-grid backward (and whatever follows) of the batch handed to call k-1.  Two
+    to call k on a second stream BESIDE the backward (MLP backward onwards) of the batch handed to call k-1.  Two
     sample-buffer sets and two graphs alternate (train on set p, march into set 1-p): nothing is copied between steps.
     Forking earlier -- beside the persistent MLP kernels, which need a whole SM's shared memory and registers -- or only
     beside Adam measured slower than no overlap.  Every call still consumes one batch and performs one full optimizer step;
@@ -836,7 +836,10 @@ class GraphedTrainStep:
                     self.step.march(self.ro, self.rd, self.perturb, into=nxt)
                     nxt["gt"].copy_(self.gt)
 
-            at = os.environ.get("LNRF_LOOKAHEAD_AT", "enc_bwd")
+            # where the side stream forks (A/B switch; measured on one B200, ms/step: none 0.405 | start 0.401 | adam 0.409 |
+            # enc_bwd 0.380 | nerf_bwd 0.375): the march cannot share an SM with the persistent MLP kernels (registers, shared memory),
+            # so forked at nerf_bwd it starts on each SM the moment that kernel's CTA retires -- ahead of the hash-grid backward
+            at = os.environ.get("LNRF_LOOKAHEAD_AT", "nerf_bwd")
             import laenerf_b200.nerf as _me
             if at == "start":
                 fork()
