@@ -180,6 +180,25 @@ LNRF_API int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, floa
                                          float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
                                          float* weights_sum, float* weights_edit_sum, float* depth, float* depth_edit,
                                          const uint8_t* edit_occ, float* image, lnrf_stream_t stream);
+/* A ray subset on a PRESCRIBED n_step sequence, all rounds in one pass -- the fix-up pass of the "auto" render schedule
+ * (laenerf_b200/nerf.py _fix_schedule_dependent_rays).  Round boundaries reach a ray's sample positions only through rays_t, which
+ * composite_rays rebuilds as rays_t + sum of deltas[.][1] (raymarching.cu:1006): additions of numbers the marcher itself produced.
+ * So the marcher can run a ray through ALL rounds of a given sequence on its own (each round starting from the t the compositor
+ * would have rebuilt), the network runs once over the samples, and the compositor walks them in order and stops where
+ * raymarching.cu:948-1035 would.  Bit-identical to lnrf_render_rounds with the same nstep_seq.
+ *   march: offsets == NULL -> count only (counts[ray] = samples until the ray leaves the volume or the sequence ends);
+ *          else write the ray's samples at row offsets[ray] (exclusive prefix sum of counts).  edit_grid != NULL: also edit_occ.
+ *   composite: per-ray outputs indexed by the subset position; ray_steps[ray] = completed samples (where the ray dies). */
+LNRF_API int lnrf_march_rays_prescribed(uint32_t n_rays, const float* rays_o, const float* rays_d, const float* nears,
+                                        const float* fars, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                        const uint8_t* density_bitfield, const uint8_t* edit_bitfield, const int32_t* nstep_seq,
+                                        uint32_t nstep_len, const int32_t* offsets, int32_t* counts, float* xyzs, float* dirs,
+                                        float* deltas, uint8_t* edit_occ, lnrf_stream_t stream);
+LNRF_API int lnrf_composite_rays_prescribed(uint32_t n_rays, float T_thresh, const int32_t* offsets, const int32_t* counts,
+                                            const float* nears, const float* sigmas, const float* rgbs, const float* deltas,
+                                            const uint8_t* edit_occ, float* weights_sum, float* weights_edit_sum, float* depth,
+                                            float* depth_edit, float* image, int32_t* ray_steps, lnrf_stream_t stream);
+
 /* Device-side replacement for `rays_alive = rays_alive[rays_alive >= 0]` (renderer.py:375): stable compaction of
  * the non-negative entries of rays_alive[0..n_alive) into out (which must not alias rays_alive); the count is
  * written to n_out (device int32[1]).  scratch: lnrf_compact_alive_scratch_bytes(n_alive) bytes, zero before first

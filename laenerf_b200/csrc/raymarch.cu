@@ -1127,6 +1127,114 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
     }
 }
 
+// =========================================================================================================
+// a ray subset on a PRESCRIBED round schedule, all rounds in one pass (the fix-up of the "auto" render schedule)
+// =========================================================================================================
+// Where a ray's samples fall depends on the round boundaries only through rays_t, which composite_rays rebuilds at the end of
+// every round as rays_t + sum of deltas[.][1] (raymarching.cu:1006) -- float additions of numbers the MARCHER produced.  The
+// network's outputs only decide where the ray stops (T < T_thresh), never where its samples lie.  So for a given n_step sequence
+// the whole ray can be marched in one go: round after round, each starting from the t the compositor would have rebuilt, until the
+// ray leaves the volume or the sequence ends; the network then runs once over all those samples and the compositor walks them in
+// order with the per-round arithmetic and stops at the reference's sample.  Same bits as running the rounds one by one
+// (lnrf_render_rounds with nstep_seq) -- in 4 launches instead of 5 per round.
+//   offsets == nullptr: count only (counts[ray] = samples up to the ray's exit); else write the ray's samples at offsets[ray].
+template <bool DISTILL>
+__global__ void __launch_bounds__(256)
+k_march_prescribed(const uint32_t n_rays, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                   const float* __restrict__ nears, const float* __restrict__ fars, const MarchParams p,
+                   const uint8_t* __restrict__ grid, const uint8_t* __restrict__ edit_grid, const int* __restrict__ seq,
+                   const uint32_t seq_len, const int* __restrict__ offsets, int* __restrict__ counts, float* __restrict__ xyzs,
+                   float* __restrict__ dirs, float* __restrict__ deltas, uint8_t* __restrict__ edit_occ) {
+    constexpr int G = kInferGroup;
+    __shared__ float s_d1[256 / G][8];
+    const Group<G> grp;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int gi = threadIdx.x / G;
+    bool active = g < n_rays;
+    Ray r = Ray{};
+    float t = 0.f, far = 0.f;
+    size_t row = 0;
+    if (active) {
+        r = make_ray(rays_o + (size_t)g * 3, rays_d + (size_t)g * 3);
+        far = fars[g];
+        t = nears[g];  // rays_t starts at near (renderer.py:349); no perturbation on this path
+        if (offsets) row = (size_t)offsets[g];
+    }
+    uint32_t total = 0;
+    for (uint32_t rd = 0; rd < seq_len; rd++) {
+        if (!__any_sync(kFull, active)) break;
+        const uint32_t n_step = (uint32_t)__ldg(seq + rd);  // <= 8
+        const uint32_t cnt = march_group<G, true>(
+            grp, p, r, grid, t, far, n_step, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
+                const float t_after = f_add(s, dt), d1 = f_add(t_after, -prev_after);
+                s_d1[gi][rank] = d1;
+                if (offsets) {
+                    const size_t o = row + rank;
+                    xyzs[o * 3] = q.x; xyzs[o * 3 + 1] = q.y; xyzs[o * 3 + 2] = q.z;
+                    dirs[o * 3] = r.dx; dirs[o * 3 + 1] = r.dy; dirs[o * 3 + 2] = r.dz;
+                    reinterpret_cast<float2*>(deltas)[o] = make_float2(dt, d1);
+                    if (DISTILL) edit_occ[o] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
+                }
+            });
+        __syncwarp();
+        if (active) {
+            float tc = t;  // what composite_rays leaves in rays_t for the next round: t += deltas[.][1], sample by sample
+            for (uint32_t j = 0; j < cnt; j++) tc = f_add(tc, s_d1[gi][j]);
+            t = tc;
+            row += cnt;
+            total += cnt;
+            if (cnt < n_step) active = false;  // the ray ran out of samples inside this round: the compositor kills it
+        }
+        __syncwarp();
+    }
+    if (g < n_rays && grp.gl == 0) counts[g] = (int)total;
+}
+
+// raymarching.cu:948-1035 / 1037-1142 over all of a ray's rounds at once (thread per ray): the per-sample arithmetic of
+// composite_infer_ray, t carried from sample to sample exactly as rays_t carries it from round to round.
+template <bool DISTILL>
+__global__ void __launch_bounds__(256)
+k_composite_prescribed(const uint32_t n_rays, const float T_thresh, const int* __restrict__ offsets, const int* __restrict__ counts,
+                       const float* __restrict__ nears, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                       const float* __restrict__ deltas, const uint8_t* __restrict__ edit_occ, float* __restrict__ weights_sum,
+                       float* __restrict__ weights_edit_sum, float* __restrict__ depth, float* __restrict__ depth_edit,
+                       float* __restrict__ image, int* __restrict__ ray_steps) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_rays) return;
+    const size_t o = (size_t)offsets[n];
+    const uint32_t count = (uint32_t)counts[n];
+    const float* ps = sigmas + o;
+    const float* pc = rgbs + o * 3;
+    const float2* pl = reinterpret_cast<const float2*>(deltas) + o;
+    float t = nears[n];
+    float weight_sum = 0.f, d = 0.f, weight_edit_sum = 0.f, d_edit = 0.f, r = 0.f, g = 0.f, b = 0.f;
+    uint32_t step = 0;
+    while (step < count) {
+        const float2 dl = __ldg(pl + step);
+        if (dl.x == 0.f) break;
+        const float alpha = 1.0f - __expf(-__ldg(ps + step) * dl.x);
+        const float T = f_add(1.0f, -weight_sum);
+        const float weight = f_mul(alpha, T);
+        weight_sum = f_add(weight_sum, weight);
+        if (DISTILL && edit_occ[o + step]) {
+            weight_edit_sum = f_add(weight_edit_sum, weight);
+            d_edit = f_fma(weight, t, d_edit);
+        }
+        t = f_add(t, dl.y);
+        d = f_fma(weight, t, d);
+        r = f_fma(weight, __ldg(pc + step * 3), r);
+        g = f_fma(weight, __ldg(pc + step * 3 + 1), g);
+        b = f_fma(weight, __ldg(pc + step * 3 + 2), b);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (ray_steps) ray_steps[n] = (int)step;
+    if (DISTILL) { weights_edit_sum[n] = weight_edit_sum; depth_edit[n] = d_edit; }
+    weights_sum[n] = weight_sum;
+    depth[n] = d;
+    image[(size_t)n * 3] = r; image[(size_t)n * 3 + 1] = g; image[(size_t)n * 3 + 2] = b;
+}
+
 // start of a device-driven render: rays_alive = 0..n_rays-1, rays_t = nears, accumulators cleared, first round published
 __global__ void __launch_bounds__(256)
 k_render_begin(int* __restrict__ ctl, const uint32_t n_rays, const uint32_t max_steps, const uint32_t row_budget, const uint32_t step_cap,
@@ -1518,6 +1626,47 @@ int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, float T_thres
                                                                           deltas, weights_sum, weights_edit_sum, depth, depth_edit,
                                                                           edit_occ, image, nullptr);
     LNRF_LAUNCH_CHECK("composite_rays_distill");
+    return LNRF_OK;
+}
+
+int lnrf_march_rays_prescribed(uint32_t n_rays, const float* rays_o, const float* rays_d, const float* nears, const float* fars, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* edit_grid,
+                               const int32_t* nstep_seq, uint32_t nstep_len, const int32_t* offsets, int32_t* counts, float* xyzs,
+                               float* dirs, float* deltas, uint8_t* edit_occ, lnrf_stream_t stream) {
+    const char* who = "march_rays_prescribed";
+    if (int e = check_march_common(C, H, max_steps, who)) return e;
+    if (n_rays == 0) return LNRF_OK;
+    LNRF_REQUIRE(rays_o && rays_d && nears && fars && grid && nstep_seq && counts, "%s: null pointer", who);
+    LNRF_REQUIRE(!offsets || (xyzs && dirs && deltas && (!edit_grid || edit_occ)), "%s: writing pass without sample buffers", who);
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "%s: deltas must be 8-byte aligned", who);
+    const MarchParams p = march_params_env(bound, dt_gamma, max_steps, C, H);
+    const uint32_t blocks = div_up(n_rays, 256u / (uint32_t)kInferGroup);
+    if (edit_grid)
+        k_march_prescribed<true><<<blocks, 256, 0, S(stream)>>>(n_rays, rays_o, rays_d, nears, fars, p, grid, edit_grid, nstep_seq, nstep_len, offsets,
+                                                               counts, xyzs, dirs, deltas, edit_occ);
+    else
+        k_march_prescribed<false><<<blocks, 256, 0, S(stream)>>>(n_rays, rays_o, rays_d, nears, fars, p, grid, nullptr, nstep_seq, nstep_len, offsets,
+                                                                counts, xyzs, dirs, deltas, nullptr);
+    LNRF_LAUNCH_CHECK(who);
+    return LNRF_OK;
+}
+
+int lnrf_composite_rays_prescribed(uint32_t n_rays, float T_thresh, const int32_t* offsets, const int32_t* counts, const float* nears,
+                                   const float* sigmas, const float* rgbs, const float* deltas, const uint8_t* edit_occ, float* weights_sum,
+                                   float* weights_edit_sum, float* depth, float* depth_edit, float* image, int32_t* ray_steps,
+                                   lnrf_stream_t stream) {
+    const char* who = "composite_rays_prescribed";
+    if (n_rays == 0) return LNRF_OK;
+    LNRF_REQUIRE(offsets && counts && nears && sigmas && rgbs && deltas && weights_sum && depth && image, "%s: null pointer", who);
+    LNRF_REQUIRE(!edit_occ || (weights_edit_sum && depth_edit), "%s: distillation needs weights_edit_sum / depth_edit", who);
+    LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "%s: deltas must be 8-byte aligned", who);
+    if (edit_occ)
+        k_composite_prescribed<true><<<div_up(n_rays, 256u), 256, 0, S(stream)>>>(n_rays, T_thresh, offsets, counts, nears, sigmas, rgbs, deltas, edit_occ,
+                                                                                  weights_sum, weights_edit_sum, depth, depth_edit, image, ray_steps);
+    else
+        k_composite_prescribed<false><<<div_up(n_rays, 256u), 256, 0, S(stream)>>>(n_rays, T_thresh, offsets, counts, nears, sigmas, rgbs, deltas, nullptr,
+                                                                                   weights_sum, nullptr, depth, nullptr, image, ray_steps);
+    LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }
 

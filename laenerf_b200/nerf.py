@@ -413,23 +413,58 @@ class NeRFNetwork(nn.Module):
 
     def _fix_schedule_dependent_rays(self, t, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
                                      rounds_per_call):
+        """Re-render the rays the fast pass flagged on the reference's n_step sequence -- all rounds in ONE pass
+        (lnrf_march_rays_prescribed -> network -> lnrf_composite_rays_prescribed, see include/laenerf_b200.h) -- and put the results
+        in their places.  LNRF_FIXUP_ROUNDS=1 runs the same sequence round by round through lnrf_render_rounds instead."""
         n_rays = rays_o.shape[0]
         dev = rays_o.device
         cap = int(max_steps) + 72
         idx = t["ray_flags"].nonzero().flatten()
-        if idx.numel() == 0:
+        nf = int(idx.numel())
+        if nf == 0:
             return None
         steps = t["ray_steps"].long().clamp_(max=cap)
         hist = torch.bincount(steps, minlength=cap + 1).cpu().numpy().astype(np.int64)
         sub_steps = steps[idx]
         sub = [x[idx].contiguous() for x in (rays_o, rays_d, nears, fars)]
+        by_rounds = os.environ.get("LNRF_FIXUP_ROUNDS", "0") == "1"
+        distill = edit_bitfield is not None
+        lib, st = N.lib(), N.stream()
         for _ in range(3):
             seq = self._reference_sequence(hist, n_rays, max_steps)
             if not seq:
                 return None
             seq_dev = torch.tensor(seq, dtype=torch.int32, device=dev)
-            t2 = self._render_rounds_on("prescribed", *sub, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh, rounds_per_call,
-                                        track=True, seq=seq_dev)
+            if by_rounds:
+                t2 = self._render_rounds_on("prescribed", *sub, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh, rounds_per_call,
+                                            track=True, seq=seq_dev)
+                rounds2, slots2 = t2["rounds"], t2["slots"]
+            else:
+                so, sd, sn_, sf = sub
+                counts = torch.empty(nf, dtype=torch.int32, device=dev)
+                geo = (float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size), dens_grid.data_ptr(),
+                       edit_bitfield.data_ptr() if distill else None, seq_dev.data_ptr(), len(seq))
+                N.check(lib.lnrf_march_rays_prescribed(nf, so.data_ptr(), sd.data_ptr(), sn_.data_ptr(), sf.data_ptr(), *geo, None,
+                                                       counts.data_ptr(), None, None, None, None, st))
+                ends = torch.cumsum(counts, 0, dtype=torch.int32)
+                offsets = (ends - counts).contiguous()
+                total = int(ends[-1].item())
+                rows = total + 128 - total % 128  # raymarching.py:331-332 padding rule; the pad rows are zeros
+                f32 = dict(dtype=torch.float32, device=dev)
+                xyzs, dirs, deltas = torch.zeros(rows, 3, **f32), torch.zeros(rows, 3, **f32), torch.zeros(rows, 2, **f32)
+                edit_occ = torch.zeros(rows, dtype=torch.uint8, device=dev) if distill else None
+                N.check(lib.lnrf_march_rays_prescribed(nf, so.data_ptr(), sd.data_ptr(), sn_.data_ptr(), sf.data_ptr(), *geo, offsets.data_ptr(),
+                                                       counts.data_ptr(), xyzs.data_ptr(), dirs.data_ptr(), deltas.data_ptr(), N.ptr(edit_occ), st))
+                sigmas, rgbs = self.forward_scaled(xyzs, dirs)
+                sigmas, rgbs = sigmas.float().contiguous(), rgbs.float().contiguous()
+                t2 = dict(weights_sum=torch.empty(nf, **f32), depth=torch.empty(nf, **f32), image=torch.empty(nf, 3, **f32),
+                          wes=torch.empty(nf, **f32) if distill else None, de=torch.empty(nf, **f32) if distill else None,
+                          ray_steps=torch.empty(nf, dtype=torch.int32, device=dev))
+                N.check(lib.lnrf_composite_rays_prescribed(nf, float(T_thresh), offsets.data_ptr(), counts.data_ptr(), sn_.data_ptr(),
+                                                           sigmas.data_ptr(), rgbs.data_ptr(), deltas.data_ptr(), N.ptr(edit_occ),
+                                                           t2["weights_sum"].data_ptr(), N.ptr(t2["wes"]), t2["depth"].data_ptr(), N.ptr(t2["de"]),
+                                                           t2["image"].data_ptr(), t2["ray_steps"].data_ptr(), st))
+                rounds2, slots2 = len(seq), rows
             new_steps = t2["ray_steps"].long().clamp_(max=cap)
             hist = hist - torch.bincount(sub_steps, minlength=cap + 1).cpu().numpy() + torch.bincount(new_steps, minlength=cap + 1).cpu().numpy()
             sub_steps = new_steps
@@ -444,9 +479,10 @@ class NeRFNetwork(nn.Module):
                 for k in ("weights_sum", "depth", "image", "wes", "de"):
                     if t.get(k) is not None:
                         t[k][idx] = t2[k]
-                t["schedule"] = (f"fast + {idx.numel()} schedule-dependent rays re-rendered on the reference's n_step sequence "
-                                 f"({len(seq)} rounds, from the histogram of the rays' death samples): bit-identical to the reference schedule")
-                t["rounds_fixup"], t["slots"] = t2["rounds"], t["slots"] + t2["slots"]
+                t["schedule"] = (f"fast + {nf} schedule-dependent rays re-rendered on the reference's n_step sequence "
+                                 f"({len(seq)} rounds, from the histogram of the rays' death samples" +
+                                 ("" if by_rounds else "; all rounds in one pass") + "): bit-identical to the reference schedule")
+                t["rounds_fixup"], t["slots"] = rounds2, t["slots"] + slots2
                 return t
         return None
 

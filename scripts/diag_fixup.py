@@ -47,3 +47,30 @@ print("seq from fast:", len(seq_f), "first mismatch at", next((i for i, (x, y) i
 bad = (r["image"] != a["image"]).any(1).nonzero().flatten()[:8]
 for i in bad.tolist():
     print(i, "flag", int(ff[i]), int(fr[i]), "steps ref/fast", int(sr[i]), int(sf[i]), r["image"][i].tolist(), a["image"][i].tolist())
+
+import time
+def timed(fn, n=3):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+    for name_, n_ in (("bonsai", 640000), ("flower", 190512)):
+        sc = scene(name_)
+        torch.manual_seed(3)
+        mb = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_scale=5.0).to(dev)
+        mb.encoder.embeddings.uniform_(-0.5, 0.5)
+        mb.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+        _, ro, rd, _ = scene_rays(name_, n_, 29)
+        ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+        mb.eval()
+        nears, fars = raymarching.near_far_from_aabb(ro, rd, mb.aabb_infer, mb.min_near)
+        args = (ro, rd, nears, fars, mb.density_bitfield, None, 0, False, 1024, 1e-4, 8)
+        t_fast = timed(lambda: mb._render_rounds_on("fast", *args, track=True))
+        mb.render_schedule = "auto"
+        t_auto = timed(lambda: mb._render_rounds_device(*args))
+        os.environ["LNRF_FIXUP_ROUNDS"] = "1"
+        t_auto_r = timed(lambda: mb._render_rounds_device(*args))
+        del os.environ["LNRF_FIXUP_ROUNDS"]
+        t_ref = timed(lambda: mb._render_rounds_on("reference", *args), 1)
+        a = mb._render_rounds_device(*args)
+        print(name_, n_, "rays: fast %.2f ms | auto (one-pass fix-up) %.2f ms | auto (fix-up by rounds) %.2f ms | reference %.2f ms |" % (t_fast, t_auto, t_auto_r, t_ref), a["schedule"][:60], "slots", a["slots"])

@@ -2,6 +2,7 @@
 section 8, checked against (a) the CPU oracle composed the way network_ff.py:51-79 composes the ops, (b) the
 module-by-module CUDA path of the same package, (c) torch.optim.Adam + torch.amp.GradScaler."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -733,7 +734,17 @@ def test_fast_render_schedule_is_bit_identical_where_the_marcher_proves_it(dev):
             mb.render_schedule = sched
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
                 outs[sched] = mb.render(ro, rd, perturb=False, bg_color=1, scale_depth=False)
-        assert outs["auto"]["schedule"].startswith("fast + "), outs["auto"]["schedule"]
+        assert outs["auto"]["schedule"].startswith("fast + ") and "one pass" in outs["auto"]["schedule"], outs["auto"]["schedule"]
+        if name == "bonsai":   # the same fix-up run round by round through the device loop (lnrf_render_rounds with nstep_seq)
+            os.environ["LNRF_FIXUP_ROUNDS"] = "1"
+            try:
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                    by_rounds = mb.render(ro, rd, perturb=False, bg_color=1, scale_depth=False)
+            finally:
+                del os.environ["LNRF_FIXUP_ROUNDS"]
+            assert "one pass" not in by_rounds["schedule"] and by_rounds["schedule"].startswith("fast + ")
+            for k in ("image", "depth", "t"):
+                assert torch.equal(outs["reference"][k], by_rounds[k]), (name, "by rounds", k)
         assert not torch.equal(outs["reference"]["image"], outs["fast"]["image"])      # the fast schedule ALONE is not exact here
         for k in ("image", "depth", "t"):
             assert torch.equal(outs["reference"][k], outs["auto"][k]), (name, k)
