@@ -645,7 +645,15 @@ __device__ __forceinline__ void composite_loss_reduce(float err, const LossArgs&
     if (s_last) {  // the last block out: fixed-order sum of the partials (thread-strided, then warps, then the 8 warp sums)
         __threadfence();
         float s = 0.f;
-        for (uint32_t i = threadIdx.x; i < gridDim.x; i += 256) s += __ldcg(la.partial + i);
+        uint32_t i = threadIdx.x;
+        for (; i + 7u * 256u < gridDim.x; i += 8u * 256u) {  // the order of one load per trip, eight of them in flight (large batches)
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) x[u] = __ldcg(la.partial + i + (uint32_t)u * 256u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += x[u];
+        }
+        for (; i < gridDim.x; i += 256) s += __ldcg(la.partial + i);
         s = warp_sum(s);
         __syncthreads();  // s_err is being reused
         if (lane == 0) s_err[warp] = s;
@@ -664,15 +672,17 @@ __global__ void __launch_bounds__(256)
 k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
                      const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // the grid is capped (composite_loss_blocks): beyond one wave a warp takes several rays, so that the block-level ticket of the
+    // loss reduction -- a fence and an atomic round trip during which the whole block holds its registers -- is paid once per block,
+    // not once per 8 rays (65 536 rays: 62 -> see profiles/ large-batch table)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float err = 0.f;
-    if (n < N) {
+    for (uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += gridDim.x * 8u) {
         const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
                        num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
         RaySums a;
         float v[3];
-        err = composite_loss_ray_fwd<false>(sigmas, rgbs, deltas, index, offset, num_steps, M, T_thresh, la, weights_sum, depth, image, lane, a, v);
+        err += composite_loss_ray_fwd<false>(sigmas, rgbs, deltas, index, offset, num_steps, M, T_thresh, la, weights_sum, depth, image, lane, a, v);
     }
     composite_loss_reduce(err, la, N, lane, warp);
 }
@@ -813,15 +823,14 @@ k_composite_loss_fwd_bwd(const float* __restrict__ sigmas, const float* __restri
                          const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
                          float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
                          float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float err = 0.f;
-    if (n < N) {
+    for (uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += gridDim.x * 8u) {
         const uint32_t index = (uint32_t)__ldg(rays + (size_t)n * 3), offset = (uint32_t)__ldg(rays + (size_t)n * 3 + 1),
                        num_steps = (uint32_t)__ldg(rays + (size_t)n * 3 + 2);
         RaySums a;
         float v[3];
-        err = composite_loss_ray_fwd<true>(sigmas, rgbs, deltas, index, offset, num_steps, M, T_thresh, la, weights_sum, depth, image, lane, a, v);
+        err += composite_loss_ray_fwd<true>(sigmas, rgbs, deltas, index, offset, num_steps, M, T_thresh, la, weights_sum, depth, image, lane, a, v);
         const bool fits = offset + num_steps <= M;
         composite_zero_uncovered(n, N, offset, num_steps, fits, M, grad_sigmas, grad_rgbs, lane);
         if (num_steps != 0 && fits) {
@@ -1492,6 +1501,12 @@ int lnrf_composite_rays_train_backward(const float* grad_weights_sum, const floa
     return LNRF_OK;
 }
 
+// blocks of the loss kernels: one warp per ray up to 8 blocks per SM, grid-stride beyond
+static uint32_t composite_loss_blocks(uint32_t N) {
+    const uint32_t want = div_up(N, 8u), cap = (uint32_t)kNumSMs * 8u;
+    return want < cap ? want : cap;
+}
+
 size_t lnrf_composite_loss_scratch_bytes(uint32_t N) { return ((size_t)div_up(N, 8u) + 4u) * sizeof(float); }
 
 int lnrf_composite_loss_train_forward(const float* sigmas, const float* rgbs, const float* deltas, const int32_t* rays,
@@ -1510,7 +1525,7 @@ int lnrf_composite_loss_train_forward(const float* sigmas, const float* rgbs, co
     la.ticket = reinterpret_cast<unsigned int*>(scratch);
     la.partial = reinterpret_cast<float*>(scratch) + 4;
     la.loss = loss;
-    k_composite_loss_fwd<<<div_up(N, 8u), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
+    k_composite_loss_fwd<<<composite_loss_blocks(N), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
     LNRF_LAUNCH_CHECK("composite_loss_train_forward");
     return LNRF_OK;
 }
@@ -1534,8 +1549,18 @@ int lnrf_composite_loss_train_forward_backward(const float* grad_loss, const flo
     la.partial = reinterpret_cast<float*>(scratch) + 4;
     la.loss = loss;
     la.grad_loss = grad_loss;
-    k_composite_loss_fwd_bwd<<<div_up(N, 8u), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image,
-                                                                   grad_sigmas, grad_rgbs);
+    // One launch while the batch is about one wave of blocks (the 4096-ray training step: latency-bound, the second pass over the
+    // ray's samples hits L1).  Large batches are throughput-bound and the two-pass warps hold their registers twice as long:
+    // measured at 65 536 rays 191 us fused against 62 + 68 us for the two kernels -- which produce the same bits.
+    if (N <= 8192u) {
+        k_composite_loss_fwd_bwd<<<composite_loss_blocks(N), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth,
+                                                                                  image, grad_sigmas, grad_rgbs);
+    } else {
+        k_composite_loss_fwd<<<composite_loss_blocks(N), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
+        LNRF_LAUNCH_CHECK(who);
+        k_composite_train_bwd<true, true><<<div_up(N, 8u), 256, 0, S(stream)>>>(nullptr, nullptr, sigmas, rgbs, deltas, rays, weights_sum,
+                                                                                image, M, N, T_thresh, grad_sigmas, grad_rgbs, la);
+    }
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }
