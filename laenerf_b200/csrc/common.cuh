@@ -37,6 +37,36 @@ extern std::atomic<uint64_t> g_launch_count;
 template <typename T>
 __host__ __device__ inline T div_up(T a, T b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (the kernels of the training step form one dependent chain) -------------------------------
+// A kernel launched through launch_pdl may START while its predecessor on the stream is still finishing: its blocks become resident
+// as the predecessor's blocks retire, run their prologue (index math, shared-memory carve-up, barrier init, TMEM allocation, loads of
+// operands nobody in the chain writes) and park at pdl_wait() until the predecessor has completed and its writes are visible.  The
+// predecessor says when that may begin with pdl_trigger() (every block: at its start -- the dependent launch fires once all blocks of
+// the predecessor are resident or done, so nothing of the predecessor ever queues behind a parked block).  In a CUDA graph the launch
+// becomes a programmatic dependency edge.  Without the attribute (plain <<<>>> launches, LNRF_PDL unset) both instructions are no-ops.
+// MEASURED AND LEFT OFF (LNRF_PDL=1 turns it on): with the wait at the top of every kernel of the step the graph replays at 0.3996
+// against 0.3978 ms without -- inside a graph the hand-over between two kernels is already ~1.5 us -- and with the software-pipelined
+// step it LOSES 24 us (0.392 vs 0.368 ms): the parked blocks of the next kernel take the SM slots that the retiring blocks free, which
+// is exactly where the look-ahead march of the next batch was running.
+bool pdl_enabled();  // lib.cu: LNRF_PDL == "1"
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- warp helpers --------------------------------------------------------------------------------------
 constexpr unsigned kFull = 0xffffffffu;
 

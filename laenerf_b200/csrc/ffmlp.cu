@@ -655,6 +655,8 @@ k_mlp_bwd2(const __half* __restrict__ grad, const __half* __restrict__ inputs, c
 __global__ void __launch_bounds__(256)
 k_wgrad_reduce(const WgradPending a, const WgradPending b) {
     __shared__ float red[8][32];
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     const uint32_t blocks_a = (a.n + 31u) / 32u;
     const bool first = blockIdx.x < blocks_a;
     const float* __restrict__ partial = first ? a.partial : b.partial;
@@ -870,7 +872,7 @@ int ffmlp_bwd_run(const char* who, const void* grad_f16, const void* inputs_f16,
 }
 
 int wgrad_reduce_pair(const char* who, const WgradPending& a, const WgradPending& b, cudaStream_t st) {
-    k_wgrad_reduce<<<div_up(a.n, 32u) + div_up(b.n, 32u), 256, 0, st>>>(a, b);
+    launch_pdl(k_wgrad_reduce, div_up(a.n, 32u) + div_up(b.n, 32u), 256, 0, st, a, b);
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }

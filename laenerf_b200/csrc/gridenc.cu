@@ -193,6 +193,8 @@ k_grid_fwd_tile(const float* __restrict__ inputs, const typename Vec2<T>::type* 
     __shared__ Level s_lv[kMaxLevels];
     __shared__ float s_in[kTile * 3];
     T2* s_out = reinterpret_cast<T2*>(s_raw);
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     if (B_dev) {  // device-side sample count (render control block, row f-3; the training marcher's counter): whole 128-row tiles up
                   // to the capacity B -- the rows between the count and the tile end are the marcher's zero padding, encoded like any
                   // other point (the network kernels work on the same 128-row tiles)
@@ -292,6 +294,8 @@ k_grid_bwd_tile(const typename Vec2<T>::type* __restrict__ grad, const float* __
     __shared__ Level s_lv[kMaxLevels];
     __shared__ float s_in[kTile * 3];
     T2* s_g = reinterpret_cast<T2*>(s_raw);
+    pdl_trigger();
+    pdl_wait();
     if (B_dev) {  // rows at or beyond the device-side count carry no gradient (and may be unwritten memory): skipped by whole tiles
         const uint32_t live = div_up((uint32_t)max(*B_dev, 0), (uint32_t)kTile);
         ntiles = live < ntiles ? live : ntiles;
@@ -647,7 +651,7 @@ static int grid_forward_t(const float* inputs, const T* emb, const GridOffsets& 
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
         auto kern = smooth ? (pair_mode() & 1 ? k_grid_fwd_tile<T, true, true> : k_grid_fwd_tile<T, true, false>)
                            : (pair_mode() & 1 ? k_grid_fwd_tile<T, false, true> : k_grid_fwd_tile<T, false, false>);
-        kern<<<grid, kGridThreads, smem, st>>>(inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs), B, L, S, H, gridtype,
+        launch_pdl(kern, grid, kGridThreads, smem, st, inputs, reinterpret_cast<const T2*>(emb), reinterpret_cast<T2*>(outputs), B, L, S, H, gridtype,
                                                ac, off, ntiles, in_bound, B_dev);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);
@@ -677,7 +681,7 @@ static int grid_backward_t(const T* grad, const float* inputs, const GridOffsets
         const size_t smem = (size_t)kTile * (L | 1u) * sizeof(T2);
         auto kern = smooth ? (pair_mode() & 2 ? k_grid_bwd_tile<T, true, true> : k_grid_bwd_tile<T, true, false>)
                            : (pair_mode() & 2 ? k_grid_bwd_tile<T, false, true> : k_grid_bwd_tile<T, false, false>);
-        kern<<<grid, kGridThreads, smem, st>>>(reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb), B, L, S, H, gridtype,
+        launch_pdl(kern, grid, kGridThreads, smem, st, reinterpret_cast<const T2*>(grad), inputs, reinterpret_cast<T2*>(grad_emb), B, L, S, H, gridtype,
                                                ac, off, ntiles, in_bound, B_dev);
     } else {
         const dim3 g(div_up(B, 256u), L, 1);

@@ -1,6 +1,7 @@
 // lib.cu -- error plumbing, version and launch accounting of liblaenerf_b200.so.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace lnrf {
 
@@ -12,6 +13,11 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(t_error, sizeof(t_error), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("LNRF_PDL"); return e && e[0] == '1'; }();  // measured: no gain, see common.cuh
+    return on;
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

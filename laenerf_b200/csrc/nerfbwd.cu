@@ -93,6 +93,8 @@ k_nerf_bwd(const __grid_constant__ CUtensorMap tm_enc, const NerfBwdArgs a) {
     uint8_t* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     const uint32_t ns = a.ns, nc = a.nc;
     uint32_t ntiles = a.ntiles;
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     if (a.M_dev) {
         const uint32_t live = div_up((uint32_t)max(*a.M_dev, 0), kRows);
         ntiles = live < ntiles ? live : ntiles;
@@ -489,7 +491,7 @@ int lnrf_nerf_backward_recompute(const float* grad_sigmas, const float* grad_rgb
         a.wgrad_sigma = (float*)wgrad_scratch; a.wgrad_color = (float*)((uint8_t*)wgrad_scratch + need_s);
         a.M_dev = M_dev; a.M = M; a.ns = ns; a.nc = nc; a.ntiles = ntiles; a.density_scale = density_scale;
         a.dbg = g_nerf_bwd_dbg;
-        k_nerf_bwd<<<grid, kBwdThreads, smem, st>>>(tm, a);
+        launch_pdl(k_nerf_bwd, grid, kBwdThreads, smem, st, tm, a);
         LNRF_LAUNCH_CHECK("nerf_backward_recompute");
     } else {
         cudaError_t e = cudaMemsetAsync(wgrad_scratch, 0, need_s + need_c, st);

@@ -47,6 +47,8 @@ k_nerf_fwd(const __half* __restrict__ enc, const float* __restrict__ dirs, const
            float* __restrict__ sigmas, float* __restrict__ rgbs, uint32_t ntiles, const int* __restrict__ M_dev,
            const uint32_t sigma_only, __half* __restrict__ h_all_out) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     if (M_dev) {  // device-side sample count: the render control block (row f-3) or the training marcher's counter; capacity = ntiles
         const uint32_t live = div_up((uint32_t)max(*M_dev, 0), kRows);
         ntiles = live < ntiles || ntiles == 0u ? live : ntiles;
@@ -246,7 +248,7 @@ int nerf_forward_dev_launch(const void* enc_f16, const float* dirs, const void* 
     memset(&tm, 0, sizeof(tm));
     const uint32_t want = div_up(div_up(M_cap, kRows), kGroups);
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
-    k_nerf_fwd<false><<<grid, 128 * kGroups, smem, st>>>((const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M_cap,
+    launch_pdl(k_nerf_fwd<false>, grid, 128 * kGroups, smem, st, (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M_cap,
                                                          ns, nc, density_scale, tm, nullptr, nullptr, sigmas, rgbs, div_up(M_cap, kRows), M_dev, 0u, nullptr);
     LNRF_LAUNCH_CHECK("render_rounds(network)");
     return LNRF_OK;
@@ -287,7 +289,7 @@ int lnrf_nerf_forward(const void* enc_f16, const float* dirs, const void* w_sigm
     const uint32_t ntiles = M / kRows;
     const uint32_t want = div_up(ntiles, kGroups);  // one persistent CTA per SM, kGroups tiles in flight each
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
-    kern<<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(kern, grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream),
         (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale,
         tm, (__half*)color_in_f16, (__half*)h0_f16, sigmas, rgbs, ntiles, nullptr, 0u, nullptr);
     LNRF_LAUNCH_CHECK("nerf_forward");
@@ -313,7 +315,7 @@ int lnrf_nerf_forward_lean(const void* enc_f16, const float* dirs, const void* w
     const uint32_t ntiles = M / kRows;
     const uint32_t want = div_up(ntiles, kGroups);
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
-    k_nerf_fwd<false><<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(k_nerf_fwd<false>, grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream),
         (const __half*)enc_f16, dirs, (const __half*)w_sigma_f16, (const __half*)w_color_f16, M, ns, nc, density_scale, tm, nullptr, nullptr,
         sigmas, rgbs, ntiles, M_dev, 0u, (__half*)h_f16);
     LNRF_LAUNCH_CHECK("nerf_forward_lean");
@@ -334,7 +336,7 @@ int lnrf_nerf_density(const void* enc_f16, const void* w_sigma_f16, uint32_t M, 
     const uint32_t ntiles = M / kRows;
     const uint32_t want = div_up(ntiles, kGroups);
     const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
-    k_nerf_fwd<false><<<grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(k_nerf_fwd<false>, grid, 128 * kGroups, smem, reinterpret_cast<cudaStream_t>(stream),
         (const __half*)enc_f16, nullptr, (const __half*)w_sigma_f16, nullptr, M, ns, 0u, density_scale, tm, nullptr, nullptr, sigmas, nullptr,
         ntiles, nullptr, 1u, nullptr);
     LNRF_LAUNCH_CHECK("nerf_density");

@@ -93,6 +93,8 @@ __device__ __forceinline__ bool grad_block_nonfinite(const OptBatch& b) {
 
 // found_inf[0] = 1.0f when any gradient element is inf/nan (never cleared here: torch's GradScaler convention)
 __global__ void __launch_bounds__(kOptBlock) k_grad_nonfinite(const OptBatch b, float* __restrict__ found_inf) {
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     const bool bad = grad_block_nonfinite(b);
     if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.0f;
 }
@@ -178,6 +180,8 @@ k_adam_step(const OptBatch b, AdamHyper h, const float* __restrict__ grad_scale,
     const int k = find_tensor(b, blockIdx.x);
     const OptTensor& t = b.t[k];
     const uint32_t nblocks = (k + 1 < (int)b.count ? b.t[k + 1].first_block : gridDim.x) - t.first_block;
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     const bool skip = found_inf != nullptr && *found_inf != 0.0f;  // GradScaler: the step is skipped, the gradient still cleared
     if (lr_scale) h.lr *= (double)*lr_scale;  // LambdaLR-style schedule factor kept on the device (CUDA-graph friendly)
     const AdamStepConsts c = adam_step_consts(h, grad_scale, step_count);
@@ -294,6 +298,8 @@ __device__ __forceinline__ void amp_update_body(const AmpUpdateArgs& u, const fl
 // (zero before first use, re-armed here).
 __global__ void __launch_bounds__(kOptBlock)
 k_grad_nonfinite_amp(const OptBatch b, const AmpUpdateArgs u, float* __restrict__ snap) {
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     const bool bad = grad_block_nonfinite(b);
     if (__syncthreads_or(bad) && threadIdx.x == 0) *u.found_inf = 1.0f;
     if (threadIdx.x == 0) {
@@ -671,7 +677,7 @@ int lnrf_grad_nonfinite_check(const lnrf_opt_tensor* tensors_host, uint32_t coun
     uint32_t grid;
     if (int e = make_batch("grad_nonfinite_check", tensors_host, count, &b, &grid, false)) return e;
     LNRF_REQUIRE(found_inf, "grad_nonfinite_check: null found_inf");
-    k_grad_nonfinite<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, found_inf);
+    launch_pdl(k_grad_nonfinite, grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream), b, found_inf);
     LNRF_LAUNCH_CHECK("grad_nonfinite_check");
     return LNRF_OK;
 }
@@ -686,9 +692,9 @@ int lnrf_adam_step(const lnrf_opt_tensor* tensors_host, uint32_t count, double l
     AdamHyper h{lr, beta1, beta2, eps, weight_decay};
     const char* es = getenv("LNRF_ADAM_STREAM");  // A/B switch (default on)
     if (!es || atoi(es) != 0)
-        k_adam_step<true><<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
+        launch_pdl(k_adam_step<true>, grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream), b, h, grad_scale, found_inf, step_count, lr_scale);
     else
-        k_adam_step<false><<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, h, grad_scale, found_inf, step_count, lr_scale);
+        launch_pdl(k_adam_step<false>, grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream), b, h, grad_scale, found_inf, step_count, lr_scale);
     LNRF_LAUNCH_CHECK("adam_step");
     return LNRF_OK;
 }
@@ -732,7 +738,7 @@ int lnrf_grad_nonfinite_check_amp_update(const lnrf_opt_tensor* tensors_host, ui
     uint32_t grid;
     if (int e = make_batch("grad_nonfinite_check_amp_update", tensors_host, count, &b, &grid, false)) return e;
     AmpUpdateArgs u{grad_scale, growth_tracker, found_inf, step_count, growth_factor, backoff_factor, growth_interval};
-    k_grad_nonfinite_amp<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, u, snapshot);
+    launch_pdl(k_grad_nonfinite_amp, grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream), b, u, snapshot);
     LNRF_LAUNCH_CHECK("grad_nonfinite_check_amp_update");
     return LNRF_OK;
 }

@@ -672,6 +672,8 @@ __global__ void __launch_bounds__(256)
 k_composite_loss_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
                      const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     // the grid is capped (composite_loss_blocks): beyond one wave a warp takes several rays, so that the block-level ticket of the
     // loss reduction -- a fence and an atomic round trip during which the whole block holds its registers -- is paid once per block,
     // not once per 8 rays (65 536 rays: 62 -> see profiles/ large-batch table)
@@ -786,6 +788,8 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
                       const int* __restrict__ rays, const float* __restrict__ weights_sum, const float* __restrict__ image,
                       uint32_t M, uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs,
                       const LossArgs la) {
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -823,6 +827,8 @@ k_composite_loss_fwd_bwd(const float* __restrict__ sigmas, const float* __restri
                          const int* __restrict__ rays, uint32_t M, uint32_t N, float T_thresh, const LossArgs la,
                          float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
                          float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    pdl_trigger();
+    pdl_wait();  // nothing below may run before the kernels ahead on the stream are complete (common.cuh)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float err = 0.f;
     for (uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < N; n += gridDim.x * 8u) {
@@ -1525,7 +1531,7 @@ int lnrf_composite_loss_train_forward(const float* sigmas, const float* rgbs, co
     la.ticket = reinterpret_cast<unsigned int*>(scratch);
     la.partial = reinterpret_cast<float*>(scratch) + 4;
     la.loss = loss;
-    k_composite_loss_fwd<<<composite_loss_blocks(N), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
+    launch_pdl(k_composite_loss_fwd, composite_loss_blocks(N), 256, 0, S(stream), sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
     LNRF_LAUNCH_CHECK("composite_loss_train_forward");
     return LNRF_OK;
 }
@@ -1553,8 +1559,8 @@ int lnrf_composite_loss_train_forward_backward(const float* grad_loss, const flo
     // ray's samples hits L1).  Large batches are throughput-bound and the two-pass warps hold their registers twice as long:
     // measured at 65 536 rays 191 us fused against 62 + 68 us for the two kernels -- which produce the same bits.
     if (N <= 8192u) {
-        k_composite_loss_fwd_bwd<<<composite_loss_blocks(N), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth,
-                                                                                  image, grad_sigmas, grad_rgbs);
+        launch_pdl(k_composite_loss_fwd_bwd, composite_loss_blocks(N), 256, 0, S(stream), sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth,
+                   image, grad_sigmas, grad_rgbs);
     } else {
         k_composite_loss_fwd<<<composite_loss_blocks(N), 256, 0, S(stream)>>>(sigmas, rgbs, deltas, rays, M, N, T_thresh, la, weights_sum, depth, image);
         LNRF_LAUNCH_CHECK(who);
@@ -1575,8 +1581,8 @@ int lnrf_composite_loss_train_backward(const float* grad_loss, const float* sigm
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(deltas) & 7) == 0, "composite_loss_train_backward: deltas must be 8-byte aligned");
     LossArgs la{};
     la.gt = gt_rgb; la.bg = bg_rgb; la.bg_scalar = bg_scalar; la.image_raw = const_cast<float*>(image_raw); la.grad_loss = grad_loss;
-    k_composite_train_bwd<true, true><<<div_up(N, 8u), 256, 0, S(stream)>>>(nullptr, nullptr, sigmas, rgbs, deltas, rays, weights_sum,
-                                                                            image, M, N, T_thresh, grad_sigmas, grad_rgbs, la);
+    launch_pdl(k_composite_train_bwd<true, true>, div_up(N, 8u), 256, 0, S(stream), nullptr, nullptr, sigmas, rgbs, deltas, rays, weights_sum,
+               image, M, N, T_thresh, grad_sigmas, grad_rgbs, la);
     LNRF_LAUNCH_CHECK("composite_loss_train_backward");
     return LNRF_OK;
 }
