@@ -26,6 +26,7 @@ from __future__ import annotations
 import argparse
 import contextlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -54,6 +55,8 @@ ALGO = {
     # row f-5: composite + blend + depth normalisation + MSE in one launch (gt 12 + image_raw 12 + nears/fars 8 B/ray on top)
     "lnrf_composite_loss_train_forward": dict(bound="hbm", per_ray=64, per_sample=24),
     "lnrf_composite_loss_train_backward": dict(bound="hbm", per_ray=60, per_sample=40),
+    # forward + backward of the tail in one launch: the samples are read once from DRAM (24 B), the gradients written (16 B)
+    "lnrf_composite_loss_train_forward_backward": dict(bound="hbm", per_ray=64, per_sample=40),
     "lnrf_ffmlp_forward": dict(bound="tensor", flops_per_sample_padded=36864 / 2),   # mean of sigma (14336) and colour (22528) nets
     "lnrf_ffmlp_backward": dict(bound="tensor", flops_per_sample_padded=73728 / 2),
     "lnrf_sh_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=12 + 64),
@@ -67,6 +70,7 @@ ALGO = {
     "lnrf_nerf_backward_recompute": dict(bound="tensor", flops_per_sample_padded=73728),
     "lnrf_adam_step": dict(bound="hbm", per_param=30),            # g16 R+W 4, p/m/v R+W 24, p16 W 2
     "lnrf_grad_nonfinite_check": dict(bound="hbm", per_param=2),
+    "lnrf_grad_nonfinite_check_amp_update": dict(bound="hbm", per_param=2),   # the same pass + GradScaler.update() by the last block
 }
 
 
@@ -386,17 +390,37 @@ def train_config(ctx, name, headline):
 
     if headline:
         # ---- end-to-end: pinned host inputs -> H2D -> step -> D2H loss, every step ------------------------------------
-        def e2e_iter(i):
+        # Every step: three pinned host tensors -> device (147 456 B), the step, and the step's loss -> a pinned host word (4 B), which
+        # the host READS one step later (event-synchronised) -- the way a training loop logs its loss without stalling the device
+        # between steps.  `e2e_blocking` beside it: `loss.item()` right after every step.
+        host_loss = torch.zeros(2, dtype=torch.float32).pin_memory()
+        loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        seen_losses = []
+
+        def e2e_iter(i, blocking=False):
             hb = host_batches[i % nb]
             if gstep is not None:
                 loss, _ = gstep(*hb)  # static device buffers are filled straight from pinned memory (non_blocking copies)
             else:
                 loss, _ = step(*(x.to(ctx.dev, non_blocking=True) for x in hb))
-            float(loss.item())
+            if blocking:
+                seen_losses.append(float(loss.item()))
+                return
+            slot = i & 1
+            host_loss[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ready[slot].record()
+            if i > 0:
+                loss_ready[slot ^ 1].synchronize()
+                seen_losses.append(float(host_loss[slot ^ 1]))
 
         e2e_ms = ctx.timed_loop(e2e_iter, steps)
+        e2e_blocking_ms = ctx.timed_loop(lambda i: e2e_iter(i, True), steps)
+        assert all(math.isfinite(x) for x in seen_losses) and len(seen_losses) >= 2 * steps - 1
         res["e2e"] = {"value": world * N_RAYS * steps / (e2e_ms * 1e-3), "unit": "rays/s",
-                      "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_batches[0]), "d2h_bytes_per_step": 4}
+                      "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_batches[0]), "d2h_bytes_per_step": 4,
+                      "loss_read": "every step's loss is copied to pinned host memory inside the timed region and read by the host one step "
+                                   "later (event-synchronised)",
+                      "blocking_read_value": world * N_RAYS * steps / (e2e_blocking_ms * 1e-3)}
 
         # ---- with the occupancy maintenance the reference pays every 16 steps (nerf/utils.py:1465-1467, renderer.py:556-649) ---------
         # The synthetic scene IS its procedural occupancy grid: letting a random-init network rewrite it would change the workload
