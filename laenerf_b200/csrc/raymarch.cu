@@ -903,6 +903,7 @@ __device__ __forceinline__ void ctl_set_round(int* ctl, uint32_t n_alive) {
     }
     uint32_t rows = n_alive * n_step;
     rows += 128u - rows % 128u;
+    ctl[15] = 0;  // kCtlCompactRows: the compact marcher of the round publishes it; 0 until then and when the frame is finished
     ctl[kCtlAlive] = fin ? 0 : (int)n_alive;
     ctl[kCtlStep] = (int)n_step;
     ctl[kCtlRows] = fin ? 0 : (int)rows;
@@ -1130,7 +1131,7 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
             if (!ctl[kCtlFinished]) {
                 ctl[kCtlSteps] += ctl[kCtlStep];
                 ctl[kCtlRounds] += 1;
-                ctl[kCtlRounds + 2] += ctl[kCtlRows];  // sample slots marched so far (what the host loop sums up)
+                ctl[kCtlRounds + 2] += ctl[15] > 0 ? ctl[15] : ctl[kCtlRows];  // sample rows marched so far (compact rounds: the real ones)
                 const uint32_t survivors = (uint32_t)((volatile int*)ctl)[kCtlRounds + 1];
                 if (survivors > 0u && (uint32_t)ctl[kCtlSteps] >= (uint32_t)ctl[kCtlMaxSteps]) {  // the cap cut rays off
                     ctl[kCtlInexact] = 1;
@@ -1139,6 +1140,207 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
                 ctl_set_round(ctl, survivors);
             }
         }
+    }
+}
+
+// =========================================================================================================
+// compact rounds of the fast schedule (rounds >= 1): a ray's samples sit behind the previous ray's, no empty slots
+// =========================================================================================================
+// The reference's layout gives every alive ray n_step slots (raymarching.cu:760) and zero-fills what the ray does not use; with up
+// to 64 samples per ray per round that is ~15 % of the rows of a frame going through encoder and network as zeros.  Here the
+// marcher parks a ray's sample positions in shared memory, the groups of a block and then the blocks (decoupled look-back, as in
+// k_march_train) agree on offsets, and the samples are written back to back; (offset, count) per alive ray is what the compositor
+// reads.  Same positions, same deltas, same per-ray arithmetic: only the row a sample lives in changes, which no output depends on.
+//   status words (scratch): flag << 32 | count, zero before the launch (k_composite_infer_compact re-arms them)
+//   ctl[15] = rows of this round, rounded up to a multiple of 128 (the pad rows are zero-filled here)
+constexpr int kCtlCompactRows = 15;
+constexpr int kCompactCap = 64;  // most samples a ray takes per round (render_begin: step_cap <= 64)
+
+constexpr int kCompactThreads = 128;  // 16 rays per block: the block waits for its longest march before the offsets are known
+
+template <bool DISTILL>
+__global__ void __launch_bounds__(kCompactThreads)
+k_march_infer_compact(const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                      const float* __restrict__ rays_d, const MarchParams p, const uint8_t* __restrict__ grid,
+                      const uint8_t* __restrict__ edit_grid, const float* __restrict__ fars, float* __restrict__ xyzs,
+                      float* __restrict__ dirs, float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, int* __restrict__ ray_off,
+                      int* __restrict__ ray_cnt, unsigned long long* __restrict__ status, int* __restrict__ ctl) {
+    constexpr int G = kInferGroup, kGroups = kCompactThreads / G;
+    __shared__ float s_t[kGroups][kCompactCap];
+    __shared__ uint32_t s_cnt[kGroups];
+    __shared__ uint32_t s_excl;
+    const Group<G> grp;
+    const uint32_t n_alive = (uint32_t)ctl[kCtlAlive], n_step = (uint32_t)ctl[kCtlStep];
+    if (ctl[kCtlRows] == 0) return;                      // finished: a queued no-op round
+    const uint32_t active_blocks = div_up(n_alive, (uint32_t)kGroups);
+    if (blockIdx.x >= active_blocks) return;
+    const int gi = threadIdx.x / G, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * kGroups + gi;
+    const bool active = g < n_alive;
+    Ray r = Ray{};
+    float t0 = 0.f, far = 0.f;
+    int index = 0;
+    if (active) {
+        index = __ldg(rays_alive + g);
+        r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
+        far = fars[index];
+        t0 = rays_t[index];  // rounds >= 1 carry no noise (raymarching.cu:746 with noise = 0 leaves t_in unchanged)
+    }
+    bool inexact = false;
+    const uint32_t cnt = march_group<G, true>(grp, p, r, grid, t0, far, n_step, active,
+                                              [&](uint32_t rank, float s, float dt, const Probe&, float prev_after) {
+                                                  s_t[gi][rank] = s;
+                                                  const float t_after = f_add(s, dt), d1 = f_add(t_after, -prev_after);
+                                                  inexact |= f_add(prev_after, d1) != t_after;
+                                              });
+    inexact = grp.ballot(inexact) != 0u;
+    if (inexact) {  // rounds >= 1 only: see k_march_infer
+        ctl[kCtlInexact] = 1;
+        if (grp.gl == 0) {
+            atomicAdd(ctl + 13, 1);
+            uint8_t* flags = ctl_ptr<uint8_t>(ctl, kCtlFlagsPtr);
+            if (flags) flags[index] = 1;
+        }
+    }
+    if (grp.gl == 0) s_cnt[gi] = active ? cnt : 0u;
+    __syncthreads();
+
+    // ---- offsets: groups inside the block, then decoupled look-back over the blocks ----
+    const uint32_t b = blockIdx.x;
+    if (warp == 0) {
+        uint32_t c = lane < kGroups ? s_cnt[lane] : 0u, incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane < kGroups) s_cnt[lane] = incl - c;  // exclusive prefix of the groups inside the block (their counts stay in registers: cnt)
+        const uint32_t agg = __shfl_sync(kFull, incl, 31);
+        uint32_t excl = 0;
+        if (b > 0) {
+            if (lane == 0) st_relaxed_u64(status + b, (1ull << 32) | agg);
+            int idx = (int)b - 1;
+            while (true) {
+                const int j = idx - lane;
+                unsigned long long st;
+                do {
+                    st = (j >= 0) ? ld_relaxed_u64(status + j) : (2ull << 32);
+                } while (__any_sync(kFull, (st >> 32) == 0ull));
+                const unsigned inc = __ballot_sync(kFull, (st >> 32) == 2ull);
+                uint32_t x = (uint32_t)st;
+                if (inc) {
+                    const int first = __ffs(inc) - 1;
+                    if (lane > first) x = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+                excl += x;
+                if (inc) break;
+                idx -= 32;
+            }
+        }
+        if (lane == 0) {
+            st_relaxed_u64(status + b, (2ull << 32) | (unsigned long long)(excl + agg));
+            s_excl = excl;
+        }
+        if (b == active_blocks - 1) {  // the frame's rows of this round: published, and the rows up to the next multiple of 128 zeroed
+            const uint32_t total = excl + agg, padded = (total + 127u) & ~127u;
+            if (lane == 0) ctl[kCtlCompactRows] = (int)padded;
+            for (uint32_t i = total * 3u + lane; i < padded * 3u; i += 32) { xyzs[i] = 0.f; dirs[i] = 0.f; }
+            for (uint32_t i = total * 2u + lane; i < padded * 2u; i += 32) deltas[i] = 0.f;
+            if (DISTILL)
+                for (uint32_t i = total + lane; i < padded; i += 32) edit_occ[i] = 0;
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const uint32_t off = s_excl + s_cnt[gi];
+    if (grp.gl == 0) { ray_off[g] = (int)off; ray_cnt[g] = (int)cnt; }
+
+    // ---- the group writes its samples back to back: flat over the ray's floats, so that consecutive lanes store consecutive words
+    // (positions recomputed from the parked t values, as k_march_train does) ----
+    const float o3[3] = {r.ox, r.oy, r.oz};
+    const float d3[3] = {r.dx, r.dy, r.dz};
+    float* px = xyzs + (size_t)off * 3;
+    float* pd = dirs + (size_t)off * 3;
+    for (uint32_t e = grp.gl; e < cnt * 3u; e += G) {
+        const uint32_t k = e / 3u, c = e - 3u * k;
+        const float oc = c == 0 ? o3[0] : (c == 1 ? o3[1] : o3[2]);
+        const float dc = c == 0 ? d3[0] : (c == 1 ? d3[1] : d3[2]);
+        px[e] = f_clamp(f_fma(s_t[gi][k], dc, oc), p.neg_bound, p.bound);
+        pd[e] = dc;
+    }
+    for (uint32_t k = grp.gl; k < cnt; k += G) {
+        const float s = s_t[gi][k];
+        const float dt = p.dt_const ? p.dt0 : march_dt(p, s);
+        const float after = f_add(s, dt);
+        float last = t0;
+        if (k > 0) {
+            const float sp = s_t[gi][k - 1];
+            last = f_add(sp, p.dt_const ? p.dt0 : march_dt(p, sp));
+        }
+        const size_t row = (size_t)off + k;
+        reinterpret_cast<float2*>(deltas)[row] = make_float2(dt, f_add(after, -last));
+        if (DISTILL) {
+            const Probe q = march_probe(p, r, s, dt);
+            edit_occ[row] = (uint8_t)((__ldg(edit_grid + (q.index >> 3)) >> (q.index & 7u)) & 1u);
+        }
+    }
+}
+
+// composite_infer_ray over a ray's compact samples (thread per alive ray); also re-arms the marcher's status words
+template <bool DISTILL>
+__global__ void __launch_bounds__(256)
+k_composite_infer_compact(const float T_thresh, int* __restrict__ rays_alive, float* __restrict__ rays_t, const float* __restrict__ sigmas,
+                          const float* __restrict__ rgbs, const float* __restrict__ deltas, float* __restrict__ weights_sum,
+                          float* __restrict__ weights_edit_sum, float* __restrict__ depth, float* __restrict__ depth_edit,
+                          const uint8_t* __restrict__ edit_occ, float* __restrict__ image, const int* __restrict__ ray_off,
+                          const int* __restrict__ ray_cnt, unsigned long long* __restrict__ status, const uint32_t n_status,
+                          const int* __restrict__ ctl) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n_status; i += nth) status[i] = 0ull;
+    const uint32_t na = (uint32_t)ctl[kCtlAlive], n_step = (uint32_t)ctl[kCtlStep];
+    int* ray_steps = ctl_ptr<int>(ctl, kCtlStepsPtr);
+    for (uint32_t n = tid; n < na; n += nth) {
+        const int index = rays_alive[n];
+        const size_t o = (size_t)ray_off[n];
+        const uint32_t count = (uint32_t)ray_cnt[n];
+        const float* ps = sigmas + o;
+        const float* pc = rgbs + o * 3;
+        const float2* pl = reinterpret_cast<const float2*>(deltas) + o;
+        const uint8_t* pe = DISTILL ? edit_occ + o : nullptr;
+        float t = rays_t[index];
+        float weight_sum = weights_sum[index], d = depth[index];
+        float weight_edit_sum = 0.f, d_edit = 0.f;
+        if (DISTILL) { weight_edit_sum = weights_edit_sum[index]; d_edit = depth_edit[index]; }
+        float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
+        uint32_t step = 0;
+        bool stopped = false;
+        while (step < count) {
+            const float2 dl = __ldg(pl + step);
+            const float alpha = 1.0f - __expf(-__ldg(ps + step) * dl.x);
+            const float T = f_add(1.0f, -weight_sum);
+            const float weight = f_mul(alpha, T);
+            weight_sum = f_add(weight_sum, weight);
+            if (DISTILL && pe[step]) {
+                weight_edit_sum = f_add(weight_edit_sum, weight);
+                d_edit = f_fma(weight, t, d_edit);
+            }
+            t = f_add(t, dl.y);
+            d = f_fma(weight, t, d);
+            r = f_fma(weight, __ldg(pc + step * 3), r);
+            g = f_fma(weight, __ldg(pc + step * 3 + 1), g);
+            b = f_fma(weight, __ldg(pc + step * 3 + 2), b);
+            if (T < T_thresh) { stopped = true; break; }
+            step++;
+        }
+        // the reference's slot layout ends a ray whose round came up short (dl.x == 0 in the next slot) or that hit T_thresh
+        if (stopped || count < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+        if (ray_steps) ray_steps[index] += (int)step;
+        if (DISTILL) { weights_edit_sum[index] = weight_edit_sum; depth_edit[index] = d_edit; }
+        weights_sum[index] = weight_sum;
+        depth[index] = d;
+        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
     }
 }
 
@@ -1329,7 +1531,10 @@ int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap
     // or next to occupied cells, 2-3 samples wanted) 8 lanes 97 us, 4 lanes 150-200 us -- a second window costs more than
     // four idle lanes.
     if (first) {
-        if (distill) LNRF_MARCH_DEV_(true, 4, 1, 64) else LNRF_MARCH_DEV_(false, 4, 1, 64)
+        static const int first_g = [] { const char* e = getenv("LNRF_MARCH_FIRST_G"); return e ? atoi(e) : 4; }();  // A/B switch
+        if (first_g == 1) { if (distill) LNRF_MARCH_DEV_(true, 1, 1, 64) else LNRF_MARCH_DEV_(false, 1, 1, 64) }
+        else if (first_g == 2) { if (distill) LNRF_MARCH_DEV_(true, 2, 1, 64) else LNRF_MARCH_DEV_(false, 2, 1, 64) }
+        else { if (distill) LNRF_MARCH_DEV_(true, 4, 1, 64) else LNRF_MARCH_DEV_(false, 4, 1, 64) }
     } else {
         if (distill) LNRF_MARCH_DEV_(true, 8, 1, 64) else LNRF_MARCH_DEV_(false, 8, 1, 64)
     }
@@ -1350,6 +1555,58 @@ int composite_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays
         k_composite_infer<false><<<blocks, 256, 0, st>>>(0u, 1u, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, nullptr,
                                                          depth, nullptr, nullptr, image, ctl);
     LNRF_LAUNCH_CHECK("render_rounds(composite)");
+    return LNRF_OK;
+}
+
+// compact rounds: scratch_m = (n_rays_cap / 16 + 2) status words (one per marcher block), then ray_off[n_rays_cap], ray_cnt[n_rays_cap]
+size_t march_compact_scratch_bytes(uint32_t n_rays_cap) {
+    return sizeof(unsigned long long) * ((size_t)div_up(n_rays_cap, 16u) + 2) + 2 * sizeof(int) * (size_t)n_rays_cap;
+}
+static void march_compact_carve(void* scratch_m, uint32_t n_rays_cap, unsigned long long** status, uint32_t* n_status, int** off, int** cnt) {
+    *status = reinterpret_cast<unsigned long long*>(scratch_m);
+    *n_status = div_up(n_rays_cap, 16u) + 2u;
+    *off = reinterpret_cast<int*>(*status + *n_status);
+    *cnt = *off + n_rays_cap;
+}
+
+int march_infer_compact_dev_launch(bool distill, int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
+                                   const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                                   uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars, float* xyzs, float* dirs,
+                                   float* deltas, uint8_t* edit_occ, void* scratch_m, cudaStream_t st) {
+    const char* who = distill ? "render_rounds(march_distill, compact)" : "render_rounds(march, compact)";
+    if (int e = check_march_common(C, H, max_steps, who)) return e;
+    if (n_rays_cap == 0) return LNRF_OK;
+    LNRF_REQUIRE(ctl && rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && dirs && deltas && scratch_m, "%s: null pointer", who);
+    const MarchParams p = march_params_env(bound, dt_gamma, max_steps, C, H);
+    unsigned long long* status; uint32_t n_status; int *off, *cnt;
+    march_compact_carve(scratch_m, n_rays_cap, &status, &n_status, &off, &cnt);
+    const uint32_t blocks = div_up(n_rays_cap, (uint32_t)kCompactThreads / (uint32_t)kInferGroup);
+    if (distill)
+        k_march_infer_compact<true><<<blocks, kCompactThreads, 0, st>>>(rays_alive, rays_t, rays_o, rays_d, p, grid, edit_grid, fars, xyzs, dirs, deltas, edit_occ,
+                                                            off, cnt, status, ctl);
+    else
+        k_march_infer_compact<false><<<blocks, kCompactThreads, 0, st>>>(rays_alive, rays_t, rays_o, rays_d, p, grid, nullptr, fars, xyzs, dirs, deltas, nullptr,
+                                                             off, cnt, status, ctl);
+    LNRF_LAUNCH_CHECK(who);
+    return LNRF_OK;
+}
+
+int composite_infer_compact_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                       const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                                       float* weights_edit_sum, float* depth, float* depth_edit, const uint8_t* edit_occ, float* image,
+                                       void* scratch_m, cudaStream_t st) {
+    if (n_rays_cap == 0) return LNRF_OK;
+    unsigned long long* status; uint32_t n_status; int *off, *cnt;
+    march_compact_carve(scratch_m, n_rays_cap, &status, &n_status, &off, &cnt);
+    const uint32_t want = div_up(n_rays_cap, 256u), cap_blocks = (uint32_t)kNumSMs * 8u;
+    const uint32_t blocks = want < cap_blocks ? want : cap_blocks;
+    if (distill)
+        k_composite_infer_compact<true><<<blocks, 256, 0, st>>>(T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, weights_edit_sum,
+                                                                depth, depth_edit, edit_occ, image, off, cnt, status, n_status, ctl);
+    else
+        k_composite_infer_compact<false><<<blocks, 256, 0, st>>>(T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, nullptr, depth,
+                                                                 nullptr, nullptr, image, off, cnt, status, n_status, ctl);
+    LNRF_LAUNCH_CHECK("render_rounds(composite, compact)");
     return LNRF_OK;
 }
 

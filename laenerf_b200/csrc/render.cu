@@ -18,7 +18,8 @@ static uint32_t sample_row_budget(const lnrf_render_desc* d) {
 
 extern "C" {
 
-size_t lnrf_render_scratch_bytes(uint32_t n_rays) { return lnrf_compact_alive_scratch_bytes(n_rays); }
+// [alive-ray compaction look-back words | compact rounds: marcher look-back words + (offset, count) per alive ray]
+size_t lnrf_render_scratch_bytes(uint32_t n_rays) { return lnrf_compact_alive_scratch_bytes(n_rays) + march_compact_scratch_bytes(n_rays); }
 
 int lnrf_render_begin(const lnrf_render_desc* d, lnrf_stream_t stream) {
     LNRF_REQUIRE(d && d->ctl, "render_begin: null descriptor / control block");
@@ -35,14 +36,27 @@ int lnrf_render_rounds(const lnrf_render_desc* d, uint32_t first_round, uint32_t
     LNRF_REQUIRE(d->rays_alive[0] && d->rays_alive[1] && d->enc_f16 && d->sigmas && d->rgbs, "render_rounds: null buffer");
     const uint32_t cap = d->n_rays;                  // ray capacity (march groups, composite, compaction)
     const uint32_t row_cap = sample_row_budget(d);   // sample-row capacity (encoder, network)
-    const int32_t* rows_dev = d->ctl + 3;  // kCtlRows
+    // fast schedule (more than 8 samples per ray per round, own row budget, no prescribed sequence): rounds >= 1 are COMPACT -- a
+    // ray's samples sit right behind the previous ray's (raymarch.cu k_march_infer_compact), the round's row count is ctl[15]
+    const bool compact_rounds = d->sample_rows > d->n_rays + 128u && d->samples_per_round > 8u && !d->nstep_seq;
+    const size_t ca_bytes = lnrf_compact_alive_scratch_bytes(cap);
+    LNRF_REQUIRE(!compact_rounds || (d->scratch && d->scratch_bytes >= ca_bytes + march_compact_scratch_bytes(cap)),
+                 "render_rounds: scratch too small for compact rounds (lnrf_render_scratch_bytes)");
+    void* scratch_m = compact_rounds ? static_cast<void*>(static_cast<uint8_t*>(d->scratch) + ca_bytes) : nullptr;
     for (uint32_t r = first_round; r < first_round + n_rounds; r++) {
         int32_t* cur = d->rays_alive[r & 1u];
         int32_t* nxt = d->rays_alive[(r + 1u) & 1u];
+        const bool compact = compact_rounds && r > 0;
+        const int32_t* rows_dev = d->ctl + (compact ? 15 : 3);  // kCtlCompactRows : kCtlRows
         const float* noises = (r == 0 && d->first_round_noises) ? d->first_round_noises : nullptr;  // perturb only on the first round
-        if (int e = march_infer_dev_launch(distill, d->ctl, cap, cur, d->rays_t, d->rays_o, d->rays_d, d->bound, d->dt_gamma, d->max_steps,
-                                           d->cascade, d->grid_size, d->density_bitfield, d->edit_bitfield, d->fars, d->xyzs, d->dirs,
-                                           d->deltas, d->edit_occ, noises, /*first=*/r == 0, st))
+        if (compact) {
+            if (int e = march_infer_compact_dev_launch(distill, d->ctl, cap, cur, d->rays_t, d->rays_o, d->rays_d, d->bound, d->dt_gamma,
+                                                       d->max_steps, d->cascade, d->grid_size, d->density_bitfield, d->edit_bitfield, d->fars,
+                                                       d->xyzs, d->dirs, d->deltas, d->edit_occ, scratch_m, st))
+                return e;
+        } else if (int e = march_infer_dev_launch(distill, d->ctl, cap, cur, d->rays_t, d->rays_o, d->rays_d, d->bound, d->dt_gamma, d->max_steps,
+                                                  d->cascade, d->grid_size, d->density_bitfield, d->edit_bitfield, d->fars, d->xyzs, d->dirs,
+                                                  d->deltas, d->edit_occ, noises, /*first=*/r == 0, st))
             return e;
         if (int e = lnrf_grid_encode_forward_world(d->xyzs, d->bound, d->embeddings_f16, d->offsets_host, d->enc_f16, row_cap + 128u, rows_dev,
                                                    d->num_levels, d->level_scale_log2, d->base_resolution, d->gridtype, d->align_corners,
@@ -51,8 +65,13 @@ int lnrf_render_rounds(const lnrf_render_desc* d, uint32_t first_round, uint32_t
         if (int e = nerf_forward_dev_launch(d->enc_f16, d->dirs, d->w_sigma_f16, d->w_color_f16, row_cap + 128u, rows_dev, d->num_layers_sigma,
                                             d->num_layers_color, d->density_scale, d->sigmas, d->rgbs, st))
             return e;
-        if (int e = composite_infer_dev_launch(distill, d->ctl, cap, d->T_thresh, cur, d->rays_t, d->sigmas, d->rgbs, d->deltas, d->weights_sum,
-                                               d->weights_edit_sum, d->depth, d->depth_edit, d->edit_occ, d->image, st))
+        if (compact) {
+            if (int e = composite_infer_compact_dev_launch(distill, d->ctl, cap, d->T_thresh, cur, d->rays_t, d->sigmas, d->rgbs, d->deltas,
+                                                           d->weights_sum, d->weights_edit_sum, d->depth, d->depth_edit, d->edit_occ, d->image,
+                                                           scratch_m, st))
+                return e;
+        } else if (int e = composite_infer_dev_launch(distill, d->ctl, cap, d->T_thresh, cur, d->rays_t, d->sigmas, d->rgbs, d->deltas, d->weights_sum,
+                                                      d->weights_edit_sum, d->depth, d->depth_edit, d->edit_occ, d->image, st))
             return e;
         if (int e = compact_alive_dev_launch(d->ctl, cap, cur, nxt, d->scratch, d->scratch_bytes, st)) return e;
     }

@@ -178,6 +178,7 @@ class NeRFNetwork(nn.Module):
         self.render_schedule = "auto"
         self._auto_fast_ok = True
         self.render_samples_per_round = 64  # "fast" only: cap on the samples a ray takes per round after the first
+        self.render_row_budget = int(os.environ.get("LNRF_RENDER_ROW_BUDGET", "24"))  # "fast" only: sample-buffer rows per ray of the frame
         self._amp_adam = None  # weak reference to the AmpAdam that owns the fp16 shadows, if any
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
                           self.in_dim_color == 32 and self.encoder_dir.degree == 4)
@@ -501,10 +502,11 @@ class NeRFNetwork(nn.Module):
         # round takes up to render_samples_per_round samples per ray -- several times fewer rounds, each of which costs ~90 us of
         # latency whatever its size
         fast = schedule == "fast"
-        # "fast": a round's row budget is 8 n_rays, or -- for the small ray sets a rank renders when a frame is tile-sharded over many
+        # "fast": a round's row budget is render_row_budget (24) x n_rays -- rounds >= 1 are compact (csrc/raymarch.cu
+        # k_march_infer_compact: no empty slots), so the budget only bounds the worst case and what it costs is address space --, or -- for the small ray sets a rank renders when a frame is tile-sharded over many
         # GPUs -- up to 4 M rows: every round costs ~100 us of latency whatever its size (march of the longest gap + four dependent
         # launches), so a small ray set should finish in as few rounds as possible (up to 64 samples per ray per round)
-        rows = (max(8 * n_rays, min(64 * n_rays, 1 << 22)) if fast else n_rays) + 128
+        rows = (max(self.render_row_budget * n_rays, min(64 * n_rays, 1 << 22)) if fast else n_rays) + 128
         if schedule == "prescribed":  # n_step per round from `seq` (at most 8): a subset of a frame on the full frame's schedule
             rows = 8 * n_rays + 128
         distill = edit_bitfield is not None
@@ -559,10 +561,12 @@ class NeRFNetwork(nn.Module):
             rounds_per_call = 32  # a prescribed schedule is run for a few thousand rays: tiny rounds, fewer host look-ups
         max_rounds = int(max_steps)  # n_step >= 1: the reference loop cannot run more rounds than this
         while launched < max_rounds:
-            k = min(rounds_per_call, max_rounds - launched)
+            # fast schedule: a frame takes ~8-10 rounds, the last of them tiny; rounds queued behind the end of the frame are no-ops
+            # that still cost five launches (~40 us) each, so after the first batch the host looks more often
+            k = min(rounds_per_call if (launched == 0 or not fast) else max(2, rounds_per_call // 3), max_rounds - launched)
             N.check(lib.lnrf_render_rounds(C.byref(d), launched, k, st))
             launched += k
-            ctl = t["ctl"].tolist()  # the one synchronisation per `rounds_per_call` rounds
+            ctl = t["ctl"].tolist()  # the one synchronisation per batch of rounds
             if ctl[6]:
                 break
         t["rounds"], t["steps"], t["slots"] = ctl[7], ctl[2], ctl[9]
