@@ -354,6 +354,12 @@ typedef struct {
     uint8_t* ray_flags;
     const int32_t* nstep_seq;
     uint32_t nstep_len;
+    /* Optional (NULL = off): device float[6] = {lo_x, lo_y, lo_z, hi_x, hi_y, hi_z}, a box that CONTAINS every occupied cell of
+     * density_bitfield on every cascade (with a margin of two cells; laenerf_b200/nerf.py occupied_box).  The marcher then ends a
+     * ray at min(far, exit of this box): beyond it no cell is occupied, so no sample is ever emitted there -- the walk to the end of
+     * the scene box that raymarching.cu:766 does for every ray (and the whole walk of a ray that misses the box) is skipped with
+     * the same samples, deltas and rays_t.  The START of a ray is never moved: the t lattice hangs on `near`. */
+    const float* occupied_box;
 } lnrf_render_desc;
 LNRF_API size_t lnrf_render_scratch_bytes(uint32_t n_rays);
 /* rays_alive[0] = 0..n_rays-1, rays_t = nears, accumulators = 0, control block = first round. */

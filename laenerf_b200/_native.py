@@ -113,7 +113,7 @@ class RenderDesc(C.Structure):
         ("weights_sum", vp), ("depth", vp), ("image", vp), ("weights_edit_sum", vp), ("depth_edit", vp),
         ("scratch", vp), ("scratch_bytes", sz),
         ("sample_rows", u32), ("samples_per_round", u32),
-        ("ray_steps", vp), ("ray_flags", vp), ("nstep_seq", vp), ("nstep_len", u32),
+        ("ray_steps", vp), ("ray_flags", vp), ("nstep_seq", vp), ("nstep_len", u32), ("occupied_box", vp)
     ]
 
 

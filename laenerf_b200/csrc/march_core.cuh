@@ -121,6 +121,23 @@ LNRF_HD Ray make_ray(const float* o, const float* d) {
     return r;
 }
 
+// End of the useful part of a ray: min(far, where it leaves `box` = {lo xyz, hi xyz}), a box that contains every occupied cell with
+// a margin (lnrf_render_desc.occupied_box).  Beyond it the reference's walk only skips empty cells, so stopping there emits the same
+// samples; a ray that misses the box emits none (-inf).  The rounding of this slab test (a few ulp of t) is far inside the margin.
+// null box: far unchanged.
+LNRF_HD float clip_far_to_box(const float* box, const Ray& r, float far) {
+    if (!box) return far;
+    const float o[3] = {r.ox, r.oy, r.oz}, rd[3] = {r.rdx, r.rdy, r.rdz};
+    float t_in = -INFINITY, t_out = INFINITY;
+    for (int a = 0; a < 3; a++) {
+        const float t1 = (box[a] - o[a]) * rd[a], t2 = (box[3 + a] - o[a]) * rd[a];  // +-inf for d = 0, NaN on a face: fmin / fmax drop NaN
+        t_in = fmaxf(t_in, fminf(t1, t2));
+        t_out = fminf(t_out, fmaxf(t1, t2));
+    }
+    if (!(t_in <= t_out)) return -INFINITY;
+    return fminf(far, t_out);
+}
+
 struct Probe {
     float x, y, z;    // clamped sample position
     float tt;         // where the reference's skip loop must get to if this cell is empty

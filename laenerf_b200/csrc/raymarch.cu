@@ -920,7 +920,8 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
               const MarchParams p, const uint8_t* __restrict__ grid, const uint8_t* __restrict__ edit_grid,
               const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
               float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, const float* __restrict__ noises,
-              uint32_t M_rows, uint32_t n_groups, const int* __restrict__ ctl, const int g_lo, const int g_hi) {
+              uint32_t M_rows, uint32_t n_groups, const int* __restrict__ ctl, const int g_lo, const int g_hi,
+              const float* __restrict__ occ_box = nullptr) {
     const Group<G> grp;
     if (ctl) {  // device-driven round: geometry from the control block; this instantiation serves n_step in [g_lo, g_hi]
         n_alive = (uint32_t)ctl[kCtlAlive];
@@ -940,7 +941,7 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_al
         if (active) {
             index = __ldg(rays_alive + g);
             r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
-            far = fars[index];
+            far = clip_far_to_box(occ_box, r, fars[index]);
             const float t_in = rays_t[index];
             const float noise = noises ? noises[g] : 0.0f;
             t = f_fma(f_clamp(f_mul(t_in, p.dt_gamma), p.dt_min, p.dt_max), noise, t_in);  // raymarching.cu:746
@@ -1164,7 +1165,8 @@ k_march_infer_compact(const int* __restrict__ rays_alive, const float* __restric
                       const float* __restrict__ rays_d, const MarchParams p, const uint8_t* __restrict__ grid,
                       const uint8_t* __restrict__ edit_grid, const float* __restrict__ fars, float* __restrict__ xyzs,
                       float* __restrict__ dirs, float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, int* __restrict__ ray_off,
-                      int* __restrict__ ray_cnt, unsigned long long* __restrict__ status, int* __restrict__ ctl) {
+                      int* __restrict__ ray_cnt, unsigned long long* __restrict__ status, int* __restrict__ ctl,
+                      const float* __restrict__ occ_box) {
     constexpr int G = kInferGroup, kGroups = kCompactThreads / G;
     __shared__ float s_t[kGroups][kCompactCap];
     __shared__ uint32_t s_cnt[kGroups];
@@ -1183,7 +1185,7 @@ k_march_infer_compact(const int* __restrict__ rays_alive, const float* __restric
     if (active) {
         index = __ldg(rays_alive + g);
         r = make_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
-        far = fars[index];
+        far = clip_far_to_box(occ_box, r, fars[index]);
         t0 = rays_t[index];  // rounds >= 1 carry no noise (raymarching.cu:746 with noise = 0 leaves t_in unchanged)
     }
     bool inexact = false;
@@ -1508,7 +1510,7 @@ int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, uint3
 int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
                            const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                            uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars, float* xyzs, float* dirs,
-                           float* deltas, uint8_t* edit_occ, const float* noises, bool first, cudaStream_t st) {
+                           float* deltas, uint8_t* edit_occ, const float* noises, bool first, const float* occ_box, cudaStream_t st) {
     const char* who = distill ? "render_rounds(march_distill)" : "render_rounds(march)";
     if (int e = check_march_common(C, H, max_steps, who)) return e;
     if (n_rays_cap == 0) return LNRF_OK;
@@ -1522,7 +1524,7 @@ int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap
         const uint32_t want = div_up(n_rays_cap + 128u, 256u / GG);                                                                   \
         k_march_infer<DD, GG><<<want < cap_blocks ? want : cap_blocks, 256, 0, st>>>(0u, 1u, rays_alive, rays_t, rays_o, rays_d, p, grid, \
                                                                                       edit_grid, fars, xyzs, dirs, deltas, edit_occ,   \
-                                                                                      noises, 0u, 0u, ctl, LO, HI);                    \
+                                                                                      noises, 0u, 0u, ctl, LO, HI, occ_box);           \
         LNRF_LAUNCH_CHECK(who);                                                                                                       \
     }
     // Group width, measured per round on the 640 000-ray lego frame (profiles/r1g_render.txt): first round (every ray walks
@@ -1572,7 +1574,7 @@ static void march_compact_carve(void* scratch_m, uint32_t n_rays_cap, unsigned l
 int march_infer_compact_dev_launch(bool distill, int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
                                    const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                                    uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars, float* xyzs, float* dirs,
-                                   float* deltas, uint8_t* edit_occ, void* scratch_m, cudaStream_t st) {
+                                   float* deltas, uint8_t* edit_occ, void* scratch_m, const float* occ_box, cudaStream_t st) {
     const char* who = distill ? "render_rounds(march_distill, compact)" : "render_rounds(march, compact)";
     if (int e = check_march_common(C, H, max_steps, who)) return e;
     if (n_rays_cap == 0) return LNRF_OK;
@@ -1583,10 +1585,10 @@ int march_infer_compact_dev_launch(bool distill, int32_t* ctl, uint32_t n_rays_c
     const uint32_t blocks = div_up(n_rays_cap, (uint32_t)kCompactThreads / (uint32_t)kInferGroup);
     if (distill)
         k_march_infer_compact<true><<<blocks, kCompactThreads, 0, st>>>(rays_alive, rays_t, rays_o, rays_d, p, grid, edit_grid, fars, xyzs, dirs, deltas, edit_occ,
-                                                            off, cnt, status, ctl);
+                                                            off, cnt, status, ctl, occ_box);
     else
         k_march_infer_compact<false><<<blocks, kCompactThreads, 0, st>>>(rays_alive, rays_t, rays_o, rays_d, p, grid, nullptr, fars, xyzs, dirs, deltas, nullptr,
-                                                             off, cnt, status, ctl);
+                                                             off, cnt, status, ctl, occ_box);
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }

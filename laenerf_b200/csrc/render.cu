@@ -52,11 +52,11 @@ int lnrf_render_rounds(const lnrf_render_desc* d, uint32_t first_round, uint32_t
         if (compact) {
             if (int e = march_infer_compact_dev_launch(distill, d->ctl, cap, cur, d->rays_t, d->rays_o, d->rays_d, d->bound, d->dt_gamma,
                                                        d->max_steps, d->cascade, d->grid_size, d->density_bitfield, d->edit_bitfield, d->fars,
-                                                       d->xyzs, d->dirs, d->deltas, d->edit_occ, scratch_m, st))
+                                                       d->xyzs, d->dirs, d->deltas, d->edit_occ, scratch_m, d->occupied_box, st))
                 return e;
         } else if (int e = march_infer_dev_launch(distill, d->ctl, cap, cur, d->rays_t, d->rays_o, d->rays_d, d->bound, d->dt_gamma, d->max_steps,
                                                   d->cascade, d->grid_size, d->density_bitfield, d->edit_bitfield, d->fars, d->xyzs, d->dirs,
-                                                  d->deltas, d->edit_occ, noises, /*first=*/r == 0, st))
+                                                  d->deltas, d->edit_occ, noises, /*first=*/r == 0, d->occupied_box, st))
             return e;
         if (int e = lnrf_grid_encode_forward_world(d->xyzs, d->bound, d->embeddings_f16, d->offsets_host, d->enc_f16, row_cap + 128u, rows_dev,
                                                    d->num_levels, d->level_scale_log2, d->base_resolution, d->gridtype, d->align_corners,

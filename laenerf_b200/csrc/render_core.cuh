@@ -15,7 +15,7 @@ int render_begin_launch(int32_t* ctl, uint32_t n_rays, uint32_t max_steps, uint3
 int march_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
                            const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                            uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars, float* xyzs, float* dirs,
-                           float* deltas, uint8_t* edit_occ, const float* noises, bool first, cudaStream_t st);
+                           float* deltas, uint8_t* edit_occ, const float* noises, bool first, const float* occ_box, cudaStream_t st);
 int composite_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, float T_thresh, int32_t* rays_alive, float* rays_t,
                                const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* weights_edit_sum,
                                float* depth, float* depth_edit, const uint8_t* edit_occ, float* image, cudaStream_t st);
@@ -24,7 +24,7 @@ size_t march_compact_scratch_bytes(uint32_t n_rays_cap);
 int march_infer_compact_dev_launch(bool distill, int32_t* ctl, uint32_t n_rays_cap, const int32_t* rays_alive, const float* rays_t,
                                    const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                                    uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* fars, float* xyzs, float* dirs,
-                                   float* deltas, uint8_t* edit_occ, void* scratch_m, cudaStream_t st);
+                                   float* deltas, uint8_t* edit_occ, void* scratch_m, const float* occ_box, cudaStream_t st);
 int composite_infer_compact_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays_cap, float T_thresh, int32_t* rays_alive, float* rays_t,
                                        const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
                                        float* weights_edit_sum, float* depth, float* depth_edit, const uint8_t* edit_occ, float* image,

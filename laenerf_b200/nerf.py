@@ -178,6 +178,8 @@ class NeRFNetwork(nn.Module):
         self.render_schedule = "auto"
         self._auto_fast_ok = True
         self.render_samples_per_round = 64  # "fast" only: cap on the samples a ray takes per round after the first
+        self.render_clip_far = os.environ.get("LNRF_RENDER_CLIP", "1") == "1"  # device loop: rays end where they leave occupied_box()
+        self._occ_box = self._occ_box_key = self._cell_coords = None
         self.render_row_budget = int(os.environ.get("LNRF_RENDER_ROW_BUDGET", "24"))  # "fast" only: sample-buffer rows per ray of the frame
         self._amp_adam = None  # weak reference to the AmpAdam that owns the fp16 shadows, if any
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
@@ -364,6 +366,34 @@ class NeRFNetwork(nn.Module):
         if total_step > 0:
             self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
         self.local_step = 0
+
+    @torch.no_grad()
+    def occupied_box(self):
+        """Device float[6] {lo xyz, hi xyz}: a world-space box around every occupied cell of density_bitfield on every cascade, two
+        cells of margin (include/laenerf_b200.h lnrf_render_desc.occupied_box).  Recomputed when the bitfield changes (fixed-shape
+        torch reductions over the H^3 cells of each cascade: no host synchronisation)."""
+        bf = self.density_bitfield
+        key = (bf.data_ptr(), bf._version)
+        if self._occ_box_key != key:
+            dev, H, Cn = bf.device, int(self.grid_size), int(self.cascade)
+            if self._cell_coords is None or self._cell_coords.device != dev:
+                self._cell_coords = raymarching.morton3D_invert(torch.arange(H ** 3, dtype=torch.int32, device=dev)).int()  # [H^3, 3]
+            shifts = torch.arange(8, dtype=torch.uint8, device=dev)
+            lo_w = torch.full((3,), float("inf"), device=dev)
+            hi_w = torch.full((3,), float("-inf"), device=dev)
+            per = H ** 3 // 8
+            for c in range(Cn):  # bit index = c * H^3 + morton(x, y, z), bit (index & 7) of byte index >> 3 (csrc/march_core.cuh march_probe)
+                occ = ((bf[c * per:(c + 1) * per, None] >> shifts) & 1).reshape(-1).bool()[:, None]
+                lo = torch.where(occ, self._cell_coords, H).amin(0).float()
+                hi = torch.where(occ, self._cell_coords, -1).amax(0).float()
+                half = float(min(2 ** c, self.bound))   # mip_bound of the cascade
+                cell = 2.0 * half / H
+                some = occ.any()
+                lo_w = torch.minimum(lo_w, torch.where(some, -half + (lo - 2.0) * cell, lo_w))
+                hi_w = torch.maximum(hi_w, torch.where(some, -half + (hi + 3.0) * cell, hi_w))
+            self._occ_box = torch.cat([lo_w, hi_w]).float().contiguous()
+            self._occ_box_key = key
+        return self._occ_box
 
     # ---- row f-3: the inference loop of run_cuda / run_cuda_distill driven from the device -----------------------------
     def _render_rounds_device(self, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
@@ -554,6 +584,9 @@ class NeRFNetwork(nn.Module):
         d.samples_per_round = int(self.render_samples_per_round) if fast else (8 if seq is not None else 0)
         d.ray_steps, d.ray_flags = N.ptr(t["ray_steps"]), N.ptr(t["ray_flags"])
         d.nstep_seq, d.nstep_len = (seq.data_ptr(), int(seq.numel())) if seq is not None else (None, 0)
+        # every schedule: a ray ends where it leaves the box around the occupied cells (exact: nothing is ever sampled beyond it)
+        t["occupied_box"] = self.occupied_box() if (self.render_clip_far and dens_grid is self.density_bitfield) else None
+        d.occupied_box = N.ptr(t["occupied_box"])
         st = N.stream()
         N.check(lib.lnrf_render_begin(C.byref(d), st))
         launched = 0
