@@ -1290,8 +1290,12 @@ k_march_infer_compact(const int* __restrict__ rays_alive, const float* __restric
     }
 }
 
-// composite_infer_ray over a ray's compact samples (thread per alive ray); also re-arms the marcher's status words
-template <bool DISTILL>
+// composite_infer_ray (raymarching.cu:948-1035 / 1037-1142) over a ray's compact samples; also re-arms the marcher's status words.
+// A ray's samples are consecutive rows, so a thread per ray reads with a stride of its neighbour's sample count: 32 sectors per load
+// instruction (257 us for the 14 M samples of the lego frame's second round).  Here G lanes share a ray: they fetch G consecutive
+// samples with one coalesced load each, and every lane then runs the reference's sequential recurrence over them, the operands
+// handed round by shuffles -- the same operations in the same order on every lane, so the ray's state never leaves registers.
+template <bool DISTILL, int G>
 __global__ void __launch_bounds__(256)
 k_composite_infer_compact(const float T_thresh, int* __restrict__ rays_alive, float* __restrict__ rays_t, const float* __restrict__ sigmas,
                           const float* __restrict__ rgbs, const float* __restrict__ deltas, float* __restrict__ weights_sum,
@@ -1303,7 +1307,9 @@ k_composite_infer_compact(const float T_thresh, int* __restrict__ rays_alive, fl
     for (uint32_t i = tid; i < n_status; i += nth) status[i] = 0ull;
     const uint32_t na = (uint32_t)ctl[kCtlAlive], n_step = (uint32_t)ctl[kCtlStep];
     int* ray_steps = ctl_ptr<int>(ctl, kCtlStepsPtr);
-    for (uint32_t n = tid; n < na; n += nth) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const unsigned gmask = G == 32 ? kFull : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));  // the rays of a warp loop independently
+    for (uint32_t n = tid / G; n < na; n += nth / G) {
         const int index = rays_alive[n];
         const size_t o = (size_t)ray_off[n];
         const uint32_t count = (uint32_t)ray_cnt[n];
@@ -1318,31 +1324,52 @@ k_composite_infer_compact(const float T_thresh, int* __restrict__ rays_alive, fl
         float r = image[(size_t)index * 3], g = image[(size_t)index * 3 + 1], b = image[(size_t)index * 3 + 2];
         uint32_t step = 0;
         bool stopped = false;
-        while (step < count) {
-            const float2 dl = __ldg(pl + step);
-            const float alpha = 1.0f - __expf(-__ldg(ps + step) * dl.x);
-            const float T = f_add(1.0f, -weight_sum);
-            const float weight = f_mul(alpha, T);
-            weight_sum = f_add(weight_sum, weight);
-            if (DISTILL && pe[step]) {
-                weight_edit_sum = f_add(weight_edit_sum, weight);
-                d_edit = f_fma(weight, t, d_edit);
+        for (uint32_t base = 0; base < count && !stopped; base += G) {
+            const uint32_t k = base + (uint32_t)gl;
+            float m_sg = 0.f, m_cr = 0.f, m_cg = 0.f, m_cb = 0.f;
+            float2 m_dl = make_float2(0.f, 0.f);
+            int m_eo = 0;
+            if (k < count) {
+                m_sg = __ldg(ps + k);
+                m_dl = __ldg(pl + k);
+                m_cr = __ldg(pc + (size_t)k * 3); m_cg = __ldg(pc + (size_t)k * 3 + 1); m_cb = __ldg(pc + (size_t)k * 3 + 2);
+                if (DISTILL) m_eo = pe[k];
             }
-            t = f_add(t, dl.y);
-            d = f_fma(weight, t, d);
-            r = f_fma(weight, __ldg(pc + step * 3), r);
-            g = f_fma(weight, __ldg(pc + step * 3 + 1), g);
-            b = f_fma(weight, __ldg(pc + step * 3 + 2), b);
-            if (T < T_thresh) { stopped = true; break; }
-            step++;
+            const uint32_t m = count - base < (uint32_t)G ? count - base : (uint32_t)G;
+            for (uint32_t j = 0; j < m; j++) {
+                const float sg = __shfl_sync(gmask, m_sg, (int)j, G), dx = __shfl_sync(gmask, m_dl.x, (int)j, G),
+                            dy = __shfl_sync(gmask, m_dl.y, (int)j, G);
+                const float cr = __shfl_sync(gmask, m_cr, (int)j, G), cg = __shfl_sync(gmask, m_cg, (int)j, G),
+                            cb = __shfl_sync(gmask, m_cb, (int)j, G);
+                const float alpha = 1.0f - __expf(-sg * dx);
+                const float T = f_add(1.0f, -weight_sum);
+                const float weight = f_mul(alpha, T);
+                weight_sum = f_add(weight_sum, weight);
+                if (DISTILL) {
+                    const int eo = __shfl_sync(gmask, m_eo, (int)j, G);
+                    if (eo) {
+                        weight_edit_sum = f_add(weight_edit_sum, weight);
+                        d_edit = f_fma(weight, t, d_edit);
+                    }
+                }
+                t = f_add(t, dy);
+                d = f_fma(weight, t, d);
+                r = f_fma(weight, cr, r);
+                g = f_fma(weight, cg, g);
+                b = f_fma(weight, cb, b);
+                if (T < T_thresh) { stopped = true; break; }
+                step++;
+            }
         }
-        // the reference's slot layout ends a ray whose round came up short (dl.x == 0 in the next slot) or that hit T_thresh
-        if (stopped || count < n_step) rays_alive[n] = -1; else rays_t[index] = t;
-        if (ray_steps) ray_steps[index] += (int)step;
-        if (DISTILL) { weights_edit_sum[index] = weight_edit_sum; depth_edit[index] = d_edit; }
-        weights_sum[index] = weight_sum;
-        depth[index] = d;
-        image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+        if (gl == 0) {
+            // the reference's slot layout ends a ray whose round came up short (dl.x == 0 in the next slot) or that hit T_thresh
+            if (stopped || count < n_step) rays_alive[n] = -1; else rays_t[index] = t;
+            if (ray_steps) ray_steps[index] += (int)step;
+            if (DISTILL) { weights_edit_sum[index] = weight_edit_sum; depth_edit[index] = d_edit; }
+            weights_sum[index] = weight_sum;
+            depth[index] = d;
+            image[(size_t)index * 3] = r; image[(size_t)index * 3 + 1] = g; image[(size_t)index * 3 + 2] = b;
+        }
     }
 }
 
@@ -1600,14 +1627,20 @@ int composite_infer_compact_dev_launch(bool distill, const int32_t* ctl, uint32_
     if (n_rays_cap == 0) return LNRF_OK;
     unsigned long long* status; uint32_t n_status; int *off, *cnt;
     march_compact_carve(scratch_m, n_rays_cap, &status, &n_status, &off, &cnt);
-    const uint32_t want = div_up(n_rays_cap, 256u), cap_blocks = (uint32_t)kNumSMs * 8u;
-    const uint32_t blocks = want < cap_blocks ? want : cap_blocks;
-    if (distill)
-        k_composite_infer_compact<true><<<blocks, 256, 0, st>>>(T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, weights_edit_sum,
-                                                                depth, depth_edit, edit_occ, image, off, cnt, status, n_status, ctl);
-    else
-        k_composite_infer_compact<false><<<blocks, 256, 0, st>>>(T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, nullptr, depth,
-                                                                 nullptr, nullptr, image, off, cnt, status, n_status, ctl);
+    static const int cg = [] { const char* e = getenv("LNRF_COMPOSITE_INFER_G"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 4 || v == 8 || v == 16) ? v : 4; }();  // measured on the lego frame: 1 lane 11.68 ms, 4: 11.22, 8: 11.30, 16: 11.68
+#define LNRF_CIC_(DD, GG)                                                                                                               \
+    {                                                                                                                                   \
+        const uint32_t want = div_up(n_rays_cap, 256u / GG), cap_blocks = (uint32_t)kNumSMs * 8u;                                       \
+        k_composite_infer_compact<DD, GG><<<want < cap_blocks ? want : cap_blocks, 256, 0, st>>>(                                       \
+            T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, DD ? weights_edit_sum : nullptr, depth, DD ? depth_edit : nullptr, \
+            DD ? edit_occ : nullptr, image, off, cnt, status, n_status, ctl);                                                           \
+    }
+    if (distill) {
+        if (cg == 1) LNRF_CIC_(true, 1) else if (cg == 16) LNRF_CIC_(true, 16) else if (cg == 8) LNRF_CIC_(true, 8) else LNRF_CIC_(true, 4)
+    } else {
+        if (cg == 1) LNRF_CIC_(false, 1) else if (cg == 16) LNRF_CIC_(false, 16) else if (cg == 8) LNRF_CIC_(false, 8) else LNRF_CIC_(false, 4)
+    }
+#undef LNRF_CIC_
     LNRF_LAUNCH_CHECK("render_rounds(composite, compact)");
     return LNRF_OK;
 }
