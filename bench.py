@@ -493,7 +493,9 @@ def render_config(ctx, model, sc, pose_index=0, frames=3):
     torch, world, rank = ctx.torch, ctx.world, ctx.rank
     ro, rd, _ = get_rays_np(sc.poses[pose_index], sc.intrinsics, sc.H, sc.W)
     # N > 1: 32 x 32 pixel tiles dealt round-robin over the ranks (contiguous row ranges leave the object to the middle ranks)
-    mine = tile_shard_indices(sc.H, sc.W, rank, world).numpy() if world > 1 else np.arange(sc.H * sc.W)
+    tile = int(os.environ.get("LNRF_RENDER_TILE", "16"))  # 16 x 16: 2500 tiles of the 800 x 800 view, ~312 per rank at N = 8 (32 x 32 left the
+    # ranks 20 % apart: the frame is as slow as its slowest share)
+    mine = tile_shard_indices(sc.H, sc.W, rank, world, tile).numpy() if world > 1 else np.arange(sc.H * sc.W)
     ro_d, rd_d = torch.from_numpy(ro[mine]).to(ctx.dev), torch.from_numpy(rd[mine]).to(ctx.dev)
     model.eval()
     real = ctx.sum_over_ranks(count_real_samples(ctx, model, ro_d, rd_d))
@@ -505,7 +507,7 @@ def render_config(ctx, model, sc, pose_index=0, frames=3):
         marks, slots = [], 0
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
             for _ in range(2):  # warm-up frames, final gather included (the first collective of a shape pays NCCL's lazy set-up)
-                gather_tiles(model.render(ro_d, rd_d, perturb=False, bg_color=1)["image"], sc.H, sc.W, rank, world)
+                gather_tiles(model.render(ro_d, rd_d, perturb=False, bg_color=1)["image"], sc.H, sc.W, rank, world, tile)
             ctx.barrier()
             e0, e1 = ev(), ev()
             e0.record()
@@ -514,7 +516,7 @@ def render_config(ctx, model, sc, pose_index=0, frames=3):
                 a.record()
                 o = model.render(ro_d, rd_d, perturb=False, bg_color=1)
                 b.record()
-                img = gather_tiles(o["image"], sc.H, sc.W, rank, world)
+                img = gather_tiles(o["image"], sc.H, sc.W, rank, world, tile)
                 c.record()
                 marks.append((a, b, c))
                 slots += o["num_points"]
