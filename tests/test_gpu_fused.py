@@ -757,3 +757,60 @@ def test_fast_render_schedule_is_bit_identical_where_the_marcher_proves_it(dev):
                 d[sched] = mb.run_cuda_distill(ro, rd, edit, perturb=False)
         for k in ("image", "weights", "weights_edit", "depth", "depth_edit"):
             assert torch.equal(d["reference"][k], d["auto"][k]), (name, "distill", k)
+
+
+@pytest.mark.parametrize("name,n", [("lego", 60000), ("bonsai", 40000)])
+def test_render_economies_change_no_bit(dev, name, n):
+    """The exact economies of the device-driven fast rounds, each switched off in turn, against all of them on:
+    rays clipped to the box around the occupied cells (lnrf_render_desc.occupied_box), compact rounds (more than 8 samples per ray
+    per round: samples back to back, 4-lane compositor) against the reference's slot layout (8 samples per round), and the box
+    itself: it must contain every occupied cell of every cascade."""
+    from laenerf_b200 import raymarching
+    from laenerf_b200.nerf import NeRFNetwork
+    sc = scene(name)
+    torch.manual_seed(7)
+    m = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_scale=5.0).to(dev)
+    with torch.no_grad():
+        m.encoder.embeddings.uniform_(-0.5, 0.5)
+    m.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+    _, ro, rd, _ = scene_rays(name, n, 31)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    m.eval()
+    m.render_schedule = "auto"   # 8 and 64 samples per round are different schedules: only "auto" makes both the reference's bits
+    edit = m.density_bitfield.clone()
+    edit[1::2] = 0
+
+    def run():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            a = m.render(ro, rd, perturb=False, bg_color=1, scale_depth=False)
+            b = m.run_cuda_distill(ro, rd, edit, perturb=False)
+        return a, b
+
+    base = run()
+    assert base[0]["rounds"] < 40
+    variants = {}
+    m.render_clip_far = False
+    variants["no clipping"] = run()
+    m.render_clip_far = True
+    m.render_samples_per_round = 8   # fixed n_step slots per ray, the reference's layout (no compaction)
+    variants["slot layout"] = run()
+    m.render_samples_per_round = 64
+    for what, (a, b) in variants.items():
+        for k in ("image", "depth", "t"):
+            assert torch.equal(base[0][k], a[k]), (name, what, k)
+        for k in ("image", "weights", "weights_edit", "depth", "depth_edit"):
+            assert torch.equal(base[1][k], b[k]), (name, what, "distill", k)
+    assert variants["slot layout"][0]["num_points"] > base[0]["num_points"]   # the slots that compaction does not march
+    # the box: every occupied cell (all cascades) inside, in world coordinates
+    box = m.occupied_box().cpu().numpy()
+    H, C_ = m.grid_size, m.cascade
+    bits = np.unpackbits(m.density_bitfield.cpu().numpy(), bitorder="little").reshape(C_, H ** 3)
+    coords = raymarching.morton3D_invert(torch.arange(H ** 3, dtype=torch.int32, device=dev)).cpu().numpy()
+    for c in range(C_):
+        occ = coords[bits[c] == 1]
+        if len(occ) == 0:
+            continue
+        half = min(2 ** c, sc.bound)
+        cell = 2.0 * half / H
+        lo, hi = -half + occ.min(0) * cell, -half + (occ.max(0) + 1) * cell
+        assert (box[:3] <= lo - 1.9 * cell).all() and (box[3:] >= hi + 1.9 * cell).all(), (c, box, lo, hi)
