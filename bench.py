@@ -46,6 +46,7 @@ WORKLOAD = "lego-shape 800x800 hash-grid NeRF training step (16 levels, 2^19 tab
 # algorithmic bytes / FLOPs per unit (restated in DESIGN.md section 8)
 ALGO = {
     "lnrf_march_rays_train": dict(bound="hbm", per_ray=48, per_sample=32),
+    "lnrf_march_rays_train_clipped": dict(bound="hbm", per_ray=48, per_sample=32),   # the same kernel, rays ending at the occupied box
     "lnrf_grid_encode_forward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
     "lnrf_grid_encode_backward": dict(bound="hbm", per_ray=0, per_sample_padded=588),
     "lnrf_grid_encode_forward_world": dict(bound="hbm", per_ray=0, per_sample_padded=588),   # same kernels, world-coordinate inputs

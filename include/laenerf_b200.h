@@ -100,6 +100,13 @@ LNRF_API int lnrf_march_rays_train(const float* rays_o, const float* rays_d, con
                                    const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                                    int32_t* rays, int32_t* counter, const float* noises, void* scratch,
                                    size_t scratch_bytes, lnrf_stream_t stream);
+/* The same with rays ending where they leave `occupied_box` (device float[6], see lnrf_render_desc.occupied_box; NULL = off):
+ * identical samples, counts and offsets -- the walk through the empty rest of the scene box is skipped. */
+LNRF_API int lnrf_march_rays_train_clipped(const float* rays_o, const float* rays_d, const uint8_t* density_bitfield, float bound,
+                                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                           const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                           int32_t* rays, int32_t* counter, const float* noises, const float* occupied_box,
+                                           void* scratch, size_t scratch_bytes, lnrf_stream_t stream);
 
 /* composite_rays_train_forward (raymarching.h:14).  sigmas [M], rgbs [M,3], deltas [M,2], rays [N,3];
  * weights_sum, depth [N], image [N,3] written at index rays[n,0] for every row n. */
@@ -434,6 +441,13 @@ LNRF_API int lnrf_occupancy_ema(float* density_grid, float* tmp_grid, uint32_t n
                                 float* mean_out, void* scratch, size_t scratch_bytes, lnrf_stream_t stream);
 /* packbits (raymarching.cu:267-300) with the threshold read from device memory; N = number of output bytes. */
 LNRF_API int lnrf_packbits_dev(const float* grid, uint32_t N, const float* thresh_dev, uint8_t* bitfield,
+                               lnrf_stream_t stream);
+/* Box around the occupied cells of a bitfield (every cascade, two cells of margin, world coordinates): box = device float[6] {lo xyz,
+ * hi xyz}, +-inf when nothing is occupied.  What lnrf_render_desc.occupied_box / lnrf_march_rays_train_clipped take.  work: device
+ * int32[lnrf_occupied_box_work_ints(C)], initialised ONCE to {H, H, H, -1, -1, -1} per cascade followed by 0 (the kernel re-arms it).
+ * One launch, no host synchronisation. */
+LNRF_API size_t lnrf_occupied_box_work_ints(uint32_t C);
+LNRF_API int lnrf_occupied_box(const uint8_t* density_bitfield, uint32_t C, uint32_t H, float bound, int32_t* work, float* box,
                                lnrf_stream_t stream);
 /* sigma net only (NeRFNetwork.density, network_ff.py:81-95): sigmas [M] = density_scale * exp(h0); M a multiple of 128. */
 LNRF_API int lnrf_nerf_density(const void* enc_f16, const void* w_sigma_f16, uint32_t M, uint32_t num_layers_sigma,

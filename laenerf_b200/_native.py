@@ -38,6 +38,7 @@ SIGNATURES = {
     "lnrf_packbits": (i32, [vp, u32, f32, vp, vp]),
     "lnrf_march_rays_train_scratch_bytes": (sz, [u32]),
     "lnrf_march_rays_train": (i32, [vp, vp, vp, f32, f32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
+    "lnrf_march_rays_train_clipped": (i32, [vp, vp, vp, f32, f32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]),
     "lnrf_composite_rays_train_forward": (i32, [vp, vp, vp, vp, u32, u32, f32, vp, vp, vp, vp]),
     "lnrf_composite_rays_train_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, f32, vp, vp, i32, vp]),
     "lnrf_composite_loss_scratch_bytes": (sz, [u32]),
@@ -76,6 +77,8 @@ SIGNATURES = {
     "lnrf_occupancy_scratch_bytes": (sz, []),
     "lnrf_occupancy_ema": (i32, [vp, vp, u32, f32, f32, vp, vp, sz, vp]),
     "lnrf_packbits_dev": (i32, [vp, u32, vp, vp, vp]),
+    "lnrf_occupied_box_work_ints": (sz, [u32]),
+    "lnrf_occupied_box": (i32, [vp, u32, u32, f32, vp, vp, vp]),
     "lnrf_nerf_density": (i32, [vp, vp, u32, u32, f32, vp, vp]),
     "lnrf_nerf_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, f32, i32, vp, vp, vp, vp, vp, vp]),
     "lnrf_nerf_wgrad_scratch_bytes": (sz, [u32, u32]),

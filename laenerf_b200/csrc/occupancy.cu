@@ -112,6 +112,70 @@ k_packbits_dev(const float* __restrict__ grid, const uint32_t N, const float* __
 using namespace lnrf;
 static inline cudaStream_t S(lnrf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+namespace lnrf {
+// Box around the occupied cells (lnrf_render_desc.occupied_box): per cascade the min / max cell coordinate of the set bits (bit index =
+// cascade * H^3 + morton(x, y, z)), then the union of the cascades' boxes in world space with two cells of margin.  One launch:
+// integer atomics into `work` (6 ints per cascade: min xyz, max xyz; + a ticket), the last block out converts and re-arms `work`.
+__global__ void __launch_bounds__(256)
+k_occupied_box(const uint8_t* __restrict__ bits, const uint32_t C, const uint32_t H, const float bound, int* __restrict__ work,
+               float* __restrict__ box) {
+    const uint32_t per = H * H * H / 8u;  // bytes per cascade
+    __shared__ bool s_last;
+    for (uint32_t c = 0; c < C; c++) {
+        int lo[3] = {(int)H, (int)H, (int)H}, hi[3] = {-1, -1, -1};
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+            uint32_t b = bits[(size_t)c * per + i];
+            while (b) {
+                const uint32_t k = (uint32_t)__ffs((int)b) - 1u;
+                b &= b - 1u;
+                const uint32_t m = i * 8u + k;
+                const int x = (int)morton3d_invert(m), y = (int)morton3d_invert(m >> 1), z = (int)morton3d_invert(m >> 2);
+                lo[0] = min(lo[0], x); lo[1] = min(lo[1], y); lo[2] = min(lo[2], z);
+                hi[0] = max(hi[0], x); hi[1] = max(hi[1], y); hi[2] = max(hi[2], z);
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = min(lo[a], __shfl_xor_sync(kFull, lo[a], o));
+                hi[a] = max(hi[a], __shfl_xor_sync(kFull, hi[a], o));
+            }
+            if ((threadIdx.x & 31) == 0) {
+                if (lo[a] < (int)H) atomicMin(work + c * 6 + a, lo[a]);
+                if (hi[a] >= 0) atomicMax(work + c * 6 + 3 + a, hi[a]);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(reinterpret_cast<unsigned int*>(work + 6 * C), 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t c = 0; c < C; c++) {
+            const float half = fminf((float)(1u << c), bound);  // mip_bound of the cascade (march_probe)
+            const float cell = 2.0f * half / (float)H;
+            for (int a = 0; a < 3; a++) {
+                const int l = __ldcg(work + c * 6 + a), h = __ldcg(work + c * 6 + 3 + a);
+                if (h >= 0) {
+                    wlo[a] = fminf(wlo[a], -half + ((float)l - 2.0f) * cell);
+                    whi[a] = fmaxf(whi[a], -half + ((float)h + 3.0f) * cell);
+                }
+                work[c * 6 + a] = (int)H;
+                work[c * 6 + 3 + a] = -1;
+            }
+        }
+        for (int a = 0; a < 3; a++) { box[a] = wlo[a]; box[3 + a] = whi[a]; }
+        work[6 * C] = 0;
+    }
+}
+
+}  // namespace lnrf
+
 extern "C" {
 
 int lnrf_occupancy_points(const int32_t* coords, const float* uniforms, uint32_t N, uint32_t H, float cascade_bound, float* xyzs,
@@ -169,6 +233,16 @@ int lnrf_packbits_dev(const float* grid, uint32_t N, const float* thresh_dev, ui
     LNRF_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15) == 0, "packbits_dev: grid must be 16-byte aligned");
     k_packbits_dev<<<div_up(N, 256u), 256, 0, S(stream)>>>(grid, N, thresh_dev, bitfield);
     LNRF_LAUNCH_CHECK("packbits_dev");
+    return LNRF_OK;
+}
+
+size_t lnrf_occupied_box_work_ints(uint32_t C) { return 6 * (size_t)C + 1; }
+
+int lnrf_occupied_box(const uint8_t* bitfield, uint32_t C, uint32_t H, float bound, int32_t* work, float* box, lnrf_stream_t stream) {
+    LNRF_REQUIRE(bitfield && work && box, "occupied_box: null pointer");
+    LNRF_REQUIRE(C >= 1 && C <= 16 && H >= 2 && H <= 1024 && (H & (H - 1)) == 0, "occupied_box: cascades must be in [1, 16] and H a power of two <= 1024");
+    k_occupied_box<<<kNumSMs * 2, 256, 0, S(stream)>>>(bitfield, C, H, bound, work, box);
+    LNRF_LAUNCH_CHECK("occupied_box");
     return LNRF_OK;
 }
 

@@ -306,7 +306,7 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
               const MarchParams p, const uint32_t N, const uint32_t M, const float* __restrict__ nears,
               const float* __restrict__ fars, const float* __restrict__ noises, float* __restrict__ xyzs,
               float* __restrict__ dirs, float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
-              unsigned long long* __restrict__ scratch) {
+              unsigned long long* __restrict__ scratch, const float* __restrict__ occ_box) {
     extern __shared__ float s_tl[];  // WARPS x max_steps visited t values
     __shared__ uint32_t s_cnt[WARPS];
     __shared__ uint32_t s_excl;
@@ -321,7 +321,7 @@ k_march_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d
     if (active) {
         r = make_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
         const float near = nears[n];
-        far = fars[n];
+        far = clip_far_to_box(occ_box, r, fars[n]);  // exact: nothing is sampled beyond the occupied cells (lnrf_march_rays_train_clipped)
         t0 = f_fma(f_clamp(f_mul(near, p.dt_gamma), p.dt_min, p.dt_max), noises[n], near);  // raymarching.cu:348-351
     } else {
         r = Ray{};
@@ -1727,6 +1727,15 @@ int lnrf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                           const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
                           const float* noises, void* scratch, size_t scratch_bytes, lnrf_stream_t stream) {
+    return lnrf_march_rays_train_clipped(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas, rays,
+                                         counter, noises, nullptr, scratch, scratch_bytes, stream);
+}
+
+int lnrf_march_rays_train_clipped(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
+                                  uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
+                                  const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                                  const float* noises, const float* occupied_box, void* scratch, size_t scratch_bytes,
+                                  lnrf_stream_t stream) {
     if (int e = check_march_common(C, H, max_steps, "march_rays_train")) return e;
     LNRF_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises, "march_rays_train: null pointer");
     LNRF_REQUIRE(M == 0 || (xyzs && dirs && deltas), "march_rays_train: null sample buffer");
@@ -1750,7 +1759,7 @@ int lnrf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
             if (e != cudaSuccess) return cuda_fail(e, "march_rays_train: smem attribute");
         }
         k_march_train<W><<<nblocks, W * 32, smem, S(stream)>>>(rays_o, rays_d, grid, p, N, M, nears, fars, noises, xyzs, dirs,
-                                                               deltas, rays, counter, sc);
+                                                               deltas, rays, counter, sc, occupied_box);
     } else {
         constexpr int W = 1;
         const size_t smem = (size_t)W * max_steps * sizeof(float);
@@ -1759,7 +1768,7 @@ int lnrf_march_rays_train(const float* rays_o, const float* rays_d, const uint8_
         cudaError_t e = cudaFuncSetAttribute(k_march_train<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "march_rays_train: smem attribute");
         k_march_train<W><<<nblocks, W * 32, smem, S(stream)>>>(rays_o, rays_d, grid, p, N, M, nears, fars, noises, xyzs, dirs,
-                                                               deltas, rays, counter, sc);
+                                                               deltas, rays, counter, sc, occupied_box);
     }
     LNRF_LAUNCH_CHECK("march_rays_train");
     k_march_train_tail<<<kNumSMs, 256, 0, S(stream)>>>(sc, nblocks, xyzs, dirs, deltas, M);

@@ -179,7 +179,7 @@ class NeRFNetwork(nn.Module):
         self._auto_fast_ok = True
         self.render_samples_per_round = 64  # "fast" only: cap on the samples a ray takes per round after the first
         self.render_clip_far = os.environ.get("LNRF_RENDER_CLIP", "1") == "1"  # device loop: rays end where they leave occupied_box()
-        self._occ_box = self._occ_box_key = self._cell_coords = None
+        self._occ_box = self._occ_box_key = self._occ_box_work = None
         self.render_row_budget = int(os.environ.get("LNRF_RENDER_ROW_BUDGET", "24"))  # "fast" only: sample-buffer rows per ray of the frame
         self._amp_adam = None  # weak reference to the AmpAdam that owns the fp16 shadows, if any
         self._fused_ok = (hidden_dim == 64 and hidden_dim_color == 64 and geo_feat_dim == 15 and self.in_dim == 32 and
@@ -241,6 +241,7 @@ class NeRFNetwork(nn.Module):
         self.mean_density = float(self.density_grid.clamp(min=0).mean().item())
         t = min(self.mean_density, self.density_thresh) if thresh is None else thresh
         raymarching.packbits(self.density_grid, t, self.density_bitfield)
+        self._bitfield_written()
 
     # ---- renderer.py:556-649 (row f-2) ----------------------------------------------------------------------------
     def _density_scaled(self, xyzs):
@@ -318,6 +319,7 @@ class NeRFNetwork(nn.Module):
         self.iter_density += 1
         N.check(lib.lnrf_packbits_dev(N.ptr(self.density_grid), self.density_bitfield.numel(), N.ptr(self._occ_mean[1:]),
                                       N.ptr(self.density_bitfield), st))
+        self._bitfield_written()  # written through a raw pointer: torch's version counter does not see it (occupied_box)
         self.update_mean_count()
 
     @torch.no_grad()
@@ -370,30 +372,26 @@ class NeRFNetwork(nn.Module):
     @torch.no_grad()
     def occupied_box(self):
         """Device float[6] {lo xyz, hi xyz}: a world-space box around every occupied cell of density_bitfield on every cascade, two
-        cells of margin (include/laenerf_b200.h lnrf_render_desc.occupied_box).  Recomputed when the bitfield changes (fixed-shape
-        torch reductions over the H^3 cells of each cascade: no host synchronisation)."""
+        cells of margin (include/laenerf_b200.h lnrf_occupied_box).  One launch into a PERSISTENT buffer (CUDA graphs that captured
+        its address keep seeing the current box) whenever the bitfield changed: torch's version counter for torch writes, an explicit
+        invalidation where this module writes it through a raw pointer (set_density_grid, update_extra_state)."""
         bf = self.density_bitfield
         key = (bf.data_ptr(), bf._version)
         if self._occ_box_key != key:
             dev, H, Cn = bf.device, int(self.grid_size), int(self.cascade)
-            if self._cell_coords is None or self._cell_coords.device != dev:
-                self._cell_coords = raymarching.morton3D_invert(torch.arange(H ** 3, dtype=torch.int32, device=dev)).int()  # [H^3, 3]
-            shifts = torch.arange(8, dtype=torch.uint8, device=dev)
-            lo_w = torch.full((3,), float("inf"), device=dev)
-            hi_w = torch.full((3,), float("-inf"), device=dev)
-            per = H ** 3 // 8
-            for c in range(Cn):  # bit index = c * H^3 + morton(x, y, z), bit (index & 7) of byte index >> 3 (csrc/march_core.cuh march_probe)
-                occ = ((bf[c * per:(c + 1) * per, None] >> shifts) & 1).reshape(-1).bool()[:, None]
-                lo = torch.where(occ, self._cell_coords, H).amin(0).float()
-                hi = torch.where(occ, self._cell_coords, -1).amax(0).float()
-                half = float(min(2 ** c, self.bound))   # mip_bound of the cascade
-                cell = 2.0 * half / H
-                some = occ.any()
-                lo_w = torch.minimum(lo_w, torch.where(some, -half + (lo - 2.0) * cell, lo_w))
-                hi_w = torch.maximum(hi_w, torch.where(some, -half + (hi + 3.0) * cell, hi_w))
-            self._occ_box = torch.cat([lo_w, hi_w]).float().contiguous()
+            if self._occ_box is None or self._occ_box.device != dev:
+                self._occ_box = torch.empty(6, dtype=torch.float32, device=dev)
+                self._occ_box_work = torch.tensor([H, H, H, -1, -1, -1] * Cn + [0], dtype=torch.int32, device=dev)
+            N.check(N.lib().lnrf_occupied_box(bf.data_ptr(), Cn, H, float(self.bound), self._occ_box_work.data_ptr(), self._occ_box.data_ptr(),
+                                              N.stream()))
             self._occ_box_key = key
         return self._occ_box
+
+    def _bitfield_written(self):
+        """density_bitfield was rewritten through a raw pointer: refresh the box now (eagerly: replays of a captured step read it)."""
+        self._occ_box_key = None
+        if self.render_clip_far and self.density_bitfield.is_cuda:
+            self.occupied_box()
 
     # ---- row f-3: the inference loop of run_cuda / run_cuda_distill driven from the device -----------------------------
     def _render_rounds_device(self, rays_o, rays_d, nears, fars, dens_grid, edit_bitfield, dt_gamma, perturb, max_steps, T_thresh,
@@ -627,9 +625,10 @@ class NeRFNetwork(nn.Module):
             self.local_step += 1
         counter.zero_()
         out = None if into is None else (into["xyzs"], into["dirs"], into["deltas"], into["rays"])
+        box = self.occupied_box() if (self.render_clip_far and dens_grid is self.density_bitfield) else None
         xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, dens_grid, self.cascade,
                                                                 self.grid_size, nears, fars, counter, self.mean_count, perturb,
-                                                                128, force_all_rays, dt_gamma, max_steps, out)
+                                                                128, force_all_rays, dt_gamma, max_steps, out, box)
         if into is not None:
             into["nears"].copy_(nears)
             into["fars"].copy_(fars)
@@ -979,6 +978,8 @@ class GraphedTrainStep:
                 return None, None
         self._load(rays_o, rays_d, gt_rgb)
         m = self.model
+        if m.render_clip_far:
+            m.occupied_box()  # the captured marcher reads the box from a persistent buffer: refresh it if the bitfield changed
         row = self._replays % 16
         if self.lookahead:
             p = self.phase

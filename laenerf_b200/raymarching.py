@@ -172,6 +172,8 @@ class _packbits(Function):
         n = grid.shape[0] * grid.shape[1] // 8
         if bitfield is None:
             bitfield = torch.empty(n, dtype=torch.uint8, device=grid.device)
+        else:
+            ctx.mark_dirty(bitfield)  # written in place through a raw pointer: bump torch's version counter (NeRFNetwork.occupied_box keys on it)
         N.check(N.lib().lnrf_packbits(N.ptr(grid), n, float(thresh), N.ptr(bitfield), N.stream()))
         return bitfield
 
@@ -183,9 +185,11 @@ class _march_rays_train(Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
-                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, out=None):
+                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, out=None, occupied_box=None):
         """raymarching.py:176-240.  `out` (not in the reference): (xyzs, dirs, deltas, rays) to march into instead of new tensors --
-        a software-pipelined training loop alternates between two sample buffers (nerf.GraphedTrainStep)."""
+        a software-pipelined training loop alternates between two sample buffers (nerf.GraphedTrainStep).  `occupied_box` (not in the
+        reference): device float[6] around every occupied cell (nerf.NeRFNetwork.occupied_box); rays end where they leave it, with
+        identical samples / counts / offsets."""
         rays_o = _cuda(rays_o).contiguous().view(-1, 3)
         rays_d = _cuda(rays_d).contiguous().view(-1, 3)
         density_bitfield = _in(_cuda(density_bitfield), torch.uint8, "density_bitfield")
@@ -216,10 +220,12 @@ class _march_rays_train(Function):
         nbytes = lib.lnrf_march_rays_train_scratch_bytes(n)
         scratch = _get_scratch("march", nbytes, dev)
         with _on(rays_o):
-            _check(lib.lnrf_march_rays_train(N.ptr(rays_o), N.ptr(rays_d), N.ptr(density_bitfield), float(bound), float(dt_gamma),
-                                             int(max_steps), n, int(C), int(H), M, N.ptr(nears), N.ptr(fars), N.ptr(xyzs),
-                                             N.ptr(dirs), N.ptr(deltas), N.ptr(rays), N.ptr(step_counter), N.ptr(noises),
-                                             N.ptr(scratch), scratch.numel() * 8, N.stream()), dev)
+            if occupied_box is not None:
+                occupied_box = _in(occupied_box, torch.float32, "occupied_box")
+            _check(lib.lnrf_march_rays_train_clipped(N.ptr(rays_o), N.ptr(rays_d), N.ptr(density_bitfield), float(bound), float(dt_gamma),
+                                                     int(max_steps), n, int(C), int(H), M, N.ptr(nears), N.ptr(fars), N.ptr(xyzs),
+                                                     N.ptr(dirs), N.ptr(deltas), N.ptr(rays), N.ptr(step_counter), N.ptr(noises),
+                                                     N.ptr(occupied_box), N.ptr(scratch), scratch.numel() * 8, N.stream()), dev)
         if force_all_rays or mean_count <= 0:  # raymarching.py:222-231 (first epochs only)
             m = int(step_counter[0].item())
             if align > 0:
