@@ -491,6 +491,24 @@ LNRF_API int lnrf_adam_step_sharded(const void* const* grad_peers_host, void* co
                                     double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
                                     float* found_inf_out, const float* step_count, const float* lr_scale,
                                     lnrf_stream_t stream);
+/* The same for a loop that alternates TWO gradient buffers (and two flag words) between consecutive steps: while the ranks read this
+ * step's buffer, the kernel clears the buffer the previous step used (other_grad_f16, other_n elements; its readers passed this step's
+ * opening barrier long ago), zeroes that step's flag word (other_flag), and performs GradScaler.update() on the live words at its end.
+ * The closing "clear + update" launch and the flag memset ahead of the inf check disappear; the barrier after the kernel stays (the
+ * peers' stores into this rank's table).  Scale and step number of THIS step are read from `snapshot` ([1], [2]), which
+ * lnrf_grad_nonfinite_check_snapshot fills ahead of the opening barrier. */
+LNRF_API int lnrf_adam_step_sharded_pipelined(const void* const* grad_peers_host, void* const* shadow_peers_host,
+                                              const float* const* flag_peers_host, uint32_t world, uint64_t lo, uint64_t n,
+                                              float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard, double lr,
+                                              double beta1, double beta2, double eps, double weight_decay, const float* snapshot,
+                                              const float* lr_scale, void* other_grad_f16, uint64_t other_n, float* other_flag,
+                                              float* grad_scale, int32_t* growth_tracker, float* found_inf, float* step_count,
+                                              float growth_factor, float backoff_factor, int32_t growth_interval,
+                                              lnrf_stream_t stream);
+/* lnrf_grad_nonfinite_check into flag_out, plus snapshot[1] = *grad_scale (1 when NULL), snapshot[2] = *step_count. */
+LNRF_API int lnrf_grad_nonfinite_check_snapshot(const lnrf_opt_tensor* tensors_host, uint32_t count, float* flag_out,
+                                                const float* grad_scale, const float* step_count, float* snapshot,
+                                                lnrf_stream_t stream);
 /* The same with the rank synchronisation inside the kernels instead of two barrier launches around it.  flag_peers: each
  * rank's peer-mapped buffer of >= 32 fp32 words -- word 0 is the non-finite flag, words 8..15 / 16..23 are written by ranks
  * 0..7 ("my gradient is complete" / "my stores into your table are complete", as epoch numbers); all zero before the first

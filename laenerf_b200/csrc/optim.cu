@@ -99,6 +99,19 @@ __global__ void __launch_bounds__(kOptBlock) k_grad_nonfinite(const OptBatch b, 
     if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1.0f;
 }
 
+// the same check; block 0 also freezes the scale and the step number of the running step (snapshot[1], snapshot[2]) for an optimizer
+// kernel that updates the live words itself (lnrf_adam_step_sharded_pipelined)
+__global__ void __launch_bounds__(kOptBlock)
+k_grad_nonfinite_snap(const OptBatch b, float* __restrict__ flag_out, const float* __restrict__ grad_scale,
+                      const float* __restrict__ step_count, float* __restrict__ snap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        snap[1] = grad_scale ? *grad_scale : 1.0f;
+        snap[2] = *step_count;
+    }
+    const bool bad = grad_block_nonfinite(b);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag_out = 1.0f;
+}
+
 struct AdamHyper {
     double lr, beta1, beta2, eps, weight_decay;
 };
@@ -480,6 +493,16 @@ struct ExchangeSync {
     uint32_t* ticket;   // local device word, zero between launches
     uint32_t me;
 };
+// Two gradient buffers alternate between consecutive steps (lnrf_adam_step_sharded_pipelined): while the ranks read THIS step's buffer,
+// each rank clears the one the previous step used (its readers are long done: they passed this step's opening barrier), zeroes that
+// step's non-finite flag word, and -- in one thread, at the very end -- performs GradScaler.update().  The separate closing launch
+// (gradient clear + scale update behind barrier B) and the flag memset ahead of the inf check disappear.
+struct ExchangeExtra {
+    uint4* clear;       // local: the OTHER gradient buffer (null: nothing to clear)
+    uint64_t clear_nvec;
+    float* other_flag;  // local: the other step's non-finite flag word
+    AmpUpdateArgs amp;  // amp.step_count == nullptr: no scale update here (grad_scale / step_count above must then be the snapshot)
+};
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -503,7 +526,7 @@ __global__ void __launch_bounds__(kOptBlock)
 k_adam_step_p2p(const PeerPtrs peers, const uint32_t R, const uint64_t lo, const uint64_t n, float* __restrict__ master,
                 float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, AdamHyper h, const float* __restrict__ grad_scale,
                 float* __restrict__ found_inf_out, const float* __restrict__ step_count, const float* __restrict__ lr_scale,
-                const ExchangeSync sync) {
+                const ExchangeSync sync, const ExchangeExtra extra) {
     uint32_t epoch = 0;
     if (sync.epoch) {
         epoch = *sync.epoch + 1u;
@@ -564,6 +587,17 @@ k_adam_step_p2p(const PeerPtrs peers, const uint32_t R, const uint64_t lo, const
 #pragma unroll
         for (int r = 0; r < kMaxPeers; r++)
             if (r < (int)R) *reinterpret_cast<uint4*>(peers.shadow[r] + lo + i) = o.u;
+    }
+    if (extra.clear) {
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < extra.clear_nvec; i += (uint64_t)gridDim.x * blockDim.x)
+            extra.clear[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (extra.other_flag) *extra.other_flag = 0.0f;
+            if (extra.amp.step_count) {  // grad_scale / step_count of THIS kernel are the snapshot: every block may still be reading them
+                const float found = skip ? 1.0f : 0.0f;
+                amp_update_body(extra.amp, &found);
+            }
+        }
     }
     if (sync.epoch) {
         __shared__ bool s_last;
@@ -756,7 +790,7 @@ static int adam_step_sharded_impl(const void* const* grad_peers_host, void* cons
                            uint32_t world, uint64_t lo, uint64_t n, float* master_shard, float* exp_avg_shard, float* exp_avg_sq_shard,
                            double lr, double beta1, double beta2, double eps, double weight_decay, const float* grad_scale,
                            float* found_inf_out, const float* step_count, const float* lr_scale, uint32_t rank, uint32_t* sync_epoch,
-                           uint32_t* sync_ticket, lnrf_stream_t stream) {
+                           uint32_t* sync_ticket, lnrf_stream_t stream, const ExchangeExtra extra = ExchangeExtra{}) {
     LNRF_REQUIRE(world >= 1 && world <= (uint32_t)kMaxPeers, "adam_step_sharded: 1..%d ranks, got %u", kMaxPeers, world);
     LNRF_REQUIRE(grad_peers_host && shadow_peers_host && flag_peers_host && master_shard && exp_avg_shard && exp_avg_sq_shard &&
                      found_inf_out && step_count,
@@ -774,7 +808,7 @@ static int adam_step_sharded_impl(const void* const* grad_peers_host, void* cons
     const uint64_t chunks = (n + kOptChunk - 1) / kOptChunk, cap = (uint64_t)kNumSMs * 8;
     ExchangeSync sy{sync_epoch, sync_ticket, rank};
     k_adam_step_p2p<<<(uint32_t)(chunks < cap ? chunks : cap), kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        pp, world, lo, n, master_shard, exp_avg_shard, exp_avg_sq_shard, h, grad_scale, found_inf_out, step_count, lr_scale, sy);
+        pp, world, lo, n, master_shard, exp_avg_shard, exp_avg_sq_shard, h, grad_scale, found_inf_out, step_count, lr_scale, sy, extra);
     LNRF_LAUNCH_CHECK("adam_step_sharded");
     return LNRF_OK;
 }
@@ -797,6 +831,34 @@ int lnrf_adam_step_sharded_sync(const void* const* grad_peers_host, void* const*
     return adam_step_sharded_impl(grad_peers_host, shadow_peers_host, flag_peers_host, world, lo, n, master_shard, exp_avg_shard,
                                   exp_avg_sq_shard, lr, beta1, beta2, eps, weight_decay, grad_scale, found_inf_out, step_count, lr_scale, rank,
                                   sync_state, sync_state + 1, stream);
+}
+
+int lnrf_adam_step_sharded_pipelined(const void* const* grad_peers_host, void* const* shadow_peers_host, const float* const* flag_peers_host,
+                                     uint32_t world, uint64_t lo, uint64_t n, float* master_shard, float* exp_avg_shard,
+                                     float* exp_avg_sq_shard, double lr, double beta1, double beta2, double eps, double weight_decay,
+                                     const float* snapshot, const float* lr_scale, void* other_grad_f16, uint64_t other_n,
+                                     float* other_flag, float* grad_scale, int32_t* growth_tracker, float* found_inf, float* step_count,
+                                     float growth_factor, float backoff_factor, int32_t growth_interval, lnrf_stream_t stream) {
+    LNRF_REQUIRE(snapshot && other_grad_f16 && other_flag && found_inf && step_count, "adam_step_sharded_pipelined: null pointer");
+    LNRF_REQUIRE(other_n % 8 == 0 && (reinterpret_cast<uintptr_t>(other_grad_f16) & 15) == 0,
+                 "adam_step_sharded_pipelined: the gradient buffers must be 16-byte vectors");
+    ExchangeExtra ex{reinterpret_cast<uint4*>(other_grad_f16), other_n / 8, other_flag,
+                     AmpUpdateArgs{grad_scale, growth_tracker, found_inf, step_count, growth_factor, backoff_factor, growth_interval}};
+    // scale and step of THIS step come from the snapshot the inf check took (snapshot[1], snapshot[2]): the live words change under the kernel
+    return adam_step_sharded_impl(grad_peers_host, shadow_peers_host, flag_peers_host, world, lo, n, master_shard, exp_avg_shard,
+                                  exp_avg_sq_shard, lr, beta1, beta2, eps, weight_decay, grad_scale ? snapshot + 1 : nullptr, found_inf,
+                                  snapshot + 2, lr_scale, 0u, nullptr, nullptr, stream, ex);
+}
+
+int lnrf_grad_nonfinite_check_snapshot(const lnrf_opt_tensor* tensors_host, uint32_t count, float* flag_out, const float* grad_scale,
+                                       const float* step_count, float* snapshot, lnrf_stream_t stream) {
+    LNRF_REQUIRE(flag_out && step_count && snapshot, "grad_nonfinite_check_snapshot: null pointer");
+    OptBatch b;
+    uint32_t grid;
+    if (int e = make_batch("grad_nonfinite_check_snapshot", tensors_host, count, &b, &grid, false)) return e;
+    k_grad_nonfinite_snap<<<grid, kOptBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(b, flag_out, grad_scale, step_count, snapshot);
+    LNRF_LAUNCH_CHECK("grad_nonfinite_check_snapshot");
+    return LNRF_OK;
 }
 
 int lnrf_exchange_tail(void* grad_f16, uint64_t n, float* scale, int32_t* growth_tracker, float* found_inf, float* step_count,

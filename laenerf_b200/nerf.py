@@ -886,6 +886,7 @@ class GraphedTrainStep:
         self.graph = None
         self.captured_mean_count = 0
         self.loss = self.out = None
+        self._pipe_opt = False
         self.sets = self.graphs = None  # lookahead: the two marched-batch buffer sets (with their targets) and the two graphs
         self.phase = 0                  # lookahead: the set the next replay trains on
 
@@ -898,6 +899,8 @@ class GraphedTrainStep:
         """Graph p: train on set p; beside its hash-grid backward, march the loaded batch into set 1-p."""
         from . import gridencoder as _ge
         cur, nxt = self.sets[p], self.sets[1 - p]
+        if self._pipe_opt:  # ray-sharded: graph p accumulates into gradient buffer p and clears buffer 1 - p inside its exchange kernel
+            self.step.optimizer.select_phase(p)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             main = torch.cuda.current_stream()
@@ -928,6 +931,8 @@ class GraphedTrainStep:
                 fork()
             self.step.reduce_and_step()
             main.wait_stream(self._side)
+        if self._pipe_opt:
+            self.step.optimizer.select_phase(None)
         return g, loss, out
 
     def capture(self, rays_o, rays_d, gt_rgb, warmup: int = 3):
@@ -943,6 +948,11 @@ class GraphedTrainStep:
                 self.step(self.ro, self.rd, self.gt, self.bg_color, self.perturb)
         torch.cuda.current_stream().wait_stream(side)
         m.local_step = 0  # the captured march always counts into step_counter[0]; rotated after each replay
+        opt = self.step.optimizer
+        self._pipe_opt = bool(self.lookahead and self.step.fused_optimizer and getattr(opt, "can_pipeline", False) and
+                              os.environ.get("LNRF_PIPELINED_EXCHANGE", "1") == "1")
+        if self._pipe_opt:
+            opt._settle_buffers()  # a re-capture starts from two clean gradient buffers
         if self.lookahead:
             # prime the pipeline: march the capture batch eagerly into set 0; set 1 is a same-shape twin
             first = self.step.march(self.ro, self.rd, self.perturb)
@@ -986,6 +996,8 @@ class GraphedTrainStep:
             self.graphs[p].replay()
             self.loss, self.out = self._results[p]
             self.phase = 1 - p
+            if self._pipe_opt:
+                self.step.optimizer._dirty_buf = p  # what the replay left for its successor (or an eager step) to clear
             # keep the 16-entry counter history the occupancy update averages (renderer.py:643-647)
             m.step_counter[row].copy_(self.sets[1 - p]["counter"], non_blocking=True)
         else:
@@ -1009,4 +1021,4 @@ class GraphedTrainStep:
         if not self.lookahead or self.sets is None:
             return None, None
         cur = self.sets[self.phase]
-        return self.step.train_on(cur, cur["gt"], self.bg_color)
+        return self.step.train_on(cur, cur["gt"], self.bg_color)  # eager, one gradient buffer: settles what the last replay left

@@ -129,6 +129,7 @@ class AmpAdam:
             except Exception as e:  # never silently: bench.py reports which exchange path ran
                 self.p2p_error = f"{type(e).__name__}: {e}"[:300]
                 self.p2p = None
+                self.__dict__.pop("_grad_bufs", None)
         if self.p2p is None:
             self.shadow_flat = torch.empty(self.P_pad, dtype=torch.half, device=dev)
             self.grad_flat = torch.zeros(self.P_pad, dtype=torch.half, device=dev)
@@ -136,9 +137,14 @@ class AmpAdam:
         self.shadow_flat.copy_(flat32)
         self.master_shard = flat32[self.lo:self.hi].clone()
         del flat32
+        self._phase = None        # None: one gradient buffer, closing clear (every eager step); 0 / 1: pipelined, see select_phase
+        self._dirty_buf = None    # pipelined: the buffer the last step left for the NEXT step's kernel to clear
+        self._grad_views = [[], []]
         off = 0
         for o, n in zip(self.owners, sizes):
             o.module._shadow_f16 = self.shadow_flat[off:off + n].view_as(o.param)
+            for b_, buf in enumerate(getattr(self, "_grad_bufs", [self.grad_flat])):
+                self._grad_views[b_].append(buf[off:off + n].view_as(o.param))
             o.module._grad_f16 = self.grad_flat[off:off + n].view_as(o.param)
             o.module._shadow_resync = self._resync_from_params  # an outside write to ANY fp32 parameter re-derives shadow + master slice
             mark_current(o.module, o.param)
@@ -146,6 +152,31 @@ class AmpAdam:
         # ONE state entry in sharded mode: the moments of this rank's slice of the flat vector
         self.state.append({"exp_avg": torch.zeros(self.Sz, dtype=torch.float32, device=dev),
                            "exp_avg_sq": torch.zeros(self.Sz, dtype=torch.float32, device=dev)})
+
+    @property
+    def can_pipeline(self) -> bool:
+        """Two peer-mapped gradient buffers exist (symmetric memory, barrier-bracketed exchange): steps may alternate between them."""
+        return bool(self.sharded and self.p2p is not None and not self.inkernel_sync and len(getattr(self, "_grad_bufs", [])) == 2)
+
+    def select_phase(self, phase):
+        """Software-pipelined sharded training (GraphedTrainStep(lookahead=True) at world_size > 1): consecutive steps accumulate into
+        alternating gradient buffers, so the exchange kernel of a step can clear the buffer of the step before it -- no closing
+        "clear + scale update" launch, no flag memset (csrc/optim.cu ExchangeExtra).  phase 0 / 1: the modules' `_grad_f16` point into
+        that buffer and step() takes the pipelined path; None: back to one buffer with the closing clear."""
+        if phase is not None and not self.can_pipeline:
+            raise RuntimeError("select_phase: needs the symmetric-memory exchange with barrier launches")
+        self._phase = phase
+        b_ = 0 if phase is None else int(phase)
+        self.grad_flat = self._grad_bufs[b_] if hasattr(self, "_grad_bufs") else self.grad_flat
+        for o, v in zip(self.owners, self._grad_views[b_]):
+            o.module._grad_f16 = v
+
+    def _settle_buffers(self):
+        """Eager step after pipelined ones: the buffer the last pipelined step filled was to be cleared by its successor."""
+        if self._dirty_buf is not None:
+            self._grad_bufs[self._dirty_buf].zero_()
+            self.flag_buf[:8].zero_()
+            self._dirty_buf = None
 
     def _flat_from_params(self, dev):
         flat = torch.zeros(self.P_pad, dtype=torch.float32, device=dev)
@@ -162,18 +193,23 @@ class AmpAdam:
         import torch.distributed._symmetric_memory as symm
         group = self.group if self.group is not None else dist.group.WORLD
         bufs, hdls = {}, {}
-        for name, numel, dt in (("grad", self.P_pad, torch.half), ("shadow", self.P_pad, torch.half), ("flag", 32, torch.float32)):
+        for name, numel, dt in (("grad", self.P_pad, torch.half), ("shadow", self.P_pad, torch.half), ("flag", 32, torch.float32),
+                                ("grad_b", self.P_pad, torch.half)):  # grad_b: the second buffer of the software-pipelined step (select_phase)
             t = symm.empty(numel, dtype=dt, device=dev)
             hdls[name] = symm.rendezvous(t, group)
             bufs[name] = t
         self.grad_flat, self.shadow_flat, self.flag_buf = bufs["grad"], bufs["shadow"], bufs["flag"]
+        self._grad_bufs = [bufs["grad"], bufs["grad_b"]]
         self.grad_flat.zero_()
+        bufs["grad_b"].zero_()
         self.flag_buf.zero_()
         ptrs = {k: [int(x) for x in hdls[k].buffer_ptrs] for k in hdls}
         if any(len(v) != self.world or not all(v) for v in ptrs.values()):
             raise RuntimeError(f"symmetric memory rendezvous returned {ptrs}")
         mk = lambda v: (C.c_void_p * self.world)(*v)
         self._peer_arrays = (mk(ptrs["grad"]), mk(ptrs["shadow"]), mk(ptrs["flag"]))
+        # phase 1 of the pipelined step: the second gradient buffer, flag word 4 of every rank's flag buffer (word 0 is phase 0's)
+        self._peer_arrays_b = (mk(ptrs["grad_b"]), self._peer_arrays[1], mk([x + 16 for x in ptrs["flag"]]))
         # LNRF_INKERNEL_SYNC=1: rank synchronisation inside the exchange kernels instead of symmetric-memory barrier launches
         self.inkernel_sync = os.environ.get("LNRF_INKERNEL_SYNC", "0") == "1" and self.world <= 8
         self._sync_state = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -265,6 +301,25 @@ class AmpAdam:
             # over NVLink, updates, and writes the new fp16 slice into every rank's table; barrier; clear the local gradient
             mark = self._mark  # LNRF_TIME_EXCHANGE=1: CUDA events between the pieces (eager steps only), see exchange_timing()
             mark("start")
+            if self._phase is not None:
+                # pipelined: inf check (+ snapshot of scale / step) -> barrier -> ONE kernel: exchange + Adam + table broadcast + clear of
+                # the OTHER gradient buffer and flag + GradScaler.update() -> barrier.  4 launches (6 on the one-buffer path below).
+                ph = self._phase
+                g, sh, fl = self._peer_arrays if ph == 0 else self._peer_arrays_b
+                my_flag = self.flag_buf.data_ptr() + 16 * ph
+                other = self._grad_bufs[1 - ph]
+                N.check(lib.lnrf_grad_nonfinite_check_snapshot(C.cast(self._one(None, None, self._grad_bufs[ph], None, self.P_pad), C.c_void_p), 1,
+                                                               my_flag, N.ptr(self._scale), N.ptr(self.step_count), N.ptr(self._snapshot), st))
+                self.p2p["grad"].barrier(channel=0)
+                N.check(lib.lnrf_adam_step_sharded_pipelined(
+                    C.cast(g, C.c_void_p), C.cast(sh, C.c_void_p), C.cast(fl, C.c_void_p), self.world, self.lo, self.Sz, N.ptr(self.master_shard),
+                    N.ptr(self.state[0]["exp_avg"]), N.ptr(self.state[0]["exp_avg_sq"]), *hyper, N.ptr(self._snapshot), N.ptr(self.lr_scale),
+                    other.data_ptr(), self.P_pad, self.flag_buf.data_ptr() + 16 * (1 - ph), N.ptr(self._scale), N.ptr(self._growth_tracker),
+                    N.ptr(self.found_inf), N.ptr(self.step_count), self.growth_factor, self.backoff_factor, self.growth_interval, st))
+                self.p2p["grad"].barrier(channel=1)
+                self._dirty_buf = ph
+                return
+            self._settle_buffers()
             if self.inkernel_sync:
                 # the ranks meet INSIDE the kernels (signal + poll on the peer-mapped flag words, csrc/optim.cu): no barrier launches,
                 # and the closing wait clears the gradient -- 3 launches instead of 6

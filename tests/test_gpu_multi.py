@@ -110,3 +110,83 @@ def test_sharded_training_tracks_single_gpu_training():
     assert np.allclose(res["losses"], res["single_losses"], rtol=2e-2), res
     # 6 Adam steps of lr 1e-2: an entry moves by <= 0.06; the two runs differ by fp16 atomic order only
     assert res["table_err_mean"] < 2e-3 and res["table_err"] < 0.08 and res["w_err"] < 0.08, res
+
+
+def _worker_pipelined(rank, world, port, out):
+    """The software-pipelined graph step on 2 ranks (two gradient buffers, exchange kernel clears the other one and updates the scale)
+    against the same graph step on one GPU: same batches on every rank => the mean gradient is the single-GPU gradient."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from cases import scene, scene_rays
+    from laenerf_b200.nerf import GraphedTrainStep, NeRFNetwork, TrainStep
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sc = scene("lego")
+
+    def make():
+        torch.manual_seed(0)
+        m = NeRFNetwork(bound=sc.bound, min_near=sc.min_near).to(dev)
+        with torch.no_grad():
+            m.encoder.embeddings.uniform_(-0.5, 0.5, generator=torch.Generator(device=dev).manual_seed(1))
+        m.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+        return m
+
+    batches = []
+    for k in range(8):
+        _, ro, rd, _ = scene_rays("lego", 4096, 70 + k)
+        batches.append((torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev),
+                        torch.rand(4096, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(k))))
+
+    def run(model, world_size):
+        g = GraphedTrainStep(TrainStep(model, world_size=world_size), 4096, perturb=False, lookahead=True)
+        g.capture(*batches[0], warmup=1)
+        losses = [float(g(*b)[0]) for b in batches[1:]] + [float(g.flush()[0])]
+        return g, losses
+
+    sharded = make()
+    gs, la = run(sharded, world)
+    res = {"pipelined": bool(gs._pipe_opt), "losses": la}
+    chk = sharded.encoder._shadow_f16.float().sum().double().reshape(1)
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    res["replicas_in_sync"] = bool(lo_.item() == hi_.item())
+    opt = gs.step.optimizer
+    res["buffers_clean"] = bool(float(opt._grad_bufs[0].float().abs().max()) == 0.0 and float(opt._grad_bufs[1].float().abs().max()) == 0.0)
+    res["step_count"] = float(opt.step_count)
+    opt.gather_master()
+    if rank == 0:
+        single = make()
+        g1, lb = run(single, 1)
+        res["single_losses"] = lb
+        res["single_step_count"] = float(g1.step.optimizer.step_count)
+        res["table_err_mean"] = float((sharded.encoder.embeddings.detach() - single.encoder.embeddings.detach()).abs().mean())
+        out.put(res)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+def test_pipelined_sharded_graph_step_tracks_the_single_gpu_graph_step():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pipelined, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert res["pipelined"] and res["replicas_in_sync"] and res["buffers_clean"], res
+    assert res["step_count"] == res["single_step_count"], res
+    assert len(res["losses"]) == 8 and np.allclose(res["losses"], res["single_losses"], rtol=2e-2), res
+    assert res["table_err_mean"] < 2e-3, res

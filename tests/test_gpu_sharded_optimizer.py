@@ -184,3 +184,73 @@ def test_in_kernel_synchronisation_variant_with_emulated_peers(dev, R):
             assert float(ranks.grad[r].float().abs().sum()) == 0.0                               # cleared by the closing kernel
             words = ranks.flag[r].view(torch.int32)
             assert words[8:8 + R].tolist() == [it + 1] * R and words[16:16 + R].tolist() == [it + 1] * R
+
+
+def test_pipelined_exchange_with_two_gradient_buffers_equals_the_one_buffer_sequence(dev):
+    """lnrf_grad_nonfinite_check_snapshot + lnrf_adam_step_sharded_pipelined (software-pipelined sharded step: two gradient buffers and
+    two flag words alternate, the kernel clears the OTHER buffer / flag and performs GradScaler.update() itself) against the one-buffer
+    sequence (check, lnrf_adam_step_sharded, lnrf_exchange_tail): same masters, moments, tables, scale, step number and growth tracker
+    over six steps with a non-finite gradient in step 2 (skip + back-off) and a growth interval of 2; the buffer of the previous step
+    is zero again after every step."""
+    from laenerf_b200 import _native as N
+    R, Sz = 4, 8 * 3000
+    lib = N.lib()
+    a = _Ranks(dev, R, Sz, seed=11)   # one buffer, closing launch
+    b = _Ranks(dev, R, Sz, seed=11)   # two buffers, pipelined
+    P = a.P
+    b.grad2 = [[b.grad[r], torch.zeros(P, dtype=torch.half, device=dev)] for r in range(R)]
+    mk = lambda ts: (C.c_void_p * R)(*[t if isinstance(t, int) else t.data_ptr() for t in ts])
+    b.arr2 = [(mk([b.grad2[r][ph] for r in range(R)]), mk(b.shadow), mk([b.flag[r].data_ptr() + 16 * ph for r in range(R)])) for ph in range(2)]
+    # per-"rank" scaler state (every rank keeps its own copy; they stay identical)
+    st = {}
+    for name, ranks in (("a", a), ("b", b)):
+        st[name] = dict(scale=[torch.full((1,), 1024.0, device=dev) for _ in range(R)], tracker=[torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(R)],
+                        step=[torch.ones(1, device=dev) for _ in range(R)], found=[torch.zeros(1, device=dev) for _ in range(R)],
+                        snap=[torch.zeros(8, device=dev) for _ in range(R)])
+    amp = (2.0, 0.5, 2)   # growth, back-off, interval
+
+    def one(grad):
+        arr = (N.OptTensor * 1)()
+        arr[0].grad, arr[0].n, arr[0].grad_dtype = grad.data_ptr(), P, N.F16
+        return arr
+
+    for it in range(6):
+        ph = it & 1
+        gen = torch.Generator(device=dev).manual_seed(500 + it)
+        grads = [(torch.randn(P, device=dev, generator=gen) * 8.0).half() for _ in range(R)]
+        if it == 2:
+            grads[1][777] = float("nan")
+        # ---- one-buffer sequence
+        for r in range(R):
+            a.grad[r].copy_(grads[r])
+            a.flag[r].zero_()
+            N.check(lib.lnrf_grad_nonfinite_check(C.cast(one(a.grad[r]), C.c_void_p), 1, N.ptr(a.flag[r]), None))
+        g, sh, fl = a.arrays
+        for r in range(R):
+            N.check(lib.lnrf_adam_step_sharded(C.cast(g, C.c_void_p), C.cast(sh, C.c_void_p), C.cast(fl, C.c_void_p), R, r * Sz, Sz, N.ptr(a.master[r]),
+                                               N.ptr(a.m[r]), N.ptr(a.v[r]), *HYPER, N.ptr(st["a"]["scale"][r]), N.ptr(st["a"]["found"][r]),
+                                               N.ptr(st["a"]["step"][r]), None, None))
+        for r in range(R):
+            N.check(lib.lnrf_exchange_tail(N.ptr(a.grad[r]), P, N.ptr(st["a"]["scale"][r]), N.ptr(st["a"]["tracker"][r]), N.ptr(st["a"]["found"][r]),
+                                           N.ptr(st["a"]["step"][r]), *amp, None))
+        # ---- pipelined: accumulate into buffer `ph`; the kernel clears buffer 1 - ph and flag word 1 - ph
+        for r in range(R):
+            assert float(b.grad2[r][ph].float().abs().max()) == 0.0      # cleared by the previous step's kernel (or never used)
+            b.grad2[r][ph].copy_(grads[r])
+            N.check(lib.lnrf_grad_nonfinite_check_snapshot(C.cast(one(b.grad2[r][ph]), C.c_void_p), 1, b.flag[r].data_ptr() + 16 * ph,
+                                                           N.ptr(st["b"]["scale"][r]), N.ptr(st["b"]["step"][r]), N.ptr(st["b"]["snap"][r]), None))
+        g, sh, fl = b.arr2[ph]
+        for r in range(R):
+            N.check(lib.lnrf_adam_step_sharded_pipelined(
+                C.cast(g, C.c_void_p), C.cast(sh, C.c_void_p), C.cast(fl, C.c_void_p), R, r * Sz, Sz, N.ptr(b.master[r]), N.ptr(b.m[r]), N.ptr(b.v[r]),
+                *HYPER, N.ptr(st["b"]["snap"][r]), None, b.grad2[r][1 - ph].data_ptr(), P, b.flag[r].data_ptr() + 16 * (1 - ph),
+                N.ptr(st["b"]["scale"][r]), N.ptr(st["b"]["tracker"][r]), N.ptr(st["b"]["found"][r]), N.ptr(st["b"]["step"][r]), *amp, None))
+        torch.cuda.synchronize()
+        for r in range(R):
+            for x, y in ((a.master[r], b.master[r]), (a.m[r], b.m[r]), (a.v[r], b.v[r]), (a.shadow[r], b.shadow[r])):
+                assert torch.equal(x, y), (it, r)
+            for k in ("scale", "tracker", "step", "found"):
+                assert torch.equal(st["a"][k][r], st["b"][k][r]), (it, r, k, st["a"][k][r], st["b"][k][r])
+            assert float(b.grad2[r][1 - ph].float().abs().max()) == 0.0 and float(b.flag[r][4 * (1 - ph)]) == 0.0
+    assert float(st["b"]["step"][0]) == 6.0      # five applied steps + 1 (the NaN step was skipped)
+    assert float(st["b"]["scale"][0]) == 1024.0 * 2.0 * 0.5 * 2.0   # grew after steps 0-1, backed off at 2, grew again after 3-4
