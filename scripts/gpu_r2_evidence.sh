@@ -9,3 +9,4 @@ echo "== bench reference arm"; timeout 600 python bench.py --impl reference --st
 echo "== ncu launches (train)"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py --steps 2 > gpurun_out/ncu_launches.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/ncu_launches.log
 echo "== ncu full"; timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"k_nerf_bwd|k_nerf_fwd|k_grid_bwd_tile|k_grid_fwd_tile|k_march_train|k_composite|k_adam_step|k_grad_nonfinite|k_wgrad_reduce" -c 14 -o gpurun_out/prof_${TAG} -f python scripts/profile_step.py --steps 1 > gpurun_out/ncu_full.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/ncu_full.log; ls -la gpurun_out/prof_${TAG}.ncu-rep
 echo "== ncu launches (render, auto schedule)"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/render_launches.csv python scripts/profile_step.py --steps 0 --render-rays 640000 --render-schedule auto > gpurun_out/ncu_render.log 2>&1; echo "rc=$?"; tail -1 gpurun_out/ncu_render.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
