@@ -513,20 +513,33 @@ __device__ __forceinline__ RaySums composite_ray_fwd(const float* __restrict__ s
         const float* pc = rgbs + (size_t)offset * 3;
         const float2* pl = reinterpret_cast<const float2*>(deltas) + offset;
         float T_carry = 1.0f, t_carry = 0.0f;
+        // the loads of chunk k + 1 are issued before the scans of chunk k: a ray's life is a chain of dependent round trips, and at
+        // large batch sizes the bytes in flight per SM are what bounds these kernels (one warp = one ray = 768 B per chunk)
+        struct Chunk { float sg, dx, dy, cr, cg, cb; };
+        auto fetch = [&](uint32_t base) {
+            Chunk c{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const uint32_t k = base + lane;
+            if (k < num_steps) {
+                const float2 dl = KEEP ? __ldg(pl + k) : __ldcs(pl + k);
+                c.sg = KEEP ? __ldg(ps + k) : __ldcs(ps + k);
+                c.dx = dl.x; c.dy = dl.y;
+                if (KEEP) {
+                    c.cr = __ldg(pc + (size_t)k * 3); c.cg = __ldg(pc + (size_t)k * 3 + 1); c.cb = __ldg(pc + (size_t)k * 3 + 2);
+                } else {
+                    c.cr = __ldcs(pc + (size_t)k * 3); c.cg = __ldcs(pc + (size_t)k * 3 + 1); c.cb = __ldcs(pc + (size_t)k * 3 + 2);
+                }
+            }
+            return c;
+        };
+        Chunk cur = fetch(0);
         for (uint32_t base = 0; base < num_steps; base += 32) {
             const uint32_t k = base + lane;
             const bool act = k < num_steps;
-            float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dd = 0.f;
-            if (act) {
-                const float2 dl = KEEP ? __ldg(pl + k) : __ldcs(pl + k);
-                alpha = 1.0f - __expf(-(KEEP ? __ldg(ps + k) : __ldcs(ps + k)) * dl.x);
-                dd = dl.y;
-                if (KEEP) {
-                    cr = __ldg(pc + (size_t)k * 3); cg = __ldg(pc + (size_t)k * 3 + 1); cb = __ldg(pc + (size_t)k * 3 + 2);
-                } else {
-                    cr = __ldcs(pc + (size_t)k * 3); cg = __ldcs(pc + (size_t)k * 3 + 1); cb = __ldcs(pc + (size_t)k * 3 + 2);
-                }
-            }
+            Chunk nxt{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (base + 32 < num_steps) nxt = fetch(base + 32);
+            const float alpha = act ? 1.0f - __expf(-cur.sg * cur.dx) : 0.f;
+            const float cr = cur.cr, cg = cur.cg, cb = cur.cb, dd = cur.dy;
+            cur = nxt;
             float P = 1.0f - alpha;  // inclusive product scan of (1 - alpha)
             float S = dd;            // inclusive sum scan of the depth deltas
 #pragma unroll
@@ -727,15 +740,26 @@ __device__ __forceinline__ void composite_ray_bwd(const float* __restrict__ sigm
 
     float T_carry = 1.0f, r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
     uint32_t base = 0;
+    struct Chunk { float sg, dt, cr, cg, cb; };  // chunk k + 1 is requested before the scans of chunk k (see composite_ray_fwd)
+    auto fetch = [&](uint32_t at) {
+        Chunk c{0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint32_t k = at + lane;
+        if (k < num_steps) {
+            c.dt = __ldcs(pl + k).x;
+            c.sg = __ldcs(ps + k);
+            c.cr = __ldcs(pc + (size_t)k * 3); c.cg = __ldcs(pc + (size_t)k * 3 + 1); c.cb = __ldcs(pc + (size_t)k * 3 + 2);
+        }
+        return c;
+    };
+    Chunk cur = fetch(0);
     for (; base < num_steps; base += 32) {
         const uint32_t k = base + lane;
         const bool act = k < num_steps;
-        float alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, dt = 0.f;
-        if (act) {
-            dt = __ldcs(pl + k).x;
-            alpha = 1.0f - __expf(-__ldcs(ps + k) * dt);
-            cr = __ldcs(pc + (size_t)k * 3); cg = __ldcs(pc + (size_t)k * 3 + 1); cb = __ldcs(pc + (size_t)k * 3 + 2);
-        }
+        Chunk nxt{0.f, 0.f, 0.f, 0.f, 0.f};
+        if (base + 32 < num_steps) nxt = fetch(base + 32);
+        const float dt = cur.dt, cr = cur.cr, cg = cur.cg, cb = cur.cb;
+        const float alpha = act ? 1.0f - __expf(-cur.sg * dt) : 0.f;
+        cur = nxt;
         float P = 1.0f - alpha;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
