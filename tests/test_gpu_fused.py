@@ -814,3 +814,48 @@ def test_render_economies_change_no_bit(dev, name, n):
         cell = 2.0 * half / H
         lo, hi = -half + occ.min(0) * cell, -half + (occ.max(0) + 1) * cell
         assert (box[:3] <= lo - 1.9 * cell).all() and (box[3:] >= hi + 1.9 * cell).all(), (c, box, lo, hi)
+
+
+def test_auto_render_schedule_edge_cases(dev):
+    """"auto" against the reference schedule where the fast path has to cope or step aside: one ray, rays that all miss the
+    occupied box, an empty occupancy grid, a max_steps cap that cuts rays off (auto must land on the reference schedule), dt_gamma > 0
+    with several cascades (non-constant step: no closed-form windows), and a ray count that is not a multiple of anything."""
+    from laenerf_b200.nerf import NeRFNetwork
+
+    def model(name, seed=9):
+        sc = scene(name)
+        torch.manual_seed(seed)
+        m = NeRFNetwork(bound=sc.bound, min_near=sc.min_near, density_scale=5.0).to(dev)
+        with torch.no_grad():
+            m.encoder.embeddings.uniform_(-0.5, 0.5)
+        m.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+        m.eval()
+        return m
+
+    def both(m, ro, rd, **kw):
+        outs = {}
+        for sched in ("reference", "auto"):
+            m.render_schedule = sched
+            m._auto_fast_ok = True
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                outs[sched] = m.render(ro, rd, perturb=False, bg_color=1, scale_depth=False, **kw)
+        for k in ("image", "depth", "t"):
+            assert torch.equal(outs["reference"][k], outs["auto"][k]), (k, kw)
+        return outs
+
+    m = model("lego")
+    _, ro, rd, _ = scene_rays("lego", 5003, 41)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    both(m, ro[:1], rd[:1])                                   # one ray
+    both(m, ro, rd)                                           # 5003 rays
+    o = both(m, ro, rd, max_steps=16)                         # the cap cuts rays off
+    assert o["auto"]["schedule"] == "reference"
+    away = both(m, ro, -rd)                                   # every ray points away from the object: all miss the occupied box
+    assert float(away["auto"]["t"].abs().max()) == 0.0 and torch.equal(away["auto"]["image"], torch.ones_like(away["auto"]["image"]))
+    m.density_bitfield.zero_()                                # nothing occupied at all: the box is (+inf, -inf)
+    empty = both(m, ro, rd)
+    assert float(empty["auto"]["t"].abs().max()) == 0.0
+    mb = model("bonsai")
+    _, ro, rd, _ = scene_rays("bonsai", 20011, 43)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    both(mb, ro, rd, dt_gamma=1.0 / 128)                      # growing steps, five cascades
