@@ -628,8 +628,21 @@ def edit_config(ctx, flower):
         sms = ctx.timed_loop(lambda i: losses.append(st(x_term, d, target)[0]), 20) / 20
         l = [float(x) for x in losses]
         timings["fused_adam" if fused else "torch_adam"] = dict(ms_per_step=sms, points_per_s=world * K / (sms * 1e-3), loss_first=l[0], loss_last=l[-1])
+        if fused and world == 1:  # the same step replayed from one CUDA graph (the eager iteration is bound by the interpreter)
+            try:
+                from laenerf_b200.style_encoder import GraphedStyleTrainStep
+                gst = GraphedStyleTrainStep(st, K)
+                gst.capture(x_term, d, target)
+                gl = []
+                for _ in range(3):
+                    gst(x_term, d, target)
+                gms = ctx.timed_loop(lambda i: gl.append(gst(x_term, d, target)[0].clone()), 50) / 50
+                timings["graph"] = dict(ms_per_step=gms, points_per_s=K / (gms * 1e-3), loss_last=float(gl[-1]))
+                del gst
+            except Exception as e:
+                timings["graph"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         del style, st
-    res["style"] = dict(timings["fused_adam"], torch_adam=timings["torch_adam"],
+    res["style"] = dict(timings["fused_adam"], torch_adam=timings["torch_adam"], cuda_graph=timings.get("graph"),
                         note="StyleTrainStep: hash grid fwd/bwd (fp32 table, as the reference runs it without autocast), SH-3, two FFMLP nets on tcgen05, "
                              "palette mix, MSE + regularisers, GradScaler + Adam; `torch_adam` = the same step with torch.optim.Adam + torch GradScaler; "
                              "N > 1: one view per rank per step, gradients averaged over ranks")

@@ -81,9 +81,20 @@ class LAENeRF(nn.Module):
             offset_in = torch.cat([offset_in, torch.zeros(offset_in.shape[0], pad, dtype=offset_in.dtype, device=offset_in.device)], dim=-1)
         return offset_in
 
+    def _active(self):
+        """Integer indices of the active palette entries.  The reference indexes with the boolean mask itself (style_encoder.py:95,
+        123, 132): every such index is a nonzero() and a device->host synchronisation, three per training iteration.  The indices are
+        cached and re-derived when the mask is replaced or written to (its version counter)."""
+        m = self.active_palets
+        key = (id(m), m._version)
+        if getattr(self, "_active_key", None) != key:
+            self._active_idx = torch.nonzero(m).flatten()
+            self._active_key = key
+        return self._active_idx
+
     def get_weights(self, x):
         x = self.encoder(x, bound=self.bound)
-        w_hat = self.weight_net(x)[:, self.active_palets]
+        w_hat = self.weight_net(x)[:, self._active()]
         return torch.softmax(w_hat, -1)
 
     def get_offsets(self, x, d):
@@ -93,18 +104,19 @@ class LAENeRF(nn.Module):
     def forward_train(self, x, d=None):
         # x: [N, 3] in [-bound, bound] (the distilled termination points `x_term` of run_cuda_distill); d: [N, 3] unit
         x = self.encoder(x, bound=self.bound)
-        w_hat = self.weight_net(x)[:, self.active_palets]
+        act = self._active()
+        w_hat = self.weight_net(x)[:, act]
         o_hat = self.offset_net(self._offset_input(x, d))
         o_hat = torch.tanh(o_hat)
         w_hat = torch.softmax(w_hat, -1)
-        pred_colors = w_hat @ self.color_palette[self.active_palets].half() + o_hat
+        pred_colors = w_hat @ self.color_palette[act].half() + o_hat
         return torch.clamp(pred_colors, 0, 1), w_hat, o_hat
 
     def forward(self, x, d=None):
         return self.forward_train(x, d)[0]
 
     def get_color_palette(self):
-        return self.color_palette[self.active_palets]
+        return self.color_palette[self._active()]
 
     def set_color_palette(self, palet):
         if self.original_color_palette is None:
@@ -187,3 +199,43 @@ class StyleTrainStep:
             self.scaler.step(self.optimizer)
             self.scaler.update()
         return loss.detach(), pred_colors.detach()
+
+
+class GraphedStyleTrainStep:
+    """A StyleTrainStep replayed from ONE CUDA graph per point count: forward_train, the four loss terms, the scaled backward and the
+    optimizer are ~60 launches of a few microseconds each, so issued from Python the iteration is bound by the interpreter (2.5 ms for
+    49 152 points; the kernels take a fraction of that).  Inputs are copied into static device buffers; `loss` / `pred` are views of
+    graph-owned memory that the next replay overwrites.  The point count is fixed per capture -- a view's masked points are padded or
+    chunked by the caller (the reference feeds one view's mask per step, nerf/utils.py:983-1034).  Single process only: the
+    data-parallel variant averages the fp32 gradients with an NCCL all-reduce per step and stays eager."""
+
+    def __init__(self, step: StyleTrainStep, n_points: int):
+        if step.world > 1:
+            raise RuntimeError("GraphedStyleTrainStep: single-process only (the data-parallel step all-reduces its gradients eagerly)")
+        self.step = step
+        dev = next(step.model.parameters()).device
+        self.x = torch.zeros(n_points, 3, device=dev)
+        self.d = torch.zeros(n_points, 3, device=dev)
+        self.t = torch.zeros(n_points, 3, device=dev)
+        self.graph = None
+        self.loss = self.pred = None
+
+    def capture(self, x_term, d, target, warmup: int = 3):
+        self.x.copy_(x_term); self.d.copy_(d); self.t.copy_(target)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self.x, self.d, self.t)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.pred = self.step(self.x, self.d, self.t)
+
+    def __call__(self, x_term, d, target):
+        if self.graph is None:
+            self.capture(x_term, d, target)
+        self.x.copy_(x_term, non_blocking=True); self.d.copy_(d, non_blocking=True); self.t.copy_(target, non_blocking=True)
+        self.graph.replay()
+        self.step.style_step += 1
+        return self.loss, self.pred

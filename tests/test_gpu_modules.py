@@ -336,3 +336,32 @@ def test_mark_untrained_grid_matches_per_cell_restatement(dev):
                     want[cas, idx] = cnt == 0 or close > 0
     assert n_marked == int(got.sum()) and 0 < n_marked < got.size
     assert (got != want).mean() < 2e-3  # fp32 boundary ties only
+
+
+def test_graphed_style_step_equals_the_eager_step(dev):
+    """GraphedStyleTrainStep replays StyleTrainStep from one CUDA graph: same losses, same parameters as the eager sequence."""
+    from types import SimpleNamespace
+    from laenerf_b200.style_encoder import GraphedStyleTrainStep, LAENeRF, StyleTrainStep
+    params = SimpleNamespace(bound=2.0, num_palette_bases=8, style_weight=0.0, weight_loss_uniform=1e-6, weight_loss_non_uniform=1e-6,
+                             offset_loss=1e-6, palette_loss_valid=1e-3, palette_loss_distinct=1e-3)
+    K = 8192
+    g = torch.Generator(device=dev).manual_seed(3)
+    batches = [((torch.rand(K, 3, device=dev, generator=g) - 0.5) * 3.0, torch.nn.functional.normalize(torch.randn(K, 3, device=dev, generator=g), dim=-1),
+                torch.rand(K, 3, device=dev, generator=g)) for _ in range(6)]
+    runs = []
+    for graphed in (False, True):
+        torch.manual_seed(1)
+        style = LAENeRF(params, dir_encoding="sphere_harmonics").to(dev)
+        st = StyleTrainStep(style, params)
+        if graphed:
+            gs = GraphedStyleTrainStep(st, K)
+            gs.capture(*batches[0], warmup=1)   # one eager step on batch 0 (lazy allocations happen outside the capture) ...
+            losses = [float(gs(*b)[0]) for b in batches]
+        else:
+            st(*batches[0])                     # ... so the eager run takes the same extra first step
+            losses = [float(st(*b)[0]) for b in batches]
+        runs.append((losses, style.encoder.embeddings.detach().clone(), style.color_palette.detach().clone()))
+    (la, ea, pa), (lb, eb, pb) = runs
+    assert all(np.isfinite(la)) and np.allclose(la, lb, rtol=2e-3), (la, lb)
+    assert float((ea - eb).abs().max()) < 1e-4 and float((pa - pb).abs().max()) < 1e-4
+    assert la[-1] < la[0]
