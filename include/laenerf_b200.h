@@ -421,6 +421,12 @@ LNRF_API int lnrf_nerf_backward_recompute(const float* grad_sigmas, const float*
                                           uint32_t M, const int32_t* M_dev, uint32_t num_layers_sigma, uint32_t num_layers_color,
                                           float density_scale, void* grad_enc_f16, void* grad_w_sigma_f16, void* grad_w_color_f16,
                                           int accumulate_wgrad, void* wgrad_scratch, size_t wgrad_scratch_bytes, lnrf_stream_t stream);
+/* accumulate_wgrad of lnrf_nerf_backward_recompute: bit 0 = add to the existing fp16 weight gradients, bit 1 = leave the per-CTA partial
+ * sums in wgrad_scratch and let the caller run their fixed-order reduction with this call -- e.g. on another stream beside the
+ * hash-grid backward, which does not depend on it (laenerf_b200/nerf.py).  Same M / layer counts / scratch as the backward call. */
+LNRF_API int lnrf_nerf_wgrad_reduce(const void* wgrad_scratch, size_t wgrad_scratch_bytes, uint32_t M, uint32_t num_layers_sigma,
+                                    uint32_t num_layers_color, void* grad_w_sigma_f16, void* grad_w_color_f16, int accumulate,
+                                    lnrf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * occupancy-grid maintenance (row f-2) -- NeRFRenderer.update_extra_state, nerf/renderer.py:556-649

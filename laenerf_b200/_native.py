@@ -86,6 +86,7 @@ SIGNATURES = {
     "lnrf_nerf_forward_lean": (i32, [vp, vp, vp, vp, u32, vp, u32, u32, f32, vp, vp, vp, vp]),
     "lnrf_nerf_backward_recompute_supported": (i32, [u32, u32]),
     "lnrf_nerf_backward_recompute": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, vp, u32, u32, f32, vp, vp, vp, i32, vp, sz, vp]),
+    "lnrf_nerf_wgrad_reduce": (i32, [vp, sz, u32, u32, u32, vp, vp, i32, vp]),
     "lnrf_grad_nonfinite_check": (i32, [vp, u32, vp, vp]),
     "lnrf_adam_step": (i32, [vp, u32, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp]),
     "lnrf_adam_step_sharded": (i32, [vp, vp, vp, u32, u64, u64, vp, vp, vp, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp]),
@@ -165,6 +166,33 @@ def ptr(t):
 def stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# Work queued on side streams whose results the optimizer reads (the weight-gradient reduction of the fused network runs beside the
+# hash-grid backward): AmpAdam.step() makes the current stream wait for them first.
+_pending_streams = []
+
+
+def defer_to_side_stream(dev):
+    """A cached side stream for `dev`, made to wait for the current stream; the caller launches on it and it is joined by join_pending()."""
+    import torch
+    key = (dev.index if dev.index is not None else torch.cuda.current_device())
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    if s not in _pending_streams:
+        _pending_streams.append(s)
+    return s
+
+
+_side_streams = {}
+
+
+def join_pending():
+    import torch
+    while _pending_streams:
+        torch.cuda.current_stream().wait_stream(_pending_streams.pop())
 
 
 def launch_count() -> int:

@@ -497,11 +497,26 @@ int lnrf_nerf_backward_recompute(const float* grad_sigmas, const float* grad_rgb
         cudaError_t e = cudaMemsetAsync(wgrad_scratch, 0, need_s + need_c, st);
         if (e != cudaSuccess) return cuda_fail(e, "nerf_backward_recompute");
     }
+    // accumulate_wgrad bit 1: the caller runs the reduction itself (lnrf_nerf_wgrad_reduce), e.g. on another stream beside the encoder
+    // backward, which does not depend on it
+    if (accumulate_wgrad & 2) return LNRF_OK;
+    return lnrf_nerf_wgrad_reduce(wgrad_scratch, wgrad_scratch_bytes, M, ns, nc, grad_w_sigma_f16, grad_w_color_f16, accumulate_wgrad & 1, stream);
+}
+
+int lnrf_nerf_wgrad_reduce(const void* wgrad_scratch, size_t wgrad_scratch_bytes, uint32_t M, uint32_t num_layers_sigma,
+                           uint32_t num_layers_color, void* grad_w_sigma_f16, void* grad_w_color_f16, int accumulate, lnrf_stream_t stream) {
+    const uint32_t ns = num_layers_sigma, nc = num_layers_color;
+    LNRF_REQUIRE(wgrad_scratch && grad_w_sigma_f16 && grad_w_color_f16, "nerf_wgrad_reduce: null pointer");
+    const size_t need_s = lnrf_ffmlp_wgrad_scratch_bytes(kEnc, 16, 64, ns), need_c = lnrf_ffmlp_wgrad_scratch_bytes(kCin, 16, 64, nc);
+    LNRF_REQUIRE(wgrad_scratch_bytes >= need_s + need_c, "nerf_wgrad_reduce: wgrad scratch too small");
+    const uint32_t np_s = 64u * (kEnc + 64u * (ns - 1u) + 16u), np_c = 64u * (kCin + 64u * (nc - 1u) + 16u);
+    const uint32_t want = div_up(M / kRows, kBG);
+    const uint32_t grid = want < (uint32_t)kNumSMs ? want : (uint32_t)kNumSMs;
     // with M_dev the number of CTAs that really had a tile is not known on the host: all `grid` slices are reduced (CTAs without a
     // tile write zeros into theirs)
-    WgradPending ps{(const float*)wgrad_scratch, M > 0 ? grid : 1u, (__half*)grad_w_sigma_f16, np_s, accumulate_wgrad};
-    WgradPending pc{(const float*)((uint8_t*)wgrad_scratch + need_s), M > 0 ? grid : 1u, (__half*)grad_w_color_f16, np_c, accumulate_wgrad};
-    return wgrad_reduce_pair("nerf_backward_recompute(wgrad)", ps, pc, st);
+    WgradPending ps{(const float*)wgrad_scratch, M > 0 ? grid : 1u, (__half*)grad_w_sigma_f16, np_s, accumulate & 1};
+    WgradPending pc{(const float*)((const uint8_t*)wgrad_scratch + need_s), M > 0 ? grid : 1u, (__half*)grad_w_color_f16, np_c, accumulate & 1};
+    return wgrad_reduce_pair("nerf_backward_recompute(wgrad)", ps, pc, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

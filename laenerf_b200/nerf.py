@@ -46,6 +46,18 @@ def _recompute_ok(ns, nc) -> bool:
     return os.environ.get("LNRF_MLP_RECOMPUTE", "1") != "0" and bool(N.lib().lnrf_nerf_backward_recompute_supported(int(ns), int(nc)))
 
 
+_WGRAD_SIDE = os.environ.get("LNRF_WGRAD_SIDE", "1") == "1"  # A/B switch: weight-gradient reduction beside the hash-grid backward
+_wgrad_scratch_cache = {}
+
+
+def _wgrad_scratch(dev, nbytes):
+    key = (dev.index, nbytes)
+    t = _wgrad_scratch_cache.get(key)
+    if t is None:
+        t = _wgrad_scratch_cache[key] = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    return t
+
+
 before_network_backward = None  # GraphedTrainStep(lookahead=True) forks the next batch's march here
 
 
@@ -116,11 +128,18 @@ class _fused_network(Function):
         gws = ctx.gw[0] if persistent else torch.empty_like(ws)
         gwc = ctx.gw[1] if persistent else torch.empty_like(wc)
         nbytes = lib.lnrf_nerf_wgrad_scratch_bytes(ns, nc)
-        scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        # persistent gradients (AmpAdam): the fixed-order reduction of the per-CTA partial sums runs on a side stream BESIDE the hash-grid
+        # backward -- neither depends on the other -- and AmpAdam.step() joins it (N.join_pending); the partial sums then live in a
+        # scratch that outlives this call (two streams touch it: no allocator recycling in between)
+        side_reduce = persistent and ctx.lean and _WGRAD_SIDE
+        scratch = _wgrad_scratch(dev, nbytes) if side_reduce else torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
         if ctx.lean:
             N.check(lib.lnrf_nerf_backward_recompute(N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(rgbs), N.ptr(h), N.ptr(enc), N.ptr(dirs),
                                                      N.ptr(ws), N.ptr(wc), M, N.ptr(m_dev), ns, nc, density_scale, N.ptr(grad_enc), N.ptr(gws),
-                                                     N.ptr(gwc), int(persistent), N.ptr(scratch), nbytes, N.stream()))
+                                                     N.ptr(gwc), int(persistent) | (2 if side_reduce else 0), N.ptr(scratch), nbytes, N.stream()))
+            if side_reduce:
+                with torch.cuda.stream(N.defer_to_side_stream(dev)):
+                    N.check(lib.lnrf_nerf_wgrad_reduce(N.ptr(scratch), nbytes, M, ns, nc, N.ptr(gws), N.ptr(gwc), 1, N.stream()))
         else:
             dh = torch.empty(M, 16, dtype=torch.half, device=dev)
             N.check(lib.lnrf_nerf_backward(N.ptr(grad_sigmas), N.ptr(grad_rgbs), N.ptr(rgbs), N.ptr(h0), N.ptr(enc), N.ptr(cin), N.ptr(ws),

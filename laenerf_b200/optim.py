@@ -385,6 +385,7 @@ class AmpAdam:
 
     @torch.no_grad()
     def step(self):
+        N.join_pending()  # e.g. the weight-gradient reduction of the fused network, queued on a side stream beside the encoder backward
         if self.sharded:
             return self._step_sharded()
         if self.world > 1:
