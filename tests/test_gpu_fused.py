@@ -859,3 +859,31 @@ def test_auto_render_schedule_edge_cases(dev):
     _, ro, rd, _ = scene_rays("bonsai", 20011, 43)
     ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
     both(mb, ro, rd, dt_gamma=1.0 / 128)                      # growing steps, five cascades
+
+
+@pytest.mark.parametrize("name", ["lego", "flower", "bonsai"])
+def test_training_march_clipped_to_the_occupied_box_is_identical(dev, name):
+    """lnrf_march_rays_train_clipped against lnrf_march_rays_train: positions, directions, deltas, ray table and counter bit for bit
+    (rays end where they leave the box around the occupied cells; nothing is ever sampled beyond it), with and without perturbation,
+    dt_gamma = 0 and > 0."""
+    from laenerf_b200 import raymarching
+    from laenerf_b200.nerf import NeRFNetwork
+    sc = scene(name)
+    m = NeRFNetwork(bound=sc.bound, min_near=sc.min_near).to(dev)
+    m.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
+    _, ro, rd, _ = scene_rays(name, 20000, 17)
+    ro, rd = torch.from_numpy(ro).to(dev), torch.from_numpy(rd).to(dev)
+    nears, fars = raymarching.near_far_from_aabb(ro, rd, m.aabb_train, m.min_near)
+    box = m.occupied_box()
+    assert torch.isfinite(box).all() and bool((box[3:] > box[:3]).all())
+    for perturb, dt_gamma in ((False, 0.0), (True, 0.0), (True, 1.0 / 256)):
+        outs = []
+        for b in (None, box):
+            torch.manual_seed(123)
+            counter = torch.zeros(2, dtype=torch.int32, device=dev)
+            o = raymarching.march_rays_train(ro, rd, m.bound, m.density_bitfield, m.cascade, m.grid_size, nears, fars, counter, -1, perturb, 128,
+                                             True, dt_gamma, 1024, None, b)
+            outs.append((*o, counter))
+        for x, y in zip(*outs):
+            assert torch.equal(x, y), (name, perturb, dt_gamma)
+        assert int(outs[0][-1][0]) > 1000
