@@ -1182,9 +1182,10 @@ k_compact_alive(const int* __restrict__ rays_alive, uint32_t n_alive, int* __res
 constexpr int kCtlCompactRows = 15;
 constexpr int kCompactCap = 64;  // most samples a ray takes per round (render_begin: step_cap <= 64)
 
+constexpr int kCompactG = 8;          // lanes per ray (default)
 constexpr int kCompactThreads = 128;  // 16 rays per block: the block waits for its longest march before the offsets are known
 
-template <bool DISTILL>
+template <bool DISTILL, int G>
 __global__ void __launch_bounds__(kCompactThreads)
 k_march_infer_compact(const int* __restrict__ rays_alive, const float* __restrict__ rays_t, const float* __restrict__ rays_o,
                       const float* __restrict__ rays_d, const MarchParams p, const uint8_t* __restrict__ grid,
@@ -1192,7 +1193,7 @@ k_march_infer_compact(const int* __restrict__ rays_alive, const float* __restric
                       float* __restrict__ dirs, float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, int* __restrict__ ray_off,
                       int* __restrict__ ray_cnt, unsigned long long* __restrict__ status, int* __restrict__ ctl,
                       const float* __restrict__ occ_box) {
-    constexpr int G = kInferGroup, kGroups = kCompactThreads / G;
+    constexpr int kGroups = kCompactThreads / G;
     __shared__ float s_t[kGroups][kCompactCap];
     __shared__ uint32_t s_cnt[kGroups];
     __shared__ uint32_t s_excl;
@@ -1612,13 +1613,13 @@ int composite_infer_dev_launch(bool distill, const int32_t* ctl, uint32_t n_rays
     return LNRF_OK;
 }
 
-// compact rounds: scratch_m = (n_rays_cap / 16 + 2) status words (one per marcher block), then ray_off[n_rays_cap], ray_cnt[n_rays_cap]
+// compact rounds: scratch_m = (n_rays_cap / 4 + 2) status words (one per marcher block at most), then ray_off[n_rays_cap], ray_cnt[n_rays_cap]
 size_t march_compact_scratch_bytes(uint32_t n_rays_cap) {
-    return sizeof(unsigned long long) * ((size_t)div_up(n_rays_cap, 16u) + 2) + 2 * sizeof(int) * (size_t)n_rays_cap;
+    return sizeof(unsigned long long) * ((size_t)div_up(n_rays_cap, 4u) + 2) + 2 * sizeof(int) * (size_t)n_rays_cap;
 }
 static void march_compact_carve(void* scratch_m, uint32_t n_rays_cap, unsigned long long** status, uint32_t* n_status, int** off, int** cnt) {
     *status = reinterpret_cast<unsigned long long*>(scratch_m);
-    *n_status = div_up(n_rays_cap, 16u) + 2u;
+    *n_status = div_up(n_rays_cap, 4u) + 2u;   // one word per marcher block; 4 rays per block with 32 lanes per ray
     *off = reinterpret_cast<int*>(*status + *n_status);
     *cnt = *off + n_rays_cap;
 }
@@ -1634,13 +1635,18 @@ int march_infer_compact_dev_launch(bool distill, int32_t* ctl, uint32_t n_rays_c
     const MarchParams p = march_params_env(bound, dt_gamma, max_steps, C, H);
     unsigned long long* status; uint32_t n_status; int *off, *cnt;
     march_compact_carve(scratch_m, n_rays_cap, &status, &n_status, &off, &cnt);
-    const uint32_t blocks = div_up(n_rays_cap, (uint32_t)kCompactThreads / (uint32_t)kInferGroup);
-    if (distill)
-        k_march_infer_compact<true><<<blocks, kCompactThreads, 0, st>>>(rays_alive, rays_t, rays_o, rays_d, p, grid, edit_grid, fars, xyzs, dirs, deltas, edit_occ,
-                                                            off, cnt, status, ctl, occ_box);
-    else
-        k_march_infer_compact<false><<<blocks, kCompactThreads, 0, st>>>(rays_alive, rays_t, rays_o, rays_d, p, grid, nullptr, fars, xyzs, dirs, deltas, nullptr,
-                                                             off, cnt, status, ctl, occ_box);
+    // lanes per ray (LNRF_COMPACT_G = 4 | 8 | 16 | 32, A/B switch; measured lego / bonsai frame: 8 lanes 11.2 / 28.1 ms, 16: 11.7 / 31.9, 32: 12.5 / 39.4): a window of G sequence members per iteration
+    // Default: 8 lanes, 4 when the scene has three or more cascades -- there most of a ray's walk crosses cells much longer than a
+    // window of sequence members (cell 0.25 against 0.027 for 8 members on cascade 4 of the bonsai shape), so narrow groups idle less:
+    // bonsai frame 28.3 -> 25.4 ms with 4 lanes, lego (one cascade) 11.4 -> 11.5.
+    static const int forced = [] { const char* e = getenv("LNRF_COMPACT_G"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 0; }();
+    const int cg = forced ? forced : (C >= 3 ? 4 : kCompactG);
+#define LNRF_MIC_(DD, GG)                                                                                                                  \
+    k_march_infer_compact<DD, GG><<<div_up(n_rays_cap, (uint32_t)kCompactThreads / GG), kCompactThreads, 0, st>>>(                          \
+        rays_alive, rays_t, rays_o, rays_d, p, grid, DD ? edit_grid : nullptr, fars, xyzs, dirs, deltas, DD ? edit_occ : nullptr, off, cnt, status, ctl, occ_box)
+    if (distill) { if (cg == 32) LNRF_MIC_(true, 32); else if (cg == 16) LNRF_MIC_(true, 16); else if (cg == 4) LNRF_MIC_(true, 4); else LNRF_MIC_(true, 8); }
+    else { if (cg == 32) LNRF_MIC_(false, 32); else if (cg == 16) LNRF_MIC_(false, 16); else if (cg == 4) LNRF_MIC_(false, 4); else LNRF_MIC_(false, 8); }
+#undef LNRF_MIC_
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }

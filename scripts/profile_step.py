@@ -21,10 +21,11 @@ ap.add_argument("--warmup", type=int, default=6)
 ap.add_argument("--render-rays", type=int, default=0, help="also profile one render of this many rays")
 ap.add_argument("--render-shard", type=int, default=0, help="render rank 0's share of a frame tile-sharded over this many ranks")
 ap.add_argument("--render-schedule", default="fast", choices=["fast", "reference", "auto"])
+ap.add_argument("--scene", default="lego", choices=["lego", "flower", "bonsai"])
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
-sc = make_scene("lego", seed=0, n_poses=4)
+sc = make_scene(args.scene, seed=0, n_poses=4)
 torch.manual_seed(0)
 model = NeRFNetwork(bound=sc.bound, min_near=sc.min_near).to(dev)
 model.set_density_grid(torch.from_numpy(sc.density_grid).to(dev), thresh=10.0)
