@@ -314,7 +314,8 @@ typedef struct {
     int32_t* ctl;                 /* device int32[32] control block: [0] n_alive [1] n_step [2] steps marched [3] rows of the
                                      round (n_alive*n_step padded past 128) [4] n_rays [5] max_steps [6] finished [7] rounds
                                      [9] sample slots marched so far [12] the result may depend on the round schedule (see
-                                     ray_flags) [13] rays that raised [12] [14] the max_steps cap cut rays off; [16..22] internal (copies of the four fields below) */
+                                     ray_flags) [13] rays that raised [12] [14] the max_steps cap cut rays off [15] rows of the running compact round; [16..22] internal
+                                     (copies of the four fields below) */
     uint32_t n_rays, max_steps;
     /* rays and marching (raymarching.march_rays arguments) */
     const float *rays_o, *rays_d, *nears, *fars;       /* [n_rays,3] x2, [n_rays] x2 */

@@ -892,6 +892,8 @@ k_composite_loss_fwd_bwd(const float* __restrict__ sigmas, const float* __restri
 //   ctl[10] row budget of the rounds after the first (n_rays: the reference schedule; more: see lnrf_render_desc.sample_rows)
 //   ctl[11] most samples a ray takes per round after the first (8: the reference schedule)
 //   ctl[12] schedule-dependence flag: set when the frame's result COULD depend on where the round boundaries fall (see below)
+//   ctl[13] rays that raised ctl[12]   ctl[14] the max_steps cap cut rays off (the frame goes to the reference schedule)
+//   ctl[15] rows of the running COMPACT round (k_march_infer_compact; 0 on slot-layout rounds and when the frame is finished)
 //   ctl[16] length of a prescribed n_step sequence (0: none)   ctl[17,18] its device address   ctl[19,20] address of the per-ray
 //   completed-step counters   ctl[21,22] address of the per-ray schedule-dependence flags (see lnrf_render_desc)
 enum { kCtlAlive = 0, kCtlStep = 1, kCtlSteps = 2, kCtlRows = 3, kCtlRays = 4, kCtlMaxSteps = 5, kCtlFinished = 6, kCtlRounds = 7,
