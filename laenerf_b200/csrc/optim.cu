@@ -56,17 +56,25 @@ __device__ __forceinline__ bool grad_block_nonfinite(const OptBatch& b) {
     bool bad = false;
     uint64_t base = (uint64_t)(blockIdx.x - t.first_block) * kOptChunk;
     if (t.g_is_f16) {
-        // four independent 16-byte loads per thread in flight: the 24.5 MB gradient is L2-resident (just written by the encoder
-        // backward), and one load per loop trip left the kernel latency-bound (10.6 us = 2.3 TB/s)
+        // up to eight independent 16-byte loads per thread in flight (predicated): the 24.5 MB gradient is L2-resident (just written by
+        // the encoder backward) and the table is ~5 chunks per block, so the whole check is ONE round trip per thread -- one load per
+        // loop trip left the kernel latency-bound (10.6 us = 2.3 TB/s), four in flight + a remainder loop still took three trips
         const uint64_t stride = (uint64_t)nblocks * kOptChunk;
         const __half* g = reinterpret_cast<const __half*>(t.g);
-        for (; base + 3 * stride + kOptChunk <= t.n; base += 4 * stride) {
-            const uint64_t i = base + (uint64_t)threadIdx.x * kOptPerThread;
-            const uint4 w0 = *reinterpret_cast<const uint4*>(g + i), w1 = *reinterpret_cast<const uint4*>(g + i + stride);
-            const uint4 w2 = *reinterpret_cast<const uint4*>(g + i + 2 * stride), w3 = *reinterpret_cast<const uint4*>(g + i + 3 * stride);
-            bad |= !(finite_h2(w0.x) && finite_h2(w0.y) && finite_h2(w0.z) && finite_h2(w0.w) && finite_h2(w1.x) && finite_h2(w1.y) &&
-                     finite_h2(w1.z) && finite_h2(w1.w) && finite_h2(w2.x) && finite_h2(w2.y) && finite_h2(w2.z) && finite_h2(w2.w) &&
-                     finite_h2(w3.x) && finite_h2(w3.y) && finite_h2(w3.z) && finite_h2(w3.w));
+        for (; base < t.n; base += 8 * stride) {
+            uint4 w[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint64_t i = base + (uint64_t)u * stride + (uint64_t)threadIdx.x * kOptPerThread;
+                w[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (i + kOptPerThread <= t.n) {
+                    w[u] = *reinterpret_cast<const uint4*>(g + i);
+                } else {
+                    for (uint64_t j = i; j < t.n; j++) bad |= !isfinite(__half2float(g[j]));  // the ragged end of the tensor (< 8 elements)
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) bad |= !(finite_h2(w[u].x) && finite_h2(w[u].y) && finite_h2(w[u].z) && finite_h2(w[u].w));
         }
     }
     for (; base < t.n; base += (uint64_t)nblocks * kOptChunk) {
