@@ -195,12 +195,16 @@ LNRF_API int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, floa
  * raymarching.cu:948-1035 would.  Bit-identical to lnrf_render_rounds with the same nstep_seq.
  *   march: offsets == NULL -> count only (counts[ray] = samples until the ray leaves the volume or the sequence ends);
  *          else write the ray's samples at row offsets[ray] (exclusive prefix sum of counts).  edit_grid != NULL: also edit_occ.
+ *          caps (optional, [n_rays]): most samples to march per ray -- with offsets = prefix sum of the caps the counting pass and the
+ *          walk behind a ray's death are spared; a ray that has not died within its cap must be redone without one.
+ *          occupied_box (optional): as in lnrf_render_desc.
  *   composite: per-ray outputs indexed by the subset position; ray_steps[ray] = completed samples (where the ray dies). */
 LNRF_API int lnrf_march_rays_prescribed(uint32_t n_rays, const float* rays_o, const float* rays_d, const float* nears,
                                         const float* fars, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
                                         const uint8_t* density_bitfield, const uint8_t* edit_bitfield, const int32_t* nstep_seq,
                                         uint32_t nstep_len, const int32_t* offsets, int32_t* counts, float* xyzs, float* dirs,
-                                        float* deltas, uint8_t* edit_occ, lnrf_stream_t stream);
+                                        float* deltas, uint8_t* edit_occ, const int32_t* caps, const float* occupied_box,
+                                        lnrf_stream_t stream);
 LNRF_API int lnrf_composite_rays_prescribed(uint32_t n_rays, float T_thresh, const int32_t* offsets, const int32_t* counts,
                                             const float* nears, const float* sigmas, const float* rgbs, const float* deltas,
                                             const uint8_t* edit_occ, float* weights_sum, float* weights_edit_sum, float* depth,

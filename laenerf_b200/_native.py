@@ -50,7 +50,7 @@ SIGNATURES = {
     "lnrf_march_rays_distill": (i32, [u32, u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]),
     "lnrf_composite_rays": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "lnrf_composite_rays_distill": (i32, [u32, u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "lnrf_march_rays_prescribed": (i32, [u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp]),
+    "lnrf_march_rays_prescribed": (i32, [u32, vp, vp, vp, vp, f32, f32, u32, u32, u32, vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "lnrf_composite_rays_prescribed": (i32, [u32, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "lnrf_compact_alive_scratch_bytes": (sz, [u32]),
     "lnrf_compact_alive": (i32, [vp, u32, vp, vp, vp, sz, vp]),

@@ -1412,13 +1412,17 @@ k_composite_infer_compact(const float T_thresh, int* __restrict__ rays_alive, fl
 // order with the per-round arithmetic and stops at the reference's sample.  Same bits as running the rounds one by one
 // (lnrf_render_rounds with nstep_seq) -- in 4 launches instead of 5 per round.
 //   offsets == nullptr: count only (counts[ray] = samples up to the ray's exit); else write the ray's samples at offsets[ray].
+//   caps (optional): most samples to march for each ray -- the caller knows roughly where a ray dies (the fast pass recorded it) and
+//   spares the walk to the far end of the ray and the counting pass (offsets = prefix sum of the caps); a ray that has not died
+//   within its cap must be redone without one.  occ_box: see clip_far_to_box.
 template <bool DISTILL>
 __global__ void __launch_bounds__(256)
 k_march_prescribed(const uint32_t n_rays, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                    const float* __restrict__ nears, const float* __restrict__ fars, const MarchParams p,
                    const uint8_t* __restrict__ grid, const uint8_t* __restrict__ edit_grid, const int* __restrict__ seq,
                    const uint32_t seq_len, const int* __restrict__ offsets, int* __restrict__ counts, float* __restrict__ xyzs,
-                   float* __restrict__ dirs, float* __restrict__ deltas, uint8_t* __restrict__ edit_occ) {
+                   float* __restrict__ dirs, float* __restrict__ deltas, uint8_t* __restrict__ edit_occ, const int* __restrict__ caps,
+                   const float* __restrict__ occ_box) {
     constexpr int G = kInferGroup;
     __shared__ float s_d1[256 / G][8];
     const Group<G> grp;
@@ -1430,16 +1434,19 @@ k_march_prescribed(const uint32_t n_rays, const float* __restrict__ rays_o, cons
     size_t row = 0;
     if (active) {
         r = make_ray(rays_o + (size_t)g * 3, rays_d + (size_t)g * 3);
-        far = fars[g];
+        far = clip_far_to_box(occ_box, r, fars[g]);
         t = nears[g];  // rays_t starts at near (renderer.py:349); no perturbation on this path
         if (offsets) row = (size_t)offsets[g];
     }
+    const uint32_t cap = (active && caps) ? (uint32_t)max(caps[g], 0) : 0xffffffffu;
     uint32_t total = 0;
     for (uint32_t rd = 0; rd < seq_len; rd++) {
         if (!__any_sync(kFull, active)) break;
         const uint32_t n_step = (uint32_t)__ldg(seq + rd);  // <= 8
+        if (active && total >= cap) active = false;
+        const uint32_t want = n_step < cap - total ? n_step : cap - total;  // group-uniform (cap, total are the ray's)
         const uint32_t cnt = march_group<G, true>(
-            grp, p, r, grid, t, far, n_step, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
+            grp, p, r, grid, t, far, active ? want : 0u, active, [&](uint32_t rank, float s, float dt, const Probe& q, float prev_after) {
                 const float t_after = f_add(s, dt), d1 = f_add(t_after, -prev_after);
                 s_d1[gi][rank] = d1;
                 if (offsets) {
@@ -1998,7 +2005,8 @@ int lnrf_composite_rays_distill(uint32_t n_alive, uint32_t n_step, float T_thres
 int lnrf_march_rays_prescribed(uint32_t n_rays, const float* rays_o, const float* rays_d, const float* nears, const float* fars, float bound,
                                float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* edit_grid,
                                const int32_t* nstep_seq, uint32_t nstep_len, const int32_t* offsets, int32_t* counts, float* xyzs,
-                               float* dirs, float* deltas, uint8_t* edit_occ, lnrf_stream_t stream) {
+                               float* dirs, float* deltas, uint8_t* edit_occ, const int32_t* caps, const float* occupied_box,
+                               lnrf_stream_t stream) {
     const char* who = "march_rays_prescribed";
     if (int e = check_march_common(C, H, max_steps, who)) return e;
     if (n_rays == 0) return LNRF_OK;
@@ -2009,10 +2017,10 @@ int lnrf_march_rays_prescribed(uint32_t n_rays, const float* rays_o, const float
     const uint32_t blocks = div_up(n_rays, 256u / (uint32_t)kInferGroup);
     if (edit_grid)
         k_march_prescribed<true><<<blocks, 256, 0, S(stream)>>>(n_rays, rays_o, rays_d, nears, fars, p, grid, edit_grid, nstep_seq, nstep_len, offsets,
-                                                               counts, xyzs, dirs, deltas, edit_occ);
+                                                               counts, xyzs, dirs, deltas, edit_occ, caps, occupied_box);
     else
         k_march_prescribed<false><<<blocks, 256, 0, S(stream)>>>(n_rays, rays_o, rays_d, nears, fars, p, grid, nullptr, nstep_seq, nstep_len, offsets,
-                                                                counts, xyzs, dirs, deltas, nullptr);
+                                                                counts, xyzs, dirs, deltas, nullptr, caps, occupied_box);
     LNRF_LAUNCH_CHECK(who);
     return LNRF_OK;
 }

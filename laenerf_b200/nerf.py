@@ -476,9 +476,10 @@ class NeRFNetwork(nn.Module):
         sub_steps = steps[idx]
         sub = [x[idx].contiguous() for x in (rays_o, rays_d, nears, fars)]
         by_rounds = os.environ.get("LNRF_FIXUP_ROUNDS", "0") == "1"
+        use_caps = os.environ.get("LNRF_FIXUP_CAPS", "1") == "1"
         distill = edit_bitfield is not None
         lib, st = N.lib(), N.stream()
-        for _ in range(3):
+        for _ in range(4):
             seq = self._reference_sequence(hist, n_rays, max_steps)
             if not seq:
                 return None
@@ -490,19 +491,35 @@ class NeRFNetwork(nn.Module):
             else:
                 so, sd, sn_, sf = sub
                 counts = torch.empty(nf, dtype=torch.int32, device=dev)
+                box = t.get("occupied_box")
                 geo = (float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size), dens_grid.data_ptr(),
                        edit_bitfield.data_ptr() if distill else None, seq_dev.data_ptr(), len(seq))
-                N.check(lib.lnrf_march_rays_prescribed(nf, so.data_ptr(), sd.data_ptr(), sn_.data_ptr(), sf.data_ptr(), *geo, None,
-                                                       counts.data_ptr(), None, None, None, None, st))
-                ends = torch.cumsum(counts, 0, dtype=torch.int32)
-                offsets = (ends - counts).contiguous()
-                total = int(ends[-1].item())
-                rows = total + 128 - total % 128  # raymarching.py:331-332 padding rule; the pad rows are zeros
                 f32 = dict(dtype=torch.float32, device=dev)
-                xyzs, dirs, deltas = torch.zeros(rows, 3, **f32), torch.zeros(rows, 3, **f32), torch.zeros(rows, 2, **f32)
-                edit_occ = torch.zeros(rows, dtype=torch.uint8, device=dev) if distill else None
-                N.check(lib.lnrf_march_rays_prescribed(nf, so.data_ptr(), sd.data_ptr(), sn_.data_ptr(), sf.data_ptr(), *geo, offsets.data_ptr(),
-                                                       counts.data_ptr(), xyzs.data_ptr(), dirs.data_ptr(), deltas.data_ptr(), N.ptr(edit_occ), st))
+
+                def march(caps):
+                    """Samples of the flagged rays on `seq`, back to back.  caps: most samples per ray (offsets = their prefix sum: one
+                    marching pass); None: a counting pass first, every ray to its far end."""
+                    if caps is None:
+                        N.check(lib.lnrf_march_rays_prescribed(nf, so.data_ptr(), sd.data_ptr(), sn_.data_ptr(), sf.data_ptr(), *geo, None,
+                                                               counts.data_ptr(), None, None, None, None, None, N.ptr(box), st))
+                        sizes = counts
+                    else:
+                        sizes = caps
+                    ends = torch.cumsum(sizes, 0, dtype=torch.int32)
+                    offsets = (ends - sizes).contiguous()
+                    total = int(ends[-1].item())
+                    rows = total + 128 - total % 128  # raymarching.py:331-332 padding rule; unused rows are zeros
+                    bufs = (torch.zeros(rows, 3, **f32), torch.zeros(rows, 3, **f32), torch.zeros(rows, 2, **f32),
+                            torch.zeros(rows, dtype=torch.uint8, device=dev) if distill else None)
+                    N.check(lib.lnrf_march_rays_prescribed(nf, so.data_ptr(), sd.data_ptr(), sn_.data_ptr(), sf.data_ptr(), *geo, offsets.data_ptr(),
+                                                           counts.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(),
+                                                           N.ptr(bufs[3]), N.ptr(caps), N.ptr(box), st))
+                    return offsets, rows, bufs
+
+                # the fast pass knows where each ray died; on the reference's sequence it dies within a few samples of that
+                seq_total = int(sum(seq))
+                caps = (sub_steps + 96).clamp(max=seq_total).int().contiguous() if use_caps else None
+                offsets, rows, (xyzs, dirs, deltas, edit_occ) = march(caps)
                 sigmas, rgbs = self.forward_scaled(xyzs, dirs)
                 sigmas, rgbs = sigmas.float().contiguous(), rgbs.float().contiguous()
                 t2 = dict(weights_sum=torch.empty(nf, **f32), depth=torch.empty(nf, **f32), image=torch.empty(nf, 3, **f32),
@@ -513,6 +530,13 @@ class NeRFNetwork(nn.Module):
                                                            t2["weights_sum"].data_ptr(), N.ptr(t2["wes"]), t2["depth"].data_ptr(), N.ptr(t2["de"]),
                                                            t2["image"].data_ptr(), t2["ray_steps"].data_ptr(), st))
                 rounds2, slots2 = len(seq), rows
+                if caps is not None:
+                    # a ray that used up its cap without dying (neither T_thresh nor the end of its samples) was cut short: redo the
+                    # pass without caps (never seen on the three scene shapes; the margin is 96 samples)
+                    cut = (t2["ray_steps"] == counts) & (counts == caps) & (caps < seq_total)
+                    if bool(cut.any().item()):
+                        use_caps = False
+                        continue
             new_steps = t2["ray_steps"].long().clamp_(max=cap)
             hist = hist - torch.bincount(sub_steps, minlength=cap + 1).cpu().numpy() + torch.bincount(new_steps, minlength=cap + 1).cpu().numpy()
             sub_steps = new_steps

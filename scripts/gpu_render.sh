@@ -1,5 +1,4 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for g in 4 8; do echo "== compact march lanes per ray $g"
-LNRF_COMPACT_G=$g timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider -x -k "schedule or economies or edge_cases" 2>&1 | tail -1
-LNRF_COMPACT_G=$g python scripts/diag_render_shards.py 2>&1 | grep "auto" | grep "world 1 \|world 8 " | cut -c1-75; done
+timeout 600 python -m pytest tests -m gpu -q -p no:cacheprovider -x -k "schedule or economies or edge_cases or refstack" 2>&1 | tail -1
+for c in 1 0; do echo "== LNRF_FIXUP_CAPS=$c"; LNRF_FIXUP_CAPS=$c python scripts/diag_fixup.py 2>&1 | grep "rays: fast" | cut -c1-150; done
