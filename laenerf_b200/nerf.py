@@ -939,7 +939,7 @@ class GraphedTrainStep:
         self.gt.copy_(gt_rgb, non_blocking=True)
 
     def _capture_pipelined(self, p):
-        """Graph p: train on set p; beside its hash-grid backward, march the loaded batch into set 1-p."""
+        """Graph p: train on set p; beside its backward (from the MLP backward on), march the loaded batch into set 1-p."""
         from . import gridencoder as _ge
         cur, nxt = self.sets[p], self.sets[1 - p]
         if self._pipe_opt:  # ray-sharded: graph p accumulates into gradient buffer p and clears buffer 1 - p inside its exchange kernel
@@ -979,6 +979,8 @@ class GraphedTrainStep:
         return g, loss, out
 
     def capture(self, rays_o, rays_d, gt_rgb, warmup: int = 3):
+        """Warm up, then capture the step (lookahead: both graphs; the given batch becomes the batch in flight).  A RE-capture with
+        lookahead discards the batch that was in flight: call flush() first if it must be trained on."""
         m = self.model
         self._load(rays_o, rays_d, gt_rgb)
         if m.mean_count <= 0:  # the first (eager) steps size the sample buffer, as in the reference
