@@ -388,10 +388,10 @@ ORC_API void orc_composite_rays_train_backward(const float* grad_weights_sum, co
 
 /* kernel_composite_rays :948-1035 and kernel_composite_rays_distill :1037-1142
  * (weights_edit_sum / depth_edit / edit_occ NULL for the plain variant). */
-ORC_API void orc_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+static void composite_rays_impl(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
                                 const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
                                 float* weights_edit_sum, float* depth, float* depth_edit, const uint8_t* edit_occ,
-                                float* image) {
+                                float* image, int32_t* steps_done) {
     for (uint32_t n = 0; n < n_alive; n++) {
         const int32_t index = rays_alive[n];
         const float* ps = sigmas + (size_t)n * n_step;
@@ -424,6 +424,7 @@ ORC_API void orc_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thres
             if (pe) pe++;
             step++;
         }
+        if (steps_done) steps_done[n] = (int32_t)step; /* bookkeeping for the tests only: `step` of :1009 when the loop ends */
         if (step < n_step) rays_alive[n] = -1; else rays_t[index] = t;
         if (weights_edit_sum) weights_edit_sum[index] = weight_edit_sum;
         weights_sum[index] = weight_sum;
@@ -431,6 +432,24 @@ ORC_API void orc_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thres
         if (depth_edit) depth_edit[index] = d_edit;
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
     }
+}
+
+ORC_API void orc_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                                float* weights_edit_sum, float* depth, float* depth_edit, const uint8_t* edit_occ,
+                                float* image) {
+    composite_rays_impl(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, weights_edit_sum, depth, depth_edit,
+                        edit_occ, image, NULL);
+}
+
+/* The same kernel, additionally reporting for every alive slot how many samples the ray completed in this round (the value of the
+ * reference's loop counter `step` when its while loop ends).  Not a reference output: the tests of the round-schedule theory
+ * (tests/test_schedule_theory.py) need to know at which sample a ray dies. */
+ORC_API void orc_composite_rays_steps(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                      const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                                      float* image, int32_t* steps_done) {
+    composite_rays_impl(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, NULL, depth, NULL, NULL, image,
+                        steps_done);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -151,6 +151,18 @@ def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, we
     return out + (weights_edit_sum, depth_edit) if distill else out
 
 
+def composite_rays_steps(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
+    """composite_rays plus, per alive slot, the samples the ray completed in this round (orc_composite_rays_steps; test bookkeeping).
+    Returns (rays_alive, rays_t, weights_sum, depth, image, steps_done)."""
+    rays_alive, rays_t = _i32(rays_alive).copy(), _f32(rays_t).copy()
+    sigmas, rgbs, deltas = _f32(sigmas), _f32(rgbs), _f32(deltas)
+    weights_sum, depth, image = _f32(weights_sum).copy(), _f32(depth).copy(), _f32(image).copy()
+    steps = np.zeros(max(int(n_alive), 1), np.int32)
+    lib().orc_composite_rays_steps(u32(n_alive), u32(n_step), f32c(T_thresh), _p(rays_alive), _p(rays_t), _p(sigmas), _p(rgbs), _p(deltas),
+                                   _p(weights_sum), _p(depth), _p(image), _p(steps))
+    return rays_alive, rays_t, weights_sum, depth, image, steps[:n_alive]
+
+
 def grid_offsets(input_dim=3, num_levels=16, level_dim=2, per_level_scale=2.0, base_resolution=16, log2_hashmap_size=19,
                  desired_resolution=None, align_corners=False):
     """Restates GridEncoder.__init__'s table sizing (gridencoder/grid.py:100-127). Returns (offsets int32[L+1], per_level_scale)."""

@@ -1,0 +1,114 @@
+"""CPU tier: the round-schedule theory of DESIGN.md section 3, checked on the ORACLE (the CPU restatement of the reference's
+marcher and compositor, raymarching.cu:722-1035) -- no CUDA involved.
+
+The reference's inference loop (renderer.py:353-379) takes n_step = clamp(N // n_alive, 1, 8) samples per alive ray per round.
+The product renders on a faster schedule and claims the reference's bits.  What that rests on, each checked here with the
+reference's own kernels:
+
+  1. per-ray independence: a ray's result depends on the n_step SEQUENCE only, not on which other rays are rendered with it --
+     any subset of rays on the reference's sequence reproduces the full-frame result bit for bit;
+  2. the sequence is a function of the rays' death samples: NeRFNetwork._reference_sequence(histogram) == the sequence the loop took;
+  3. rays whose result differs between two schedules exist on a scene with cameras inside the volume (so the problem is real), while
+     every ray that comes out the same on both schedules also dies at the same sample (its death sample is schedule-independent);
+  4. the fix-up: start from the fast schedule's death samples, re-render the differing rays on the sequence reconstructed from the
+     histogram, iterate to a fixed point -> the reference schedule's results, bit for bit, for every ray.
+"""
+import numpy as np
+import pytest
+
+from cases import scene, scene_rays
+
+pyo = pytest.importorskip("oracle.pyoracle")
+
+
+def _field(xyzs):
+    """A deterministic 'network': density and colour as smooth functions of the position (schedule-independent by construction)."""
+    x, y, z = xyzs[:, 0].astype(np.float32), xyzs[:, 1].astype(np.float32), xyzs[:, 2].astype(np.float32)
+    sig = (6.0 * (0.5 + 0.5 * np.sin(np.float32(3.1) * x + np.float32(1.7) * y - np.float32(2.3) * z))).astype(np.float32)
+    rgb = np.stack([0.5 + 0.5 * np.sin(2 * x), 0.5 + 0.5 * np.cos(3 * y), 0.5 + 0.5 * np.sin(x + z)], -1).astype(np.float32)
+    return sig, rgb
+
+
+class _Frame:
+    def __init__(self, name, n, seed):
+        self.sc, self.ro, self.rd, _ = scene_rays(name, n, seed)
+        self.nears, self.fars = pyo.near_far_from_aabb(self.ro, self.rd, self.sc.aabb, self.sc.min_near)
+        self.n = n
+
+    def render(self, schedule, subset=None, max_steps=1024, T=1e-4):
+        """schedule: "reference" | "fast" | list of n_step (prescribed).  Returns dict(ws, depth, image, steps, seq)."""
+        sc = self.sc
+        idx = np.arange(self.n, dtype=np.int32) if subset is None else np.asarray(subset, np.int32)
+        ro, rd, nears, fars = self.ro[idx], self.rd[idx], self.nears[idx], self.fars[idx]
+        N = len(idx)
+        alive = np.arange(N, dtype=np.int32)
+        rays_t = nears.copy()
+        ws, depth, image = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+        steps = np.zeros(N, np.int64)
+        seq, step, r = [], 0, 0
+        while step < max_steps and len(alive) > 0:
+            if isinstance(schedule, list):
+                if r >= len(schedule):
+                    break
+                n_step = schedule[r]
+            elif schedule == "reference":
+                n_step = max(min(N // len(alive), 8), 1)          # renderer.py:357
+            else:
+                n_step = 1 if r == 0 else 32                       # "fast": far fewer, far longer rounds
+            M_rows = len(alive) * n_step
+            M_rows += 128 - M_rows % 128
+            xyzs, dirs, deltas = pyo.march_rays(len(alive), n_step, alive, rays_t, ro, rd, sc.bound, sc.density_bitfield, sc.cascade, 128, nears,
+                                                fars, np.zeros(len(alive), np.float32), M_rows, 0.0, max_steps)
+            sig, rgb = _field(xyzs)
+            alive2, rays_t, ws, depth, image, done = pyo.composite_rays_steps(len(alive), n_step, alive, rays_t, sig, rgb, deltas, ws, depth, image, T)
+            steps[alive] += done
+            alive = alive2[alive2 >= 0]                            # renderer.py:375
+            seq.append(n_step)
+            step += n_step
+            r += 1
+        return dict(ws=ws, depth=depth, image=image, steps=steps, seq=seq)
+
+
+@pytest.mark.parametrize("name,n", [("bonsai", 700), ("lego", 500)])
+def test_round_schedule_theory_on_the_oracle(name, n):
+    from laenerf_b200.nerf import NeRFNetwork
+    fr = _Frame(name, n, 11)
+    ref = fr.render("reference")
+    fast = fr.render("fast")
+    assert len(fast["seq"]) < len(ref["seq"]) / 2
+    same = (ref["ws"] == fast["ws"]) & (ref["depth"] == fast["depth"]) & (ref["image"] == fast["image"]).all(1)
+    # 3. schedule-independent rays die at the same sample; on the bonsai shape some rays DO depend on the schedule
+    assert (ref["steps"][same] == fast["steps"][same]).all()
+    if name == "bonsai":
+        assert 0 < (~same).sum() < n // 4, int((~same).sum())
+    # 2. the sequence follows from the histogram of the death samples
+    cap = 1024 + 72
+    hist = np.bincount(np.minimum(ref["steps"], cap), minlength=cap + 1)
+    assert NeRFNetwork._reference_sequence(hist, n, 1024) == ref["seq"]
+    # 1. any subset on the reference's sequence reproduces the full-frame result
+    rng = np.random.default_rng(0)
+    subset = np.unique(np.concatenate([np.nonzero(~same)[0], rng.choice(n, 40, replace=False)]))
+    part = fr.render(list(ref["seq"]), subset=subset)
+    for k in ("ws", "depth", "image", "steps"):
+        assert np.array_equal(part[k], ref[k][subset]), k
+    # 4. the fix-up from the FAST pass's information alone
+    bad = np.nonzero(~same)[0]
+    steps = fast["steps"].copy()
+    out = {k: fast[k].copy() for k in ("ws", "depth", "image")}
+    for _ in range(4):
+        hist = np.bincount(np.minimum(steps, cap), minlength=cap + 1)
+        seq = NeRFNetwork._reference_sequence(hist, n, 1024)
+        if len(bad) == 0:
+            break
+        redo = fr.render(seq, subset=bad)
+        steps[bad] = redo["steps"]
+        for k in out:
+            out[k][bad] = redo[k]
+        hist2 = np.bincount(np.minimum(steps, cap), minlength=cap + 1)
+        if NeRFNetwork._reference_sequence(hist2, n, 1024) == seq:
+            break
+    else:
+        pytest.fail("no fixed point")
+    assert seq == ref["seq"]
+    for k in out:
+        assert np.array_equal(out[k], ref[k]), k
