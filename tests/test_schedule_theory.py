@@ -112,3 +112,69 @@ def test_round_schedule_theory_on_the_oracle(name, n):
     assert seq == ref["seq"]
     for k in out:
         assert np.array_equal(out[k], ref[k]), k
+
+
+def _occupied_box(sc):
+    """numpy mirror of csrc/occupancy.cu k_occupied_box: box around every occupied cell of every cascade, two cells of margin."""
+    H = 128
+    lo_w, hi_w = np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+    bits = np.unpackbits(sc.density_bitfield, bitorder="little").reshape(sc.cascade, H ** 3)
+    coords = pyo.morton3D_invert(np.arange(H ** 3, dtype=np.int32))
+    for c in range(sc.cascade):
+        occ = coords[bits[c] == 1]
+        if len(occ) == 0:
+            continue
+        half = np.float32(min(2 ** c, sc.bound))
+        cell = np.float32(2.0) * half / np.float32(H)
+        lo_w = np.minimum(lo_w, -half + (occ.min(0).astype(np.float32) - np.float32(2.0)) * cell)
+        hi_w = np.maximum(hi_w, -half + (occ.max(0).astype(np.float32) + np.float32(3.0)) * cell)
+    return np.concatenate([lo_w, hi_w]).astype(np.float32)
+
+
+def _clip_far(box, ro, rd, fars):
+    """numpy mirror of csrc/march_core.cuh clip_far_to_box (float32 slab test; a miss gives -inf)."""
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        rdi = (np.float32(1.0) / rd.astype(np.float32)).astype(np.float32)
+        t1 = ((box[None, :3] - ro) * rdi).astype(np.float32)
+        t2 = ((box[None, 3:] - ro) * rdi).astype(np.float32)
+        t_in = np.fmax.reduce(np.fmin(t1, t2), axis=1)     # fmin / fmax drop NaN, as the device's fminf / fmaxf do
+        t_out = np.fmin.reduce(np.fmax(t1, t2), axis=1)
+    out = np.fmin(fars, t_out).astype(np.float32)
+    out[~(t_in <= t_out)] = -np.inf
+    return out
+
+
+@pytest.mark.parametrize("name", ["lego", "flower", "bonsai"])
+def test_clipping_far_to_the_occupied_box_is_exact_on_the_oracle(name):
+    """DESIGN.md section 3, economy (2): the reference's marchers with `far` clipped to the exit of the box around the occupied cells
+    emit the same samples -- training march (counts, offsets, positions, deltas) and the inference loop (image, depth, weights, death
+    samples) -- and a good part of the rays of the object-centred scene end much earlier."""
+    n = 400
+    fr = _Frame(name, n, 23)
+    sc = fr.sc
+    box = _occupied_box(sc)
+    clipped = _clip_far(box, fr.ro, fr.rd, fr.fars)
+    assert (clipped <= fr.fars).all()
+    if name == "lego":
+        assert (clipped < fr.fars - 0.2).mean() > 0.5        # most rays leave the object's box long before the scene box
+    rng = np.random.default_rng(3)
+    noises = rng.random(n, dtype=np.float32)
+    M = n * 1024
+    for dt_gamma in (0.0, 1.0 / 256):
+        a = pyo.march_rays_train(fr.ro, fr.rd, sc.density_bitfield, sc.bound, dt_gamma, 1024, sc.cascade, 128, M, fr.nears, fr.fars, noises)
+        b = pyo.march_rays_train(fr.ro, fr.rd, sc.density_bitfield, sc.bound, dt_gamma, 1024, sc.cascade, 128, M, fr.nears, clipped, noises)
+        total = int(a[4][0])
+        assert total == int(b[4][0]) and total > 100
+        for x, y in zip(a[:3], b[:3]):
+            assert np.array_equal(x[:total], y[:total])
+        assert np.array_equal(a[3], b[3])
+    ref = fr.render("reference")
+    keep = fr.fars
+    fr.fars = clipped
+    try:
+        cl = fr.render("reference")
+    finally:
+        fr.fars = keep
+    assert cl["seq"] == ref["seq"]
+    for k in ("ws", "depth", "image", "steps"):
+        assert np.array_equal(cl[k], ref[k]), k
