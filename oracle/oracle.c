@@ -271,12 +271,13 @@ ORC_API void orc_march_rays_train(const float* rays_o, const float* rays_d, cons
 
 /* kernel_march_rays :700-805 and kernel_march_rays_distill :811-926 (edit_grid/edit_occ may be NULL).
  * Output buffers must be zero-initialised by the caller (raymarching.py:334-336, 394-397). */
-ORC_API void orc_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+static void march_rays_impl(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
                             const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
                             uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* nears,
                             const float* fars, float* xyzs, float* dirs, float* deltas, uint8_t* edit_occ,
-                            const float* noises) {
+                            const float* noises, uint8_t* inexact) {
     for (uint32_t n = 0; n < n_alive; n++) {
+        if (inexact) inexact[n] = 0;
         const int32_t index = rays_alive[n];
         const float noise = noises[n];
         march_ctx m;
@@ -302,6 +303,9 @@ ORC_API void orc_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* ra
                 t += dt;
                 pl[0] = dt;
                 pl[1] = t - last_t;
+                /* test bookkeeping: is the delta the compositor will add back to rays_t (:1006) an EXACT difference?  If
+                 * fl(last_t + delta) == t for every sample, rays_t is rebuilt to the marcher's own t wherever a round ends. */
+                if (inexact) { volatile float back = last_t + pl[1]; if (back != t) inexact[n] = 1; }
                 last_t = t;
                 px += 3; pd += 3; pl += 2;
                 if (pe) {
@@ -314,6 +318,25 @@ ORC_API void orc_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* ra
             }
         }
     }
+}
+
+ORC_API void orc_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                            const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                            uint32_t C, uint32_t H, const uint8_t* grid, const uint8_t* edit_grid, const float* nears,
+                            const float* fars, float* xyzs, float* dirs, float* deltas, uint8_t* edit_occ,
+                            const float* noises) {
+    march_rays_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, edit_grid, nears, fars, xyzs,
+                    dirs, deltas, edit_occ, noises, NULL);
+}
+
+/* The same kernel, additionally reporting per alive slot whether any delta emitted in this round was NOT an exact difference
+ * (see march_rays_impl).  Not a reference output: tests/test_schedule_theory.py checks the product's exactness criterion with it. */
+ORC_API void orc_march_rays_track(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                                  const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                                  uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars, float* xyzs,
+                                  float* dirs, float* deltas, const float* noises, uint8_t* inexact) {
+    march_rays_impl(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, NULL, nears, fars, xyzs, dirs,
+                    deltas, NULL, noises, inexact);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -135,6 +135,21 @@ def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfi
     return (xyzs, dirs, deltas) if edit_occ is None else (xyzs, dirs, deltas, edit_occ)
 
 
+def march_rays_track(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfield, C_, H, nears, fars, noises, M_rows,
+                     dt_gamma=0.0, max_steps=1024):
+    """march_rays plus, per alive slot, whether a delta emitted in this round was not an exact difference (orc_march_rays_track; test
+    bookkeeping).  Returns (xyzs, dirs, deltas, inexact)."""
+    rays_o, rays_d = _f32(rays_o).reshape(-1, 3), _f32(rays_d).reshape(-1, 3)
+    rays_alive, rays_t, nears, fars, noises = _i32(rays_alive), _f32(rays_t), _f32(nears), _f32(fars), _f32(noises)
+    bitfield = _u8(bitfield)
+    xyzs, dirs, deltas = np.zeros((M_rows, 3), np.float32), np.zeros((M_rows, 3), np.float32), np.zeros((M_rows, 2), np.float32)
+    inexact = np.zeros(max(int(n_alive), 1), np.uint8)
+    lib().orc_march_rays_track(u32(n_alive), u32(n_step), _p(rays_alive), _p(rays_t), _p(rays_o), _p(rays_d), f32c(bound), f32c(dt_gamma),
+                               u32(max_steps), u32(C_), u32(H), _p(bitfield), _p(nears), _p(fars), _p(xyzs), _p(dirs), _p(deltas),
+                               _p(noises), _p(inexact))
+    return xyzs, dirs, deltas, inexact[:n_alive]
+
+
 def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2,
                    weights_edit_sum=None, depth_edit=None, edit_occ=None):
     """Returns updated copies: (rays_alive, rays_t, weights_sum, depth, image[, weights_edit_sum, depth_edit])."""

@@ -10,6 +10,9 @@ reference's own kernels:
   2. the sequence is a function of the rays' death samples: NeRFNetwork._reference_sequence(histogram) == the sequence the loop took;
   3. rays whose result differs between two schedules exist on a scene with cameras inside the volume (so the problem is real), while
      every ray that comes out the same on both schedules also dies at the same sample (its death sample is schedule-independent);
+     and the product's exactness criterion -- "no delta emitted after round 0 was an inexact difference" -- is SOUND: every ray that
+     differs carries the flag (computed here from the reference marcher's own t and last_t) or was cut off by the max_steps cap,
+     the one other way a schedule leaves a trace (the product detects that too and falls back);
   4. the fix-up: start from the fast schedule's death samples, re-render the differing rays on the sequence reconstructed from the
      histogram, iterate to a fixed point -> the reference schedule's results, bit for bit, for every ray.
 """
@@ -45,6 +48,7 @@ class _Frame:
         rays_t = nears.copy()
         ws, depth, image = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
         steps = np.zeros(N, np.int64)
+        flags = np.zeros(N, bool)   # the product's criterion (csrc/raymarch.cu kCtlInexact): an inexact delta after round 0
         seq, step, r = [], 0, 0
         while step < max_steps and len(alive) > 0:
             if isinstance(schedule, list):
@@ -57,8 +61,10 @@ class _Frame:
                 n_step = 1 if r == 0 else 32                       # "fast": far fewer, far longer rounds
             M_rows = len(alive) * n_step
             M_rows += 128 - M_rows % 128
-            xyzs, dirs, deltas = pyo.march_rays(len(alive), n_step, alive, rays_t, ro, rd, sc.bound, sc.density_bitfield, sc.cascade, 128, nears,
-                                                fars, np.zeros(len(alive), np.float32), M_rows, 0.0, max_steps)
+            xyzs, dirs, deltas, inexact = pyo.march_rays_track(len(alive), n_step, alive, rays_t, ro, rd, sc.bound, sc.density_bitfield, sc.cascade,
+                                                               128, nears, fars, np.zeros(len(alive), np.float32), M_rows, 0.0, max_steps)
+            if r > 0:
+                flags[alive] |= inexact.astype(bool)
             sig, rgb = _field(xyzs)
             alive2, rays_t, ws, depth, image, done = pyo.composite_rays_steps(len(alive), n_step, alive, rays_t, sig, rgb, deltas, ws, depth, image, T)
             steps[alive] += done
@@ -66,7 +72,9 @@ class _Frame:
             seq.append(n_step)
             step += n_step
             r += 1
-        return dict(ws=ws, depth=depth, image=image, steps=steps, seq=seq)
+        cut = np.zeros(N, bool)
+        cut[alive] = True   # rays the max_steps cap cut off (still alive when the loop ended)
+        return dict(ws=ws, depth=depth, image=image, steps=steps, seq=seq, flags=flags, cut=cut)
 
 
 @pytest.mark.parametrize("name,n", [("bonsai", 700), ("lego", 500)])
@@ -81,6 +89,14 @@ def test_round_schedule_theory_on_the_oracle(name, n):
     assert (ref["steps"][same] == fast["steps"][same]).all()
     if name == "bonsai":
         assert 0 < (~same).sum() < n // 4, int((~same).sum())
+    # 3b. the product's criterion is sound: every ray that differs was flagged by the FAST pass (an inexact delta after round 0);
+    # rays without a flag come out the same on both schedules.  (The flag may over-report: it is a sufficient condition.)
+    # A ray that is still alive when the loop runs into max_steps is cut at a schedule-dependent sample (the rounds hand out 1024-1031
+    # samples on one schedule, 1025 on the other): the product sends such a frame to the reference schedule (ctl[14], "cap cut").
+    cut = ref["cut"] | fast["cut"]
+    assert not (~same & ~fast["flags"] & ~cut).any(), int((~same & ~fast["flags"] & ~cut).sum())
+    if name == "lego":
+        assert not fast["flags"].any() and same.all()      # cameras outside the volume: the frame is provably schedule-independent
     # 2. the sequence follows from the histogram of the death samples
     cap = 1024 + 72
     hist = np.bincount(np.minimum(ref["steps"], cap), minlength=cap + 1)
