@@ -1,5 +1,5 @@
 // render_core.cuh -- internal launchers of the device-driven inference rounds (row f-3), shared between raymarch.cu,
-// nerfnet.cu and render.cu.  `ctl` is the int32[16] device control block documented in raymarch.cu.
+// nerfnet.cu and render.cu.  `ctl` is the int32[32] device control block documented in raymarch.cu.
 #pragma once
 #include "common.cuh"
 
