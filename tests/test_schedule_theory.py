@@ -194,3 +194,45 @@ def test_clipping_far_to_the_occupied_box_is_exact_on_the_oracle(name):
     assert cl["seq"] == ref["seq"]
     for k in ("ws", "depth", "image", "steps"):
         assert np.array_equal(cl[k], ref[k]), k
+
+
+def test_one_pass_rerender_equals_the_round_by_round_loop_on_the_oracle():
+    """What lnrf_march_rays_prescribed + lnrf_composite_rays_prescribed do, restated with the oracle's kernels: a
+    ray is marched through ALL rounds of a given n_step sequence on its own -- each round starting from the t the compositor would have
+    rebuilt, rays_t + the round's deltas[.][1] added one by one (raymarching.cu:1006) -- the 'network' runs once over those samples,
+    and the compositor walks them in ONE call.  Image, depth, weights and death sample equal the round-by-round loop's, bit for bit."""
+    fr = _Frame("bonsai", 300, 5)
+    sc = fr.sc
+    ref = fr.render("reference")
+    seq = ref["seq"]
+    rng = np.random.default_rng(1)
+    for i in rng.choice(fr.n, 60, replace=False):
+        ro, rd = fr.ro[i:i + 1], fr.rd[i:i + 1]
+        nears, fars = fr.nears[i:i + 1], fr.fars[i:i + 1]
+        alive = np.zeros(1, np.int32)
+        t = nears.copy()
+        xs, ds = [], []
+        for n_step in seq:                                   # the marcher alone, round after round
+            M_rows = n_step + 128 - n_step % 128
+            xyzs, _, deltas = pyo.march_rays(1, n_step, alive, t, ro, rd, sc.bound, sc.density_bitfield, sc.cascade, 128, nears, fars,
+                                             np.zeros(1, np.float32), M_rows, 0.0, 1024)
+            cnt = int((deltas[:n_step, 0] != 0).sum())
+            xs.append(xyzs[:cnt]); ds.append(deltas[:cnt])
+            for k in range(cnt):                             # what composite_rays leaves in rays_t
+                t = (t + deltas[k, 1]).astype(np.float32)
+            if cnt < n_step:
+                break
+        xyz = np.concatenate(xs) if xs else np.zeros((0, 3), np.float32)
+        dl = np.concatenate(ds) if ds else np.zeros((0, 2), np.float32)
+        total = len(xyz)
+        if total == 0:
+            assert ref["ws"][i] == 0 and ref["steps"][i] == 0
+            continue
+        sig, rgb = _field(xyz)
+        pad = np.zeros((1, 2), np.float32)                   # one empty slot behind the samples: the loop's `deltas == 0` exit
+        _, _, ws, depth, image, done = pyo.composite_rays_steps(1, total + 1, alive, nears.copy(), np.append(sig, np.float32(0)),
+                                                                np.concatenate([rgb, np.zeros((1, 3), np.float32)]),
+                                                                np.concatenate([dl, pad]), np.zeros(1, np.float32), np.zeros(1, np.float32),
+                                                                np.zeros((1, 3), np.float32), 1e-4)
+        assert ws[0] == ref["ws"][i] and depth[0] == ref["depth"][i] and np.array_equal(image[0], ref["image"][i]), i
+        assert int(done[0]) == int(ref["steps"][i]), i
